@@ -1,0 +1,268 @@
+"""ctypes binding of include/fbpr_b200.h.  Mirrors the reference's operator surface
+(featureExtra / extractSurroundingKeyFrames / downsampleCurrentScan / scan2MapOptimization /
+transformUpdate / registration) on frame SLOTS of one device-resident handle."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+FLAG_NOT_ENOUGH_FEATURES = 1
+FLAG_TOO_FEW_CORRESPONDENCES = 2
+FLAG_DEGENERATE = 4
+FLAG_CONVERGED = 8
+MEM_HOST, MEM_DEVICE = 0, 1
+
+RAW_POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("intensity", "<f4"), ("ring", "<i4"), ("time", "<f4")])
+RESULT_DTYPE = np.dtype([("pose", "<f4", (6,)), ("iters", "<i4"), ("flags", "<u4")])
+
+_BUF_NAMES = ["START_RING", "END_RING", "COL_IND", "RANGE", "CLOUD", "CURVATURE", "PICKED", "LABEL",
+              "CORNER", "CORNER_INDEX", "SURF", "RING_SURF_COUNT", "RING_SURF_COUNT_DS",
+              "CORNER_DS", "SURF_DS", "MAP_CORNER", "MAP_SURF",
+              "KNN_CORNER", "KNN_SURF", "KNN_D2_CORNER", "KNN_D2_SURF",
+              "COEFF_CORNER", "COEFF_SURF", "FLAG_CORNER", "FLAG_SURF", "ATA", "ATB", "X", "POSE_TRACE", "WINNER_RAW"]
+BUF = {n: i for i, n in enumerate(_BUF_NAMES)}
+_BUF_DTYPE = dict(START_RING=(np.int32, 1), END_RING=(np.int32, 1), COL_IND=(np.int32, 1), RANGE=(np.float32, 1),
+                  CLOUD=(np.float32, 4), CURVATURE=(np.float32, 1), PICKED=(np.int32, 1), LABEL=(np.int32, 1),
+                  CORNER=(np.float32, 4), CORNER_INDEX=(np.int32, 1), SURF=(np.float32, 4),
+                  RING_SURF_COUNT=(np.int32, 1), RING_SURF_COUNT_DS=(np.int32, 1),
+                  CORNER_DS=(np.float32, 4), SURF_DS=(np.float32, 4), MAP_CORNER=(np.float32, 4), MAP_SURF=(np.float32, 4),
+                  KNN_CORNER=(np.int32, 5), KNN_SURF=(np.int32, 5), KNN_D2_CORNER=(np.float32, 5), KNN_D2_SURF=(np.float32, 5),
+                  COEFF_CORNER=(np.float32, 4), COEFF_SURF=(np.float32, 4), FLAG_CORNER=(np.uint8, 1), FLAG_SURF=(np.uint8, 1),
+                  ATA=(np.float32, 6), ATB=(np.float32, 1), X=(np.float32, 1), POSE_TRACE=(np.float32, 6), WINNER_RAW=(np.int32, 1))
+
+
+class FbprError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """fbpr_params: the params.yaml knobs the path reads + device capacities."""
+    _fields_ = [("N_SCAN", C.c_int32), ("Horizon_SCAN", C.c_int32),
+                ("edgeThreshold", C.c_float), ("surfThreshold", C.c_float),
+                ("edgeFeatureMinValidNum", C.c_int32), ("surfFeatureMinValidNum", C.c_int32),
+                ("odometrySurfLeafSize", C.c_float), ("mappingCornerLeafSize", C.c_float), ("mappingSurfLeafSize", C.c_float),
+                ("z_tollerance", C.c_float), ("rotation_tollerance", C.c_float),
+                ("numberOfCores", C.c_int32), ("surroundingKeyframeSearchRadius", C.c_float),
+                ("max_frames", C.c_int32), ("max_raw_points", C.c_int32),
+                ("max_map_corner", C.c_int32), ("max_map_surf", C.c_int32), ("max_keyframe_points", C.c_int32),
+                ("knn_cell_corner", C.c_float), ("knn_cell_surf", C.c_float),
+                ("grid_cells_corner", C.c_int32), ("grid_cells_surf", C.c_int32),
+                ("lm_cluster_size", C.c_int32)]
+
+    @classmethod
+    def from_dict(cls, d, **extra):
+        p = cls()
+        names = {n for n, _ in cls._fields_}
+        for k, v in {**d, **extra}.items():
+            if k in names:
+                setattr(p, k, v)
+        if p.max_frames <= 0:
+            p.max_frames = 1
+        return p
+
+
+class CloudInfoView(C.Structure):
+    _fields_ = [("startRingIndex", C.POINTER(C.c_int32)), ("endRingIndex", C.POINTER(C.c_int32)),
+                ("pointColInd", C.POINTER(C.c_int32)), ("pointRange", C.POINTER(C.c_float)),
+                ("cloud_deskewed", C.POINTER(C.c_float)), ("n_valid", C.c_int32),
+                ("imuAvailable", C.c_int64), ("imuRollInit", C.c_float), ("imuPitchInit", C.c_float), ("imuYawInit", C.c_float)]
+
+
+def library_path():
+    return os.path.join(_HERE, "libfbpr_b200.so")
+
+
+def load_library():
+    """Load libfbpr_b200.so; raise loudly if it has not been built (there is no fallback path)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise FbprError(f"{path} is missing: build it with `make` or `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(the CUDA library is the only implementation; there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.fbpr_last_error.restype = C.c_char_p
+    lib.fbpr_stream.restype = C.c_void_p
+    lib.fbpr_stream.argtypes = [C.c_void_p]
+    lib.fbpr_kernel_launches.restype = C.c_int64
+    lib.fbpr_kernel_launches.argtypes = [C.c_void_p]
+    lib.fbpr_get_buffer.restype = C.c_int64
+    lib.fbpr_get_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]
+    lib.fbpr_destroy.argtypes = [C.c_void_p]
+    lib.fbpr_destroy.restype = None
+    _LIB = lib
+    return lib
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def pack_raw(scan):
+    """synth scan dict (SoA) -> array of fbpr_raw_point records."""
+    n = int(scan["n"])
+    raw = np.zeros(n, RAW_POINT_DTYPE)
+    for k in ("x", "y", "z", "intensity", "ring", "time"):
+        raw[k] = scan[k][:n]
+    return raw
+
+
+class Registration:
+    """One device-resident handle = `max_frames` frame slots on one GPU and one stream."""
+
+    def __init__(self, params, device=0, **extra):
+        self.lib = load_library()
+        self.params = params if isinstance(params, Params) else Params.from_dict(params, **extra)
+        self.h = C.c_void_p()
+        rc = self.lib.fbpr_create(C.byref(self.params), int(device), C.byref(self.h))
+        if rc != 0:
+            self.h = None
+            raise FbprError(self.lib.fbpr_last_error().decode())
+        self.F = self.params.max_frames
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fbpr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise FbprError(self.lib.fbpr_last_error().decode())
+        return rc
+
+    # ---- inputs
+    def set_raw_scan(self, slot, raw, imu=None, imu_available=0, deskew_flag=1, imu_roll_init=0.0, imu_pitch_init=0.0):
+        raw = np.ascontiguousarray(raw, dtype=RAW_POINT_DTYPE)
+        if imu is not None and imu_available:
+            args = (C.c_double(imu["timeScanCur"]), _vp(imu["imuTime"]), _vp(imu["imuRotX"]), _vp(imu["imuRotY"]), _vp(imu["imuRotZ"]),
+                    C.c_int(int(imu["imuPointerCur"])))
+        else:
+            args = (C.c_double(0.0), None, None, None, None, C.c_int(0))
+        self._ck(self.lib.fbpr_set_raw_scan(self.h, slot, _vp(raw), len(raw), MEM_HOST, C.c_int64(imu_available), C.c_int(deskew_flag),
+                                            *args, C.c_float(imu_roll_init), C.c_float(imu_pitch_init)))
+        self._keep = [raw]
+
+    def set_raw_scan_device(self, slot, dev_ptr, n, imu=None, imu_available=0, deskew_flag=1):
+        if imu is not None and imu_available:
+            args = (C.c_double(imu["timeScanCur"]), _vp(imu["imuTime"]), _vp(imu["imuRotX"]), _vp(imu["imuRotY"]), _vp(imu["imuRotZ"]),
+                    C.c_int(int(imu["imuPointerCur"])))
+        else:
+            args = (C.c_double(0.0), None, None, None, None, C.c_int(0))
+        self._ck(self.lib.fbpr_set_raw_scan(self.h, slot, C.c_void_p(dev_ptr), int(n), MEM_DEVICE, C.c_int64(imu_available),
+                                            C.c_int(deskew_flag), *args, C.c_float(0.0), C.c_float(0.0)))
+
+    def set_cloud_info(self, slot, ci, imu_available=0, imu_roll_init=0.0, imu_pitch_init=0.0):
+        sr = np.ascontiguousarray(ci["startRingIndex"], np.int32); er = np.ascontiguousarray(ci["endRingIndex"], np.int32)
+        col = np.ascontiguousarray(ci["pointColInd"], np.int32); rng = _f32(ci["pointRange"]); cl = _f32(ci["cloud_deskewed"])
+        v = CloudInfoView(sr.ctypes.data_as(C.POINTER(C.c_int32)), er.ctypes.data_as(C.POINTER(C.c_int32)),
+                          col.ctypes.data_as(C.POINTER(C.c_int32)), rng.ctypes.data_as(C.POINTER(C.c_float)),
+                          cl.ctypes.data_as(C.POINTER(C.c_float)), len(col), imu_available, imu_roll_init, imu_pitch_init, 0.0)
+        self._ck(self.lib.fbpr_set_cloud_info(self.h, slot, C.byref(v), MEM_HOST))
+
+    def set_feature_clouds(self, slot, corner, surf):
+        c = _f32(corner).reshape(-1, 4); s = _f32(surf).reshape(-1, 4)
+        self._ck(self.lib.fbpr_set_feature_clouds(self.h, slot, _vp(c), len(c), _vp(s), len(s), MEM_HOST))
+
+    def set_local_map(self, slot, corner, surf):
+        c = _f32(corner).reshape(-1, 4); s = _f32(surf).reshape(-1, 4)
+        self._ck(self.lib.fbpr_set_local_map(self.h, slot, _vp(c), len(c), _vp(s), len(s), MEM_HOST))
+
+    def set_local_map_device(self, slot, corner_ptr, n_corner, surf_ptr, n_surf):
+        self._ck(self.lib.fbpr_set_local_map(self.h, slot, C.c_void_p(corner_ptr), int(n_corner), C.c_void_p(surf_ptr), int(n_surf), MEM_DEVICE))
+
+    def set_pose(self, slot, pose6):
+        p = _f32(pose6)
+        self._ck(self.lib.fbpr_set_pose(self.h, slot, _vp(p)))
+
+    def set_poses(self, first, poses6):
+        p = _f32(poses6).reshape(-1, 6)
+        self._ck(self.lib.fbpr_set_poses(self.h, first, len(p), _vp(p), MEM_HOST))
+
+    def set_poses_device(self, first, count, dev_ptr):
+        self._ck(self.lib.fbpr_set_poses(self.h, first, count, C.c_void_p(dev_ptr), MEM_DEVICE))
+
+    # ---- operators (reference names)
+    def project(self, first=0, count=1): self._ck(self.lib.fbpr_project(self.h, first, count))
+    def featureExtra(self, first=0, count=1): self._ck(self.lib.fbpr_feature_extract(self.h, first, count))
+    def downsampleCurrentScan(self, first=0, count=1): self._ck(self.lib.fbpr_downsample_current_scan(self.h, first, count))
+    def scan2MapOptimization(self, first=0, count=1): self._ck(self.lib.fbpr_scan2map_optimization(self.h, first, count))
+    def transformUpdate(self, first=0, count=1): self._ck(self.lib.fbpr_transform_update(self.h, first, count))
+
+    def extractSurroundingKeyFrames(self, slot, key_poses6, corner_frames, surf_frames, last_key_xyz):
+        K = len(corner_frames)
+        kp = _f32(key_poses6).reshape(K, 6)
+        coff = np.zeros(K + 1, np.int32); soff = np.zeros(K + 1, np.int32)
+        coff[1:] = np.cumsum([len(c) for c in corner_frames]); soff[1:] = np.cumsum([len(s) for s in surf_frames])
+        call = _f32(np.concatenate(corner_frames)).reshape(-1, 4); sall = _f32(np.concatenate(surf_frames)).reshape(-1, 4)
+        lk = _f32(last_key_xyz)
+        self._ck(self.lib.fbpr_extract_surrounding_keyframes(self.h, slot, K, _vp(kp), _vp(call), _vp(coff), _vp(sall), _vp(soff), _vp(lk), MEM_HOST))
+        self.sync()
+
+    def registration(self, slot, corner_global, surf_global, pose12):
+        c = _f32(corner_global).reshape(-1, 4); s = _f32(surf_global).reshape(-1, 4)
+        T = _f32(pose12).reshape(-1).copy()
+        self._ck(self.lib.fbpr_registration(self.h, slot, _vp(c), len(c), _vp(s), len(s), MEM_HOST, _vp(T)))
+        return T.reshape(3, 4)
+
+    def run_frames(self, first=0, count=1, with_projection=True, with_features=True):
+        self._ck(self.lib.fbpr_run_frames(self.h, first, count, int(with_projection), int(with_features)))
+
+    def use_graphs(self, on=True): self._ck(self.lib.fbpr_use_graphs(self.h, int(on)))
+    def sync(self): self._ck(self.lib.fbpr_sync(self.h))
+    def stream(self): return self.lib.fbpr_stream(self.h)
+    def kernel_launches(self): return int(self.lib.fbpr_kernel_launches(self.h))
+    def set_debug_iteration(self, it): self._ck(self.lib.fbpr_set_debug_iteration(self.h, int(it)))
+
+    # ---- results
+    def get_results(self, first=0, count=1):
+        out = np.zeros(count, RESULT_DTYPE)
+        self._ck(self.lib.fbpr_get_results(self.h, first, count, _vp(out), MEM_HOST))
+        return out
+
+    def get_results_device(self, first, count, dev_ptr):
+        self._ck(self.lib.fbpr_get_results(self.h, first, count, C.c_void_p(dev_ptr), MEM_DEVICE))
+
+    def get_pose(self, slot=0):
+        r = self.get_results(slot, 1)[0]
+        return r["pose"].copy(), int(r["iters"]), int(r["flags"])
+
+    def get_counts(self, slot=0):
+        c = np.zeros(8, np.int32)
+        self._ck(self.lib.fbpr_get_counts(self.h, slot, _vp(c)))
+        return dict(zip(["n_raw", "n_valid", "n_corner", "n_surf", "n_corner_ds", "n_surf_ds", "n_map_corner", "n_map_surf"], map(int, c)))
+
+    def get_buffer(self, slot, name):
+        dt, w = _BUF_DTYPE[name]
+        cap = max(self.params.N_SCAN * self.params.Horizon_SCAN, self.params.max_map_corner, self.params.max_map_surf, 65536) * 5 * 4 + 1024
+        buf = np.zeros(cap, np.uint8)
+        nb = self._ck(self.lib.fbpr_get_buffer(self.h, slot, BUF[name], _vp(buf), cap))
+        out = buf[:nb].view(dt).copy()
+        return out.reshape(-1, w) if w > 1 else out
+
+    # ---- stand-alone primitives
+    def voxel_grid(self, xyzi, leaf):
+        p = _f32(xyzi).reshape(-1, 4); n = len(p)
+        out = np.zeros((max(n, 1), 4), np.float32); pk = np.zeros(max(n, 1), np.int32); ok = np.zeros(max(n, 1), np.int32)
+        m = self._ck(self.lib.fbpr_voxel_grid(self.h, _vp(p), n, C.c_float(leaf), _vp(out), _vp(pk), _vp(ok), MEM_HOST))
+        return dict(points=out[:m].copy(), point_keys=pk[:n].copy(), out_keys=ok[:m].copy())
+
+    def knn5(self, map_xyzi, q_xyz, cell=0.25):
+        m = _f32(map_xyzi).reshape(-1, 4); q = _f32(q_xyz).reshape(-1, 3); nq = len(q)
+        idx = np.zeros((max(nq, 1), 5), np.int32); d2 = np.zeros((max(nq, 1), 5), np.float32)
+        self._ck(self.lib.fbpr_knn5(self.h, _vp(m), len(m), C.c_float(cell), _vp(q), nq, _vp(idx), _vp(d2), MEM_HOST))
+        return idx[:nq], d2[:nq]

@@ -1,0 +1,720 @@
+// capi.cu -- the C ABI (include/fbpr_b200.h): handle, HBM layout, operator sequencing.
+// Plain pointers and sizes only; no torch types.  Every operator enqueues its kernels on the
+// handle's stream and returns; nothing here computes on the CPU and nothing falls back.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "internal.cuh"
+
+// ---- kernel-side argument blocks and launchers (defined in the other translation units) ----
+void fbpr_launch_projection(const ProjArgs& a, int count, cudaStream_t st, long long* launches);
+int fbpr_launch_features(const FeatArgs& a, int count, cudaStream_t st, long long* launches);
+size_t fbpr_feat_ring_smem(const FeatArgs& a);
+void fbpr_launch_voxel(const VoxSeg* d_segs, int nsegs, int max_n, int tiles_cap, cudaStream_t st, long long* launches);
+int fbpr_voxel_tile();
+void fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cells_cap, cudaStream_t st, long long* launches);
+void fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, cudaStream_t st, long long* launches);
+int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, cudaStream_t st, long long* launches);
+void fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float rot_tol, float z_tol, cudaStream_t st, long long* launches);
+void fbpr_launch_keyframe_transform(const float* d_poses6, int K, const float4* d_in, const int* d_off, float4* d_out, int* d_n_out,
+                                    const float* d_last_xyz, float radius, int max_pts, int* d_outoff, float* d_T,
+                                    cudaStream_t st, long long* launches);
+void fbpr_launch_crop_box(const float4* d_in, int n, const float* d_pose12, float4* d_out, int cap, int* d_n_out, int* d_tile,
+                          cudaStream_t st, long long* launches);
+void fbpr_launch_pose_decompose(const float* d_pose12, FrameMeta* meta, int slot, cudaStream_t st, long long* launches);
+void fbpr_launch_pose_compose(const FrameMeta* meta, int slot, float* d_pose12, cudaStream_t st, long long* launches);
+
+// ---- error reporting -------------------------------------------------------------------------
+static thread_local std::string g_err;
+int fbpr_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s:%d: %s -> %s", file, line, what, cudaGetErrorString(e));
+    g_err = buf;
+    return -2;
+}
+int fbpr_fail_msg(const char* msg) { g_err = msg; return -1; }
+
+// ---- handle ------------------------------------------------------------------------------------
+struct fbpr_handle {
+    fbpr_params p;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    int F = 0, P = 0, rawCap = 0, cornerCap = 0, mapCornerCap = 0, mapSurfCap = 0, kfCap = 0;
+    int tilesCap = 0, cellsCorner = 0, cellsSurf = 0, cluster = 8;
+    float cellCorner = 0.5f, cellSurf = 0.25f;
+    std::vector<void*> allocs;
+    size_t bytes = 0;
+    // per-slot arrays
+    FrameMeta* meta = nullptr;
+    fbpr_raw_point* raw = nullptr;
+    double *imuTime = nullptr, *imuRotX = nullptr, *imuRotY = nullptr, *imuRotZ = nullptr;
+    int *pix = nullptr, *ringCount = nullptr, *startRing = nullptr, *endRing = nullptr, *colInd = nullptr, *winner = nullptr;
+    float *range = nullptr, *curv = nullptr;
+    float4 *cloud = nullptr, *surfStage = nullptr, *surf = nullptr, *surfDS = nullptr, *corner = nullptr, *cornerDS = nullptr;
+    int *picked = nullptr, *label = nullptr, *ringCorner = nullptr, *cornerStage = nullptr, *ringSurf = nullptr, *ringSurfDS = nullptr, *cornerIndex = nullptr;
+    float4 *mapCorner = nullptr, *mapSurf = nullptr;
+    float* poseTrace = nullptr;
+    // descriptors
+    VoxSeg* d_scanSegs = nullptr;      // [2F]  downsampleCurrentScan
+    GridSeg* d_gridSegs = nullptr;     // [2F]  map index
+    std::vector<GridSeg> h_gridSegs;
+    VoxSeg* d_kfSegs = nullptr;        // [2F]  extractCloud VoxelGrid (keyframe concat -> local map)
+    float4 *kfCorner = nullptr, *kfSurf = nullptr;   // [F][kfCap] transformed keyframe concat
+    int* kfCount = nullptr;            // [F][2]
+    // stand-alone ops scratch (grown on demand)
+    VoxSeg* d_soloVox = nullptr; int soloVoxCap = 0; std::vector<void*> soloVoxAllocs;
+    float4 *soloIn = nullptr, *soloOut = nullptr; int *soloN = nullptr, *soloNout = nullptr, *soloPK = nullptr, *soloOK = nullptr;
+    GridSeg* d_soloGrid = nullptr; int soloGridCap = 0; float soloGridCell = 0; std::vector<void*> soloGridAllocs;
+    float4* soloMap = nullptr; int* soloMapN = nullptr;
+    // debug capture (slots < dbgSlots)
+    int debugIter = -1, dbgSlots = 0;
+    int *knnC = nullptr, *knnS = nullptr; float *d2C = nullptr, *d2S = nullptr; float4 *coeffC = nullptr, *coeffS = nullptr;
+    unsigned char *flagC = nullptr, *flagS = nullptr; float *dbgAtA = nullptr, *dbgAtB = nullptr, *dbgX = nullptr;
+    // registration() scratch
+    float4 *regGlobal = nullptr; int regGlobalCap = 0; int* regTile = nullptr; float* regPose = nullptr;
+    int globalCornerN = -1, globalSurfN = 0;   // resident global maps (fbpr_set_global_map)
+    // graphs
+    bool useGraphs = false;
+    std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> graphs;
+    std::map<std::tuple<int, int, int, int>, long long> graphLaunches;
+};
+
+template <typename T>
+static int dev_alloc(fbpr_handle* h, T** p, size_t count, bool zero = true) {
+    void* q = nullptr;
+    size_t bytes = count * sizeof(T); if (bytes == 0) bytes = sizeof(T);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) return fbpr_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    if (zero) { e = cudaMemsetAsync(q, 0, bytes, h->stream); if (e != cudaSuccess) return fbpr_fail(e, "cudaMemsetAsync", __FILE__, __LINE__); }
+    h->allocs.push_back(q); h->bytes += bytes;
+    *p = reinterpret_cast<T*>(q);
+    return 0;
+}
+#define ALLOC(ptr, count) do { int rc_ = dev_alloc(h, &(ptr), (size_t)(count)); if (rc_) return rc_; } while (0)
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+static cudaMemcpyKind kind_in(int mem) { return mem == FBPR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
+
+static int check_range(fbpr_handle* h, int first, int count) {
+    if (!h) return fbpr_fail_msg("null handle");
+    if (first < 0 || count < 0 || first + count > h->F) return fbpr_fail_msg("slot range out of bounds");
+    return 0;
+}
+
+static int build_vox_segs(fbpr_handle* h, std::vector<VoxSeg>& segs, VoxSeg** d_out) {
+    for (auto& s : segs) {
+        for (int b = 0; b < 2; b++) { ALLOC(s.key[b], s.cap); ALLOC(s.val[b], s.cap); }
+        ALLOC(s.tile_hist, (size_t)256 * h->tilesCap);
+        ALLOC(s.bbox, 8);
+        ALLOC(s.run_tile, h->tilesCap + 1);
+        ALLOC(s.desc, 1);
+    }
+    ALLOC(*d_out, segs.size());
+    FBPR_CUDA_OK(cudaMemcpyAsync(*d_out, segs.data(), segs.size() * sizeof(VoxSeg), cudaMemcpyHostToDevice, h->stream));
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" {
+
+const char* fbpr_last_error(void) { return g_err.c_str(); }
+
+int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
+    if (!params || !out) return fbpr_fail_msg("null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) return fbpr_fail(e == cudaSuccess ? cudaErrorNoDevice : e, "no usable CUDA device (this library has no CPU fallback)", __FILE__, __LINE__);
+    if (device < 0 || device >= ndev) return fbpr_fail_msg("device index out of range");
+    FBPR_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FBPR_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fbpr_fail_msg("libfbpr_b200 is built for sm_100a (B200) only");
+    if (params->N_SCAN <= 0 || params->Horizon_SCAN <= 0 || params->max_frames <= 0) return fbpr_fail_msg("bad N_SCAN / Horizon_SCAN / max_frames");
+    fbpr_handle* h = new fbpr_handle();
+    h->p = *params; h->device = device;
+    FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const int F = h->F = params->max_frames;
+    const int N = params->N_SCAN, H = params->Horizon_SCAN;
+    const int P = h->P = N * H;
+    h->rawCap = params->max_raw_points > 0 ? params->max_raw_points : (int)(P * 1.02) + 64;
+    h->cornerCap = N * FBPR_SEGS * FBPR_CORNERS_PER_SEG;
+    h->mapCornerCap = params->max_map_corner > 0 ? params->max_map_corner : 65536;
+    h->mapSurfCap = params->max_map_surf > 0 ? params->max_map_surf : 262144;
+    h->kfCap = params->max_keyframe_points;
+    h->cellCorner = params->knn_cell_corner > 0 ? params->knn_cell_corner : 0.5f;
+    h->cellSurf = params->knn_cell_surf > 0 ? params->knn_cell_surf : 0.25f;
+    h->cellsCorner = params->grid_cells_corner > 0 ? params->grid_cells_corner : 262144;
+    h->cellsSurf = params->grid_cells_surf > 0 ? params->grid_cells_surf : 1048576;
+    h->cluster = params->lm_cluster_size > 0 ? params->lm_cluster_size : 8;
+    if (h->cluster != 1 && h->cluster != 2 && h->cluster != 4 && h->cluster != 8 && h->cluster != 16) return fbpr_fail_msg("lm_cluster_size must be 1,2,4,8 or 16");
+    int maxVox = P; if (h->kfCap > maxVox) maxVox = h->kfCap;
+    h->tilesCap = (maxVox + fbpr_voxel_tile() - 1) / fbpr_voxel_tile() + 1;
+
+    ALLOC(h->meta, F);
+    ALLOC(h->raw, (size_t)F * h->rawCap);
+    ALLOC(h->imuTime, (size_t)F * FBPR_IMU_CAP); ALLOC(h->imuRotX, (size_t)F * FBPR_IMU_CAP);
+    ALLOC(h->imuRotY, (size_t)F * FBPR_IMU_CAP); ALLOC(h->imuRotZ, (size_t)F * FBPR_IMU_CAP);
+    ALLOC(h->pix, (size_t)F * P); ALLOC(h->colInd, (size_t)F * P); ALLOC(h->winner, (size_t)F * P);
+    ALLOC(h->picked, (size_t)F * P); ALLOC(h->label, (size_t)F * P);
+    ALLOC(h->range, (size_t)F * P); ALLOC(h->curv, (size_t)F * P);
+    ALLOC(h->cloud, (size_t)F * P); ALLOC(h->surfStage, (size_t)F * P); ALLOC(h->surf, (size_t)F * P); ALLOC(h->surfDS, (size_t)F * P);
+    ALLOC(h->ringCount, (size_t)F * N); ALLOC(h->startRing, (size_t)F * N); ALLOC(h->endRing, (size_t)F * N);
+    ALLOC(h->ringCorner, (size_t)F * N); ALLOC(h->ringSurf, (size_t)F * N); ALLOC(h->ringSurfDS, (size_t)F * N);
+    ALLOC(h->cornerStage, (size_t)F * h->cornerCap);
+    ALLOC(h->corner, (size_t)F * h->cornerCap); ALLOC(h->cornerDS, (size_t)F * h->cornerCap); ALLOC(h->cornerIndex, (size_t)F * h->cornerCap);
+    ALLOC(h->mapCorner, (size_t)F * h->mapCornerCap); ALLOC(h->mapSurf, (size_t)F * h->mapSurfCap);
+    ALLOC(h->poseTrace, (size_t)F * FBPR_MAX_ITERS * 6);
+    ALLOC(h->regPose, 16);
+
+    // downsampleCurrentScan segments: (slot, corner), (slot, surf)
+    {
+        std::vector<VoxSeg> segs(2 * (size_t)F);
+        for (int f = 0; f < F; f++) {
+            VoxSeg c = {}; c.in = h->corner + (size_t)f * h->cornerCap; c.n_in = &h->meta[f].n_corner;
+            c.out = h->cornerDS + (size_t)f * h->cornerCap; c.n_out = &h->meta[f].n_corner_ds;
+            c.leaf = params->mappingCornerLeafSize; c.cap = h->cornerCap;
+            VoxSeg s = {}; s.in = h->surf + (size_t)f * P; s.n_in = &h->meta[f].n_surf;
+            s.out = h->surfDS + (size_t)f * P; s.n_out = &h->meta[f].n_surf_ds;
+            s.leaf = params->mappingSurfLeafSize; s.cap = P;
+            segs[2 * f] = c; segs[2 * f + 1] = s;
+        }
+        int rc = build_vox_segs(h, segs, &h->d_scanSegs); if (rc) return rc;
+    }
+    // map index segments
+    {
+        h->h_gridSegs.resize(2 * (size_t)F);
+        for (int f = 0; f < F; f++) {
+            for (int k = 0; k < 2; k++) {
+                GridSeg g = {};
+                g.cap = k == 0 ? h->mapCornerCap : h->mapSurfCap;
+                g.cells_cap = k == 0 ? h->cellsCorner : h->cellsSurf;
+                g.h0 = k == 0 ? h->cellCorner : h->cellSurf;
+                g.pts = (k == 0 ? h->mapCorner + (size_t)f * h->mapCornerCap : h->mapSurf + (size_t)f * h->mapSurfCap);
+                g.n = k == 0 ? &h->meta[f].n_map_corner : &h->meta[f].n_map_surf;
+                ALLOC(g.sorted, g.cap); ALLOC(g.cell_start, g.cells_cap + 2); ALLOC(g.cell_cursor, g.cells_cap + 2);
+                ALLOC(g.cell_of, g.cap); ALLOC(g.tile_sum, g.cells_cap / 4096 + 4); ALLOC(g.bbox, 8); ALLOC(g.desc, 1);
+                h->h_gridSegs[2 * f + k] = g;
+            }
+        }
+        ALLOC(h->d_gridSegs, 2 * (size_t)F);
+        FBPR_CUDA_OK(cudaMemcpyAsync(h->d_gridSegs, h->h_gridSegs.data(), h->h_gridSegs.size() * sizeof(GridSeg), cudaMemcpyHostToDevice, h->stream));
+    }
+    // extractCloud: transformed keyframe concat -> VoxelGrid -> local map
+    if (h->kfCap > 0) {
+        ALLOC(h->kfCorner, (size_t)F * h->kfCap); ALLOC(h->kfSurf, (size_t)F * h->kfCap); ALLOC(h->kfCount, (size_t)F * 2);
+        std::vector<VoxSeg> segs(2 * (size_t)F);
+        for (int f = 0; f < F; f++) {
+            VoxSeg c = {}; c.in = h->kfCorner + (size_t)f * h->kfCap; c.n_in = h->kfCount + 2 * f;
+            c.out = h->mapCorner + (size_t)f * h->mapCornerCap; c.n_out = &h->meta[f].n_map_corner;
+            c.leaf = params->mappingCornerLeafSize; c.cap = h->kfCap;
+            VoxSeg s = {}; s.in = h->kfSurf + (size_t)f * h->kfCap; s.n_in = h->kfCount + 2 * f + 1;
+            s.out = h->mapSurf + (size_t)f * h->mapSurfCap; s.n_out = &h->meta[f].n_map_surf;
+            s.leaf = params->mappingSurfLeafSize; s.cap = h->kfCap;
+            segs[2 * f] = c; segs[2 * f + 1] = s;
+        }
+        int rc = build_vox_segs(h, segs, &h->d_kfSegs); if (rc) return rc;
+    }
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return 0;
+}
+
+void fbpr_destroy(fbpr_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
+    for (void* p : h->allocs) cudaFree(p);
+    for (void* p : h->soloVoxAllocs) cudaFree(p);
+    for (void* p : h->soloGridAllocs) cudaFree(p);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int fbpr_sync(fbpr_handle* h) {
+    if (!h) return fbpr_fail_msg("null handle");
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    FBPR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+void* fbpr_stream(fbpr_handle* h) { return h ? (void*)h->stream : nullptr; }
+int64_t fbpr_kernel_launches(fbpr_handle* h) { return h ? h->launches : 0; }
+int fbpr_use_graphs(fbpr_handle* h, int on) { if (!h) return fbpr_fail_msg("null handle"); h->useGraphs = on != 0; return 0; }
+
+// ---- inputs ----------------------------------------------------------------------------------
+int fbpr_set_raw_scan(fbpr_handle* h, int slot, const fbpr_raw_point* pts, int n, int mem,
+                      int64_t imuAvailable, int deskewFlag, double timeScanCur,
+                      const double* imuTime, const double* imuRotX, const double* imuRotY, const double* imuRotZ,
+                      int imuPointerCur, float imuRollInit, float imuPitchInit) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    if (n < 0 || n > h->rawCap) return fbpr_fail_msg("raw scan larger than max_raw_points");
+    if (imuAvailable != 0 && deskewFlag != -1) {
+        if (!imuTime || !imuRotX || !imuRotY || !imuRotZ) return fbpr_fail_msg("IMU ramp missing while imuAvailable != 0");
+        if (imuPointerCur < 0 || imuPointerCur >= FBPR_IMU_CAP) return fbpr_fail_msg("imuPointerCur out of range");
+    }
+    cudaSetDevice(h->device);
+    if (n > 0) FBPR_CUDA_OK(cudaMemcpyAsync(h->raw + (size_t)slot * h->rawCap, pts, (size_t)n * sizeof(fbpr_raw_point), kind_in(mem), h->stream));
+    if (imuAvailable != 0 && deskewFlag != -1) {
+        size_t nb = (size_t)(imuPointerCur + 1) * sizeof(double);
+        FBPR_CUDA_OK(cudaMemcpyAsync(h->imuTime + (size_t)slot * FBPR_IMU_CAP, imuTime, nb, cudaMemcpyHostToDevice, h->stream));
+        FBPR_CUDA_OK(cudaMemcpyAsync(h->imuRotX + (size_t)slot * FBPR_IMU_CAP, imuRotX, nb, cudaMemcpyHostToDevice, h->stream));
+        FBPR_CUDA_OK(cudaMemcpyAsync(h->imuRotY + (size_t)slot * FBPR_IMU_CAP, imuRotY, nb, cudaMemcpyHostToDevice, h->stream));
+        FBPR_CUDA_OK(cudaMemcpyAsync(h->imuRotZ + (size_t)slot * FBPR_IMU_CAP, imuRotZ, nb, cudaMemcpyHostToDevice, h->stream));
+    }
+    FrameMeta m = {};
+    m.n_raw = n; m.deskewFlag = deskewFlag; m.imuPointerCur = imuPointerCur; m.imuAvailable = imuAvailable;
+    m.timeScanCur = timeScanCur; m.imuRollInit = imuRollInit; m.imuPitchInit = imuPitchInit;
+    char* base = reinterpret_cast<char*>(h->meta + slot);
+    FBPR_CUDA_OK(cudaMemcpyAsync(base + offsetof(FrameMeta, n_raw), &m.n_raw, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    FBPR_CUDA_OK(cudaMemcpyAsync(base + offsetof(FrameMeta, deskewFlag), &m.deskewFlag,
+                                 offsetof(FrameMeta, pose) - offsetof(FrameMeta, deskewFlag), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int fbpr_set_cloud_info(fbpr_handle* h, int slot, const fbpr_cloud_info_view* ci, int mem) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    if (!ci || ci->n_valid < 0 || ci->n_valid > h->P) return fbpr_fail_msg("bad cloud_info view");
+    cudaSetDevice(h->device);
+    const int N = h->p.N_SCAN; const size_t nv = (size_t)ci->n_valid;
+    cudaMemcpyKind k = kind_in(mem);
+    FBPR_CUDA_OK(cudaMemcpyAsync(h->startRing + (size_t)slot * N, ci->startRingIndex, N * sizeof(int), k, h->stream));
+    FBPR_CUDA_OK(cudaMemcpyAsync(h->endRing + (size_t)slot * N, ci->endRingIndex, N * sizeof(int), k, h->stream));
+    if (nv) {
+        FBPR_CUDA_OK(cudaMemcpyAsync(h->colInd + (size_t)slot * h->P, ci->pointColInd, nv * sizeof(int), k, h->stream));
+        FBPR_CUDA_OK(cudaMemcpyAsync(h->range + (size_t)slot * h->P, ci->pointRange, nv * sizeof(float), k, h->stream));
+        FBPR_CUDA_OK(cudaMemcpyAsync(h->cloud + (size_t)slot * h->P, ci->cloud_deskewed, nv * sizeof(float4), k, h->stream));
+    }
+    FrameMeta m = {};
+    m.n_valid = ci->n_valid; m.imuAvailable = ci->imuAvailable; m.imuRollInit = ci->imuRollInit; m.imuPitchInit = ci->imuPitchInit;
+    char* base = reinterpret_cast<char*>(h->meta + slot);
+    FBPR_CUDA_OK(cudaMemcpyAsync(base + offsetof(FrameMeta, n_valid), &m.n_valid, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    FBPR_CUDA_OK(cudaMemcpyAsync(base + offsetof(FrameMeta, imuAvailable), &m.imuAvailable, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    FBPR_CUDA_OK(cudaMemcpyAsync(base + offsetof(FrameMeta, imuRollInit), &m.imuRollInit, 2 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int fbpr_set_feature_clouds(fbpr_handle* h, int slot, const float* corner, int nC, const float* surf, int nS, int mem) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    if (nC < 0 || nC > h->cornerCap || nS < 0 || nS > h->P) return fbpr_fail_msg("feature cloud exceeds capacity");
+    cudaSetDevice(h->device);
+    if (nC) FBPR_CUDA_OK(cudaMemcpyAsync(h->corner + (size_t)slot * h->cornerCap, corner, (size_t)nC * sizeof(float4), kind_in(mem), h->stream));
+    if (nS) FBPR_CUDA_OK(cudaMemcpyAsync(h->surf + (size_t)slot * h->P, surf, (size_t)nS * sizeof(float4), kind_in(mem), h->stream));
+    int v[2] = { nC, nS };
+    FBPR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->meta + slot) + offsetof(FrameMeta, n_corner), v, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int fbpr_set_local_map(fbpr_handle* h, int slot, const float* corner, int nC, const float* surf, int nS, int mem) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    if (nC < 0 || nC > h->mapCornerCap || nS < 0 || nS > h->mapSurfCap) return fbpr_fail_msg("local map exceeds max_map_corner / max_map_surf");
+    cudaSetDevice(h->device);
+    if (nC) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapCorner + (size_t)slot * h->mapCornerCap, corner, (size_t)nC * sizeof(float4), kind_in(mem), h->stream));
+    if (nS) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapSurf + (size_t)slot * h->mapSurfCap, surf, (size_t)nS * sizeof(float4), kind_in(mem), h->stream));
+    int v[2] = { nC, nS };
+    FBPR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->meta + slot) + offsetof(FrameMeta, n_map_corner), v, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int fbpr_set_pose(fbpr_handle* h, int slot, const float pose6[6]) { return fbpr_set_poses(h, slot, 1, pose6, FBPR_MEM_HOST); }
+
+int fbpr_set_poses(fbpr_handle* h, int first, int count, const float* pose6, int mem) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    if (count == 0) return 0;
+    cudaSetDevice(h->device);
+    FBPR_CUDA_OK(cudaMemcpy2DAsync(reinterpret_cast<char*>(h->meta + first) + offsetof(FrameMeta, pose), sizeof(FrameMeta),
+                                   pose6, 6 * sizeof(float), 6 * sizeof(float), count, kind_in(mem), h->stream));
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- graph capture helper ------------------------------------------------------------------------
+template <typename Fn>
+static int run_op(fbpr_handle* h, int op, int first, int count, Fn&& enqueue) {
+    cudaSetDevice(h->device);
+    if (!h->useGraphs) return enqueue();
+    auto key = std::make_tuple(op, first, count, h->debugIter);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+        long long before = h->launches;
+        FBPR_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue();
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fbpr_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+        cudaGraphExec_t ex = nullptr;
+        e = cudaGraphInstantiate(&ex, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fbpr_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+        h->graphs[key] = ex;
+        h->graphLaunches[key] = h->launches - before;   // kernels one replay stands for
+        h->launches = before;
+        it = h->graphs.find(key);
+    }
+    FBPR_CUDA_OK(cudaGraphLaunch(it->second, h->stream));
+    h->launches += h->graphLaunches[key];
+    return 0;
+}
+
+// ---- operators -------------------------------------------------------------------------------
+static ProjArgs proj_args(fbpr_handle* h, int first) {
+    ProjArgs a = {};
+    a.meta = h->meta; a.raw = h->raw; a.rawCap = h->rawCap;
+    a.imuTime = h->imuTime; a.imuRotX = h->imuRotX; a.imuRotY = h->imuRotY; a.imuRotZ = h->imuRotZ;
+    a.pix = h->pix; a.ringCount = h->ringCount; a.startRing = h->startRing; a.endRing = h->endRing;
+    a.colInd = h->colInd; a.range = h->range; a.cloud = h->cloud; a.winner = h->winner;
+    a.N_SCAN = h->p.N_SCAN; a.H = h->p.Horizon_SCAN; a.P = h->P; a.first = first;
+    return a;
+}
+static FeatArgs feat_args(fbpr_handle* h, int first) {
+    FeatArgs a = {};
+    a.meta = h->meta; a.startRing = h->startRing; a.endRing = h->endRing;
+    a.colInd = h->colInd; a.range = h->range; a.cloud = h->cloud;
+    a.curv = h->curv; a.picked = h->picked; a.label = h->label;
+    a.ringCorner = h->ringCorner; a.cornerStage = h->cornerStage; a.ringSurf = h->ringSurf; a.ringSurfDS = h->ringSurfDS;
+    a.surfStage = h->surfStage; a.corner = h->corner; a.cornerIndex = h->cornerIndex; a.cornerCap = h->cornerCap; a.surf = h->surf;
+    a.N_SCAN = h->p.N_SCAN; a.H = h->p.Horizon_SCAN; a.P = h->P;
+    a.edgeThreshold = h->p.edgeThreshold; a.surfThreshold = h->p.surfThreshold; a.leaf = h->p.odometrySurfLeafSize;
+    a.segPad = next_pow2(a.H / 6 + 2); a.voxPad = next_pow2(a.H); a.wcap = a.H + 32;
+    a.first = first;
+    return a;
+}
+static LmArgs lm_args(fbpr_handle* h, int first) {
+    LmArgs a = {};
+    a.meta = h->meta; a.cornerDS = h->cornerDS; a.cornerCap = h->cornerCap; a.surfDS = h->surfDS; a.surfCap = h->P;
+    a.gsegs = h->d_gridSegs; a.first = first;
+    a.edgeMin = h->p.edgeFeatureMinValidNum; a.surfMin = h->p.surfFeatureMinValidNum;
+    a.z_tol = h->p.z_tollerance; a.rot_tol = h->p.rotation_tollerance;
+    a.debug_iter = (h->debugIter >= 0 && first + 0 < h->dbgSlots) ? h->debugIter : -1;
+    a.knnC = h->knnC; a.d2C = h->d2C; a.coeffC = h->coeffC; a.flagC = h->flagC;
+    a.knnS = h->knnS; a.d2S = h->d2S; a.coeffS = h->coeffS; a.flagS = h->flagS;
+    a.dbgAtA = h->dbgAtA; a.dbgAtB = h->dbgAtB; a.dbgX = h->dbgX; a.poseTrace = h->poseTrace;
+    return a;
+}
+
+static int enqueue_project(fbpr_handle* h, int first, int count) { fbpr_launch_projection(proj_args(h, first), count, h->stream, &h->launches); return 0; }
+static int enqueue_features(fbpr_handle* h, int first, int count) { return fbpr_launch_features(feat_args(h, first), count, h->stream, &h->launches); }
+static int enqueue_downsample(fbpr_handle* h, int first, int count) {
+    fbpr_launch_voxel(h->d_scanSegs + 2 * (size_t)first, 2 * count, h->P, h->tilesCap, h->stream, &h->launches); return 0;
+}
+static int enqueue_scan2map(fbpr_handle* h, int first, int count) {
+    int maxMap = h->mapCornerCap > h->mapSurfCap ? h->mapCornerCap : h->mapSurfCap;
+    int maxCells = h->cellsCorner > h->cellsSurf ? h->cellsCorner : h->cellsSurf;
+    fbpr_launch_grid_build(h->d_gridSegs + 2 * (size_t)first, 2 * count, maxMap, maxCells, h->stream, &h->launches);
+    LmArgs a = lm_args(h, first);
+    if (a.debug_iter >= 0 && first + count > h->dbgSlots) return fbpr_fail_msg("debug capture only covers the first slots");
+    return fbpr_launch_lm(a, count, h->cluster, h->stream, &h->launches);
+}
+
+extern "C" {
+
+int fbpr_project(fbpr_handle* h, int first, int count) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    return run_op(h, 1, first, count, [&] { return enqueue_project(h, first, count); });
+}
+int fbpr_feature_extract(fbpr_handle* h, int first, int count) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    if (fbpr_feat_ring_smem(feat_args(h, first)) > 200 * 1024) return fbpr_fail_msg("Horizon_SCAN too large for the per-ring shared-memory kernel");
+    return run_op(h, 2, first, count, [&] { return enqueue_features(h, first, count); });
+}
+int fbpr_downsample_current_scan(fbpr_handle* h, int first, int count) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    return run_op(h, 3, first, count, [&] { return enqueue_downsample(h, first, count); });
+}
+int fbpr_scan2map_optimization(fbpr_handle* h, int first, int count) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    return run_op(h, 4, first, count, [&] { return enqueue_scan2map(h, first, count); });
+}
+int fbpr_transform_update(fbpr_handle* h, int first, int count) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    cudaSetDevice(h->device);
+    fbpr_launch_transform_update(h->meta, first, count, h->p.rotation_tollerance, h->p.z_tollerance, h->stream, &h->launches);
+    return 0;
+}
+int fbpr_run_frames(fbpr_handle* h, int first, int count, int with_projection, int with_features) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    int op = 8 + (with_projection ? 1 : 0) + (with_features ? 2 : 0);
+    return run_op(h, op, first, count, [&] {
+        int r = 0;
+        if (with_projection) r = enqueue_project(h, first, count);
+        if (!r && with_features) r = enqueue_features(h, first, count);
+        if (!r) r = enqueue_downsample(h, first, count);
+        if (!r) r = enqueue_scan2map(h, first, count);
+        return r;
+    });
+}
+
+int fbpr_extract_surrounding_keyframes(fbpr_handle* h, int slot, int K, const float* key_poses6,
+                                       const float* corner_xyzi, const int32_t* corner_off,
+                                       const float* surf_xyzi, const int32_t* surf_off,
+                                       const float last_key_xyz[3], int mem) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    if (h->kfCap <= 0) return fbpr_fail_msg("handle created with max_keyframe_points = 0");
+    if (mem != FBPR_MEM_HOST) return fbpr_fail_msg("extract_surrounding_keyframes takes host buffers");
+    if (K < 0) return fbpr_fail_msg("bad K");
+    const int nc = K ? corner_off[K] : 0, ns = K ? surf_off[K] : 0;
+    if (nc > h->kfCap || ns > h->kfCap) return fbpr_fail_msg("keyframe clouds exceed max_keyframe_points");
+    cudaSetDevice(h->device);
+    // staging: poses, offsets, raw keyframe clouds (freed after the launches complete)
+    float* d_poses = nullptr; int* d_coff = nullptr; int* d_soff = nullptr; float4* d_cin = nullptr; float4* d_sin = nullptr; float* d_last = nullptr;
+    FBPR_CUDA_OK(cudaMallocAsync(&d_poses, sizeof(float) * 6 * (K + 1), h->stream));
+    FBPR_CUDA_OK(cudaMallocAsync(&d_coff, sizeof(int) * (K + 1), h->stream));
+    FBPR_CUDA_OK(cudaMallocAsync(&d_soff, sizeof(int) * (K + 1), h->stream));
+    FBPR_CUDA_OK(cudaMallocAsync(&d_cin, sizeof(float4) * (nc + 1), h->stream));
+    FBPR_CUDA_OK(cudaMallocAsync(&d_sin, sizeof(float4) * (ns + 1), h->stream));
+    FBPR_CUDA_OK(cudaMallocAsync(&d_last, sizeof(float) * 4, h->stream));
+    int* d_outoff = nullptr; float* d_T = nullptr;
+    FBPR_CUDA_OK(cudaMallocAsync(&d_outoff, sizeof(int) * (K + 2), h->stream));
+    FBPR_CUDA_OK(cudaMallocAsync(&d_T, sizeof(float) * 12 * (K + 1), h->stream));
+    if (K) {
+        FBPR_CUDA_OK(cudaMemcpyAsync(d_poses, key_poses6, sizeof(float) * 6 * K, cudaMemcpyHostToDevice, h->stream));
+        FBPR_CUDA_OK(cudaMemcpyAsync(d_coff, corner_off, sizeof(int) * (K + 1), cudaMemcpyHostToDevice, h->stream));
+        FBPR_CUDA_OK(cudaMemcpyAsync(d_soff, surf_off, sizeof(int) * (K + 1), cudaMemcpyHostToDevice, h->stream));
+        if (nc) FBPR_CUDA_OK(cudaMemcpyAsync(d_cin, corner_xyzi, sizeof(float4) * nc, cudaMemcpyHostToDevice, h->stream));
+        if (ns) FBPR_CUDA_OK(cudaMemcpyAsync(d_sin, surf_xyzi, sizeof(float4) * ns, cudaMemcpyHostToDevice, h->stream));
+    }
+    FBPR_CUDA_OK(cudaMemcpyAsync(d_last, last_key_xyz, sizeof(float) * 3, cudaMemcpyHostToDevice, h->stream));
+    fbpr_launch_keyframe_transform(d_poses, K, d_cin, d_coff, h->kfCorner + (size_t)slot * h->kfCap, h->kfCount + 2 * slot,
+                                   d_last, h->p.surroundingKeyframeSearchRadius, nc, d_outoff, d_T, h->stream, &h->launches);
+    fbpr_launch_keyframe_transform(d_poses, K, d_sin, d_soff, h->kfSurf + (size_t)slot * h->kfCap, h->kfCount + 2 * slot + 1,
+                                   d_last, h->p.surroundingKeyframeSearchRadius, ns, d_outoff, d_T, h->stream, &h->launches);
+    fbpr_launch_voxel(h->d_kfSegs + 2 * (size_t)slot, 2, h->kfCap, h->tilesCap, h->stream, &h->launches);
+    cudaFreeAsync(d_poses, h->stream); cudaFreeAsync(d_coff, h->stream); cudaFreeAsync(d_soff, h->stream);
+    cudaFreeAsync(d_cin, h->stream); cudaFreeAsync(d_sin, h->stream); cudaFreeAsync(d_last, h->stream);
+    cudaFreeAsync(d_outoff, h->stream); cudaFreeAsync(d_T, h->stream);
+    return 0;
+}
+
+static int upload_global(fbpr_handle* h, const float* corner_global, int nCg, const float* surf_global, int nSg, int mem) {
+    if (nCg + nSg > h->regGlobalCap) {
+        int cap = nCg + nSg + 1024;
+        FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+        ALLOC(h->regGlobal, cap); h->regGlobalCap = cap;
+    }
+    if (nCg) FBPR_CUDA_OK(cudaMemcpyAsync(h->regGlobal, corner_global, sizeof(float4) * nCg, kind_in(mem), h->stream));
+    if (nSg) FBPR_CUDA_OK(cudaMemcpyAsync(h->regGlobal + nCg, surf_global, sizeof(float4) * nSg, kind_in(mem), h->stream));
+    return 0;
+}
+
+int fbpr_set_global_map(fbpr_handle* h, const float* corner, int nC, const float* surf, int nS, int mem) {
+    if (!h) return fbpr_fail_msg("null handle");
+    if (nC < 0 || nS < 0) return fbpr_fail_msg("bad sizes");
+    cudaSetDevice(h->device);
+    int rc = upload_global(h, corner, nC, surf, nS, mem); if (rc) return rc;
+    h->globalCornerN = nC; h->globalSurfN = nS;
+    return 0;
+}
+
+int fbpr_registration(fbpr_handle* h, int slot, const float* corner_global, int nCg, const float* surf_global, int nSg, int mem, float pose12[12]) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    if (nCg < 0 || nSg < 0 || !pose12) return fbpr_fail_msg("bad registration arguments");
+    cudaSetDevice(h->device);
+    const float4* d_c = reinterpret_cast<const float4*>(corner_global);
+    const float4* d_s = reinterpret_cast<const float4*>(surf_global);
+    if (!corner_global && !surf_global) {
+        if (h->globalCornerN < 0) return fbpr_fail_msg("no global map: pass the maps or call fbpr_set_global_map first");
+        nCg = h->globalCornerN; nSg = h->globalSurfN;
+        d_c = h->regGlobal; d_s = h->regGlobal + nCg;
+    } else if (mem == FBPR_MEM_HOST) {
+        rc = upload_global(h, corner_global, nCg, surf_global, nSg, mem); if (rc) return rc;
+        h->globalCornerN = -1;
+        d_c = h->regGlobal; d_s = h->regGlobal + nCg;
+    }
+    const int need = nCg > nSg ? nCg : nSg;
+    if (!h->regTile) ALLOC(h->regTile, 1 << 16);
+    if (need / 2048 + 2 > (1 << 16)) return fbpr_fail_msg("global map too large for the CropBox scratch");
+    FBPR_CUDA_OK(cudaMemcpyAsync(h->regPose, pose12, sizeof(float) * 12, cudaMemcpyHostToDevice, h->stream));
+    // CropBox +-30/+-30/+-10 m around the guess (mapOptmization.h:284-304), order preserving
+    fbpr_launch_crop_box(d_c, nCg, h->regPose, h->mapCorner + (size_t)slot * h->mapCornerCap, h->mapCornerCap, &h->meta[slot].n_map_corner, h->regTile, h->stream, &h->launches);
+    fbpr_launch_crop_box(d_s, nSg, h->regPose, h->mapSurf + (size_t)slot * h->mapSurfCap, h->mapSurfCap, &h->meta[slot].n_map_surf, h->regTile, h->stream, &h->launches);
+    fbpr_launch_pose_decompose(h->regPose, h->meta, slot, h->stream, &h->launches);            // :309-310
+    rc = enqueue_downsample(h, slot, 1); if (rc) return rc;                                    // :313
+    rc = enqueue_scan2map(h, slot, 1); if (rc) return rc;                                      // :317
+    fbpr_launch_pose_compose(h->meta, slot, h->regPose, h->stream, &h->launches);              // :326
+    FBPR_CUDA_OK(cudaMemcpyAsync(pose12, h->regPose, sizeof(float) * 12, cudaMemcpyDeviceToHost, h->stream));
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    FBPR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- results ---------------------------------------------------------------------------------
+int fbpr_get_results(fbpr_handle* h, int first, int count, fbpr_result* out, int mem) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    if (count == 0) return 0;
+    cudaSetDevice(h->device);
+    static_assert(offsetof(FrameMeta, iters) == offsetof(FrameMeta, pose) + 24 && offsetof(FrameMeta, flags) == offsetof(FrameMeta, pose) + 28, "result fields must be contiguous");
+    FBPR_CUDA_OK(cudaMemcpy2DAsync(out, sizeof(fbpr_result), reinterpret_cast<char*>(h->meta + first) + offsetof(FrameMeta, pose), sizeof(FrameMeta),
+                                   sizeof(fbpr_result), count, mem == FBPR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    if (mem == FBPR_MEM_HOST) { FBPR_CUDA_OK(cudaStreamSynchronize(h->stream)); FBPR_CUDA_OK(cudaGetLastError()); }
+    return 0;
+}
+int fbpr_get_pose(fbpr_handle* h, int slot, float pose6[6], int32_t* iters, uint32_t* flags) {
+    fbpr_result r;
+    int rc = fbpr_get_results(h, slot, 1, &r, FBPR_MEM_HOST); if (rc) return rc;
+    if (pose6) memcpy(pose6, r.pose, sizeof(r.pose));
+    if (iters) *iters = r.iters;
+    if (flags) *flags = r.flags;
+    return 0;
+}
+int fbpr_get_counts(fbpr_handle* h, int slot, int32_t counts[8]) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    cudaSetDevice(h->device);
+    FBPR_CUDA_OK(cudaMemcpyAsync(counts, h->meta + slot, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int fbpr_set_debug_iteration(fbpr_handle* h, int iter) {
+    if (!h) return fbpr_fail_msg("null handle");
+    cudaSetDevice(h->device);
+    if (iter >= 0 && h->dbgSlots == 0) {
+        const int S = h->F < 2 ? h->F : 2;
+        ALLOC(h->knnC, (size_t)S * h->cornerCap * 5); ALLOC(h->d2C, (size_t)S * h->cornerCap * 5);
+        ALLOC(h->coeffC, (size_t)S * h->cornerCap); ALLOC(h->flagC, (size_t)S * h->cornerCap);
+        ALLOC(h->knnS, (size_t)S * h->P * 5); ALLOC(h->d2S, (size_t)S * h->P * 5);
+        ALLOC(h->coeffS, (size_t)S * h->P); ALLOC(h->flagS, (size_t)S * h->P);
+        ALLOC(h->dbgAtA, (size_t)S * 36); ALLOC(h->dbgAtB, (size_t)S * 6); ALLOC(h->dbgX, (size_t)S * 6);
+        h->dbgSlots = S;
+    }
+    h->debugIter = iter;
+    return 0;
+}
+
+int64_t fbpr_get_buffer(fbpr_handle* h, int slot, int which, void* dst, int64_t cap_bytes) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    cudaSetDevice(h->device);
+    FrameMeta m;
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    FBPR_CUDA_OK(cudaMemcpy(&m, h->meta + slot, sizeof(m), cudaMemcpyDeviceToHost));
+    const size_t P = h->P, N = h->p.N_SCAN, CC = h->cornerCap;
+    const void* src = nullptr; size_t bytes = 0;
+    const bool dbg = slot < h->dbgSlots;
+    switch (which) {
+    case FBPR_BUF_START_RING: src = h->startRing + slot * N; bytes = N * 4; break;
+    case FBPR_BUF_END_RING: src = h->endRing + slot * N; bytes = N * 4; break;
+    case FBPR_BUF_COL_IND: src = h->colInd + slot * P; bytes = (size_t)m.n_valid * 4; break;
+    case FBPR_BUF_RANGE: src = h->range + slot * P; bytes = (size_t)m.n_valid * 4; break;
+    case FBPR_BUF_CLOUD: src = h->cloud + slot * P; bytes = (size_t)m.n_valid * 16; break;
+    case FBPR_BUF_WINNER_RAW: src = h->winner + slot * P; bytes = (size_t)m.n_valid * 4; break;
+    case FBPR_BUF_CURVATURE: src = h->curv + slot * P; bytes = (size_t)m.n_valid * 4; break;
+    case FBPR_BUF_PICKED: src = h->picked + slot * P; bytes = (size_t)m.n_valid * 4; break;
+    case FBPR_BUF_LABEL: src = h->label + slot * P; bytes = (size_t)m.n_valid * 4; break;
+    case FBPR_BUF_CORNER: src = h->corner + slot * CC; bytes = (size_t)m.n_corner * 16; break;
+    case FBPR_BUF_CORNER_INDEX: src = h->cornerIndex + slot * CC; bytes = (size_t)m.n_corner * 4; break;
+    case FBPR_BUF_SURF: src = h->surf + slot * P; bytes = (size_t)m.n_surf * 16; break;
+    case FBPR_BUF_RING_SURF_COUNT: src = h->ringSurf + slot * N; bytes = N * 4; break;
+    case FBPR_BUF_RING_SURF_COUNT_DS: src = h->ringSurfDS + slot * N; bytes = N * 4; break;
+    case FBPR_BUF_CORNER_DS: src = h->cornerDS + slot * CC; bytes = (size_t)m.n_corner_ds * 16; break;
+    case FBPR_BUF_SURF_DS: src = h->surfDS + slot * P; bytes = (size_t)m.n_surf_ds * 16; break;
+    case FBPR_BUF_MAP_CORNER: src = h->mapCorner + (size_t)slot * h->mapCornerCap; bytes = (size_t)m.n_map_corner * 16; break;
+    case FBPR_BUF_MAP_SURF: src = h->mapSurf + (size_t)slot * h->mapSurfCap; bytes = (size_t)m.n_map_surf * 16; break;
+    case FBPR_BUF_POSE_TRACE: src = h->poseTrace + (size_t)slot * FBPR_MAX_ITERS * 6; bytes = (size_t)FBPR_MAX_ITERS * 24; break;
+    case FBPR_BUF_KNN_CORNER: if (dbg) { src = h->knnC + slot * CC * 5; bytes = (size_t)m.n_corner_ds * 20; } break;
+    case FBPR_BUF_KNN_D2_CORNER: if (dbg) { src = h->d2C + slot * CC * 5; bytes = (size_t)m.n_corner_ds * 20; } break;
+    case FBPR_BUF_COEFF_CORNER: if (dbg) { src = h->coeffC + slot * CC; bytes = (size_t)m.n_corner_ds * 16; } break;
+    case FBPR_BUF_FLAG_CORNER: if (dbg) { src = h->flagC + slot * CC; bytes = (size_t)m.n_corner_ds; } break;
+    case FBPR_BUF_KNN_SURF: if (dbg) { src = h->knnS + slot * P * 5; bytes = (size_t)m.n_surf_ds * 20; } break;
+    case FBPR_BUF_KNN_D2_SURF: if (dbg) { src = h->d2S + slot * P * 5; bytes = (size_t)m.n_surf_ds * 20; } break;
+    case FBPR_BUF_COEFF_SURF: if (dbg) { src = h->coeffS + slot * P; bytes = (size_t)m.n_surf_ds * 16; } break;
+    case FBPR_BUF_FLAG_SURF: if (dbg) { src = h->flagS + slot * P; bytes = (size_t)m.n_surf_ds; } break;
+    case FBPR_BUF_ATA: if (dbg) { src = h->dbgAtA + slot * 36; bytes = 144; } break;
+    case FBPR_BUF_ATB: if (dbg) { src = h->dbgAtB + slot * 6; bytes = 24; } break;
+    case FBPR_BUF_X: if (dbg) { src = h->dbgX + slot * 6; bytes = 24; } break;
+    default: break;
+    }
+    if (!src) return fbpr_fail_msg("buffer not available (unknown id, or debug capture not enabled for this slot)");
+    if ((int64_t)bytes > cap_bytes) return fbpr_fail_msg("destination too small");
+    if (bytes) FBPR_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return (int64_t)bytes;
+}
+
+// ---- stand-alone VoxelGrid / k-NN ---------------------------------------------------------------
+int fbpr_voxel_grid(fbpr_handle* h, const float* xyzi, int n, float leaf, float* out_xyzi, int32_t* point_keys, int32_t* out_keys, int mem) {
+    if (!h) return fbpr_fail_msg("null handle");
+    if (n < 0) return fbpr_fail_msg("bad n");
+    cudaSetDevice(h->device);
+    if (n + 1 > h->soloVoxCap) {
+        FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+        for (void* p : h->soloVoxAllocs) cudaFree(p);
+        h->soloVoxAllocs.clear();
+        int cap = n + 1024;
+        auto A = [&](void** p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes); if (e == cudaSuccess) { cudaMemset(*p, 0, bytes); h->soloVoxAllocs.push_back(*p); } return e; };
+        VoxSeg s = {};
+        int tiles = (cap + fbpr_voxel_tile() - 1) / fbpr_voxel_tile() + 1;
+        FBPR_CUDA_OK(A((void**)&h->soloIn, sizeof(float4) * cap)); FBPR_CUDA_OK(A((void**)&h->soloOut, sizeof(float4) * cap));
+        FBPR_CUDA_OK(A((void**)&h->soloN, 16)); FBPR_CUDA_OK(A((void**)&h->soloNout, 16));
+        FBPR_CUDA_OK(A((void**)&h->soloPK, sizeof(int) * cap)); FBPR_CUDA_OK(A((void**)&h->soloOK, sizeof(int) * cap));
+        for (int b = 0; b < 2; b++) { FBPR_CUDA_OK(A((void**)&s.key[b], 4 * (size_t)cap)); FBPR_CUDA_OK(A((void**)&s.val[b], 4 * (size_t)cap)); }
+        FBPR_CUDA_OK(A((void**)&s.tile_hist, 4 * (size_t)256 * tiles)); FBPR_CUDA_OK(A((void**)&s.bbox, 32));
+        FBPR_CUDA_OK(A((void**)&s.run_tile, 4 * (size_t)(tiles + 1))); FBPR_CUDA_OK(A((void**)&s.desc, sizeof(VoxDesc)));
+        FBPR_CUDA_OK(A((void**)&h->d_soloVox, sizeof(VoxSeg)));
+        s.in = h->soloIn; s.n_in = h->soloN; s.out = h->soloOut; s.n_out = h->soloNout; s.cap = cap;
+        s.point_keys = h->soloPK; s.out_keys = h->soloOK; s.leaf = leaf;
+        FBPR_CUDA_OK(cudaMemcpy(h->d_soloVox, &s, sizeof(s), cudaMemcpyHostToDevice));
+        h->soloVoxCap = cap;
+    }
+    // leaf may change between calls: patch it in the descriptor
+    FBPR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->d_soloVox) + offsetof(VoxSeg, leaf), &leaf, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    FBPR_CUDA_OK(cudaMemcpyAsync(h->soloN, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (n) FBPR_CUDA_OK(cudaMemcpyAsync(h->soloIn, xyzi, sizeof(float4) * (size_t)n, kind_in(mem), h->stream));
+    int tiles_cap = (h->soloVoxCap + fbpr_voxel_tile() - 1) / fbpr_voxel_tile() + 1;
+    fbpr_launch_voxel(h->d_soloVox, 1, n > 0 ? n : 1, tiles_cap, h->stream, &h->launches);
+    int m = 0;
+    FBPR_CUDA_OK(cudaMemcpyAsync(&m, h->soloNout, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    FBPR_CUDA_OK(cudaGetLastError());
+    cudaMemcpyKind ko = mem == FBPR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (m) FBPR_CUDA_OK(cudaMemcpy(out_xyzi, h->soloOut, sizeof(float4) * (size_t)m, ko));
+    if (point_keys && n) FBPR_CUDA_OK(cudaMemcpy(point_keys, h->soloPK, sizeof(int) * (size_t)n, ko));
+    if (out_keys && m) FBPR_CUDA_OK(cudaMemcpy(out_keys, h->soloOK, sizeof(int) * (size_t)m, ko));
+    return m;
+}
+
+int fbpr_knn5(fbpr_handle* h, const float* map_xyzi, int n_map, float cell, const float* q_xyz, int nq, int32_t* idx, float* d2, int mem) {
+    if (!h) return fbpr_fail_msg("null handle");
+    if (n_map < 0 || nq < 0) return fbpr_fail_msg("bad sizes");
+    if (mem != FBPR_MEM_HOST) return fbpr_fail_msg("fbpr_knn5 takes host buffers");
+    cudaSetDevice(h->device);
+    const int cells = 1 << 21;
+    if (n_map + 1 > h->soloGridCap || cell != h->soloGridCell) {
+        FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+        for (void* p : h->soloGridAllocs) cudaFree(p);
+        h->soloGridAllocs.clear();
+        int cap = n_map + 1024;
+        auto A = [&](void** p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes); if (e == cudaSuccess) { cudaMemset(*p, 0, bytes); h->soloGridAllocs.push_back(*p); } return e; };
+        GridSeg g = {};
+        FBPR_CUDA_OK(A((void**)&h->soloMap, sizeof(float4) * cap)); FBPR_CUDA_OK(A((void**)&h->soloMapN, 16));
+        FBPR_CUDA_OK(A((void**)&g.sorted, sizeof(float4) * cap)); FBPR_CUDA_OK(A((void**)&g.cell_start, 4 * (size_t)(cells + 2)));
+        FBPR_CUDA_OK(A((void**)&g.cell_cursor, 4 * (size_t)(cells + 2))); FBPR_CUDA_OK(A((void**)&g.cell_of, 4 * (size_t)cap));
+        FBPR_CUDA_OK(A((void**)&g.tile_sum, 4 * (size_t)(cells / 4096 + 4))); FBPR_CUDA_OK(A((void**)&g.bbox, 32)); FBPR_CUDA_OK(A((void**)&g.desc, sizeof(GridDesc)));
+        FBPR_CUDA_OK(A((void**)&h->d_soloGrid, sizeof(GridSeg)));
+        g.pts = h->soloMap; g.n = h->soloMapN; g.cap = cap; g.cells_cap = cells; g.h0 = cell;
+        FBPR_CUDA_OK(cudaMemcpy(h->d_soloGrid, &g, sizeof(g), cudaMemcpyHostToDevice));
+        h->soloGridCap = cap; h->soloGridCell = cell;
+    }
+    FBPR_CUDA_OK(cudaMemcpyAsync(h->soloMapN, &n_map, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (n_map) FBPR_CUDA_OK(cudaMemcpyAsync(h->soloMap, map_xyzi, sizeof(float4) * (size_t)n_map, cudaMemcpyHostToDevice, h->stream));
+    fbpr_launch_grid_build(h->d_soloGrid, 1, n_map > 0 ? n_map : 1, cells, h->stream, &h->launches);
+    float* d_q = nullptr; int* d_idx = nullptr; float* d_d2 = nullptr;
+    FBPR_CUDA_OK(cudaMallocAsync(&d_q, sizeof(float) * 3 * (size_t)(nq + 1), h->stream));
+    FBPR_CUDA_OK(cudaMallocAsync(&d_idx, sizeof(int) * 5 * (size_t)(nq + 1), h->stream));
+    FBPR_CUDA_OK(cudaMallocAsync(&d_d2, sizeof(float) * 5 * (size_t)(nq + 1), h->stream));
+    if (nq) FBPR_CUDA_OK(cudaMemcpyAsync(d_q, q_xyz, sizeof(float) * 3 * (size_t)nq, cudaMemcpyHostToDevice, h->stream));
+    fbpr_launch_knn5(h->d_soloGrid, d_q, nq, d_idx, d_d2, h->stream, &h->launches);
+    if (nq) {
+        FBPR_CUDA_OK(cudaMemcpyAsync(idx, d_idx, sizeof(int) * 5 * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));
+        FBPR_CUDA_OK(cudaMemcpyAsync(d2, d_d2, sizeof(float) * 5 * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));
+    }
+    cudaFreeAsync(d_q, h->stream); cudaFreeAsync(d_idx, h->stream); cudaFreeAsync(d_d2, h->stream);
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    FBPR_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,421 @@
+// features.cu -- LOAM feature front-end: smoothness, occlusion masks, per-ring corner / surface
+// selection and the per-ring VoxelGrid of surface points.
+//
+// Replaces FeatureExtraction::calculateSmoothness (featureExtraction.h:109-131),
+// markOccludedPoints (:134-176) and extractFeatures (:178-294).
+//
+// Kernel 1 (feat_smooth): coalesced +-5 stencil on the flat ring-major range array; the
+//   occlusion marks are evaluated in GATHER form (each index looks at the <= 13 source
+//   positions that could mark it), so there are no scattered writes and no ordering issue.
+// Kernel 2 (feat_ring): one CTA per ring, everything in shared memory:
+//   - the 6 segment sorts (featureExtraction.h:203) run as ONE bitonic network over
+//     (curvature bits, index) keys -- a total order, ties broken by point index;
+//   - the corner loop (:208-242) is walked by one thread but only over keys > edgeThreshold;
+//   - the "flat" loop (:245-276) is a lexicographically-first maximal independent set in
+//     sorted order; it is evaluated exactly in parallel rounds (a candidate is decided once all
+//     lower-ranked candidates that could suppress it are decided), reproducing the sequential
+//     result including the marks that leak into the next segment;
+//   - surface = every in-segment index that is not a corner (:279-284), stream-compacted;
+//   - the ring's pcl::VoxelGrid (:287-292): bbox, keys, bitonic sort of (key, seq), runs,
+//     sequential in-order centroids.
+// Kernel 3 (feat_gather): ring-order concatenation of corners and down-sampled surface points.
+// Quirks reproduced on purpose: slot `ep` is never sorted and is
+// visited first by the corner loop and last by the flat loop; cloudSmoothness slots outside
+// [5, n-5) hold {0.0f, ind 0}; the 21st corner breaks before marking.
+#include "internal.cuh"
+
+
+namespace {
+
+constexpr int TPB1 = 256;
+constexpr int RING_TPB = 512;
+constexpr int CORNERS_PER_RING = FBPR_SEGS * FBPR_CORNERS_PER_SEG;
+
+__global__ void __launch_bounds__(TPB1) feat_smooth(FeatArgs a) {
+    const int slot = a.first + blockIdx.y;
+    const int n = a.meta[slot].n_valid;
+    const float* r = a.range + (size_t)slot * a.P;
+    const int* col = a.colInd + (size_t)slot * a.P;
+    float* curv = a.curv + (size_t)slot * a.P;
+    int* picked = a.picked + (size_t)slot * a.P;
+    int* label = a.label + (size_t)slot * a.P;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        float c = 0.f;
+        if (j >= 5 && j < n - 5) {
+            float d = r[j - 5] + r[j - 4] + r[j - 3] + r[j - 2] + r[j - 1] - r[j] * 10
+                    + r[j + 1] + r[j + 2] + r[j + 3] + r[j + 4] + r[j + 5];
+            c = d * d;
+        }
+        int pk = 0;
+        // sources i in [j, j+5] mark i-5..i when depth1 - depth2 > 0.3;  i in [j-6, j-1] mark i+1..i+6 when depth2 - depth1 > 0.3
+        for (int i = j - 6; i <= j + 5; i++) {
+            if (i < 5 || i >= n - 6) continue;
+            int cd = abs(col[i + 1] - col[i]);
+            if (cd >= 10) continue;
+            float d1 = r[i], d2 = r[i + 1];
+            bool A = (double)(d1 - d2) > 0.3;
+            bool B = !A && (double)(d2 - d1) > 0.3;
+            if (i >= j ? A : B) pk = 1;
+        }
+        if (j >= 5 && j < n - 6) {
+            float diff1 = fabsf(r[j - 1] - r[j]), diff2 = fabsf(r[j + 1] - r[j]);
+            if ((double)diff1 > 0.02 * (double)r[j] && (double)diff2 > 0.02 * (double)r[j]) pk = 1;
+        }
+        curv[j] = c; picked[j] = pk; label[j] = 0;
+    }
+}
+
+// ---- block helpers -----------------------------------------------------------------------
+__device__ inline int block_excl_scan(int v, int* total, int* ws) {
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
+    __syncthreads();
+    if (l == 31) ws[w] = incl;
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int q = 0; q < RING_TPB / 32; q++) { int c = ws[q]; if (q < w) off += c; tot += c; }
+    *total = tot;
+    return off + incl - v;
+}
+
+// bitonic network over `count` keys made of aligned blocks of `blk` (pow2); every block ends ascending
+__device__ inline void bitonic_blocks(unsigned long long* keys, int count, int blk) {
+    for (int k = 2; k <= blk; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < count; t += RING_TPB) {
+                int p = t ^ j;
+                if (p > t) {
+                    bool asc = ((t & k) == 0) || (k == blk);
+                    unsigned long long x = keys[t], y = keys[p];
+                    if ((x > y) == asc) { keys[t] = y; keys[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+enum : unsigned char { ST_NONE = 0, ST_UNDECIDED = 1, ST_PICKED = 2, ST_DEAD = 3 };
+
+__global__ void __launch_bounds__(RING_TPB) feat_ring(FeatArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const int slot = a.first + blockIdx.y, ring = blockIdx.x;
+    const int n = a.meta[slot].n_valid;
+    const int s = a.startRing[slot * a.N_SCAN + ring], e = a.endRing[slot * a.N_SCAN + ring];
+    const int tid = threadIdx.x;
+    // carve shared memory
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    const int keyCount = max(FBPR_SEGS * a.segPad, a.voxPad);
+    float* s_curv = reinterpret_cast<float*>(s_keys + keyCount);
+    int* s_col = reinterpret_cast<int*>(s_curv + a.wcap);
+    int* s_list = s_col + a.wcap;                         // surface candidate list (global indices)
+    unsigned short* s_rank = reinterpret_cast<unsigned short*>(s_list + a.wcap);
+    unsigned char* s_picked = reinterpret_cast<unsigned char*>(s_rank + a.wcap);
+    signed char* s_label = reinterpret_cast<signed char*>(s_picked + a.wcap);
+    unsigned char* s_state = reinterpret_cast<unsigned char*>(s_label + a.wcap);
+    unsigned char* s_fwd = s_state + a.wcap;
+    unsigned char* s_bwd = s_fwd + a.wcap;
+    __shared__ int s_corner[CORNERS_PER_RING];
+    __shared__ int s_ncorner, s_ws[RING_TPB / 32];
+    __shared__ int s_sp[FBPR_SEGS], s_ep[FBPR_SEGS];
+    __shared__ unsigned s_bb[6];
+    __shared__ int s_vox[8];          // overflow, min_b[3], m1, m2
+    __shared__ float s_inv;
+
+    const float* g_curv = a.curv + (size_t)slot * a.P;
+    const int* g_col = a.colInd + (size_t)slot * a.P;
+    int* g_picked = a.picked + (size_t)slot * a.P;
+    int* g_label = a.label + (size_t)slot * a.P;
+    const float4* g_cloud = a.cloud + (size_t)slot * a.P;
+
+    if (tid == 0) s_ncorner = 0;
+    if (tid < FBPR_SEGS) {
+        int j = tid;
+        s_sp[j] = (s * (6 - j) + e * j) / 6;
+        s_ep[j] = (s * (5 - j) + e * (j + 1)) / 6 - 1;
+    }
+    // window [w0, w1] of flat indices this ring may read or mark
+    const int w0 = max(s - 6, 0), w1 = min(e + 5, n - 1);
+    const int W = w1 - w0 + 1;
+    const bool any = (e - 1 > s) && W > 0 && W <= a.wcap && n > 0;
+    __syncthreads();
+    int nsurf = 0;
+    if (any) {
+        for (int t = tid; t < W; t += RING_TPB) {
+            int g = w0 + t;
+            s_curv[t] = g_curv[g]; s_col[t] = g_col[g];
+            s_picked[t] = (unsigned char)(g_picked[g] != 0); s_label[t] = 0; s_state[t] = ST_NONE;
+        }
+        __syncthreads();
+        // static suppression reach of every index (featureExtraction.h:226-240)
+        for (int t = tid; t < W; t += RING_TPB) {
+            int g = w0 + t, f = 0, b = 0;
+            for (int l = 1; l <= 5; l++) {
+                int q = g + l; if (q > w1) break;
+                if (abs(s_col[q - w0] - s_col[q - 1 - w0]) > 10) break;
+                f = l;
+            }
+            for (int l = -1; l >= -5; l--) {
+                int q = g + l; if (q < 0 || q < w0) break;
+                if (abs(s_col[q - w0] - s_col[q + 1 - w0]) > 10) break;
+                b = -l;
+            }
+            s_fwd[t] = (unsigned char)f; s_bwd[t] = (unsigned char)b;
+        }
+        // sort keys of all six segments: cloudSmoothness[k] = {curv[k], k} inside [5, n-5), else {0.0f, 0}
+        for (int t = tid; t < FBPR_SEGS * a.segPad; t += RING_TPB) {
+            int j = t / a.segPad, q = t - j * a.segPad;
+            int sp = s_sp[j], ep = s_ep[j];
+            unsigned long long key = ~0ull;
+            if (sp < ep && q < ep - sp) {
+                int k = sp + q;
+                if (k >= 5 && k < n - 5) key = ((unsigned long long)__float_as_uint(s_curv[k - w0]) << 32) | (unsigned)k;
+                else key = 0ull;
+            }
+            s_keys[t] = key;
+        }
+        __syncthreads();
+        bitonic_blocks(s_keys, FBPR_SEGS * a.segPad, a.segPad);
+
+        for (int j = 0; j < FBPR_SEGS; j++) {
+            const int sp = s_sp[j], ep = s_ep[j];
+            if (sp >= ep) continue;                                   // uniform across the CTA
+            const int len = ep - sp;
+            const unsigned long long* keys = s_keys + j * a.segPad;
+            // ---- corner loop (:208-242), one thread, early exit once sorted curvature <= edgeThreshold
+            if (tid == 0) {
+                int cnt = 0;
+                for (int v = len; v >= 0; v--) {
+                    int ind; float cv;
+                    if (v == len) { ind = (ep >= 5 && ep < n - 5) ? ep : 0; }
+                    else { ind = (int)(unsigned)(keys[v] & 0xffffffffu); }
+                    cv = (ind >= w0 && ind <= w1) ? s_curv[ind - w0] : 0.f;
+                    if (v < len && !(cv > a.edgeThreshold)) break;   // sorted ascending: nothing below can qualify
+                    if (ind < w0 || ind > w1) continue;
+                    if (s_picked[ind - w0] == 0 && cv > a.edgeThreshold) {
+                        cnt++;
+                        if (cnt <= FBPR_CORNERS_PER_SEG) { s_label[ind - w0] = 1; s_corner[s_ncorner++] = ind; }
+                        else break;
+                        s_picked[ind - w0] = 1;
+                        int f = s_fwd[ind - w0], b = s_bwd[ind - w0];
+                        for (int l = 1; l <= f; l++) s_picked[ind + l - w0] = 1;
+                        for (int l = 1; l <= b; l++) s_picked[ind - l - w0] = 1;
+                    }
+                }
+                // quirk slot: a sorted entry whose index lies outside the segment (cloudSmoothness slot < 5 -> ind 0)
+                // is ranked first in the flat loop; handle it sequentially before the parallel rounds
+                int ind0 = (int)(unsigned)(keys[0] & 0xffffffffu);
+                if (len > 0 && (ind0 < sp || ind0 > ep) && ind0 >= w0 && ind0 <= w1) {
+                    if (s_picked[ind0 - w0] == 0 && s_curv[ind0 - w0] < a.surfThreshold) {
+                        s_label[ind0 - w0] = -1; s_picked[ind0 - w0] = 1;
+                        int f = s_fwd[ind0 - w0], b = s_bwd[ind0 - w0];
+                        for (int l = 1; l <= f; l++) s_picked[ind0 + l - w0] = 1;
+                        for (int l = 1; l <= b; l++) s_picked[ind0 - l - w0] = 1;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- flat loop (:245-276) as parallel lexicographically-first MIS
+            for (int v = tid; v <= len; v += RING_TPB) {
+                int ind = v == len ? ((ep >= 5 && ep < n - 5) ? ep : 0) : (int)(unsigned)(keys[v] & 0xffffffffu);
+                if (ind < sp || ind > ep) continue;
+                s_rank[ind - w0] = (unsigned short)v;
+                unsigned char st = ST_NONE;
+                if (s_curv[ind - w0] < a.surfThreshold) st = s_picked[ind - w0] ? ST_DEAD : ST_UNDECIDED;
+                s_state[ind - w0] = st;
+            }
+            __syncthreads();
+            while (true) {
+                // phase 1: decide from a consistent snapshot
+                unsigned char newst[(4096 + RING_TPB - 1) / RING_TPB];
+                int pending = 0, slotk = 0;
+                for (int g = sp + tid; g <= ep; g += RING_TPB, slotk++) {
+                    unsigned char st = s_state[g - w0];
+                    newst[slotk] = st;
+                    if (st != ST_UNDECIDED) continue;
+                    const unsigned short rk = s_rank[g - w0];
+                    bool dead = false, wait = false;
+                    const int qlo = max(g - 5, sp), qhi = min(g + 5, ep);
+                    for (int q = qlo; q <= qhi; q++) {
+                        if (q == g) continue;
+                        unsigned char sq = s_state[q - w0];
+                        if (sq != ST_PICKED && sq != ST_UNDECIDED) continue;
+                        if (s_rank[q - w0] >= rk) continue;
+                        bool covers = q < g ? (g - q <= s_fwd[q - w0]) : (q - g <= s_bwd[q - w0]);
+                        if (!covers) continue;
+                        if (sq == ST_PICKED) dead = true; else wait = true;
+                    }
+                    if (dead) newst[slotk] = ST_DEAD;
+                    else if (!wait) newst[slotk] = ST_PICKED;
+                    else pending = 1;
+                }
+                __syncthreads();
+                slotk = 0;
+                for (int g = sp + tid; g <= ep; g += RING_TPB, slotk++) s_state[g - w0] = newst[slotk];
+                if (!__syncthreads_or(pending)) break;
+            }
+            // apply picks: label -1, mark self and reach
+            for (int g = sp + tid; g <= ep; g += RING_TPB) {
+                if (s_state[g - w0] == ST_PICKED) {
+                    s_label[g - w0] = -1; s_picked[g - w0] = 1;
+                    int f = s_fwd[g - w0], b = s_bwd[g - w0];
+                    for (int l = 1; l <= f; l++) s_picked[g + l - w0] = 1;
+                    for (int l = 1; l <= b; l++) s_picked[g - l - w0] = 1;
+                }
+            }
+            __syncthreads();
+            for (int g = sp + tid; g <= ep; g += RING_TPB) s_state[g - w0] = ST_NONE;
+            __syncthreads();
+        }
+        // ---- write back labels / marks (1s only: neighbouring rings' windows overlap)
+        for (int t = tid; t < W; t += RING_TPB) {
+            if (s_picked[t]) g_picked[w0 + t] = 1;
+            if (s_label[t] != 0) g_label[w0 + t] = s_label[t];
+        }
+        // ---- surface candidates: every in-segment k with label <= 0, ascending (:279-284)
+        int carry = 0;
+        for (int base = 0; base < W; base += RING_TPB) {
+            int t = base + tid, g = w0 + t;
+            int flag = 0;
+            if (t < W && s_label[t] <= 0) {
+                for (int j = 0; j < FBPR_SEGS; j++) if (s_sp[j] < s_ep[j] && g >= s_sp[j] && g <= s_ep[j]) flag = 1;
+            }
+            int tot, off = block_excl_scan(flag, &tot, s_ws);
+            if (flag) s_list[carry + off] = g;
+            carry += tot;
+        }
+        nsurf = carry;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.ringCorner[slot * a.N_SCAN + ring] = s_ncorner;
+        a.ringSurf[slot * a.N_SCAN + ring] = nsurf;
+    }
+    for (int t = tid; t < s_ncorner; t += RING_TPB) a.cornerStage[((size_t)slot * a.N_SCAN + ring) * CORNERS_PER_RING + t] = s_corner[t];
+
+    // ---- per-ring VoxelGrid (featureExtraction.h:287-292)
+    float4* stage = a.surfStage + (size_t)slot * a.P + (size_t)ring * a.H;
+    int nout = 0;
+    if (nsurf > 0) {
+        unsigned mn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, mx[3] = { 0u, 0u, 0u };
+        for (int t = tid; t < nsurf; t += RING_TPB) {
+            float4 p = g_cloud[s_list[t]];
+            unsigned ex = f2ord(p.x), ey = f2ord(p.y), ez = f2ord(p.z);
+            mn[0] = min(mn[0], ex); mn[1] = min(mn[1], ey); mn[2] = min(mn[2], ez);
+            mx[0] = max(mx[0], ex); mx[1] = max(mx[1], ey); mx[2] = max(mx[2], ez);
+        }
+        if (tid < 3) s_bb[tid] = 0xffffffffu; else if (tid < 6) s_bb[tid] = 0u;
+        __syncthreads();
+        for (int c = 0; c < 3; c++) {
+            for (int o = 16; o; o >>= 1) { mn[c] = min(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = max(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
+            if ((tid & 31) == 0) { atomicMin(&s_bb[c], mn[c]); atomicMax(&s_bb[3 + c], mx[c]); }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const float inv = 1.0f / a.leaf;
+            s_inv = inv;
+            float fmn[3], fmx[3];
+            for (int c = 0; c < 3; c++) { fmn[c] = ord2f(s_bb[c]); fmx[c] = ord2f(s_bb[3 + c]); }
+            long long ex = (long long)((fmx[0] - fmn[0]) * inv) + 1, ey = (long long)((fmx[1] - fmn[1]) * inv) + 1, ez = (long long)((fmx[2] - fmn[2]) * inv) + 1;
+            bool over = ex > 0x7fffffffLL || ey > 0x7fffffffLL || ez > 0x7fffffffLL;
+            if (!over) { over = ex * ey > 0x7fffffffLL; if (!over) over = ex * ey * ez > 0x7fffffffLL; }
+            s_vox[0] = over ? 1 : 0;
+            int div[3];
+            for (int c = 0; c < 3; c++) { s_vox[1 + c] = (int)floorf(fmn[c] * inv); div[c] = (int)floorf(fmx[c] * inv) - s_vox[1 + c] + 1; }
+            s_vox[4] = div[0]; s_vox[5] = div[0] * div[1];
+        }
+        __syncthreads();
+        if (s_vox[0]) {                                   // leaf too small: output = input
+            for (int t = tid; t < nsurf; t += RING_TPB) stage[t] = g_cloud[s_list[t]];
+            nout = nsurf;
+        } else {
+            const float inv = s_inv;
+            for (int t = tid; t < a.voxPad; t += RING_TPB) {
+                unsigned long long key = ~0ull;
+                if (t < nsurf) {
+                    float4 p = g_cloud[s_list[t]];
+                    int i0 = (int)(floorf(p.x * inv) - (float)s_vox[1]);
+                    int i1 = (int)(floorf(p.y * inv) - (float)s_vox[2]);
+                    int i2 = (int)(floorf(p.z * inv) - (float)s_vox[3]);
+                    int k = i0 + i1 * s_vox[4] + i2 * s_vox[5];
+                    key = ((unsigned long long)(unsigned)k << 32) | (unsigned)t;
+                }
+                s_keys[t] = key;
+            }
+            __syncthreads();
+            bitonic_blocks(s_keys, a.voxPad, a.voxPad);
+            int carry = 0;
+            for (int base = 0; base < nsurf; base += RING_TPB) {
+                int t = base + tid;
+                int flag = (t < nsurf) && (t == 0 || (s_keys[t] >> 32) != (s_keys[t - 1] >> 32));
+                int tot, off = block_excl_scan(flag, &tot, s_ws);
+                if (flag) {
+                    unsigned kk = (unsigned)(s_keys[t] >> 32);
+                    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int c = 0;
+                    for (int q = t; q < nsurf && (unsigned)(s_keys[q] >> 32) == kk; q++) {
+                        float4 p = g_cloud[s_list[(unsigned)(s_keys[q] & 0xffffffffu)]];
+                        sx += p.x; sy += p.y; sz += p.z; si += p.w; c++;
+                    }
+                    float fc = (float)c;
+                    stage[carry + off] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
+                }
+                carry += tot;
+            }
+            nout = carry;
+        }
+    }
+    if (tid == 0) a.ringSurfDS[slot * a.N_SCAN + ring] = nout;
+}
+
+__global__ void __launch_bounds__(256) feat_gather(FeatArgs a) {
+    const int slot = a.first + blockIdx.y, ring = blockIdx.x;
+    __shared__ int s_cb, s_sb, s_ct, s_st;
+    if (threadIdx.x < 32) {
+        int cb = 0, sb = 0, ct = 0, st = 0;
+        for (int r = threadIdx.x; r < a.N_SCAN; r += 32) {
+            int c = a.ringCorner[slot * a.N_SCAN + r], sdc = a.ringSurfDS[slot * a.N_SCAN + r];
+            ct += c; st += sdc; if (r < ring) { cb += c; sb += sdc; }
+        }
+        for (int o = 16; o; o >>= 1) {
+            cb += __shfl_xor_sync(0xffffffffu, cb, o); sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            ct += __shfl_xor_sync(0xffffffffu, ct, o); st += __shfl_xor_sync(0xffffffffu, st, o);
+        }
+        if (threadIdx.x == 0) { s_cb = cb; s_sb = sb; s_ct = ct; s_st = st; }
+    }
+    __syncthreads();
+    const float4* cloud = a.cloud + (size_t)slot * a.P;
+    const int nc = a.ringCorner[slot * a.N_SCAN + ring], ns = a.ringSurfDS[slot * a.N_SCAN + ring];
+    float4* corner = a.corner + (size_t)slot * a.cornerCap;
+    int* cidx = a.cornerIndex + (size_t)slot * a.cornerCap;
+    const int* cst = a.cornerStage + ((size_t)slot * a.N_SCAN + ring) * CORNERS_PER_RING;
+    for (int t = threadIdx.x; t < nc; t += blockDim.x) { int g = cst[t]; corner[s_cb + t] = cloud[g]; cidx[s_cb + t] = g; }
+    float4* surf = a.surf + (size_t)slot * a.P;
+    const float4* stage = a.surfStage + (size_t)slot * a.P + (size_t)ring * a.H;
+    for (int t = threadIdx.x; t < ns; t += blockDim.x) surf[s_sb + t] = stage[t];
+    if (ring == 0 && threadIdx.x == 0) { a.meta[slot].n_corner = s_ct; a.meta[slot].n_surf = s_st; }
+}
+
+}  // namespace
+
+size_t fbpr_feat_ring_smem(const FeatArgs& a) {
+    size_t keyCount = (size_t)(FBPR_SEGS * a.segPad > a.voxPad ? FBPR_SEGS * a.segPad : a.voxPad);
+    return keyCount * 8 + (size_t)a.wcap * (4 + 4 + 4 + 2 + 1 + 1 + 1 + 1 + 1) + 64;
+}
+
+int fbpr_launch_features(const FeatArgs& a, int count, cudaStream_t st, long long* launches) {
+    if (count <= 0) return 0;
+    static size_t configured = 0;
+    size_t smem = fbpr_feat_ring_smem(a);
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(feat_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(feat_ring smem)", __FILE__, __LINE__);
+        configured = smem;
+    }
+    int b = (a.P + TPB1 * 2 - 1) / (TPB1 * 2);
+    feat_smooth<<<dim3(b, count), TPB1, 0, st>>>(a);
+    feat_ring<<<dim3(a.N_SCAN, count), RING_TPB, smem, st>>>(a);
+    feat_gather<<<dim3(a.N_SCAN, count), 256, 0, st>>>(a);
+    if (launches) *launches += 3;
+    return 0;
+}

@@ -1,0 +1,171 @@
+// internal.cuh -- device-side data layout shared by the kernels of libfbpr_b200.so.
+//
+// Layout in HBM (DESIGN.md "Data layout"): every per-frame array is stored slot-major with a
+// fixed per-slot stride (capacity), points are float4 XYZI (16 B), indices / keys are int32.
+// Sizes that depend on the data (n_valid, n_corner, ...) live in FrameMeta in device memory and
+// are read by the kernels themselves, so no operator ever needs a host round trip.
+//
+// Arithmetic contract (mirrors the CPU reference op-for-op): this
+// library is compiled with -fmad=false -prec-div=true -prec-sqrt=true and never uses fast
+// intrinsics on the parity path; f32 trig is (float)sin((double)x).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fbpr_b200.h"
+
+#define FBPR_IMU_CAP 512          // IMU ramp samples kept per frame
+#define FBPR_MAX_ITERS 30         // mapOptmization.h:1417
+#define FBPR_CORNERS_PER_SEG 20   // featureExtraction.h:217
+#define FBPR_SEGS 6               // featureExtraction.h:192
+
+struct FrameMeta {
+    int n_raw, n_valid, n_corner, n_surf, n_corner_ds, n_surf_ds, n_map_corner, n_map_surf;
+    int first_valid_raw;          // min raw index that passed the projection gates (defines transStartInverse)
+    int deskewFlag, imuPointerCur, pad0;
+    long long imuAvailable;
+    double timeScanCur;
+    float imuRollInit, imuPitchInit;
+    float pose[6];                // transformTobeMapped: roll, pitch, yaw, x, y, z
+    int iters;
+    unsigned flags;
+    int nSel;                     // rows of the last executed iteration
+    int isDegenerate;
+};
+
+// uniform-grid index of one local map (replaces the per-frame FLANN kd-tree, mapOptmization.h:1413-1414)
+struct GridDesc {
+    float ox, oy, oz;             // origin = bbox min
+    float h, inv_h;               // cell edge
+    int dx, dy, dz;               // cells per axis
+    int ncells;
+    int n;                        // points indexed
+    int rmax;                     // shells needed to cover the 1 m ball
+    int pad;
+};
+
+// one VoxelGrid problem (pcl::VoxelGrid restatement)
+struct VoxDesc {
+    int n;                        // input points
+    int overflow;                 // dx*dy*dz > INT_MAX: output = input
+    int npass;                    // 8-bit radix passes needed for the key range
+    int min_b[3];
+    int div_b[3];
+    float inv_leaf;
+    int n_out;
+    int pad;
+};
+
+struct VoxSeg {                   // host-built descriptor of one VoxelGrid segment
+    const float4* in;             // input cloud
+    const int* n_in;              // device pointer to its size
+    float4* out;
+    int* n_out;
+    float leaf;
+    int cap;                      // capacity of in / out / scratch
+    unsigned* key[2];             // ping-pong keys
+    unsigned* val[2];             // ping-pong point indices
+    unsigned* tile_hist;          // [256][tiles_cap]
+    unsigned* bbox;               // 6 ordered-uint encoded floats: min xyz, max xyz
+    int* run_tile;                // [tiles_cap+1] run starts per tile / scanned
+    VoxDesc* desc;
+    int* point_keys;              // optional: per input point key (parity getter)
+    int* out_keys;                // optional: per output voxel key
+};
+
+struct GridSeg {                  // host-built descriptor of one map-index segment
+    const float4* pts;            // map points (XYZI, original order)
+    const int* n;                 // device pointer to count
+    float4* sorted;               // cell-contiguous copy, w = original index bits
+    int* cell_start;              // [cells_cap+1]
+    int* cell_cursor;             // [cells_cap+1] fill cursor, ends up = cell end
+    int* cell_of;                 // [cap] cell id per point
+    int* tile_sum;                // scan scratch
+    unsigned* bbox;               // 6 encoded floats
+    GridDesc* desc;
+    float h0;                     // requested cell edge
+    int cap, cells_cap;
+};
+
+
+// ---- kernel argument blocks (passed by value) ----------------------------------------------
+struct ProjArgs {
+    FrameMeta* meta;
+    const fbpr_raw_point* raw; int rawCap;
+    const double* imuTime; const double* imuRotX; const double* imuRotY; const double* imuRotZ;   // [slot][FBPR_IMU_CAP]
+    int* pix;                     // [slot][P] winning raw index per pixel
+    int* ringCount;               // [slot][N_SCAN]
+    int* startRing; int* endRing; // [slot][N_SCAN]
+    int* colInd; float* range; float4* cloud; int* winner;   // [slot][P]
+    int N_SCAN, H, P;
+    int first;
+};
+
+struct FeatArgs {
+    FrameMeta* meta;
+    const int* startRing; const int* endRing;     // [slot][N_SCAN]
+    const int* colInd; const float* range; const float4* cloud;   // [slot][P]
+    float* curv; int* picked; int* label;         // [slot][P]
+    int* ringCorner;                              // [slot][N_SCAN] corners per ring
+    int* cornerStage;                             // [slot][N_SCAN][120] indices
+    int* ringSurf; int* ringSurfDS;               // [slot][N_SCAN]
+    float4* surfStage;                            // [slot][P] ring r at r*H
+    float4* corner; int* cornerIndex; int cornerCap;   // [slot][cornerCap]
+    float4* surf;                                 // [slot][P]
+    int N_SCAN, H, P;
+    float edgeThreshold, surfThreshold, leaf;
+    int segPad, voxPad, wcap;                     // pow2 paddings, window capacity
+    int first;
+};
+
+struct LmArgs {
+    FrameMeta* meta;
+    const float4* cornerDS; int cornerCap;
+    const float4* surfDS; int surfCap;
+    const GridSeg* gsegs;         // [2*slot + kind]
+    int first;
+    int edgeMin, surfMin;
+    float z_tol, rot_tol;
+    // debug capture (slots < dbgSlots only)
+    int debug_iter;
+    int* knnC; float* d2C; float4* coeffC; unsigned char* flagC;
+    int* knnS; float* d2S; float4* coeffS; unsigned char* flagS;
+    float* dbgAtA; float* dbgAtB; float* dbgX;      // [slot][36], [slot][6], [slot][6]
+    float* poseTrace;                               // [slot][30][6]
+};
+
+// ordered-uint encoding of floats for atomicMin/atomicMax
+__host__ __device__ inline unsigned f2ord(float f) {
+    unsigned u;
+#ifdef __CUDA_ARCH__
+    u = __float_as_uint(f);
+#else
+    union { float f; unsigned u; } c; c.f = f; u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float ord2f(unsigned u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { float f; unsigned u; } c; c.u = u; return c.f;
+#endif
+}
+
+// f32 trig contract
+__device__ inline float sinf_c(float x) { return (float)sin((double)x); }
+__device__ inline float cosf_c(float x) { return (float)cos((double)x); }
+
+// pcl::getTransformation(x,y,z,roll,pitch,yaw) -> 3x4 row-major, f32
+__device__ inline void get_transformation(float x, float y, float z, float roll, float pitch, float yaw, float T[12]) {
+    float A = cosf_c(yaw), B = sinf_c(yaw), C = cosf_c(pitch), D = sinf_c(pitch), E = cosf_c(roll), F = sinf_c(roll);
+    float DE = D * E, DF = D * F;
+    T[0] = A * C; T[1] = A * DF - B * E; T[2]  = B * F + A * DE; T[3]  = x;
+    T[4] = B * C; T[5] = A * E + B * DF; T[6]  = B * DE - A * F; T[7]  = y;
+    T[8] = -D;    T[9] = C * F;          T[10] = C * E;          T[11] = z;
+}
+
+#define FBPR_CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fbpr_fail(e_, #expr, __FILE__, __LINE__); } while (0)
+int fbpr_fail(cudaError_t e, const char* what, const char* file, int line);
+int fbpr_fail_msg(const char* msg);

@@ -1,0 +1,421 @@
+// lm.cu -- the scan-to-map Gauss-Newton ("LM") loop, all iterations in ONE kernel launch.
+//
+// Replaces, per frame (mapOptmization.h): the loop of scan2MapOptimization (:1417-1436) with
+// cornerOptimization (:1002-1124), surfOptimization (:1126-1215), combineOptimizationCoeffs
+// (:1218-1243), LMOptimization (:1246-1401) and transformUpdate (:1444-1479).
+//
+// B200 mapping: one thread-block CLUSTER per frame.  Every thread owns feature points
+// (transform -> exact 5-NN in the grid index -> line / plane fit -> coefficient -> Jacobian row)
+// and accumulates the 21+6 unique entries of J^T J / J^T r in f64; a warp-shuffle + shared-memory
+// block reduce produces one partial per CTA; after ONE hardware cluster barrier every CTA pulls
+// all partials through distributed shared memory in rank order and redundantly solves the 6x6
+// system (QR, degeneracy projection at iteration 0, pose update, convergence test), so a frame
+// needs one cluster.sync() per iteration and no grid-wide or host synchronisation at all.
+// Independent frames are independent clusters (blockIdx.x / cluster size).
+//
+// Bound: latency (<= 30 dependent iterations) and L2 gathers of map cells; never tensor cores
+// (contractions are K=3 and 6x6).  Compulsory traffic per iteration: 16 B per feature point +
+// 5 x 16 B neighbours (B_iter = 96 * (n_c + n_s)).
+#include <cooperative_groups.h>
+
+#include "internal.cuh"
+#include "mapgrid.cuh"
+#include "smallmat.cuh"
+
+namespace cg = cooperative_groups;
+
+
+namespace {
+
+constexpr int LM_TPB = 256;
+constexpr int NACC = 28;          // 21 (upper triangle of A^T A) + 6 (A^T b) + 1 (row count)
+
+__device__ __forceinline__ void transform_point(const float* T, float4 p, float& x, float& y, float& z) {
+    x = T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3];
+    y = T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7];
+    z = T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11];
+}
+
+// cornerOptimization body for one point (mapOptmization.h:1026-1121)
+__device__ inline bool corner_fit(const float4* __restrict__ mpts, const Knn5& r, float x0, float y0, float z0, float4& coeff) {
+    float px[5], py[5], pz[5];
+    #pragma unroll
+    for (int j = 0; j < 5; j++) { float4 m = mpts[r.pos[j]]; px[j] = m.x; py[j] = m.y; pz[j] = m.z; }
+    float cx = 0, cy = 0, cz = 0;
+    #pragma unroll
+    for (int j = 0; j < 5; j++) { cx += px[j]; cy += py[j]; cz += pz[j]; }
+    cx /= 5; cy /= 5; cz /= 5;
+    float a11 = 0, a12 = 0, a13 = 0, a22 = 0, a23 = 0, a33 = 0;
+    #pragma unroll
+    for (int j = 0; j < 5; j++) {
+        float ax = px[j] - cx, ay = py[j] - cy, az = pz[j] - cz;
+        a11 += ax * ax; a12 += ax * ay; a13 += ax * az;
+        a22 += ay * ay; a23 += ay * az;
+        a33 += az * az;
+    }
+    a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
+    float A1[9] = { a11, a12, a13, a12, a22, a23, a13, a23, a33 }, D1[3], V1[9];
+    dev_jacobi<3>(A1, D1, V1);
+    if (!(D1[0] > 3 * D1[1])) return false;
+    float x1 = (float)((double)cx + 0.1 * (double)V1[0]);
+    float y1 = (float)((double)cy + 0.1 * (double)V1[1]);
+    float z1 = (float)((double)cz + 0.1 * (double)V1[2]);
+    float x2 = (float)((double)cx - 0.1 * (double)V1[0]);
+    float y2 = (float)((double)cy - 0.1 * (double)V1[1]);
+    float z2 = (float)((double)cz - 0.1 * (double)V1[2]);
+    float a012 = sqrtf(((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) * ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1))
+                     + ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1)) * ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1))
+                     + ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1)) * ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1)));
+    float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+    float la = ((y1 - y2) * ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1))
+              + (z1 - z2) * ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1))) / a012 / l12;
+    float lb = -((x1 - x2) * ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1))
+               - (z1 - z2) * ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1))) / a012 / l12;
+    float lc = -((x1 - x2) * ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1))
+               + (y1 - y2) * ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1))) / a012 / l12;
+    float ld2 = a012 / l12;
+    float s = (float)(1.0 - 0.9 * (double)fabsf(ld2));
+    coeff = make_float4(s * la, s * lb, s * lc, s * ld2);
+    return (double)s > 0.1;
+}
+
+// surfOptimization body for one point (mapOptmization.h:1153-1212)
+__device__ inline bool surf_fit(const float4* __restrict__ mpts, const Knn5& r, float x0, float y0, float z0, float4& coeff) {
+    float A0[15];
+    #pragma unroll
+    for (int j = 0; j < 5; j++) { float4 m = mpts[r.pos[j]]; A0[3 * j] = m.x; A0[3 * j + 1] = m.y; A0[3 * j + 2] = m.z; }
+    float X0[3];
+    dev_plane_solve(A0, X0);
+    float pa = X0[0], pb = X0[1], pc = X0[2], pd = 1;
+    float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+    pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+    #pragma unroll
+    for (int j = 0; j < 5; j++)
+        if ((double)fabsf(pa * A0[3 * j] + pb * A0[3 * j + 1] + pc * A0[3 * j + 2] + pd) > 0.2) return false;
+    float pd2 = pa * x0 + pb * y0 + pc * z0 + pd;
+    float s = (float)(1.0 - 0.9 * (double)fabsf(pd2) / (double)sqrtf(sqrtf(x0 * x0 + y0 * y0 + z0 * z0)));
+    coeff = make_float4(s * pa, s * pb, s * pc, s * pd2);
+    return (double)s > 0.1;
+}
+
+// tf::Quaternion / tf::Matrix3x3 helpers (f64) for transformUpdate (mapOptmization.h:1459-1472)
+__device__ inline void q_set_rpy(double roll, double pitch, double yaw, double q[4]) {
+    double hy = yaw * 0.5, hp = pitch * 0.5, hr = roll * 0.5;
+    double cy = cos(hy), sy = sin(hy), cp = cos(hp), sp = sin(hp), cr = cos(hr), sr = sin(hr);
+    q[0] = sr * cp * cy - cr * sp * sy; q[1] = cr * sp * cy + sr * cp * sy;
+    q[2] = cr * cp * sy - sr * sp * cy; q[3] = cr * cp * cy + sr * sp * sy;
+}
+__device__ inline double q_dot(const double a[4], const double b[4]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3]; }
+__device__ inline void q_slerp(const double a[4], const double b[4], double t, double o[4]) {
+    double s = sqrt(q_dot(a, a) * q_dot(b, b));
+    double d = q_dot(a, b);
+    double theta = (d < 0 ? acos(-d / s) * 2.0 : acos(d / s) * 2.0) / 2.0;
+    if (theta != 0.0) {
+        double dd = 1.0 / sin(theta), s0 = sin((1.0 - t) * theta), s1 = sin(t * theta);
+        double sg = d < 0 ? -1.0 : 1.0;
+        for (int k = 0; k < 4; k++) o[k] = (a[k] * s0 + sg * b[k] * s1) * dd;
+    } else {
+        for (int k = 0; k < 4; k++) o[k] = a[k];
+    }
+}
+__device__ inline void q_get_rpy(const double q[4], double& roll, double& pitch, double& yaw) {
+    const double PI = 3.14159265358979323846;
+    double d = q_dot(q, q), s = 2.0 / d;
+    double xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+    double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+    double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs, yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+    double m00 = 1.0 - (yy + zz), m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+    double m01 = xy - wz, m02 = xz + wy;
+    if (fabs(m20) >= 1) {
+        yaw = 0;
+        double delta = atan2(m01, m02);
+        if (m20 < 0) { pitch = PI / 2.0; roll = delta; } else { pitch = -PI / 2.0; roll = delta; }
+    } else {
+        pitch = -asin(m20);
+        roll = atan2(m21 / cos(pitch), m22 / cos(pitch));
+        yaw = atan2(m10 / cos(pitch), m00 / cos(pitch));
+    }
+}
+__device__ inline float clampf(float v, float lim) { if (v < -lim) v = -lim; if (v > lim) v = lim; return v; }
+
+__device__ inline void transform_update(float* pose, long long imuAvailable, float imuRollInit, float imuPitchInit, float rot_tol, float z_tol) {
+    if (imuAvailable == 1 && fabs((double)imuPitchInit) < 1.4) {
+        double q0[4], q1[4], qm[4], r, p, y;
+        q_set_rpy((double)pose[0], 0, 0, q0); q_set_rpy((double)imuRollInit, 0, 0, q1);
+        q_slerp(q0, q1, 0.05, qm); q_get_rpy(qm, r, p, y);
+        pose[0] = (float)r;
+        q_set_rpy(0, (double)pose[1], 0, q0); q_set_rpy(0, (double)imuPitchInit, 0, q1);
+        q_slerp(q0, q1, 0.05, qm); q_get_rpy(qm, r, p, y);
+        pose[1] = (float)p;
+    }
+    pose[0] = clampf(pose[0], rot_tol);
+    pose[1] = clampf(pose[1], rot_tol);
+    pose[5] = clampf(pose[5], z_tol);
+}
+
+// LMOptimization after the reduction (mapOptmization.h:1336-1400), one thread.
+// Returns 1 when converged.  matP is the reference's LOCAL zero-initialised matrix (:1278).
+__device__ inline int lm_solve_step(const float* AtA, const float* AtB, int iter, int& isDegenerate, float* pose, float* Xout) {
+    float Aw[36], bw[6], X[6];
+    for (int k = 0; k < 36; k++) Aw[k] = AtA[k];
+    for (int k = 0; k < 6; k++) bw[k] = AtB[k];
+    dev_qr_solve6(Aw, bw, X);
+    float matP[36];
+    for (int k = 0; k < 36; k++) matP[k] = 0.f;
+    if (iter == 0) {
+        float E[6], V[36], V2[36], Vinv[36];
+        for (int k = 0; k < 36; k++) Aw[k] = AtA[k];
+        dev_jacobi<6>(Aw, E, V);
+        for (int k = 0; k < 36; k++) V2[k] = V[k];
+        isDegenerate = 0;
+        for (int i = 5; i >= 0; i--) {
+            if (E[i] < 100.f) { for (int j = 0; j < 6; j++) V2[i * 6 + j] = 0; isDegenerate = 1; }
+            else break;
+        }
+        for (int k = 0; k < 36; k++) Aw[k] = V[k];
+        dev_lu_invert6(Aw, Vinv);
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < 6; j++) {
+                double s = 0.0;
+                for (int q = 0; q < 6; q++) s += (double)Vinv[i * 6 + q] * (double)V2[q * 6 + j];
+                matP[i * 6 + j] = (float)s;
+            }
+    }
+    if (isDegenerate) {
+        float X2[6];
+        for (int k = 0; k < 6; k++) X2[k] = X[k];
+        for (int i = 0; i < 6; i++) {
+            double s = 0.0;
+            for (int q = 0; q < 6; q++) s += (double)matP[i * 6 + q] * (double)X2[q];
+            X[i] = (float)s;
+        }
+    }
+    for (int k = 0; k < 6; k++) { pose[k] += X[k]; Xout[k] = X[k]; }
+    double r0 = (double)(X[0] * 57.29578f), r1 = (double)(X[1] * 57.29578f), r2 = (double)(X[2] * 57.29578f);
+    double t0 = (double)(X[3] * 100), t1 = (double)(X[4] * 100), t2 = (double)(X[5] * 100);
+    float deltaR = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+    float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+    return ((double)deltaR < 0.05 && (double)deltaT < 0.05) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(LM_TPB) lm_kernel(LmArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int slot = a.first + (int)(blockIdx.x / C);
+    FrameMeta& M = a.meta[slot];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    __shared__ double part[2][NACC];               // this CTA's partial sums, double-buffered by iteration parity
+    __shared__ double wred[LM_TPB / 32][NACC];
+    __shared__ float sh_pose[6], sh_T[12], sh_trig[6], sh_AtA[36], sh_AtB[6];
+    __shared__ int sh_stop, sh_nsel;
+
+    const int nC = M.n_corner_ds, nS = M.n_surf_ds;
+    if (!(nC > a.edgeMin && nS > a.surfMin)) {     // mapOptmization.h:1410 / :1439-1441
+        if (rank == 0 && tid == 0) { M.flags = FBPR_FLAG_NOT_ENOUGH_FEATURES; M.iters = 0; M.nSel = 0; M.isDegenerate = 0; }
+        return;
+    }
+    const GridSeg gc = a.gsegs[2 * slot], gs = a.gsegs[2 * slot + 1];
+    const GridDesc gdc = *gc.desc, gds = *gs.desc;
+    const float4* cpts = a.cornerDS + (size_t)slot * a.cornerCap;
+    const float4* spts = a.surfDS + (size_t)slot * a.surfCap;
+    if (tid < 6) sh_pose[tid] = M.pose[tid];
+    __syncthreads();
+
+    unsigned flags = 0; int isDegenerate = 0; int iters = 0;
+    for (int iter = 0; iter < FBPR_MAX_ITERS; iter++) {
+        // --- pose -> rigid transform + the six sines/cosines LMOptimization needs (:1259-1264)
+        if (tid < 6) {
+            float ang = sh_pose[tid % 3];            // 0 roll, 1 pitch, 2 yaw
+            sh_trig[tid] = tid < 3 ? sinf_c(ang) : cosf_c(ang);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // pcl::getTransformation from the shared trig values (same expression order as Appendix B-4)
+            float F = sh_trig[0], D = sh_trig[1], B = sh_trig[2], E = sh_trig[3], Cc = sh_trig[4], A = sh_trig[5];
+            float DE = D * E, DF = D * F;
+            sh_T[0] = A * Cc; sh_T[1] = A * DF - B * E; sh_T[2]  = B * F + A * DE; sh_T[3]  = sh_pose[3];
+            sh_T[4] = B * Cc; sh_T[5] = A * E + B * DF; sh_T[6]  = B * DE - A * F; sh_T[7]  = sh_pose[4];
+            sh_T[8] = -D;     sh_T[9] = Cc * F;         sh_T[10] = Cc * E;         sh_T[11] = sh_pose[5];
+        }
+        __syncthreads();
+        float T[12];
+        #pragma unroll
+        for (int k = 0; k < 12; k++) T[k] = sh_T[k];
+        const float srz = sh_trig[0], srx = sh_trig[1], sry = sh_trig[2], crz = sh_trig[3], crx = sh_trig[4], cry = sh_trig[5];
+
+        double acc[NACC];
+        #pragma unroll
+        for (int k = 0; k < NACC; k++) acc[k] = 0.0;
+        const bool cap = iter == a.debug_iter;
+
+        for (int i = rank * LM_TPB + tid; i < nC + nS; i += C * LM_TPB) {
+            const bool isCorner = i < nC;
+            const int li = isCorner ? i : i - nC;
+            const float4 pOri = isCorner ? cpts[li] : spts[li];
+            float x0, y0, z0;
+            transform_point(T, pOri, x0, y0, z0);
+            Knn5 r;
+            #pragma unroll
+            for (int k = 0; k < 5; k++) { r.d[k] = 3.0e38f; r.id[k] = -1; r.pos[k] = 0; }
+            float4 coeff = make_float4(0, 0, 0, 0);
+            bool ok;
+            if (isCorner) {
+                ok = gdc.n >= 5 && grid_knn5(gdc, gc.cell_start, gc.cell_cursor, gc.sorted, x0, y0, z0, r);
+                bool near = ok;
+                if (ok) ok = corner_fit(gc.sorted, r, x0, y0, z0, coeff);
+                if (cap) {
+                    size_t o = (size_t)slot * a.cornerCap + li;
+                    for (int k = 0; k < 5; k++) { a.knnC[5 * o + k] = near ? r.id[k] : -1; a.d2C[5 * o + k] = r.d[k]; }
+                    a.coeffC[o] = coeff; a.flagC[o] = ok ? 1 : 0;
+                }
+            } else {
+                ok = gds.n >= 5 && grid_knn5(gds, gs.cell_start, gs.cell_cursor, gs.sorted, x0, y0, z0, r);
+                bool near = ok;
+                if (ok) ok = surf_fit(gs.sorted, r, x0, y0, z0, coeff);
+                if (cap) {
+                    size_t o = (size_t)slot * a.surfCap + li;
+                    for (int k = 0; k < 5; k++) { a.knnS[5 * o + k] = near ? r.id[k] : -1; a.d2S[5 * o + k] = r.d[k]; }
+                    a.coeffS[o] = coeff; a.flagS[o] = ok ? 1 : 0;
+                }
+            }
+            if (ok) {
+                // Jacobian row, lidar -> "camera" axis permutation (mapOptmization.h:1286-1332)
+                const float ox = pOri.y, oy = pOri.z, oz = pOri.x;
+                const float kx = coeff.y, ky = coeff.z, kz = coeff.x;
+                float arx = (crx * sry * srz * ox + crx * crz * sry * oy - srx * sry * oz) * kx
+                          + (-srx * srz * ox - crz * srx * oy - crx * oz) * ky
+                          + (crx * cry * srz * ox + crx * cry * crz * oy - cry * srx * oz) * kz;
+                float ary = ((cry * srx * srz - crz * sry) * ox
+                          + (sry * srz + cry * crz * srx) * oy + crx * cry * oz) * kx
+                          + ((-cry * crz - srx * sry * srz) * ox
+                          + (cry * srz - crz * srx * sry) * oy - crx * sry * oz) * kz;
+                float arz = ((crz * srx * sry - cry * srz) * ox + (-cry * crz - srx * sry * srz) * oy) * kx
+                          + (crx * crz * ox - crx * srz * oy) * ky
+                          + ((sry * srz + cry * crz * srx) * ox + (crz * sry - cry * srx * srz) * oy) * kz;
+                const double row[6] = { (double)arz, (double)arx, (double)ary, (double)kz, (double)kx, (double)ky };
+                const double b = (double)(-coeff.w);
+                int q = 0;
+                #pragma unroll
+                for (int rr = 0; rr < 6; rr++) {
+                    #pragma unroll
+                    for (int cc = rr; cc < 6; cc++) acc[q++] += row[rr] * row[cc];
+                }
+                #pragma unroll
+                for (int rr = 0; rr < 6; rr++) acc[21 + rr] += row[rr] * b;
+                acc[27] += 1.0;
+            }
+        }
+        // --- block reduce (warp shuffles, then shared memory in fixed warp order)
+        #pragma unroll
+        for (int k = 0; k < NACC; k++) {
+            double v = acc[k];
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) wred[warp][k] = v;
+        }
+        __syncthreads();
+        const int buf = iter & 1;
+        if (tid < NACC) {
+            double v = 0.0;
+            for (int w = 0; w < LM_TPB / 32; w++) v += wred[w][tid];
+            part[buf][tid] = v;
+        }
+        cluster.sync();
+        // --- every CTA pulls all partials through DSMEM in rank order and solves redundantly
+        if (tid < NACC) {
+            double v = 0.0;
+            for (int rk = 0; rk < C; rk++) {
+                const double* remote = cluster.map_shared_rank(&part[buf][0], rk);
+                v += remote[tid];
+            }
+            if (tid < 21) {
+                // unpack the upper triangle index tid -> (r, c)
+                int rr = 0, q = tid;
+                while (q >= 6 - rr) { q -= 6 - rr; rr++; }
+                int cc = rr + q;
+                float fv = (float)v;
+                sh_AtA[rr * 6 + cc] = fv; sh_AtA[cc * 6 + rr] = fv;
+            } else if (tid < 27) {
+                sh_AtB[tid - 21] = (float)v;
+            } else {
+                sh_nsel = (int)(v + 0.5);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int stop = 0;
+            iters = iter + 1;
+            if (sh_nsel < 50) {                     // :1267-1270: LMOptimization returns false, pose unchanged;
+                flags |= FBPR_FLAG_TOO_FEW_CORRESPONDENCES;   // every remaining iteration repeats identically
+                iters = FBPR_MAX_ITERS; stop = 1;
+            } else {
+                float pose[6], X[6];
+                for (int k = 0; k < 6; k++) pose[k] = sh_pose[k];
+                int conv = lm_solve_step(sh_AtA, sh_AtB, iter, isDegenerate, pose, X);
+                for (int k = 0; k < 6; k++) sh_pose[k] = pose[k];
+                if (conv) { flags |= FBPR_FLAG_CONVERGED; stop = 1; }
+                if (rank == 0 && cap) {
+                    for (int k = 0; k < 36; k++) a.dbgAtA[(size_t)slot * 36 + k] = sh_AtA[k];
+                    for (int k = 0; k < 6; k++) { a.dbgAtB[(size_t)slot * 6 + k] = sh_AtB[k]; a.dbgX[(size_t)slot * 6 + k] = X[k]; }
+                }
+            }
+            if (rank == 0 && a.poseTrace) {
+                for (int k = 0; k < 6; k++) a.poseTrace[((size_t)slot * FBPR_MAX_ITERS + iter) * 6 + k] = sh_pose[k];
+            }
+            sh_stop = stop;
+        }
+        __syncthreads();
+        if (sh_stop) break;
+    }
+    cluster.sync();                                 // nobody leaves while a peer may still read its partials
+    if (rank == 0 && tid == 0) {
+        float pose[6];
+        for (int k = 0; k < 6; k++) pose[k] = sh_pose[k];
+        if (isDegenerate) flags |= FBPR_FLAG_DEGENERATE;
+        transform_update(pose, M.imuAvailable, M.imuRollInit, M.imuPitchInit, a.rot_tol, a.z_tol);
+        for (int k = 0; k < 6; k++) M.pose[k] = pose[k];
+        M.iters = iters; M.flags = flags; M.nSel = sh_nsel; M.isDegenerate = isDegenerate;
+    }
+}
+
+__global__ void transform_update_kernel(FrameMeta* meta, int first, int count, float rot_tol, float z_tol) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    FrameMeta& M = meta[first + i];
+    float pose[6];
+    for (int k = 0; k < 6; k++) pose[k] = M.pose[k];
+    transform_update(pose, M.imuAvailable, M.imuRollInit, M.imuPitchInit, rot_tol, z_tol);
+    for (int k = 0; k < 6; k++) M.pose[k] = pose[k];
+}
+
+}  // namespace
+
+int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, cudaStream_t st, long long* launches) {
+    if (count <= 0) return 0;
+    static int configured = 0;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(lm_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(NonPortableClusterSizeAllowed)", __FILE__, __LINE__);
+        configured = 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(count * cluster_size));
+    cfg.blockDim = dim3(LM_TPB);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lm_kernel, args);
+    if (e != cudaSuccess) return fbpr_fail(e, "cudaLaunchKernelEx(lm_kernel)", __FILE__, __LINE__);
+    if (launches) *launches += 1;
+    return 0;
+}
+
+void fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float rot_tol, float z_tol, cudaStream_t st, long long* launches) {
+    if (count <= 0) return;
+    transform_update_kernel<<<(count + 63) / 64, 64, 0, st>>>(meta, first, count, rot_tol, z_tol);
+    if (launches) *launches += 1;
+}

@@ -1,0 +1,217 @@
+// mapgrid.cu -- device build of the uniform-grid map index (one per local map per frame).
+//
+// Replaces kdtree{Corner,Surf}FromMap->setInputCloud (mapOptmization.h:1413-1414), which the
+// reference re-runs every frame on one thread.  Here: bbox reduce -> cell id per point +
+// histogram (atomics) -> exclusive scan over cells -> scatter into cell-contiguous order
+// (counting sort).  Order inside a cell is arbitrary; exactness of the k-NN does not depend on
+// it because candidates are ranked by (d^2, original index).
+// HBM-bound: reads each map point twice (16 B) and writes it once; the cell arrays are
+// L2-resident.  blockIdx.y = segment (2 maps x frame slots).
+#include "internal.cuh"
+#include "mapgrid.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int TILE = 2048;
+constexpr int IPT = TILE / TPB;
+constexpr int SCAN_TILE = 4096;   // cells per CTA in the cell scan
+
+__device__ inline unsigned warp_min_u(unsigned v) { for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ inline unsigned warp_max_u(unsigned v) { for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+
+__global__ void grid_init(const GridSeg* segs) {
+    const GridSeg& s = segs[blockIdx.x];
+    if (threadIdx.x < 3) s.bbox[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) s.bbox[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(TPB) grid_minmax(const GridSeg* segs) {
+    const GridSeg& s = segs[blockIdx.y];
+    int n = min(*s.n, s.cap);
+    int base = blockIdx.x * TILE;
+    if (base >= n) return;
+    unsigned mn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, mx[3] = { 0u, 0u, 0u };
+    for (int k = 0; k < IPT; k++) {
+        int i = base + k * TPB + threadIdx.x;
+        if (i < n) {
+            float4 p = s.pts[i];
+            unsigned ex = f2ord(p.x), ey = f2ord(p.y), ez = f2ord(p.z);
+            mn[0] = min(mn[0], ex); mn[1] = min(mn[1], ey); mn[2] = min(mn[2], ez);
+            mx[0] = max(mx[0], ex); mx[1] = max(mx[1], ey); mx[2] = max(mx[2], ez);
+        }
+    }
+    __shared__ unsigned sm[6][TPB / 32];
+    for (int c = 0; c < 3; c++) { mn[c] = warp_min_u(mn[c]); mx[c] = warp_max_u(mx[c]); }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) for (int c = 0; c < 3; c++) { sm[c][w] = mn[c]; sm[3 + c][w] = mx[c]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        unsigned v = sm[threadIdx.x][0];
+        for (int k = 1; k < TPB / 32; k++) v = threadIdx.x < 3 ? min(v, sm[threadIdx.x][k]) : max(v, sm[threadIdx.x][k]);
+        if (threadIdx.x < 3) atomicMin(&s.bbox[threadIdx.x], v); else atomicMax(&s.bbox[threadIdx.x], v);
+    }
+}
+
+// choose the cell edge (>= requested, doubled until the dense grid fits cells_cap) and zero the counters
+__global__ void __launch_bounds__(TPB) grid_setup_zero(const GridSeg* segs) {
+    const GridSeg& s = segs[blockIdx.y];
+    __shared__ GridDesc gd;
+    if (threadIdx.x == 0) {
+        int n = min(*s.n, s.cap); if (n < 0) n = 0;
+        GridDesc g;
+        g.n = n;
+        float mn[3] = { 0, 0, 0 }, mx[3] = { 0, 0, 0 };
+        if (n > 0) for (int c = 0; c < 3; c++) { mn[c] = ord2f(s.bbox[c]); mx[c] = ord2f(s.bbox[3 + c]); }
+        float h = s.h0;
+        while (true) {
+            float inv = 1.0f / h;
+            long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1, dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+            if (dx < 2000000 && dy < 2000000 && dz < 2000000 && dx * dy * dz <= (long long)s.cells_cap) {
+                g.dx = (int)dx; g.dy = (int)dy; g.dz = (int)dz; g.h = h; g.inv_h = inv; break;
+            }
+            h *= 2.0f;
+        }
+        g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
+        g.ncells = g.dx * g.dy * g.dz;
+        int rmax = 1; while ((float)rmax * g.h * 0.9995f < 1.0f) rmax++;
+        g.rmax = rmax; g.pad = 0;
+        gd = g;
+        if (blockIdx.x == 0) *s.desc = g;
+    }
+    __syncthreads();
+    const int nc = gd.ncells;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= nc; c += gridDim.x * blockDim.x) s.cell_start[c] = 0;
+}
+
+__device__ inline int cell_of_point(const GridDesc& g, float4 p) {
+    int cx = (int)floorf((p.x - g.ox) * g.inv_h), cy = (int)floorf((p.y - g.oy) * g.inv_h), cz = (int)floorf((p.z - g.oz) * g.inv_h);
+    cx = min(max(cx, 0), g.dx - 1); cy = min(max(cy, 0), g.dy - 1); cz = min(max(cz, 0), g.dz - 1);
+    return (cz * g.dy + cy) * g.dx + cx;
+}
+
+__global__ void __launch_bounds__(TPB) grid_count(const GridSeg* segs) {
+    const GridSeg& s = segs[blockIdx.y];
+    const GridDesc g = *s.desc;
+    int base = blockIdx.x * TILE;
+    if (base >= g.n) return;
+    for (int k = 0; k < IPT; k++) {
+        int i = base + k * TPB + threadIdx.x;
+        if (i < g.n) { int c = cell_of_point(g, s.pts[i]); s.cell_of[i] = c; atomicAdd(&s.cell_start[c], 1); }
+    }
+}
+
+// three-phase exclusive scan over the cells of every segment
+__global__ void __launch_bounds__(1024) grid_scan_tiles(const GridSeg* segs) {
+    const GridSeg& s = segs[blockIdx.y];
+    const int nc = s.desc->ncells + 1;
+    int base = blockIdx.x * SCAN_TILE;
+    if (base >= nc) return;
+    int v[4], sum = 0;
+    for (int k = 0; k < 4; k++) { int c = base + threadIdx.x * 4 + k; v[k] = c < nc ? s.cell_start[c] : 0; sum += v[k]; }
+    __shared__ int ws[32];
+    int incl = sum, l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
+    if (l == 31) ws[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int a = ws[l], ia = a;
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, ia, o); if (l >= o) ia += u; }
+        ws[l] = ia - a;
+        if (l == 31) s.tile_sum[blockIdx.x] = ia;
+    }
+    __syncthreads();
+    int run = ws[w] + incl - sum;
+    for (int k = 0; k < 4; k++) { int c = base + threadIdx.x * 4 + k; if (c < nc) { s.cell_start[c] = run; run += v[k]; } }
+}
+
+__global__ void __launch_bounds__(1024) grid_scan_sums(const GridSeg* segs) {
+    const GridSeg& s = segs[blockIdx.x];
+    const int nt = (s.desc->ncells + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    __shared__ int ws[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b = 0; b < nt; b += 1024) {
+        int e = b + threadIdx.x;
+        int v = e < nt ? s.tile_sum[e] : 0;
+        int incl = v, l = threadIdx.x & 31, w = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
+        if (l == 31) ws[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int a = ws[l], ia = a;
+            for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, ia, o); if (l >= o) ia += u; }
+            ws[l] = ia - a;
+        }
+        __syncthreads();
+        int excl = carry + ws[w] + incl - v;
+        if (e < nt) s.tile_sum[e] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) grid_scan_add(const GridSeg* segs) {
+    const GridSeg& s = segs[blockIdx.y];
+    const int nc = s.desc->ncells + 1;
+    int base = blockIdx.x * SCAN_TILE;
+    if (base >= nc) return;
+    int add = s.tile_sum[blockIdx.x];
+    for (int k = 0; k < 4; k++) {
+        int c = base + threadIdx.x * 4 + k;
+        if (c < nc) { int v = s.cell_start[c] + add; s.cell_start[c] = v; s.cell_cursor[c] = v; }
+    }
+}
+
+__global__ void __launch_bounds__(TPB) grid_scatter(const GridSeg* segs) {
+    const GridSeg& s = segs[blockIdx.y];
+    const int n = s.desc->n;
+    int base = blockIdx.x * TILE;
+    if (base >= n) return;
+    for (int k = 0; k < IPT; k++) {
+        int i = base + k * TPB + threadIdx.x;
+        if (i < n) {
+            float4 p = s.pts[i];
+            int pos = atomicAdd(&s.cell_cursor[s.cell_of[i]], 1);
+            s.sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+        }
+    }
+}
+
+// stand-alone query kernel behind fbpr_knn5 (parity tests of the index itself)
+__global__ void __launch_bounds__(128) knn5_query(const GridSeg* segs, const float* __restrict__ q, int nq, int* idx, float* d2) {
+    const GridSeg& s = segs[0];
+    const GridDesc g = *s.desc;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    Knn5 r;
+    bool ok = g.n >= 5 && grid_knn5(g, s.cell_start, s.cell_cursor, s.sorted, q[3 * i], q[3 * i + 1], q[3 * i + 2], r);
+    for (int k = 0; k < 5; k++) { idx[5 * i + k] = ok ? r.id[k] : -1; d2[5 * i + k] = r.d[k]; }
+}
+
+}  // namespace
+
+void fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cells_cap, cudaStream_t st, long long* launches) {
+    if (nsegs <= 0) return;
+    int tiles = (max_n + TILE - 1) / TILE; if (tiles < 1) tiles = 1;
+    int stiles = (cells_cap + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    dim3 g(tiles, nsegs), gs(stiles, nsegs);
+    grid_init<<<nsegs, 32, 0, st>>>(d_segs);
+    grid_minmax<<<g, TPB, 0, st>>>(d_segs);
+    int zb = (cells_cap + TPB * 8) / (TPB * 8); if (zb > 1024) zb = 1024;
+    grid_setup_zero<<<dim3(zb, nsegs), TPB, 0, st>>>(d_segs);
+    grid_count<<<g, TPB, 0, st>>>(d_segs);
+    grid_scan_tiles<<<gs, 1024, 0, st>>>(d_segs);
+    grid_scan_sums<<<nsegs, 1024, 0, st>>>(d_segs);
+    grid_scan_add<<<gs, 1024, 0, st>>>(d_segs);
+    grid_scatter<<<g, TPB, 0, st>>>(d_segs);
+    if (launches) *launches += 8;
+}
+
+void fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, cudaStream_t st, long long* launches) {
+    if (nq <= 0) return;
+    knn5_query<<<(nq + 127) / 128, 128, 0, st>>>(d_seg, d_q, nq, d_idx, d_d2);
+    if (launches) *launches += 1;
+}

@@ -1,0 +1,155 @@
+// mapops.cu -- local-map providers around the registration path.
+//
+//   keyframe transform + concat : extractCloud / transformPointCloud (mapOptmization.h:909-944, :405-425)
+//   CropBox                     : the fork's registration() local map (mapOptmization.h:284-304),
+//                                 pcl::CropBox = inclusive AABB test, input order preserved
+//   pose decompose / compose    : pcl::getTranslationAndEulerAngles (:309-310), pcl::getTransformation (:326)
+// All are HBM-bound streaming kernels (16 B in, 16 B out per kept point).
+#include "internal.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int TILE = 2048;
+constexpr int IPT = TILE / TPB;
+
+// one CTA: keep flags (distance re-check, :924), output offsets, one 3x4 transform per keyframe
+__global__ void kf_prepare(const float* poses6, int K, const int* off, const float* last_xyz, float radius,
+                           int* outoff, float* T, int* n_out) {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const float* p = poses6 + 6 * i;
+        get_transformation(p[3], p[4], p[5], p[0], p[1], p[2], T + 12 * i);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < K; i++) {
+            const float* p = poses6 + 6 * i;
+            float ddx = p[3] - last_xyz[0], ddy = p[4] - last_xyz[1], ddz = p[5] - last_xyz[2];
+            bool keep = !(sqrtf(ddx * ddx + ddy * ddy + ddz * ddz) > radius);
+            outoff[i] = keep ? run : -1;
+            if (keep) run += off[i + 1] - off[i];
+        }
+        outoff[K] = run;
+        *n_out = run;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) kf_transform(int K, const float4* in, const int* off, const int* outoff, const float* T, float4* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = K;                      // keyframe k with off[k] <= i < off[k+1]
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
+    int base = outoff[lo];
+    if (base < 0) return;
+    const float* t = T + 12 * lo;
+    float4 p = in[i], q;
+    q.x = t[0] * p.x + t[1] * p.y + t[2] * p.z + t[3];
+    q.y = t[4] * p.x + t[5] * p.y + t[6] * p.z + t[7];
+    q.z = t[8] * p.x + t[9] * p.y + t[10] * p.z + t[11];
+    q.w = p.w;
+    out[base + (i - off[lo])] = q;
+}
+
+__device__ inline bool in_box(float4 p, const float* pose12) {
+    const float mnx = -30.0f + pose12[3], mxx = 30.0f + pose12[3];
+    const float mny = -30.0f + pose12[7], mxy = 30.0f + pose12[7];
+    const float mnz = -10.0f + pose12[11], mxz = 10.0f + pose12[11];
+    return !(p.x < mnx || p.y < mny || p.z < mnz || p.x > mxx || p.y > mxy || p.z > mxz);
+}
+
+__global__ void __launch_bounds__(TPB) crop_count(const float4* in, int n, const float* pose12, int* tile) {
+    int base = blockIdx.x * TILE, cnt = 0;
+    for (int k = 0; k < IPT; k++) { int i = base + k * TPB + threadIdx.x; if (i < n && in_box(in[i], pose12)) cnt++; }
+    __shared__ int ws[TPB / 32];
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < TPB / 32; k++) t += ws[k]; tile[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(1024) crop_scan(int* tile, int ntiles, int* n_out, int cap) {
+    __shared__ int ws[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b = 0; b < ntiles; b += 1024) {
+        int e = b + threadIdx.x;
+        int v = e < ntiles ? tile[e] : 0;
+        int incl = v, l = threadIdx.x & 31, w = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
+        if (l == 31) ws[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int a = ws[l], ia = a;
+            for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, ia, o); if (l >= o) ia += u; }
+            ws[l] = ia - a;
+        }
+        __syncthreads();
+        int excl = carry + ws[w] + incl - v;
+        if (e < ntiles) tile[e] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = min(carry, cap);      // points beyond the slot's map capacity are dropped
+}
+
+__global__ void __launch_bounds__(TPB) crop_emit(const float4* in, int n, const float* pose12, const int* tile, float4* out, int cap) {
+    // blocked layout (thread t owns IPT consecutive points) keeps the input order
+    int start = blockIdx.x * TILE + threadIdx.x * IPT;
+    float4 p[IPT]; int flags = 0, cnt = 0;
+    for (int k = 0; k < IPT; k++) { int i = start + k; if (i < n) { p[k] = in[i]; if (in_box(p[k], pose12)) { flags |= 1 << k; cnt++; } } }
+    __shared__ int ws[TPB / 32];
+    int incl = cnt, l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
+    if (l == 31) ws[w] = incl;
+    __syncthreads();
+    int woff = 0; for (int q = 0; q < w; q++) woff += ws[q];
+    int slot = tile[blockIdx.x] + woff + incl - cnt;
+    for (int k = 0; k < IPT; k++) if (flags & (1 << k)) { if (slot < cap) out[slot] = p[k]; slot++; }
+}
+
+__global__ void pose_decompose(const float* T, FrameMeta* meta, int slot) {
+    if (threadIdx.x != 0) return;
+    FrameMeta& M = meta[slot];
+    M.pose[3] = T[3]; M.pose[4] = T[7]; M.pose[5] = T[11];
+    M.pose[0] = (float)atan2((double)T[9], (double)T[10]);
+    M.pose[1] = (float)asin((double)(-T[8]));
+    M.pose[2] = (float)atan2((double)T[4], (double)T[0]);
+}
+__global__ void pose_compose(const FrameMeta* meta, int slot, float* T) {
+    if (threadIdx.x != 0) return;
+    const FrameMeta& M = meta[slot];
+    float t[12];
+    get_transformation(M.pose[3], M.pose[4], M.pose[5], M.pose[0], M.pose[1], M.pose[2], t);
+    for (int k = 0; k < 12; k++) T[k] = t[k];
+}
+
+}  // namespace
+
+void fbpr_launch_keyframe_transform(const float* d_poses6, int K, const float4* d_in, const int* d_off, float4* d_out, int* d_n_out,
+                                    const float* d_last_xyz, float radius, int max_pts, int* d_outoff, float* d_T,
+                                    cudaStream_t st, long long* launches) {
+    kf_prepare<<<1, 256, 0, st>>>(d_poses6, K, d_off, d_last_xyz, radius, d_outoff, d_T, d_n_out);
+    if (max_pts > 0 && K > 0) kf_transform<<<(max_pts + TPB - 1) / TPB, TPB, 0, st>>>(K, d_in, d_off, d_outoff, d_T, d_out, max_pts);
+    if (launches) *launches += (max_pts > 0 && K > 0) ? 2 : 1;
+}
+
+void fbpr_launch_crop_box(const float4* d_in, int n, const float* d_pose12, float4* d_out, int cap, int* d_n_out, int* d_tile,
+                          cudaStream_t st, long long* launches) {
+    int tiles = (n + TILE - 1) / TILE;
+    if (tiles > 0) crop_count<<<tiles, TPB, 0, st>>>(d_in, n, d_pose12, d_tile);
+    crop_scan<<<1, 1024, 0, st>>>(d_tile, tiles, d_n_out, cap);
+    if (tiles > 0) crop_emit<<<tiles, TPB, 0, st>>>(d_in, n, d_pose12, d_tile, d_out, cap);
+    if (launches) *launches += tiles > 0 ? 3 : 1;
+}
+
+void fbpr_launch_pose_decompose(const float* d_pose12, FrameMeta* meta, int slot, cudaStream_t st, long long* launches) {
+    pose_decompose<<<1, 32, 0, st>>>(d_pose12, meta, slot);
+    if (launches) *launches += 1;
+}
+void fbpr_launch_pose_compose(const FrameMeta* meta, int slot, float* d_pose12, cudaStream_t st, long long* launches) {
+    pose_compose<<<1, 32, 0, st>>>(meta, slot, d_pose12);
+    if (launches) *launches += 1;
+}

@@ -1,0 +1,206 @@
+/*
+ * fbpr_b200.h -- C ABI of the B200-native scan-to-map registration hot path.
+ *
+ * This is the drop-in boundary for the LOAM/LIO-SAM hot path of
+ * qpc001/Feature_Base_Pointcloud_Registration.  The reference has no FFI layer: the path sits
+ * behind the public member functions of two classes.  Each entry
+ * point below names the reference interface it replaces (file:line under the reference tree).
+ * The C++ host classes in feature_base_pointcloud_registration_b200/host/ keep the reference's
+ * method and member names on top of this ABI; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is caller-owned; `mem` says where it lives;
+ *   - a handle owns `max_frames` independent FRAME SLOTS (one lidar frame + its local map +
+ *     its pose each) on ONE device and ONE stream; every operator works on the slot range
+ *     [first, first+count) in one batch of launches, so slot 0 / count 1 is the reference's
+ *     single-frame call and count = F is the batched, independent-frames mode;
+ *   - operators are asynchronous on the handle's stream; getters and fbpr_sync() synchronise;
+ *   - return 0 on success, < 0 on a usage/CUDA error (fbpr_last_error() has the text);
+ *     semantic outcomes of a frame are reported in its `flags` word;
+ *   - a handle is not thread-safe (mirrors the reference's std::mutex mtx, mapOptmization.h:133);
+ *     distinct handles may be used concurrently on distinct GPUs;
+ *   - there is NO CPU fallback: every entry point fails if the CUDA device is unusable.
+ * Points are XYZI float4 (x, y, z, intensity), 16 bytes, the GPU layout of pcl::PointXYZI
+ * (utility.h:55).  Poses are float[6] = (roll, pitch, yaw, x, y, z) = transformTobeMapped
+ * (mapOptmization.h:131) unless stated otherwise.
+ */
+#ifndef FBPR_B200_H
+#define FBPR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FBPR_API __attribute__((visibility("default")))
+
+typedef struct fbpr_handle fbpr_handle;
+
+enum { FBPR_MEM_HOST = 0, FBPR_MEM_DEVICE = 1 };
+
+/* semantic outcomes of scan2MapOptimization for one frame (mapOptmization.h:1403-1442) */
+enum {
+    FBPR_FLAG_NOT_ENOUGH_FEATURES      = 1u,  /* :1410 gate failed; pose unchanged; transformUpdate skipped (:1439-1441) */
+    FBPR_FLAG_TOO_FEW_CORRESPONDENCES  = 2u,  /* an iteration had < 50 rows (:1267-1270)                               */
+    FBPR_FLAG_DEGENERATE               = 4u,  /* isDegenerate set at iteration 0 (:1346-1371)                          */
+    FBPR_FLAG_CONVERGED                = 8u   /* LMOptimization returned true before iteration 30 (:1397-1399)         */
+};
+
+/* The knobs the path reads: include/utility.h:164-198, values of config/params.yaml:19-67. */
+typedef struct fbpr_params {
+    int32_t N_SCAN;
+    int32_t Horizon_SCAN;
+    float   edgeThreshold;
+    float   surfThreshold;
+    int32_t edgeFeatureMinValidNum;
+    int32_t surfFeatureMinValidNum;
+    float   odometrySurfLeafSize;
+    float   mappingCornerLeafSize;
+    float   mappingSurfLeafSize;
+    float   z_tollerance;
+    float   rotation_tollerance;
+    int32_t numberOfCores;                   /* accepted for drop-in compatibility; unused on the GPU */
+    float   surroundingKeyframeSearchRadius;
+    /* capacities and device-side tuning (no reference counterpart) */
+    int32_t max_frames;                      /* frame slots                                             */
+    int32_t max_raw_points;                  /* raw PointXYZIRT records per frame (0 = N_SCAN*Horizon_SCAN*1.02+64) */
+    int32_t max_map_corner;                  /* local-map capacity per frame (after VoxelGrid)          */
+    int32_t max_map_surf;
+    int32_t max_keyframe_points;             /* extractCloud concat capacity per frame and kind (0 = no keyframe operator) */
+    float   knn_cell_corner;                 /* uniform-grid cell edge for the corner / surf map index (0 = 0.5 / 0.25) */
+    float   knn_cell_surf;
+    int32_t grid_cells_corner;               /* dense-grid cell budget per map index (0 = 262144 / 1048576); the cell */
+    int32_t grid_cells_surf;                 /*   edge is doubled until the map's bounding box fits the budget        */
+    int32_t lm_cluster_size;                 /* CTAs cooperating on one frame's LM loop: 1,2,4,8,16 (0 = 8) */
+} fbpr_params;
+
+/* one frame's outcome: transformTobeMapped after transformUpdate, iterations executed, FBPR_FLAG_* */
+typedef struct fbpr_result {
+    float    pose[6];
+    int32_t  iters;
+    uint32_t flags;
+} fbpr_result;
+
+/* PointXYZIRT as the projection consumes it (imageProjection.cpp:8-21), packed to 24 bytes. */
+typedef struct fbpr_raw_point {
+    float   x, y, z, intensity;
+    int32_t ring;
+    float   time;
+} fbpr_raw_point;
+
+/* feature_matching::cloud_info (msg/cloud_info.msg:1-34) as a view over caller memory. */
+typedef struct fbpr_cloud_info_view {
+    const int32_t* startRingIndex;           /* [N_SCAN]  */
+    const int32_t* endRingIndex;             /* [N_SCAN]  */
+    const int32_t* pointColInd;              /* [n_valid] */
+    const float*   pointRange;               /* [n_valid] */
+    const float*   cloud_deskewed;           /* [n_valid] XYZI */
+    int32_t        n_valid;
+    int64_t        imuAvailable;
+    float          imuRollInit, imuPitchInit, imuYawInit;
+} fbpr_cloud_info_view;
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+/* replaces: the constructors / allocateMemory of FeatureExtraction (featureExtraction.h:43-77)
+   and mapOptimization (mapOptmization.h:153-261), minus ROS and PCD IO. */
+FBPR_API int  fbpr_create(const fbpr_params* params, int device, fbpr_handle** out);
+FBPR_API void fbpr_destroy(fbpr_handle* h);
+FBPR_API int  fbpr_sync(fbpr_handle* h);
+FBPR_API const char* fbpr_last_error(void);
+FBPR_API void* fbpr_stream(fbpr_handle* h);               /* cudaStream_t the handle launches on   */
+FBPR_API int64_t fbpr_kernel_launches(fbpr_handle* h);    /* kernels launched (or graph-replayed) so far */
+FBPR_API int  fbpr_use_graphs(fbpr_handle* h, int on);    /* capture each operator sequence once, replay after */
+
+/* ---- inputs ---------------------------------------------------------------------------- */
+/* replaces: cachePointCloud + deskewInfo outputs (imageProjection.cpp:229-301, :303-393): the raw
+   cloud and the integrated IMU rotation ramp of one sweep.  imu_* may be NULL when imuAvailable == 0. */
+FBPR_API int fbpr_set_raw_scan(fbpr_handle* h, int slot, const fbpr_raw_point* pts, int n, int mem,
+                               int64_t imuAvailable, int deskewFlag, double timeScanCur,
+                               const double* imuTime, const double* imuRotX, const double* imuRotY,
+                               const double* imuRotZ, int imuPointerCur,
+                               float imuRollInit, float imuPitchInit);
+/* replaces: the cloud_info message handed to featureExtra() (featureExtraction.h:79-92). */
+FBPR_API int fbpr_set_cloud_info(fbpr_handle* h, int slot, const fbpr_cloud_info_view* ci, int mem);
+/* replaces: fromROSMsg(cloud_corner / cloud_surface) into laserCloud{Corner,Surf}Last (mapOptmization.h:272-273). */
+FBPR_API int fbpr_set_feature_clouds(fbpr_handle* h, int slot, const float* corner_xyzi, int n_corner,
+                                     const float* surf_xyzi, int n_surf, int mem);
+/* replaces: laserCloud{Corner,Surf}FromMapDS as produced by CropBox (mapOptmization.h:284-304) or extractCloud (:948-954). */
+FBPR_API int fbpr_set_local_map(fbpr_handle* h, int slot, const float* corner_xyzi, int n_corner,
+                                const float* surf_xyzi, int n_surf, int mem);
+/* replaces: transformTobeMapped[] initialisation (mapOptmization.h:309-310 / updateInitialGuess). */
+FBPR_API int fbpr_set_pose(fbpr_handle* h, int slot, const float pose6[6]);
+FBPR_API int fbpr_set_poses(fbpr_handle* h, int first, int count, const float* pose6, int mem);
+
+/* ---- operators (slot range [first, first+count)) ----------------------------------------- */
+/* replaces: ImageProjection::projectPointCloud + cloudExtraction (imageProjection.cpp:583-670). */
+FBPR_API int fbpr_project(fbpr_handle* h, int first, int count);
+/* replaces: FeatureExtraction::featureExtra (featureExtraction.h:79-103): calculateSmoothness,
+   markOccludedPoints, extractFeatures; results become laserCloud{Corner,Surf}Last of the slot. */
+FBPR_API int fbpr_feature_extract(fbpr_handle* h, int first, int count);
+/* replaces: mapOptimization::extractSurroundingKeyFrames -> extractCloud (mapOptmization.h:909-978):
+   transform K selected keyframes by their poses, concatenate in list order, VoxelGrid both kinds.
+   Keyframe SELECTION stays with the caller. Clouds are concatenated with
+   CSR offsets (K+1 entries). */
+FBPR_API int fbpr_extract_surrounding_keyframes(fbpr_handle* h, int slot, int K, const float* key_poses6,
+                                                const float* corner_xyzi, const int32_t* corner_off,
+                                                const float* surf_xyzi, const int32_t* surf_off,
+                                                const float last_key_xyz[3], int mem);
+/* replaces: mapOptimization::downsampleCurrentScan (mapOptmization.h:981-993). */
+FBPR_API int fbpr_downsample_current_scan(fbpr_handle* h, int first, int count);
+/* replaces: mapOptimization::scan2MapOptimization (mapOptmization.h:1403-1442) including the two
+   per-frame kd-tree builds (:1413-1414, here: uniform-grid index builds), the <= 30 iteration loop
+   of cornerOptimization / surfOptimization / combineOptimizationCoeffs / LMOptimization, and
+   transformUpdate (:1444-1479).  No host round trip inside. */
+FBPR_API int fbpr_scan2map_optimization(fbpr_handle* h, int first, int count);
+/* replaces: mapOptimization::transformUpdate on its own (mapOptmization.h:1444-1479). */
+FBPR_API int fbpr_transform_update(fbpr_handle* h, int first, int count);
+/* replaces: mapOptimization::registration (mapOptmization.h:263-343) for one slot: CropBox of the
+   given GLOBAL maps around pose (+-30/+-30/+-10 m), Affine -> (rpy,xyz), downsampleCurrentScan,
+   scan2MapOptimization, back to Affine.  pose12 is a 3x4 row-major rigid transform, in/out.
+   The slot's feature clouds must be present (fbpr_feature_extract or fbpr_set_feature_clouds). */
+/* replaces: the map load of the fork's constructor (mapOptmization.h:245-260, minus PCD IO and its VoxelGrid):
+   keeps corner_GlobalMap / surf_GlobalMap resident in HBM; fbpr_registration() then takes NULL maps. */
+FBPR_API int fbpr_set_global_map(fbpr_handle* h, const float* corner_xyzi, int n_corner,
+                                 const float* surf_xyzi, int n_surf, int mem);
+FBPR_API int fbpr_registration(fbpr_handle* h, int slot, const float* corner_global_xyzi, int n_corner,
+                               const float* surf_global_xyzi, int n_surf, int mem, float pose12[12]);
+/* the whole per-frame path in one call: project -> feature_extract -> downsample -> scan2map */
+FBPR_API int fbpr_run_frames(fbpr_handle* h, int first, int count, int with_projection, int with_features);
+
+/* ---- results ----------------------------------------------------------------------------- */
+FBPR_API int fbpr_get_pose(fbpr_handle* h, int slot, float pose6[6], int32_t* iters, uint32_t* flags);
+FBPR_API int fbpr_get_results(fbpr_handle* h, int first, int count, fbpr_result* out, int mem);
+/* counts[8] = n_raw, n_valid, n_corner, n_surf, n_corner_ds, n_surf_ds, n_map_corner, n_map_surf */
+FBPR_API int fbpr_get_counts(fbpr_handle* h, int slot, int32_t counts[8]);
+
+/* ---- parity / debug getters (host destinations) --------------------------------------------- */
+enum {
+    FBPR_BUF_START_RING = 0, FBPR_BUF_END_RING, FBPR_BUF_COL_IND, FBPR_BUF_RANGE, FBPR_BUF_CLOUD,
+    FBPR_BUF_CURVATURE, FBPR_BUF_PICKED, FBPR_BUF_LABEL,
+    FBPR_BUF_CORNER, FBPR_BUF_CORNER_INDEX, FBPR_BUF_SURF, FBPR_BUF_RING_SURF_COUNT, FBPR_BUF_RING_SURF_COUNT_DS,
+    FBPR_BUF_CORNER_DS, FBPR_BUF_SURF_DS, FBPR_BUF_MAP_CORNER, FBPR_BUF_MAP_SURF,
+    FBPR_BUF_KNN_CORNER, FBPR_BUF_KNN_SURF, FBPR_BUF_KNN_D2_CORNER, FBPR_BUF_KNN_D2_SURF,
+    FBPR_BUF_COEFF_CORNER, FBPR_BUF_COEFF_SURF, FBPR_BUF_FLAG_CORNER, FBPR_BUF_FLAG_SURF,
+    FBPR_BUF_ATA, FBPR_BUF_ATB, FBPR_BUF_X, FBPR_BUF_POSE_TRACE, FBPR_BUF_WINNER_RAW
+};
+/* copies buffer `which` of `slot` to dst (at most cap_bytes); returns the byte count, < 0 on error */
+FBPR_API int64_t fbpr_get_buffer(fbpr_handle* h, int slot, int which, void* dst, int64_t cap_bytes);
+/* capture per-point kNN / coefficients / AtA / AtB / X of LM iteration `iter` on the next scan2map (-1 = off) */
+FBPR_API int fbpr_set_debug_iteration(fbpr_handle* h, int iter);
+
+/* stand-alone VoxelGrid (pcl::VoxelGrid<PointXYZI>::filter; call sites featureExtraction.h:289-290,
+   mapOptmization.h:251-257,:948-953,:985-991).  out_xyzi capacity n; point_keys (n) and out_keys
+   (n) may be NULL.  Returns the number of output points, < 0 on error. */
+FBPR_API int fbpr_voxel_grid(fbpr_handle* h, const float* xyzi, int n, float leaf, float* out_xyzi,
+                             int32_t* point_keys, int32_t* out_keys, int mem);
+/* stand-alone exact 5-NN (pcl::KdTreeFLANN::nearestKSearch k=5, mapOptmization.h:1020,:1143) of nq
+   XYZ queries against an XYZI map: idx/d2 are nq x 5, ascending (d2, idx); neighbours are exact
+   inside the 1 m ball, entries whose 5th distance is >= 1 m^2 are marked by idx = -1. */
+FBPR_API int fbpr_knn5(fbpr_handle* h, const float* map_xyzi, int n_map, float cell, const float* q_xyz,
+                       int nq, int32_t* idx, float* d2, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBPR_B200_H */

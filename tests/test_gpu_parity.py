@@ -1,0 +1,299 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical
+seeded synthetic inputs.  Bars (BASELINE.json north_star): voxel keys, selected-feature indices
+and kNN index sets bit-exact; per-point residual coefficients within 1e-5 relative; final pose
+within 1e-4 m / 1e-4 rad; iteration counts equal."""
+import numpy as np
+import pytest
+
+import oracle
+import synth
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_T = 1e-4      # metres
+POSE_TOL_R = 1e-4      # radians
+RES_REL_TOL = 1e-5     # per-point residual / coefficient, relative
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import feature_base_pointcloud_registration_b200 as m
+    return m
+
+
+def _reg(fb, params, **extra):
+    kw = dict(max_frames=1, max_map_corner=65536, max_map_surf=262144)
+    kw.update(extra)
+    return fb.Registration(params, **kw)
+
+
+# ------------------------------------------------------------------ VoxelGrid
+@pytest.mark.parametrize("n,leaf", [(0, 0.2), (1, 0.2), (7, 0.4), (5000, 0.4), (70000, 0.2), (300000, 0.4)])
+def test_voxel_grid_bit_exact(fb, n, leaf):
+    rng = np.random.default_rng(n + 1)
+    pts = np.concatenate([rng.uniform(-30, 30, (n, 3)), rng.uniform(0, 255, (n, 1))], 1).astype(np.float32)
+    if n > 100:
+        pts[: n // 2, 2] = rng.normal(0, 0.02, n // 2)            # dense floor: long runs per voxel
+        pts[n // 2: n // 2 + 50] = pts[:50]                       # exact duplicates
+    r = _reg(fb, synth.params_for(1))
+    got = r.voxel_grid(pts, leaf)
+    want = oracle.voxel_grid(pts, leaf)
+    assert np.array_equal(got["point_keys"], want["point_keys"])
+    assert np.array_equal(got["out_keys"], want["out_keys"])
+    assert np.array_equal(got["points"], want["points"])          # in-index-order f32 sums: bit-exact
+
+
+def test_voxel_grid_overflow_path(fb):
+    far = np.array([[0, 0, 0, 1], [1e6, 1e6, 1e6, 2], [5, 5, 5, 3]], np.float32)
+    r = _reg(fb, synth.params_for(1))
+    got = r.voxel_grid(far, 0.01)
+    assert np.array_equal(got["points"], far)                     # PCL copies input to output
+
+
+# ------------------------------------------------------------------ exact 5-NN on the grid index
+@pytest.mark.parametrize("cell", [0.25, 0.5, 1.0])
+def test_knn5_index_sets_bit_exact(fb, cell):
+    fr = synth.make_frame(1, 5)
+    m = fr["map_surf"]
+    rng = np.random.default_rng(3)
+    q = (m[rng.choice(len(m), 20000), :3] + rng.normal(0, 0.08, (20000, 3))).astype(np.float32)
+    q[:500] += rng.uniform(-3, 3, (500, 3)).astype(np.float32)    # some far from any surface
+    q[500:700] = m[1000:1200, :3]                                 # exactly on map points
+    r = _reg(fb, fr["params"])
+    idx, d2 = r.knn5(m, q, cell=cell)
+    ridx, rd2 = oracle.knn5(m, q)
+    accept = rd2[:, 4] < 1.0
+    assert accept.sum() > 15000
+    assert np.array_equal(idx[accept], ridx[accept])
+    assert np.array_equal(d2[accept], rd2[accept])
+    assert np.all(idx[~accept] == -1)
+
+
+def test_knn5_ties_and_tiny_maps(fb):
+    rng = np.random.default_rng(4)
+    m = np.concatenate([rng.uniform(-2, 2, (3000, 3)), np.zeros((3000, 1))], 1).astype(np.float32)
+    m[1500:1700] = m[100:300]                                     # duplicates -> distance ties broken by index
+    q = m[100:300, :3].copy()
+    r = _reg(fb, synth.params_for(1))
+    idx, d2 = r.knn5(m, q, cell=0.25)
+    ridx, rd2 = oracle.knn5(m, q, brute=True)
+    assert np.array_equal(idx, ridx) and np.array_equal(d2, rd2)
+    idx, _ = r.knn5(m[:4], q[:10], cell=0.25)                     # fewer than 5 map points: reject
+    assert np.all(idx == -1)
+
+
+# ------------------------------------------------------------------ projection
+@pytest.mark.parametrize("config", [1, 3])
+def test_projection_matches_oracle(fb, config):
+    fr = synth.make_frame(config, 2)
+    P = fr["params"]
+    want = oracle.project(P, fr["scan"], fr["imu"], fr["imu_available"])
+    r = _reg(fb, P)
+    r.set_raw_scan(0, fb.api.pack_raw(fr["scan"]), imu=fr["imu"], imu_available=fr["imu_available"])
+    r.project(0, 1)
+    r.sync()
+    assert r.get_counts(0)["n_valid"] == want["n_valid"]
+    assert np.array_equal(r.get_buffer(0, "START_RING"), want["startRingIndex"])
+    assert np.array_equal(r.get_buffer(0, "END_RING"), want["endRingIndex"])
+    assert np.array_equal(r.get_buffer(0, "COL_IND"), want["pointColInd"])
+    assert np.array_equal(r.get_buffer(0, "WINNER_RAW"), want["winner_raw"])       # first hit wins
+    assert np.array_equal(r.get_buffer(0, "RANGE"), want["pointRange"])
+    cloud = r.get_buffer(0, "CLOUD")
+    if fr["imu_available"]:
+        assert np.allclose(cloud, want["cloud_deskewed"], rtol=0, atol=2e-5)       # device f64 trig vs glibc: <= 1 ulp of f32 trig
+        assert np.mean(cloud == want["cloud_deskewed"]) > 0.99
+    else:
+        assert np.array_equal(cloud, want["cloud_deskewed"])
+
+
+# ------------------------------------------------------------------ features
+@pytest.mark.parametrize("config,frame", [(1, 0), (1, 1), (2, 0), (3, 0), (0, 0)])
+def test_feature_extraction_bit_exact(fb, config, frame):
+    fr = synth.make_frame(config, frame)
+    P = fr["params"]
+    ci = oracle.project(P, fr["scan"], fr["imu"], 0)              # no deskew: identical bytes on both sides
+    want = oracle.extract_features(P, ci)
+    r = _reg(fb, P)
+    r.set_cloud_info(0, ci)
+    r.featureExtra(0, 1)
+    r.sync()
+    assert np.array_equal(r.get_buffer(0, "CURVATURE"), want["curvature"])
+    assert np.array_equal(r.get_buffer(0, "LABEL"), want["label"])
+    assert np.array_equal(r.get_buffer(0, "PICKED"), want["picked"])
+    assert np.array_equal(r.get_buffer(0, "CORNER_INDEX"), want["corner_index"])   # order: ring, segment, pick order
+    assert np.array_equal(r.get_buffer(0, "CORNER"), want["corner"])
+    assert np.array_equal(r.get_buffer(0, "RING_SURF_COUNT"), want["ring_surf_count"])
+    assert np.array_equal(r.get_buffer(0, "RING_SURF_COUNT_DS"), want["ring_surf_count_ds"])
+    assert np.array_equal(r.get_buffer(0, "SURF"), want["surface"])               # per-ring VoxelGrid centroids
+
+
+def test_feature_extraction_ragged_and_empty(fb):
+    fr = synth.make_frame(1, 7, small=(16, 600, 2000, 8000))
+    P = fr["params"]
+    scan = dict(fr["scan"])
+    keep = ~np.isin(scan["ring"], [3, 4])                         # two empty rings
+    keep &= ~((scan["ring"] == 7) & (np.arange(scan["n"]) % 40 != 0))   # one ring with ~15 points
+    for k in ("x", "y", "z", "intensity", "ring", "time"):
+        scan[k] = scan[k][:scan["n"]][keep]
+    scan["n"] = int(keep.sum())
+    ci = oracle.project(P, scan, fr["imu"], 0)
+    want = oracle.extract_features(P, ci)
+    r = _reg(fb, P)
+    r.set_cloud_info(0, ci)
+    r.featureExtra(0, 1)
+    r.sync()
+    assert np.array_equal(r.get_buffer(0, "LABEL"), want["label"])
+    assert np.array_equal(r.get_buffer(0, "CORNER_INDEX"), want["corner_index"])
+    assert np.array_equal(r.get_buffer(0, "SURF"), want["surface"])
+    # completely empty frame
+    empty = dict(startRingIndex=np.full(16, 4, np.int32), endRingIndex=np.full(16, -6, np.int32),
+                 pointColInd=np.zeros(0, np.int32), pointRange=np.zeros(0, np.float32), cloud_deskewed=np.zeros((0, 4), np.float32))
+    r.set_cloud_info(0, empty)
+    r.featureExtra(0, 1)
+    r.sync()
+    c = r.get_counts(0)
+    assert c["n_corner"] == 0 and c["n_surf"] == 0
+
+
+# ------------------------------------------------------------------ scan-to-map
+def _oracle_scan2map(fr, debug_iter=0):
+    P = fr["params"]
+    ci = oracle.project(P, fr["scan"], fr["imu"], 0)
+    fe = oracle.extract_features(P, ci)
+    mo = oracle.MapOptimization(P)
+    mo.set_scan(fe["corner"], fe["surface"])
+    mo.set_map(fr["map_corner"], fr["map_surf"])
+    mo.downsample()
+    pose, iters, flags, _ = mo.scan2map(fr["guess"], debug_iter=debug_iter)
+    return fe, mo, pose, iters, flags
+
+
+@pytest.mark.parametrize("config,frame,debug_iter", [(1, 0, 0), (1, 1, 2), (2, 0, 1), (3, 1, 0), (0, 0, 0)])
+def test_scan2map_matches_oracle(fb, config, frame, debug_iter):
+    fr = synth.make_frame(config, frame)
+    fe, mo, pose_w, iters_w, flags_w = _oracle_scan2map(fr, debug_iter)
+    dbg = mo.debug()
+    r = _reg(fb, fr["params"])
+    r.set_feature_clouds(0, fe["corner"], fe["surface"])
+    r.set_local_map(0, fr["map_corner"], fr["map_surf"])
+    r.set_pose(0, fr["guess"])
+    r.set_debug_iteration(debug_iter)
+    r.downsampleCurrentScan(0, 1)
+    r.scan2MapOptimization(0, 1)
+    r.sync()
+    # VoxelGrid of the current scan: bit-exact
+    assert np.array_equal(r.get_buffer(0, "CORNER_DS"), mo.get_cloud(0))
+    assert np.array_equal(r.get_buffer(0, "SURF_DS"), mo.get_cloud(1))
+    pose, iters, flags = r.get_pose(0)
+    if dbg["iter"] == debug_iter:
+        for kind, K in (("CORNER", "corner"), ("SURF", "surf")):
+            knn = r.get_buffer(0, "KNN_" + kind); d2 = r.get_buffer(0, "KNN_D2_" + kind)
+            accept = dbg[K + "D2"][:, 4] < 1.0
+            assert np.array_equal(knn[accept], dbg[K + "Knn"][accept]), kind      # kNN index sets bit-exact
+            assert np.array_equal(d2[accept], dbg[K + "D2"][accept])
+            flag = r.get_buffer(0, "FLAG_" + kind)
+            assert np.array_equal(flag, dbg[K + "Flag"]), kind
+            sel = flag.astype(bool)
+            co = r.get_buffer(0, "COEFF_" + kind)[sel]; cw = dbg[K + "Coeff"][sel]
+            err = np.abs(co - cw) / np.maximum(np.abs(cw), 1e-3)
+            assert err.max() <= RES_REL_TOL, (kind, err.max())
+        assert np.allclose(r.get_buffer(0, "ATA"), dbg["AtA"], rtol=1e-6, atol=0)
+        assert np.allclose(r.get_buffer(0, "ATB"), dbg["AtB"], rtol=1e-5, atol=1e-6)
+    assert iters == iters_w                                          # iteration-count parity
+    assert flags == flags_w
+    assert np.max(np.abs(pose[3:] - pose_w[3:])) <= POSE_TOL_T
+    assert np.max(np.abs(pose[:3] - pose_w[:3])) <= POSE_TOL_R
+
+
+def test_degenerate_corridor_reproduces_matP_quirk(fb):
+    fr = synth.make_frame(0, 0)
+    fe, mo, pose_w, iters_w, flags_w = _oracle_scan2map(fr, 0)
+    assert flags_w & oracle.FLAG_DEGENERATE and iters_w == 2          # zero step at iteration 1 (mapOptmization.h:1278)
+    r = _reg(fb, fr["params"])
+    r.set_feature_clouds(0, fe["corner"], fe["surface"])
+    r.set_local_map(0, fr["map_corner"], fr["map_surf"])
+    r.set_pose(0, fr["guess"])
+    r.downsampleCurrentScan(0, 1); r.scan2MapOptimization(0, 1)
+    pose, iters, flags = r.get_pose(0)
+    assert (iters, flags) == (iters_w, flags_w)
+    assert np.allclose(pose, pose_w, atol=1e-4)
+
+
+def test_not_enough_features_and_too_few_correspondences(fb):
+    fr = synth.make_frame(1, 2, small=(16, 600, 2000, 8000))
+    P = fr["params"]
+    ci = oracle.project(P, fr["scan"], fr["imu"], 0)
+    fe = oracle.extract_features(P, ci)
+    r = _reg(fb, P)
+    # (a) gate: <= edgeFeatureMinValidNum corners -> pose unchanged, flag set
+    r.set_feature_clouds(0, fe["corner"][:5], fe["surface"])
+    r.set_local_map(0, fr["map_corner"], fr["map_surf"])
+    r.set_pose(0, fr["guess"])
+    r.downsampleCurrentScan(0, 1); r.scan2MapOptimization(0, 1)
+    pose, iters, flags = r.get_pose(0)
+    assert flags == fb.FLAG_NOT_ENOUGH_FEATURES and iters == 0 and np.array_equal(pose, fr["guess"])
+    # (b) map far away: no neighbours within 1 m -> < 50 rows -> 30 idle iterations, pose unchanged
+    far_c = fr["map_corner"].copy(); far_c[:, :3] += 500
+    far_s = fr["map_surf"].copy(); far_s[:, :3] += 500
+    mo = oracle.MapOptimization(P)
+    mo.set_scan(fe["corner"], fe["surface"]); mo.set_map(far_c, far_s); mo.downsample()
+    pose_w, iters_w, flags_w, _ = mo.scan2map(fr["guess"])
+    r.set_feature_clouds(0, fe["corner"], fe["surface"])
+    r.set_local_map(0, far_c, far_s)
+    r.set_pose(0, fr["guess"])
+    r.downsampleCurrentScan(0, 1); r.scan2MapOptimization(0, 1)
+    pose, iters, flags = r.get_pose(0)
+    assert (iters, flags) == (iters_w, flags_w) == (30, fb.FLAG_TOO_FEW_CORRESPONDENCES)
+    assert np.array_equal(pose, pose_w)
+
+
+def test_transform_update_imu_slerp_and_clamps(fb):
+    P = dict(synth.params_for(1)); P["z_tollerance"] = 0.5; P["rotation_tollerance"] = 0.3
+    mo = oracle.MapOptimization(P)
+    mo.set_imu(1, 0.12, -0.07)
+    pose = np.array([0.05, 0.02, 1.0, 3.0, 4.0, 0.9], np.float32)
+    want = mo.transform_update(pose)
+    r = _reg(fb, P)
+    ci = dict(startRingIndex=np.full(16, 4, np.int32), endRingIndex=np.full(16, -6, np.int32), pointColInd=np.zeros(0, np.int32),
+              pointRange=np.zeros(0, np.float32), cloud_deskewed=np.zeros((0, 4), np.float32))
+    r.set_cloud_info(0, ci, imu_available=1, imu_roll_init=0.12, imu_pitch_init=-0.07)
+    r.set_pose(0, pose)
+    r.transformUpdate(0, 1)
+    got, _, _ = r.get_pose(0)
+    assert np.allclose(got, want, atol=1e-6)
+    assert got[5] == np.float32(0.5)
+
+
+# ------------------------------------------------------------------ whole path, single frame and batch
+@pytest.mark.parametrize("config", [1, 3])
+def test_end_to_end_pose_and_batch_equals_single(fb, config):
+    frames = [synth.make_frame(config, f) for f in range(3)]
+    P = frames[0]["params"]
+    want = []
+    for fr in frames:
+        ci = oracle.project(P, fr["scan"], fr["imu"], fr["imu_available"])
+        fe = oracle.extract_features(P, ci)
+        mo = oracle.MapOptimization(P)
+        mo.set_imu(fr["imu_available"], 0.0, 0.0)                    # transformUpdate slerps towards the IMU attitude
+        mo.set_scan(fe["corner"], fe["surface"]); mo.set_map(fr["map_corner"], fr["map_surf"]); mo.downsample()
+        want.append(mo.scan2map(fr["guess"])[:3])
+    r = _reg(fb, P, max_frames=3)
+    for s, fr in enumerate(frames):
+        r.set_raw_scan(s, fb.api.pack_raw(fr["scan"]), imu=fr["imu"], imu_available=fr["imu_available"])
+        r.set_local_map(s, fr["map_corner"], fr["map_surf"])
+    r.set_poses(0, np.stack([fr["guess"] for fr in frames]))
+    r.run_frames(0, 3)                                               # batched: all three frames in one set of launches
+    res = r.get_results(0, 3)
+    for s in range(3):
+        pw, iw, fw = want[s]
+        assert int(res[s]["iters"]) == iw and int(res[s]["flags"]) == fw
+        assert np.max(np.abs(res[s]["pose"][3:] - pw[3:])) <= POSE_TOL_T
+        assert np.max(np.abs(res[s]["pose"][:3] - pw[:3])) <= POSE_TOL_R
+    # the same frames one at a time (and through CUDA graphs) give identical bytes
+    r.use_graphs(True)
+    for rep in range(2):
+        for s in range(3):
+            r.set_pose(s, frames[s]["guess"])
+            r.run_frames(s, 1)
+        again = r.get_results(0, 3)
+        assert np.array_equal(again["pose"], res["pose"]) and np.array_equal(again["iters"], res["iters"])
