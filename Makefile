@@ -8,7 +8,7 @@ CSRC := $(PKG)/csrc
 CU := $(CSRC)/capi.cu $(CSRC)/voxel.cu $(CSRC)/mapgrid.cu $(CSRC)/lm.cu $(CSRC)/projection.cu $(CSRC)/features.cu $(CSRC)/mapops.cu
 HDR := $(CSRC)/internal.cuh $(CSRC)/mapgrid.cuh $(CSRC)/smallmat.cuh include/fbpr_b200.h
 # -fmad=false / -prec-div / -prec-sqrt: the kernels mirror the reference's f32 arithmetic op for op
-NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true \
+NVFLAGS := $(EXTRA) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true \
            -ccbin /usr/bin/g++ -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v
 
 all: $(PKG)/libfbpr_b200.so synth/libsynth.so oracle/liboracle.so $(PKG)/host/libfeature_matching_b200.so

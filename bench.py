@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- scan-to-map registration throughput / latency on B200 (BASELINE.json metric).
+
+A "step" = one pass of the whole hot path (projection+deskew -> smoothness/features -> VoxelGrid ->
+map index -> all LM iterations -> transformUpdate) over one batch of F independent synthetic
+64-beam frames per GPU, each against its own 200 k-point local map (BASELINE configs[3], i.e.
+config 3's frame geometry; F = 128 per GPU so that 8 GPUs process config 4's 1024 frames).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames-per-gpu F]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
+  python bench.py --impl reference ...      # the reference's CPU path (oracle restatement) on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = frames/s over all ranks with inputs resident in HBM;
+`e2e` = the same through the C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region;
+`latency_ms_per_frame` = one frame at a time on one GPU (the north-star "< 1 ms / frame").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scan-to-map frames/sec/box (64-beam synthetic)"
+CONFIG = 4   # synth config id: HDL-64E-like 64x2048 scan, own 200k map per frame
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=128)
+    ap.add_argument("--ref-frames", type=int, default=6, help="frames per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--cluster", type=int, default=0, help="lm_cluster_size override")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-frames", type=int, default=48)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(counts, iters):
+    """SURVEY.md 8(d) per-frame algorithmic bytes, split by stage (16 B / point, 24 B / raw record)."""
+    n_raw, n_valid, n_corner, n_surf, n_cds, n_sds, m_c, m_s = counts
+    return dict(project=24 * n_raw + 24 * n_valid,
+                features=24 * n_valid + 16 * (n_corner + n_surf),
+                downsample=16 * (n_corner + n_cds) + 16 * (n_surf + n_sds),
+                map_index=16 * (m_c + m_s),
+                lm=iters * 96 * (n_cds + n_sds))
+
+
+def oracle_frame(oracle, fr, threads):
+    """The reference's CPU path for one frame (projection -> features -> downsample -> scan2map)."""
+    P = dict(fr["params"]); P["numberOfCores"] = threads
+    ci = oracle.project(P, fr["scan"], fr["imu"], fr["imu_available"])
+    fe = oracle.extract_features(P, ci)
+    mo = oracle.MapOptimization(P)
+    mo.set_imu(fr["imu_available"], 0.0, 0.0)
+    mo.set_scan(fe["corner"], fe["surface"]); mo.set_map(fr["map_corner"], fr["map_surf"]); mo.downsample()
+    pose, iters, flags, secs = mo.scan2map(fr["guess"])
+    return pose, iters, flags
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import oracle          # bench.py's reference / cpu_baseline legs are the only product-side users of oracle/
+    import synth
+    threads = os.cpu_count() or 1
+    frames = [synth.make_frame(CONFIG, f) for f in range(args.ref_frames)]
+    for _ in range(args.warmup):
+        oracle_frame(oracle, frames[0], threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for fr in frames:
+            oracle_frame(oracle, fr, threads)
+    dt = time.perf_counter() - t0
+    nfr = args.steps * len(frames)
+    val = nfr / dt
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "configs[3]/[2]: synthetic HDL-64E-like 64x2048 frames, each vs its own 200k-pt corner/surf local map, "
+                                  "projection+deskew, features, VoxelGrid, <=30 LM iterations", "frames_per_step": len(frames)},
+           "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port",
+                            "sample": f"{len(frames)} frames/step x {args.steps} steps, C++ restatement of the reference (oracle/), "
+                                      f"OpenMP numberOfCores={threads}, {cpu_model()}"},
+           "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "ms_per_frame": 1e3 / val, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import synth
+    import feature_base_pointcloud_registration_b200 as fb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    F = args.frames_per_gpu
+    cfg = synth.CONFIGS[CONFIG]
+    params = synth.params_for(CONFIG)
+    frames = [synth.make_frame(CONFIG, rank * F + i) for i in range(F)]
+    extra = dict(max_frames=F, max_map_corner=cfg["map_corner"] + 64, max_map_surf=cfg["map_surf"] + 64)
+    if args.cluster:
+        extra["lm_cluster_size"] = args.cluster
+    reg = fb.Registration(params, device=local_rank, **extra)
+    stream = torch.cuda.ExternalStream(reg.stream(), device=torch.device("cuda", local_rank))
+
+    # ---- host inputs in pinned memory (what a caller would hand to the C ABI)
+    raws = [fb.api.pack_raw(fr["scan"]) for fr in frames]
+    pin = []
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
+        pin.append(t)
+        return t.data_ptr()
+
+    finputs = []
+    h2d = 0
+    for fr, raw in zip(frames, raws):
+        finputs.append(dict(raw_ptr=pinned(raw), n_raw=len(raw), imu=fr["imu"], imu_available=fr["imu_available"],
+                            map_corner_ptr=pinned(fr["map_corner"]), n_map_corner=len(fr["map_corner"]),
+                            map_surf_ptr=pinned(fr["map_surf"]), n_map_surf=len(fr["map_surf"]), pose=fr["guess"]))
+        h2d += raw.nbytes + fr["map_corner"].nbytes + fr["map_surf"].nbytes
+    h2d += F * 128 + (4 * 8 * 512 * F if frames[0]["imu_available"] else 0)     # packed scalars + IMU ramps
+    d2h = F * 32
+    fin = reg.make_frame_inputs(finputs)
+    guesses = torch.from_numpy(np.stack([fr["guess"] for fr in frames])).cuda()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- upload once: inputs are resident in HBM for the `value` measurement
+    reg.set_frames(0, fin)
+    reg.sync()
+
+    def step_resident():
+        reg.set_poses_device(0, F, guesses.data_ptr())      # the pose is in/out: restore the guesses (D2D, 24 B/frame)
+        reg.run_frames(0, F)
+
+    for _ in range(args.warmup):
+        step_resident()
+    reg.sync()
+    res = reg.get_results(0, F)
+    counts = [list(reg.get_counts(s).values()) for s in range(F)]
+    reg.enable_stage_timing(True)
+    reg.get_stage_ms(reset=True)
+    launches0 = reg.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    reg.sync()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = reg.kernel_launches() - launches0
+    stage = reg.get_stage_ms(reset=True)
+    reg.enable_stage_timing(False)
+    value = world * F * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers in, host results out, every step
+    def step_e2e():
+        reg.set_frames(0, fin)
+        reg.run_frames(0, F)
+        return reg.get_results(0, F)                          # D2H + sync
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    t_host0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_e2e = step_e2e()
+    e3.record(stream)
+    reg.sync()
+    t_host = (time.perf_counter() - t_host0) * 1e3
+    barrier()
+    ms_e2e = max_over_ranks(max(e2.elapsed_time(e3), t_host))
+    e2e_value = world * F * args.steps / (ms_e2e * 1e-3)
+    assert np.array_equal(res_e2e["iters"], res["iters"])
+
+    # ---- single-frame latency (rank 0 reports; one frame at a time, CUDA-graph replay)
+    lat = None
+    if rank == 0:
+        nlat = min(F, args.latency_frames)
+        reg.use_graphs(True)
+        times = []
+        for rep in range(3):
+            for s in range(nlat):
+                reg.set_pose(s, frames[s]["guess"])
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                reg.sync()
+                a.record(stream)
+                reg.run_frames(s, 1)
+                b.record(stream)
+                reg.sync()
+                if rep > 0:
+                    times.append(a.elapsed_time(b))
+        reg.use_graphs(False)
+        lat = dict(median=float(np.median(times)), p95=float(np.percentile(times, 95)), frames=nlat,
+                   note="one frame at a time, whole path, distinct (scan,map) pairs rotate so each map starts L2-cold")
+
+    # ---- gather result poses over NCCL (32 B / frame), the only collective of the job
+    if dist is not None:
+        mine = torch.empty(F * 8, dtype=torch.float32, device="cuda")
+        reg.get_results_device(0, F, mine.data_ptr())
+        reg.sync()
+        allres = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, allres, dst=0)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (algorithmic bytes / live CUDA-event time)
+    peak, peak_src = measured_peak()
+    alg = {k: 0 for k in fb.api.STAGES}
+    for c, it in zip(counts, res["iters"]):
+        for k, v in algorithmic_bytes(c, int(it)).items():
+            alg[k] += v
+    stages = {}
+    for k in fb.api.STAGES:
+        ms, calls = stage[k]
+        per = ms / max(calls, 1)
+        stages[k] = dict(ms_per_step=per, alg_bytes_per_step=alg[k], alg_GBps=(alg[k] / (per * 1e-3) / 1e9) if per > 0 else None)
+    dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
+    kernel_names = dict(project="proj_scatter+proj_compact", features="feat_ring", downsample="rs_scatter (radix-sort VoxelGrid)",
+                        map_index="grid_count+grid_scatter", lm="lm_kernel")
+    ach = stages[dom]["alg_GBps"] or 0.0
+    roofline = dict(bound="hbm", kernel=kernel_names[dom], stage=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
+                    traffic=None, peak_source=peak_src,
+                    note="achieved = SURVEY 8(d) algorithmic bytes of this stage for the F frames of one step / its CUDA-event time; "
+                         "the LM loop is latency/L2-gather bound by design (<=30 dependent iterations), see DESIGN.md")
+    whole = sum(alg.values())
+    frame_GBps = whole / (ms_total / args.steps * 1e-3) / 1e9
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle      # cpu_baseline leg: the oracle is only the thing timed here, never part of the GPU path
+        nb = min(F, 6)
+        oracle_frame(oracle, frames[0], 4)
+        best = None
+        for th in sorted({4, os.cpu_count() or 1}):
+            t0 = time.perf_counter()
+            for fr in frames[:nb]:
+                pw, iw, fw = oracle_frame(oracle, fr, th)
+            dt = time.perf_counter() - t0
+            v = nb / dt
+            if best is None or v > best[0]:
+                best = (v, th)
+        # parity spot-check of the benchmarked frames against the CPU path
+        ok = 0
+        for s in range(nb):
+            pw, iw, fw = oracle_frame(oracle, frames[s], os.cpu_count() or 1)
+            if iw == int(res[s]["iters"]) and np.max(np.abs(pw - res[s]["pose"])) <= 1e-4:
+                ok += 1
+        cpu = dict(value=best[0], unit="frames/s", cores=best[1], kind="port",
+                   sample=f"{nb} of the benchmarked frames, whole path, C++ restatement of the reference (oracle/), OpenMP on {best[1]} threads "
+                          f"(numberOfCores=4 also tried), {cpu_model()}",
+                   parity_frames_ok=f"{ok}/{nb}")
+
+    out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "configs[3]/[2]: synthetic HDL-64E-like 64x2048 frames, each vs its own 200k-pt corner/surf local map, "
+                                  "projection+deskew, features, VoxelGrid, <=30 LM iterations",
+                      "frames_per_gpu": F, "frames_per_step": world * F, "lm_cluster_size": reg.params.lm_cluster_size or 8,
+                      "l2": "inputs larger than L2: %.0f MB of scans+maps per GPU per step" % (h2d / 1e6)},
+           "ms_per_frame": ms_total / args.steps / F,
+           "latency_ms_per_frame": lat,
+           "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": ms_e2e / args.steps},
+           "gpu_launches": int(launches),
+           "clocks": clocks,
+           "roofline": roofline,
+           "stages": stages,
+           "whole_path_alg_GBps": frame_GBps,
+           "iters": {"mean": float(np.mean(res["iters"])), "max": int(np.max(res["iters"])), "converged": int(np.sum((res["flags"] & 8) != 0))},
+           "cpu_baseline": cpu}
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,7 +50,7 @@ class Params(C.Structure):
                 ("max_map_corner", C.c_int32), ("max_map_surf", C.c_int32), ("max_keyframe_points", C.c_int32),
                 ("knn_cell_corner", C.c_float), ("knn_cell_surf", C.c_float),
                 ("grid_cells_corner", C.c_int32), ("grid_cells_surf", C.c_int32),
-                ("lm_cluster_size", C.c_int32)]
+                ("lm_cluster_size", C.c_int32), ("lm_single_frame_mode", C.c_int32)]
 
     @classmethod
     def from_dict(cls, d, **extra):
@@ -71,8 +71,20 @@ class CloudInfoView(C.Structure):
                 ("imuAvailable", C.c_int64), ("imuRollInit", C.c_float), ("imuPitchInit", C.c_float), ("imuYawInit", C.c_float)]
 
 
+class FrameInput(C.Structure):
+    _fields_ = [("raw", C.c_void_p), ("n_raw", C.c_int32), ("deskewFlag", C.c_int32), ("imuAvailable", C.c_int64),
+                ("timeScanCur", C.c_double), ("imuTime", C.c_void_p), ("imuRotX", C.c_void_p), ("imuRotY", C.c_void_p), ("imuRotZ", C.c_void_p),
+                ("imuPointerCur", C.c_int32), ("imuRollInit", C.c_float), ("imuPitchInit", C.c_float),
+                ("map_corner_xyzi", C.c_void_p), ("n_map_corner", C.c_int32), ("map_surf_xyzi", C.c_void_p), ("n_map_surf", C.c_int32),
+                ("pose", C.c_float * 6)]
+
+
+STAGES = ["project", "features", "downsample", "map_index", "lm"]
+
+
 def library_path():
-    return os.path.join(_HERE, "libfbpr_b200.so")
+    # FBPR_B200_LIB lets a developer A/B two builds of the same library; it is still the CUDA library
+    return os.environ.get("FBPR_B200_LIB") or os.path.join(_HERE, "libfbpr_b200.so")
 
 
 def load_library():
@@ -195,6 +207,36 @@ class Registration:
 
     def set_poses_device(self, first, count, dev_ptr):
         self._ck(self.lib.fbpr_set_poses(self.h, first, count, C.c_void_p(dev_ptr), MEM_DEVICE))
+
+    def make_frame_inputs(self, frames):
+        """frames: list of dicts with raw_ptr/n_raw, imu (dict or None), imu_available, map_corner_ptr/n, map_surf_ptr/n, pose.
+        Pointers are integers (host or device addresses); the arrays must stay alive until the copies complete."""
+        arr = (FrameInput * len(frames))()
+        for i, f in enumerate(frames):
+            a = arr[i]
+            a.raw = f.get("raw_ptr"); a.n_raw = int(f.get("n_raw", 0)); a.deskewFlag = int(f.get("deskew_flag", 1))
+            a.imuAvailable = int(f.get("imu_available", 0))
+            imu = f.get("imu")
+            if imu is not None and a.imuAvailable:
+                a.timeScanCur = float(imu["timeScanCur"]); a.imuPointerCur = int(imu["imuPointerCur"])
+                a.imuTime = imu["imuTime"].ctypes.data; a.imuRotX = imu["imuRotX"].ctypes.data
+                a.imuRotY = imu["imuRotY"].ctypes.data; a.imuRotZ = imu["imuRotZ"].ctypes.data
+            a.imuRollInit = float(f.get("imu_roll_init", 0.0)); a.imuPitchInit = float(f.get("imu_pitch_init", 0.0))
+            a.map_corner_xyzi = f.get("map_corner_ptr"); a.n_map_corner = int(f.get("n_map_corner", 0))
+            a.map_surf_xyzi = f.get("map_surf_ptr"); a.n_map_surf = int(f.get("n_map_surf", 0))
+            for q in range(6):
+                a.pose[q] = float(f["pose"][q])
+        return arr
+
+    def set_frames(self, first, frame_inputs, mem=MEM_HOST):
+        self._ck(self.lib.fbpr_set_frames(self.h, first, len(frame_inputs), frame_inputs, mem))
+
+    def enable_stage_timing(self, on=True): self._ck(self.lib.fbpr_enable_stage_timing(self.h, int(on)))
+
+    def get_stage_ms(self, reset=True):
+        ms = (C.c_float * 5)(); calls = (C.c_int32 * 5)()
+        self._ck(self.lib.fbpr_get_stage_ms(self.h, ms, calls, int(reset)))
+        return {n: (float(ms[i]), int(calls[i])) for i, n in enumerate(STAGES)}
 
     # ---- operators (reference names)
     def project(self, first=0, count=1): self._ck(self.lib.fbpr_project(self.h, first, count))

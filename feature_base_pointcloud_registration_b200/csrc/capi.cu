@@ -17,8 +17,9 @@ size_t fbpr_feat_ring_smem(const FeatArgs& a);
 void fbpr_launch_voxel(const VoxSeg* d_segs, int nsegs, int max_n, int tiles_cap, cudaStream_t st, long long* launches);
 int fbpr_voxel_tile();
 void fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cells_cap, cudaStream_t st, long long* launches);
-void fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, cudaStream_t st, long long* launches);
-int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, cudaStream_t st, long long* launches);
+void fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, int thread_mode, cudaStream_t st, long long* launches);
+int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blocks, cudaStream_t st, long long* launches);
+int fbpr_lm_grid_blocks(int device);
 void fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float rot_tol, float z_tol, cudaStream_t st, long long* launches);
 void fbpr_launch_keyframe_transform(const float* d_poses6, int K, const float4* d_in, const int* d_off, float4* d_out, int* d_n_out,
                                     const float* d_last_xyz, float radius, int max_pts, int* d_outoff, float* d_T,
@@ -59,6 +60,7 @@ struct fbpr_handle {
     int *picked = nullptr, *label = nullptr, *ringCorner = nullptr, *cornerStage = nullptr, *ringSurf = nullptr, *ringSurfDS = nullptr, *cornerIndex = nullptr;
     float4 *mapCorner = nullptr, *mapSurf = nullptr;
     float* poseTrace = nullptr;
+    int* knnPos = nullptr; double* partials = nullptr; double* partialsGrid = nullptr; int lmGridBlocks = 0; bool lmWholeGpu = true;
     // descriptors
     VoxSeg* d_scanSegs = nullptr;      // [2F]  downsampleCurrentScan
     GridSeg* d_gridSegs = nullptr;     // [2F]  map index
@@ -78,6 +80,12 @@ struct fbpr_handle {
     // registration() scratch
     float4 *regGlobal = nullptr; int regGlobalCap = 0; int* regTile = nullptr; float* regPose = nullptr;
     int globalCornerN = -1, globalSurfN = 0;   // resident global maps (fbpr_set_global_map)
+    // batched input staging (pinned) + stage timing
+    FrameMeta* h_metaStage = nullptr; double* h_imuStage = nullptr; cudaEvent_t stageDone = nullptr; bool stagePending = false;
+    bool timing = false;
+    struct TimedSpan { int stage; cudaEvent_t a, b; };
+    std::vector<TimedSpan> spans; size_t spansUsed = 0;
+    float stageMs[FBPR_STAGE_COUNT] = { 0, 0, 0, 0, 0 }; int stageCalls[FBPR_STAGE_COUNT] = { 0, 0, 0, 0, 0 };
     // graphs
     bool useGraphs = false;
     std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> graphs;
@@ -169,6 +177,12 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     ALLOC(h->corner, (size_t)F * h->cornerCap); ALLOC(h->cornerDS, (size_t)F * h->cornerCap); ALLOC(h->cornerIndex, (size_t)F * h->cornerCap);
     ALLOC(h->mapCorner, (size_t)F * h->mapCornerCap); ALLOC(h->mapSurf, (size_t)F * h->mapSurfCap);
     ALLOC(h->poseTrace, (size_t)F * FBPR_MAX_ITERS * 6);
+    ALLOC(h->knnPos, (size_t)F * (h->cornerCap + P) * 5);
+    ALLOC(h->partials, (size_t)F * 2 * 16 * 28);
+    ALLOC(h->partialsGrid, (size_t)2 * 1024 * 28 + (size_t)1024 * 512 * 8);   // + profile dump area (FBPR_LM_PROFILE builds)
+    h->lmGridBlocks = fbpr_lm_grid_blocks(device);
+    if (h->lmGridBlocks > 1024) h->lmGridBlocks = 1024;
+    h->lmWholeGpu = params->lm_single_frame_mode == 0;
     ALLOC(h->regPose, 16);
 
     // downsampleCurrentScan segments: (slot, corner), (slot, surf)
@@ -229,6 +243,10 @@ void fbpr_destroy(fbpr_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
+    for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    if (h->stageDone) cudaEventDestroy(h->stageDone);
+    if (h->h_metaStage) cudaFreeHost(h->h_metaStage);
+    if (h->h_imuStage) cudaFreeHost(h->h_imuStage);
     for (void* p : h->allocs) cudaFree(p);
     for (void* p : h->soloVoxAllocs) cudaFree(p);
     for (void* p : h->soloGridAllocs) cudaFree(p);
@@ -322,6 +340,55 @@ int fbpr_set_local_map(fbpr_handle* h, int slot, const float* corner, int nC, co
 
 int fbpr_set_pose(fbpr_handle* h, int slot, const float pose6[6]) { return fbpr_set_poses(h, slot, 1, pose6, FBPR_MEM_HOST); }
 
+int fbpr_set_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input* fr, int mem) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    if (count == 0) return 0;
+    if (!fr) return fbpr_fail_msg("null frames");
+    cudaSetDevice(h->device);
+    if (!h->h_metaStage) {
+        FBPR_CUDA_OK(cudaHostAlloc((void**)&h->h_metaStage, sizeof(FrameMeta) * (size_t)h->F, cudaHostAllocDefault));
+        FBPR_CUDA_OK(cudaHostAlloc((void**)&h->h_imuStage, sizeof(double) * 4 * (size_t)h->F * FBPR_IMU_CAP, cudaHostAllocDefault));
+        FBPR_CUDA_OK(cudaEventCreateWithFlags(&h->stageDone, cudaEventDisableTiming));
+    }
+    if (h->stagePending) { FBPR_CUDA_OK(cudaEventSynchronize(h->stageDone)); h->stagePending = false; }
+    bool anyImu = false;
+    const cudaMemcpyKind k = kind_in(mem);
+    for (int i = 0; i < count; i++) {
+        const fbpr_frame_input& f = fr[i];
+        const int slot = first + i;
+        if (f.n_raw < 0 || f.n_raw > h->rawCap) return fbpr_fail_msg("raw scan larger than max_raw_points");
+        if (f.n_map_corner < 0 || f.n_map_corner > h->mapCornerCap || f.n_map_surf < 0 || f.n_map_surf > h->mapSurfCap)
+            return fbpr_fail_msg("local map exceeds max_map_corner / max_map_surf");
+        FrameMeta m = {};
+        m.n_raw = f.raw ? f.n_raw : 0; m.n_map_corner = f.map_corner_xyzi ? f.n_map_corner : 0; m.n_map_surf = f.map_surf_xyzi ? f.n_map_surf : 0;
+        m.deskewFlag = f.deskewFlag; m.imuAvailable = f.imuAvailable; m.timeScanCur = f.timeScanCur; m.imuPointerCur = f.imuPointerCur;
+        m.imuRollInit = f.imuRollInit; m.imuPitchInit = f.imuPitchInit;
+        for (int q = 0; q < 6; q++) m.pose[q] = f.pose[q];
+        h->h_metaStage[i] = m;
+        if (f.imuAvailable != 0 && f.deskewFlag != -1) {
+            if (!f.imuTime || !f.imuRotX || !f.imuRotY || !f.imuRotZ) return fbpr_fail_msg("IMU ramp missing while imuAvailable != 0");
+            if (f.imuPointerCur < 0 || f.imuPointerCur >= FBPR_IMU_CAP) return fbpr_fail_msg("imuPointerCur out of range");
+            const size_t nb = (size_t)(f.imuPointerCur + 1) * sizeof(double);
+            const double* src[4] = { f.imuTime, f.imuRotX, f.imuRotY, f.imuRotZ };
+            for (int a = 0; a < 4; a++) memcpy(h->h_imuStage + ((size_t)a * count + i) * FBPR_IMU_CAP, src[a], nb);
+            anyImu = true;
+        }
+        if (m.n_raw) FBPR_CUDA_OK(cudaMemcpyAsync(h->raw + (size_t)slot * h->rawCap, f.raw, (size_t)m.n_raw * sizeof(fbpr_raw_point), k, h->stream));
+        if (m.n_map_corner) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapCorner + (size_t)slot * h->mapCornerCap, f.map_corner_xyzi, (size_t)m.n_map_corner * sizeof(float4), k, h->stream));
+        if (m.n_map_surf) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapSurf + (size_t)slot * h->mapSurfCap, f.map_surf_xyzi, (size_t)m.n_map_surf * sizeof(float4), k, h->stream));
+    }
+    FBPR_CUDA_OK(cudaMemcpyAsync(h->meta + first, h->h_metaStage, sizeof(FrameMeta) * (size_t)count, cudaMemcpyHostToDevice, h->stream));
+    if (anyImu) {
+        double* dst[4] = { h->imuTime, h->imuRotX, h->imuRotY, h->imuRotZ };
+        for (int a = 0; a < 4; a++)
+            FBPR_CUDA_OK(cudaMemcpyAsync(dst[a] + (size_t)first * FBPR_IMU_CAP, h->h_imuStage + (size_t)a * count * FBPR_IMU_CAP,
+                                         sizeof(double) * (size_t)count * FBPR_IMU_CAP, cudaMemcpyHostToDevice, h->stream));
+    }
+    FBPR_CUDA_OK(cudaEventRecord(h->stageDone, h->stream));
+    h->stagePending = true;
+    return 0;
+}
+
 int fbpr_set_poses(fbpr_handle* h, int first, int count, const float* pose6, int mem) {
     int rc = check_range(h, first, count); if (rc) return rc;
     if (count == 0) return 0;
@@ -389,6 +456,7 @@ static LmArgs lm_args(fbpr_handle* h, int first) {
     LmArgs a = {};
     a.meta = h->meta; a.cornerDS = h->cornerDS; a.cornerCap = h->cornerCap; a.surfDS = h->surfDS; a.surfCap = h->P;
     a.gsegs = h->d_gridSegs; a.first = first;
+    a.knnPos = h->knnPos; a.qCap = h->cornerCap + h->P; a.partials = h->partials; a.teamMax = 16; a.partialsGrid = h->partialsGrid; a.gridMax = 1024;
     a.edgeMin = h->p.edgeFeatureMinValidNum; a.surfMin = h->p.surfFeatureMinValidNum;
     a.z_tol = h->p.z_tollerance; a.rot_tol = h->p.rotation_tollerance;
     a.debug_iter = (h->debugIter >= 0 && first + 0 < h->dbgSlots) ? h->debugIter : -1;
@@ -398,18 +466,45 @@ static LmArgs lm_args(fbpr_handle* h, int first) {
     return a;
 }
 
-static int enqueue_project(fbpr_handle* h, int first, int count) { fbpr_launch_projection(proj_args(h, first), count, h->stream, &h->launches); return 0; }
-static int enqueue_features(fbpr_handle* h, int first, int count) { return fbpr_launch_features(feat_args(h, first), count, h->stream, &h->launches); }
+struct StageTimer {                      // records an event pair around one stage when timing is on (never inside a capture)
+    fbpr_handle* h; int idx = -1;
+    StageTimer(fbpr_handle* h_, int stage) : h(h_) {
+        if (!h->timing || h->useGraphs) return;
+        if (h->spansUsed == h->spans.size()) {
+            fbpr_handle::TimedSpan sp; sp.stage = stage;
+            if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return;
+            h->spans.push_back(sp);
+        }
+        idx = (int)h->spansUsed++;
+        h->spans[idx].stage = stage;
+        cudaEventRecord(h->spans[idx].a, h->stream);
+    }
+    ~StageTimer() { if (idx >= 0) cudaEventRecord(h->spans[idx].b, h->stream); }
+};
+
+static int enqueue_project(fbpr_handle* h, int first, int count) {
+    StageTimer t(h, FBPR_STAGE_PROJECT);
+    fbpr_launch_projection(proj_args(h, first), count, h->stream, &h->launches); return 0;
+}
+static int enqueue_features(fbpr_handle* h, int first, int count) {
+    StageTimer t(h, FBPR_STAGE_FEATURES);
+    return fbpr_launch_features(feat_args(h, first), count, h->stream, &h->launches);
+}
 static int enqueue_downsample(fbpr_handle* h, int first, int count) {
+    StageTimer t(h, FBPR_STAGE_DOWNSAMPLE);
     fbpr_launch_voxel(h->d_scanSegs + 2 * (size_t)first, 2 * count, h->P, h->tilesCap, h->stream, &h->launches); return 0;
 }
 static int enqueue_scan2map(fbpr_handle* h, int first, int count) {
     int maxMap = h->mapCornerCap > h->mapSurfCap ? h->mapCornerCap : h->mapSurfCap;
     int maxCells = h->cellsCorner > h->cellsSurf ? h->cellsCorner : h->cellsSurf;
-    fbpr_launch_grid_build(h->d_gridSegs + 2 * (size_t)first, 2 * count, maxMap, maxCells, h->stream, &h->launches);
+    {
+        StageTimer t(h, FBPR_STAGE_MAP_INDEX);
+        fbpr_launch_grid_build(h->d_gridSegs + 2 * (size_t)first, 2 * count, maxMap, maxCells, h->stream, &h->launches);
+    }
     LmArgs a = lm_args(h, first);
     if (a.debug_iter >= 0 && first + count > h->dbgSlots) return fbpr_fail_msg("debug capture only covers the first slots");
-    return fbpr_launch_lm(a, count, h->cluster, h->stream, &h->launches);
+    StageTimer t(h, FBPR_STAGE_LM);
+    return fbpr_launch_lm(a, count, h->cluster, h->lmWholeGpu ? h->lmGridBlocks : 0, h->stream, &h->launches);
 }
 
 extern "C" {
@@ -570,6 +665,30 @@ int fbpr_get_counts(fbpr_handle* h, int slot, int32_t counts[8]) {
     return 0;
 }
 
+int fbpr_enable_stage_timing(fbpr_handle* h, int on) { if (!h) return fbpr_fail_msg("null handle"); h->timing = on != 0; return 0; }
+
+int fbpr_get_stage_ms(fbpr_handle* h, float ms[FBPR_STAGE_COUNT], int32_t calls[FBPR_STAGE_COUNT], int reset) {
+    if (!h) return fbpr_fail_msg("null handle");
+    cudaSetDevice(h->device);
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < h->spansUsed; i++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, h->spans[i].a, h->spans[i].b) == cudaSuccess) { h->stageMs[h->spans[i].stage] += t; h->stageCalls[h->spans[i].stage]++; }
+    }
+    h->spansUsed = 0;
+    for (int s = 0; s < FBPR_STAGE_COUNT; s++) { if (ms) ms[s] = h->stageMs[s]; if (calls) calls[s] = h->stageCalls[s]; }
+    if (reset) for (int s = 0; s < FBPR_STAGE_COUNT; s++) { h->stageMs[s] = 0.f; h->stageCalls[s] = 0; }
+    return 0;
+}
+
+// profile builds only (-DFBPR_LM_PROFILE): copies the per-thread phase clocks of the last lm_kernel launch
+extern "C" __attribute__((visibility("default"))) int fbpr_debug_lm_profile(fbpr_handle* h, long long* out, int ctas) {
+    cudaSetDevice(h->device);
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    FBPR_CUDA_OK(cudaMemcpy(out, h->partialsGrid + 2 * 1024 * 28, sizeof(long long) * (size_t)ctas * 512 * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int fbpr_set_debug_iteration(fbpr_handle* h, int iter) {
     if (!h) return fbpr_fail_msg("null handle");
     cudaSetDevice(h->device);
@@ -706,7 +825,7 @@ int fbpr_knn5(fbpr_handle* h, const float* map_xyzi, int n_map, float cell, cons
     FBPR_CUDA_OK(cudaMallocAsync(&d_idx, sizeof(int) * 5 * (size_t)(nq + 1), h->stream));
     FBPR_CUDA_OK(cudaMallocAsync(&d_d2, sizeof(float) * 5 * (size_t)(nq + 1), h->stream));
     if (nq) FBPR_CUDA_OK(cudaMemcpyAsync(d_q, q_xyz, sizeof(float) * 3 * (size_t)nq, cudaMemcpyHostToDevice, h->stream));
-    fbpr_launch_knn5(h->d_soloGrid, d_q, nq, d_idx, d_d2, h->stream, &h->launches);
+    fbpr_launch_knn5(h->d_soloGrid, d_q, nq, d_idx, d_d2, 0, h->stream, &h->launches);
     if (nq) {
         FBPR_CUDA_OK(cudaMemcpyAsync(idx, d_idx, sizeof(int) * 5 * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));
         FBPR_CUDA_OK(cudaMemcpyAsync(d2, d_d2, sizeof(float) * 5 * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));

@@ -27,7 +27,10 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int LM_TPB = 256;
+#ifndef FBPR_LM_TPB
+#define FBPR_LM_TPB 512
+#endif
+constexpr int LM_TPB = FBPR_LM_TPB;
 constexpr int NACC = 28;          // 21 (upper triangle of A^T A) + 6 (A^T b) + 1 (row count)
 
 __device__ __forceinline__ void transform_point(const float* T, float4 p, float& x, float& y, float& z) {
@@ -37,10 +40,10 @@ __device__ __forceinline__ void transform_point(const float* T, float4 p, float&
 }
 
 // cornerOptimization body for one point (mapOptmization.h:1026-1121)
-__device__ inline bool corner_fit(const float4* __restrict__ mpts, const Knn5& r, float x0, float y0, float z0, float4& coeff) {
+__device__ inline bool corner_fit(const float4* __restrict__ mpts, const int* pos, float x0, float y0, float z0, float4& coeff) {
     float px[5], py[5], pz[5];
     #pragma unroll
-    for (int j = 0; j < 5; j++) { float4 m = mpts[r.pos[j]]; px[j] = m.x; py[j] = m.y; pz[j] = m.z; }
+    for (int j = 0; j < 5; j++) { float4 m = mpts[pos[j]]; px[j] = m.x; py[j] = m.y; pz[j] = m.z; }
     float cx = 0, cy = 0, cz = 0;
     #pragma unroll
     for (int j = 0; j < 5; j++) { cx += px[j]; cy += py[j]; cz += pz[j]; }
@@ -54,8 +57,8 @@ __device__ inline bool corner_fit(const float4* __restrict__ mpts, const Knn5& r
         a33 += az * az;
     }
     a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
-    float A1[9] = { a11, a12, a13, a12, a22, a23, a13, a23, a33 }, D1[3], V1[9];
-    dev_jacobi<3>(A1, D1, V1);
+    float D1[3], V1[9];
+    dev_jacobi3(a11, a12, a13, a22, a23, a33, D1, V1);
     if (!(D1[0] > 3 * D1[1])) return false;
     float x1 = (float)((double)cx + 0.1 * (double)V1[0]);
     float y1 = (float)((double)cy + 0.1 * (double)V1[1]);
@@ -80,10 +83,10 @@ __device__ inline bool corner_fit(const float4* __restrict__ mpts, const Knn5& r
 }
 
 // surfOptimization body for one point (mapOptmization.h:1153-1212)
-__device__ inline bool surf_fit(const float4* __restrict__ mpts, const Knn5& r, float x0, float y0, float z0, float4& coeff) {
+__device__ inline bool surf_fit(const float4* __restrict__ mpts, const int* pos, float x0, float y0, float z0, float4& coeff) {
     float A0[15];
     #pragma unroll
-    for (int j = 0; j < 5; j++) { float4 m = mpts[r.pos[j]]; A0[3 * j] = m.x; A0[3 * j + 1] = m.y; A0[3 * j + 2] = m.z; }
+    for (int j = 0; j < 5; j++) { float4 m = mpts[pos[j]]; A0[3 * j] = m.x; A0[3 * j + 1] = m.y; A0[3 * j + 2] = m.z; }
     float X0[3];
     dev_plane_solve(A0, X0);
     float pa = X0[0], pb = X0[1], pc = X0[2], pd = 1;
@@ -162,7 +165,9 @@ __device__ inline int lm_solve_step(const float* AtA, const float* AtB, int iter
     dev_qr_solve6(Aw, bw, X);
     float matP[36];
     for (int k = 0; k < 36; k++) matP[k] = 0.f;
-    if (iter == 0) {
+    if (iter == 0 && dev_surely_not_degenerate(AtA)) {
+        isDegenerate = 0;                            // every eigenvalue is provably >= 100: matP is never used
+    } else if (iter == 0) {
         float E[6], V[36], V2[36], Vinv[36];
         for (int k = 0; k < 36; k++) Aw[k] = AtA[k];
         dev_jacobi<6>(Aw, E, V);
@@ -198,16 +203,23 @@ __device__ inline int lm_solve_step(const float* AtA, const float* AtB, int iter
     return ((double)deltaR < 0.05 && (double)deltaT < 0.05) ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(LM_TPB) lm_kernel(LmArgs a) {
+// One LM iteration = phase A (warp per query: exact 5-NN) -> phase B (thread per query: fit,
+// Jacobian row, f64 accumulation) -> CTA reduce -> team barrier -> every CTA sums all partials
+// in a fixed order and solves redundantly.  The TEAM of one frame is a thread-block cluster
+// (GRID = false, many frames per launch) or the whole cooperative grid (GRID = true, one frame).
+template <bool GRID>
+__global__ void __launch_bounds__(LM_TPB, 1) lm_kernel(LmArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
-    const int C = (int)cluster.num_blocks();
-    const int rank = (int)cluster.block_rank();
-    const int slot = a.first + (int)(blockIdx.x / C);
+    cg::grid_group grid = cg::this_grid();
+    const int C = GRID ? (int)gridDim.x : (int)cluster.num_blocks();        // CTAs in the team
+    const int rank = GRID ? (int)blockIdx.x : (int)cluster.block_rank();
+    const int slot = GRID ? a.first : a.first + (int)(blockIdx.x / C);
     FrameMeta& M = a.meta[slot];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int WPB = LM_TPB / 32;
 
-    __shared__ double part[2][NACC];               // this CTA's partial sums, double-buffered by iteration parity
-    __shared__ double wred[LM_TPB / 32][NACC];
+    __shared__ double wred[WPB][NACC];
+    __shared__ double sh_tot[NACC];
     __shared__ float sh_pose[6], sh_T[12], sh_trig[6], sh_AtA[36], sh_AtB[6];
     __shared__ int sh_stop, sh_nsel;
 
@@ -216,15 +228,29 @@ __global__ void __launch_bounds__(LM_TPB) lm_kernel(LmArgs a) {
         if (rank == 0 && tid == 0) { M.flags = FBPR_FLAG_NOT_ENOUGH_FEATURES; M.iters = 0; M.nSel = 0; M.isDegenerate = 0; }
         return;
     }
+    const int nQ = nC + nS;
     const GridSeg gc = a.gsegs[2 * slot], gs = a.gsegs[2 * slot + 1];
     const GridDesc gdc = *gc.desc, gds = *gs.desc;
     const float4* cpts = a.cornerDS + (size_t)slot * a.cornerCap;
     const float4* spts = a.surfDS + (size_t)slot * a.surfCap;
+    int* knn = a.knnPos + (size_t)slot * a.qCap * 5;
+    double* part = GRID ? a.partialsGrid : a.partials + (size_t)slot * 2 * a.teamMax * NACC;
+    const int teamStride = GRID ? a.gridMax : a.teamMax;
     if (tid < 6) sh_pose[tid] = M.pose[tid];
     __syncthreads();
 
     unsigned flags = 0; int isDegenerate = 0; int iters = 0;
+#ifdef FBPR_LM_PROFILE
+    long long pf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; long long pc = 0;
+    long long kq[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+#define PF_START() pc = clock64()
+#define PF_MARK(i) { long long now_ = clock64(); pf[i] += now_ - pc; pc = now_; }
+#else
+#define PF_START()
+#define PF_MARK(i)
+#endif
     for (int iter = 0; iter < FBPR_MAX_ITERS; iter++) {
+        PF_START();
         // --- pose -> rigid transform + the six sines/cosines LMOptimization needs (:1259-1264)
         if (tid < 6) {
             float ang = sh_pose[tid % 3];            // 0 roll, 1 pitch, 2 yaw
@@ -243,42 +269,74 @@ __global__ void __launch_bounds__(LM_TPB) lm_kernel(LmArgs a) {
         float T[12];
         #pragma unroll
         for (int k = 0; k < 12; k++) T[k] = sh_T[k];
-        const float srz = sh_trig[0], srx = sh_trig[1], sry = sh_trig[2], crz = sh_trig[3], crx = sh_trig[4], cry = sh_trig[5];
-
-        double acc[NACC];
-        #pragma unroll
-        for (int k = 0; k < NACC; k++) acc[k] = 0.0;
         const bool cap = iter == a.debug_iter;
+        PF_MARK(0);
 
-        for (int i = rank * LM_TPB + tid; i < nC + nS; i += C * LM_TPB) {
-            const bool isCorner = i < nC;
-            const int li = isCorner ? i : i - nC;
+        // --- phase A: one warp per query, exact 5-NN inside the 1 m ball on the grid index
+        const int nW = C * WPB;
+#ifdef FBPR_KNN_PROFILE
+        long long kqt = clock64();
+#endif
+        for (int q = rank * WPB + warp; q < nQ; q += nW) {
+            const bool isCorner = q < nC;
+            const int li = isCorner ? q : q - nC;
             const float4 pOri = isCorner ? cpts[li] : spts[li];
             float x0, y0, z0;
             transform_point(T, pOri, x0, y0, z0);
-            Knn5 r;
-            #pragma unroll
-            for (int k = 0; k < 5; k++) { r.d[k] = 3.0e38f; r.id[k] = -1; r.pos[k] = 0; }
-            float4 coeff = make_float4(0, 0, 0, 0);
+            WarpKnn5 r;
             bool ok;
-            if (isCorner) {
-                ok = gdc.n >= 5 && grid_knn5(gdc, gc.cell_start, gc.cell_cursor, gc.sorted, x0, y0, z0, r);
-                bool near = ok;
-                if (ok) ok = corner_fit(gc.sorted, r, x0, y0, z0, coeff);
+#ifdef FBPR_KNN_PROFILE
+            { long long n_ = clock64(); pf[0] += 0; kq[6] += n_ - kqt; kqt = n_; }
+            if (isCorner) ok = gdc.n >= 5 && warp_knn5(gdc, gc.cell_start, gc.cell_cursor, gc.sorted, x0, y0, z0, r, kq);
+            else          ok = gds.n >= 5 && warp_knn5(gds, gs.cell_start, gs.cell_cursor, gs.sorted, x0, y0, z0, r, kq);
+            kqt = clock64(); kq[7] += 1;
+#else
+            if (isCorner) ok = gdc.n >= 5 && warp_knn5(gdc, gc.cell_start, gc.cell_cursor, gc.sorted, x0, y0, z0, r);
+            else          ok = gds.n >= 5 && warp_knn5(gds, gs.cell_start, gs.cell_cursor, gs.sorted, x0, y0, z0, r);
+#endif
+            if (lane < 5) {
+                int v = r.pos[0];
+                if (lane == 1) v = r.pos[1]; else if (lane == 2) v = r.pos[2]; else if (lane == 3) v = r.pos[3]; else if (lane == 4) v = r.pos[4];
+                knn[(size_t)q * 5 + lane] = ok ? v : -1;
                 if (cap) {
-                    size_t o = (size_t)slot * a.cornerCap + li;
-                    for (int k = 0; k < 5; k++) { a.knnC[5 * o + k] = near ? r.id[k] : -1; a.d2C[5 * o + k] = r.d[k]; }
-                    a.coeffC[o] = coeff; a.flagC[o] = ok ? 1 : 0;
+                    unsigned long long kk = r.key[0];
+                    if (lane == 1) kk = r.key[1]; else if (lane == 2) kk = r.key[2]; else if (lane == 3) kk = r.key[3]; else if (lane == 4) kk = r.key[4];
+                    const bool have = (isCorner ? gdc.n : gds.n) >= 5;
+                    size_t o = isCorner ? (size_t)slot * a.cornerCap + li : (size_t)slot * a.surfCap + li;
+                    int* kd = isCorner ? a.knnC : a.knnS; float* dd = isCorner ? a.d2C : a.d2S;
+                    kd[5 * o + lane] = ok ? (int)(unsigned)(kk & 0xffffffffu) : -1;
+                    dd[5 * o + lane] = have ? __uint_as_float((unsigned)(kk >> 32)) : 3.0e38f;
                 }
-            } else {
-                ok = gds.n >= 5 && grid_knn5(gds, gs.cell_start, gs.cell_cursor, gs.sorted, x0, y0, z0, r);
-                bool near = ok;
-                if (ok) ok = surf_fit(gs.sorted, r, x0, y0, z0, coeff);
-                if (cap) {
-                    size_t o = (size_t)slot * a.surfCap + li;
-                    for (int k = 0; k < 5; k++) { a.knnS[5 * o + k] = near ? r.id[k] : -1; a.d2S[5 * o + k] = r.d[k]; }
-                    a.coeffS[o] = coeff; a.flagS[o] = ok ? 1 : 0;
-                }
+            }
+        }
+        PF_MARK(1);
+        __syncthreads();                             // this CTA's phase-B threads consume what its own warps produced
+        PF_MARK(2);
+
+        // --- phase B: one thread per query: line / plane fit, coefficient, Jacobian row, f64 accumulation
+        const float srz = sh_trig[0], srx = sh_trig[1], sry = sh_trig[2], crz = sh_trig[3], crx = sh_trig[4], cry = sh_trig[5];
+        double acc[NACC];
+        #pragma unroll
+        for (int k = 0; k < NACC; k++) acc[k] = 0.0;
+        for (int j = tid; ; j += LM_TPB) {
+            const int q = rank * WPB + (j % WPB) + (j / WPB) * nW;      // the j-th query this CTA's warps handled
+            if (q >= nQ) break;
+            int pos[5];
+            #pragma unroll
+            for (int k = 0; k < 5; k++) pos[k] = knn[(size_t)q * 5 + k];
+            const bool isCorner = q < nC;
+            const int li = isCorner ? q : q - nC;
+            float4 coeff = make_float4(0, 0, 0, 0);
+            bool ok = pos[4] >= 0;
+            const float4 pOri = isCorner ? cpts[li] : spts[li];
+            if (ok) {
+                float x0, y0, z0;
+                transform_point(T, pOri, x0, y0, z0);
+                ok = isCorner ? corner_fit(gc.sorted, pos, x0, y0, z0, coeff) : surf_fit(gs.sorted, pos, x0, y0, z0, coeff);
+            }
+            if (cap) {
+                if (isCorner) { size_t o = (size_t)slot * a.cornerCap + li; a.coeffC[o] = coeff; a.flagC[o] = ok ? 1 : 0; }
+                else          { size_t o = (size_t)slot * a.surfCap + li;   a.coeffS[o] = coeff; a.flagS[o] = ok ? 1 : 0; }
             }
             if (ok) {
                 // Jacobian row, lidar -> "camera" axis permutation (mapOptmization.h:1286-1332)
@@ -296,18 +354,19 @@ __global__ void __launch_bounds__(LM_TPB) lm_kernel(LmArgs a) {
                           + ((sry * srz + cry * crz * srx) * ox + (crz * sry - cry * srx * srz) * oy) * kz;
                 const double row[6] = { (double)arz, (double)arx, (double)ary, (double)kz, (double)kx, (double)ky };
                 const double b = (double)(-coeff.w);
-                int q = 0;
+                int qq = 0;
                 #pragma unroll
                 for (int rr = 0; rr < 6; rr++) {
                     #pragma unroll
-                    for (int cc = rr; cc < 6; cc++) acc[q++] += row[rr] * row[cc];
+                    for (int cc = rr; cc < 6; cc++) acc[qq++] += row[rr] * row[cc];
                 }
                 #pragma unroll
                 for (int rr = 0; rr < 6; rr++) acc[21 + rr] += row[rr] * b;
                 acc[27] += 1.0;
             }
         }
-        // --- block reduce (warp shuffles, then shared memory in fixed warp order)
+        PF_MARK(3);
+        // --- CTA reduce (warp shuffles, then shared memory in fixed warp order) -> one partial per CTA in global memory
         #pragma unroll
         for (int k = 0; k < NACC; k++) {
             double v = acc[k];
@@ -316,24 +375,34 @@ __global__ void __launch_bounds__(LM_TPB) lm_kernel(LmArgs a) {
         }
         __syncthreads();
         const int buf = iter & 1;
+        double* mypart = part + ((size_t)buf * teamStride + rank) * NACC;
         if (tid < NACC) {
             double v = 0.0;
-            for (int w = 0; w < LM_TPB / 32; w++) v += wred[w][tid];
-            part[buf][tid] = v;
+            for (int w = 0; w < WPB; w++) v += wred[w][tid];
+            mypart[tid] = v;
+            __threadfence();
         }
-        cluster.sync();
-        // --- every CTA pulls all partials through DSMEM in rank order and solves redundantly
+        PF_MARK(4);
+        if (GRID) grid.sync(); else cluster.sync();
+        PF_MARK(5);
+        // --- every CTA sums all partials in the same fixed order (bitwise identical everywhere), then solves redundantly
+        if (tid < NACC * 8) {
+            const int v = tid >> 3, s8 = tid & 7;
+            double sum = 0.0;
+            const double* base = part + (size_t)buf * teamStride * NACC + v;
+            for (int rk = s8; rk < C; rk += 8) sum += __ldcg(base + (size_t)rk * NACC);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            if (s8 == 0) sh_tot[v] = sum;
+        }
+        __syncthreads();
         if (tid < NACC) {
-            double v = 0.0;
-            for (int rk = 0; rk < C; rk++) {
-                const double* remote = cluster.map_shared_rank(&part[buf][0], rk);
-                v += remote[tid];
-            }
+            const double v = sh_tot[tid];
             if (tid < 21) {
-                // unpack the upper triangle index tid -> (r, c)
-                int rr = 0, q = tid;
-                while (q >= 6 - rr) { q -= 6 - rr; rr++; }
-                int cc = rr + q;
+                int rr = 0, qx = tid;                 // unpack the upper-triangle index
+                while (qx >= 6 - rr) { qx -= 6 - rr; rr++; }
+                int cc = rr + qx;
                 float fv = (float)v;
                 sh_AtA[rr * 6 + cc] = fv; sh_AtA[cc * 6 + rr] = fv;
             } else if (tid < 27) {
@@ -343,6 +412,7 @@ __global__ void __launch_bounds__(LM_TPB) lm_kernel(LmArgs a) {
             }
         }
         __syncthreads();
+        PF_MARK(6);
         if (tid == 0) {
             int stop = 0;
             iters = iter + 1;
@@ -360,15 +430,24 @@ __global__ void __launch_bounds__(LM_TPB) lm_kernel(LmArgs a) {
                     for (int k = 0; k < 6; k++) { a.dbgAtB[(size_t)slot * 6 + k] = sh_AtB[k]; a.dbgX[(size_t)slot * 6 + k] = X[k]; }
                 }
             }
-            if (rank == 0 && a.poseTrace) {
+            if (rank == 0 && a.poseTrace)
                 for (int k = 0; k < 6; k++) a.poseTrace[((size_t)slot * FBPR_MAX_ITERS + iter) * 6 + k] = sh_pose[k];
-            }
             sh_stop = stop;
         }
         __syncthreads();
+        PF_MARK(7);
         if (sh_stop) break;
     }
-    cluster.sync();                                 // nobody leaves while a peer may still read its partials
+#ifdef FBPR_LM_PROFILE
+    if (slot == a.first && a.partialsGrid) {        // profile dump: [rank][thread][8] after the partial buffers
+        long long* out = reinterpret_cast<long long*>(a.partialsGrid + 2 * (size_t)a.gridMax * NACC);
+#ifdef FBPR_KNN_PROFILE
+        for (int k = 0; k < 8; k++) if (tid < 512) out[((size_t)rank * 512 + tid) * 8 + k] = kq[k];
+#else
+        for (int k = 0; k < 8; k++) if (tid < 512) out[((size_t)rank * 512 + tid) * 8 + k] = pf[k];
+#endif
+    }
+#endif
     if (rank == 0 && tid == 0) {
         float pose[6];
         for (int k = 0; k < 6; k++) pose[k] = sh_pose[k];
@@ -391,24 +470,41 @@ __global__ void transform_update_kernel(FrameMeta* meta, int first, int count, f
 
 }  // namespace
 
-int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, cudaStream_t st, long long* launches) {
+int fbpr_lm_grid_blocks(int device) {
+    // co-resident CTAs of the cooperative (one frame on the whole GPU) variant: one per SM
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    int per = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lm_kernel<true>, LM_TPB, 0) != cudaSuccess || per < 1) return 0;
+    return sms;
+}
+
+int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blocks, cudaStream_t st, long long* launches) {
     if (count <= 0) return 0;
     static int configured = 0;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(lm_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaError_t e = cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(NonPortableClusterSizeAllowed)", __FILE__, __LINE__);
         configured = 1;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(count * cluster_size));
     cfg.blockDim = dim3(LM_TPB);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, lm_kernel, args);
+    cudaError_t e;
+    if (count == 1 && grid_blocks > 0) {           // one frame: the whole GPU cooperates, grid-wide barrier per iteration
+        cfg.gridDim = dim3((unsigned)grid_blocks);
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        e = cudaLaunchKernelEx(&cfg, lm_kernel<true>, args);
+    } else {                                        // many frames: one cluster per frame, hardware cluster barrier per iteration
+        cfg.gridDim = dim3((unsigned)(count * cluster_size));
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        e = cudaLaunchKernelEx(&cfg, lm_kernel<false>, args);
+    }
     if (e != cudaSuccess) return fbpr_fail(e, "cudaLaunchKernelEx(lm_kernel)", __FILE__, __LINE__);
     if (launches) *launches += 1;
     return 0;

@@ -72,7 +72,8 @@ typedef struct fbpr_params {
     float   knn_cell_surf;
     int32_t grid_cells_corner;               /* dense-grid cell budget per map index (0 = 262144 / 1048576); the cell */
     int32_t grid_cells_surf;                 /*   edge is doubled until the map's bounding box fits the budget        */
-    int32_t lm_cluster_size;                 /* CTAs cooperating on one frame's LM loop: 1,2,4,8,16 (0 = 8) */
+    int32_t lm_cluster_size;                 /* CTAs cooperating on one frame's LM loop in batched calls: 1,2,4,8,16 (0 = 8) */
+    int32_t lm_single_frame_mode;            /* count == 1 calls: 0 = whole GPU cooperates (grid barrier), 1 = one cluster   */
 } fbpr_params;
 
 /* one frame's outcome: transformTobeMapped after transformUpdate, iterations executed, FBPR_FLAG_* */
@@ -132,6 +133,24 @@ FBPR_API int fbpr_set_local_map(fbpr_handle* h, int slot, const float* corner_xy
 FBPR_API int fbpr_set_pose(fbpr_handle* h, int slot, const float pose6[6]);
 FBPR_API int fbpr_set_poses(fbpr_handle* h, int first, int count, const float* pose6, int mem);
 
+/* one frame's inputs for the batched upload below; pointers may be NULL when a stage is not used */
+typedef struct fbpr_frame_input {
+    const fbpr_raw_point* raw;  int32_t n_raw;
+    int32_t        deskewFlag;               /* -1: cloud has no time field (imageProjection.cpp:548) */
+    int64_t        imuAvailable;
+    double         timeScanCur;
+    const double*  imuTime; const double* imuRotX; const double* imuRotY; const double* imuRotZ;
+    int32_t        imuPointerCur;
+    float          imuRollInit, imuPitchInit;
+    const float*   map_corner_xyzi; int32_t n_map_corner;
+    const float*   map_surf_xyzi;   int32_t n_map_surf;
+    float          pose[6];
+} fbpr_frame_input;
+/* batched form of fbpr_set_raw_scan + fbpr_set_local_map + fbpr_set_pose for `count` independent frames
+   (BASELINE config 4: 1024 frames, each against its own local map): one async copy per cloud, one packed
+   copy for all the scalars.  The slots' counters and results are reset. */
+FBPR_API int fbpr_set_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input* frames, int mem);
+
 /* ---- operators (slot range [first, first+count)) ----------------------------------------- */
 /* replaces: ImageProjection::projectPointCloud + cloudExtraction (imageProjection.cpp:583-670). */
 FBPR_API int fbpr_project(fbpr_handle* h, int first, int count);
@@ -173,6 +192,13 @@ FBPR_API int fbpr_get_pose(fbpr_handle* h, int slot, float pose6[6], int32_t* it
 FBPR_API int fbpr_get_results(fbpr_handle* h, int first, int count, fbpr_result* out, int mem);
 /* counts[8] = n_raw, n_valid, n_corner, n_surf, n_corner_ds, n_surf_ds, n_map_corner, n_map_surf */
 FBPR_API int fbpr_get_counts(fbpr_handle* h, int slot, int32_t counts[8]);
+
+/* per-stage device time, measured with CUDA events on the handle's stream around each stage's launches
+   (replaces the reference's TicToc around scan2MapOptimization, mapOptmization.h:315-318, tic_toc.hpp:14-33).
+   Only active when graphs are off.  ms / calls are accumulated since the last reset. */
+enum { FBPR_STAGE_PROJECT = 0, FBPR_STAGE_FEATURES, FBPR_STAGE_DOWNSAMPLE, FBPR_STAGE_MAP_INDEX, FBPR_STAGE_LM, FBPR_STAGE_COUNT };
+FBPR_API int fbpr_enable_stage_timing(fbpr_handle* h, int on);
+FBPR_API int fbpr_get_stage_ms(fbpr_handle* h, float ms[FBPR_STAGE_COUNT], int32_t calls[FBPR_STAGE_COUNT], int reset);
 
 /* ---- parity / debug getters (host destinations) --------------------------------------------- */
 enum {
