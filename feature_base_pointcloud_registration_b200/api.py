@@ -50,7 +50,7 @@ class Params(C.Structure):
                 ("max_map_corner", C.c_int32), ("max_map_surf", C.c_int32), ("max_keyframe_points", C.c_int32),
                 ("knn_cell_corner", C.c_float), ("knn_cell_surf", C.c_float),
                 ("grid_cells_corner", C.c_int32), ("grid_cells_surf", C.c_int32),
-                ("lm_cluster_size", C.c_int32), ("lm_single_frame_mode", C.c_int32)]
+                ("lm_cluster_size", C.c_int32), ("lm_single_frame_mode", C.c_int32), ("knn_first_radius", C.c_float)]
 
     @classmethod
     def from_dict(cls, d, **extra):
@@ -303,7 +303,8 @@ class Registration:
         m = self._ck(self.lib.fbpr_voxel_grid(self.h, _vp(p), n, C.c_float(leaf), _vp(out), _vp(pk), _vp(ok), MEM_HOST))
         return dict(points=out[:m].copy(), point_keys=pk[:n].copy(), out_keys=ok[:m].copy())
 
-    def knn5(self, map_xyzi, q_xyz, cell=0.25):
+    def knn5(self, map_xyzi, q_xyz, cell=0.25, first_radius=1):
+        self._ck(self.lib.fbpr_knn5_first_radius(self.h, int(first_radius)))
         m = _f32(map_xyzi).reshape(-1, 4); q = _f32(q_xyz).reshape(-1, 3); nq = len(q)
         idx = np.zeros((max(nq, 1), 5), np.int32); d2 = np.zeros((max(nq, 1), 5), np.float32)
         self._ck(self.lib.fbpr_knn5(self.h, _vp(m), len(m), C.c_float(cell), _vp(q), nq, _vp(idx), _vp(d2), MEM_HOST))

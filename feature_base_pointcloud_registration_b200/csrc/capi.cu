@@ -17,7 +17,7 @@ size_t fbpr_feat_ring_smem(const FeatArgs& a);
 void fbpr_launch_voxel(const VoxSeg* d_segs, int nsegs, int max_n, int tiles_cap, cudaStream_t st, long long* launches);
 int fbpr_voxel_tile();
 void fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cells_cap, cudaStream_t st, long long* launches);
-void fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, int thread_mode, cudaStream_t st, long long* launches);
+void fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, int rad0, cudaStream_t st, long long* launches);
 int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blocks, cudaStream_t st, long long* launches);
 int fbpr_lm_grid_blocks(int device);
 void fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float rot_tol, float z_tol, cudaStream_t st, long long* launches);
@@ -60,7 +60,7 @@ struct fbpr_handle {
     int *picked = nullptr, *label = nullptr, *ringCorner = nullptr, *cornerStage = nullptr, *ringSurf = nullptr, *ringSurfDS = nullptr, *cornerIndex = nullptr;
     float4 *mapCorner = nullptr, *mapSurf = nullptr;
     float* poseTrace = nullptr;
-    int* knnPos = nullptr; double* partials = nullptr; double* partialsGrid = nullptr; int lmGridBlocks = 0; bool lmWholeGpu = true;
+    float4* qhist = nullptr; double* partials = nullptr; double* partialsGrid = nullptr; int lmGridBlocks = 0; bool lmWholeGpu = true;
     // descriptors
     VoxSeg* d_scanSegs = nullptr;      // [2F]  downsampleCurrentScan
     GridSeg* d_gridSegs = nullptr;     // [2F]  map index
@@ -72,7 +72,7 @@ struct fbpr_handle {
     VoxSeg* d_soloVox = nullptr; int soloVoxCap = 0; std::vector<void*> soloVoxAllocs;
     float4 *soloIn = nullptr, *soloOut = nullptr; int *soloN = nullptr, *soloNout = nullptr, *soloPK = nullptr, *soloOK = nullptr;
     GridSeg* d_soloGrid = nullptr; int soloGridCap = 0; float soloGridCell = 0; std::vector<void*> soloGridAllocs;
-    float4* soloMap = nullptr; int* soloMapN = nullptr;
+    float4* soloMap = nullptr; int* soloMapN = nullptr; int knnRad0 = 1;
     // debug capture (slots < dbgSlots)
     int debugIter = -1, dbgSlots = 0;
     int *knnC = nullptr, *knnS = nullptr; float *d2C = nullptr, *d2S = nullptr; float4 *coeffC = nullptr, *coeffS = nullptr;
@@ -177,9 +177,9 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     ALLOC(h->corner, (size_t)F * h->cornerCap); ALLOC(h->cornerDS, (size_t)F * h->cornerCap); ALLOC(h->cornerIndex, (size_t)F * h->cornerCap);
     ALLOC(h->mapCorner, (size_t)F * h->mapCornerCap); ALLOC(h->mapSurf, (size_t)F * h->mapSurfCap);
     ALLOC(h->poseTrace, (size_t)F * FBPR_MAX_ITERS * 6);
-    ALLOC(h->knnPos, (size_t)F * (h->cornerCap + P) * 5);
+    ALLOC(h->qhist, (size_t)F * (h->cornerCap + P));
     ALLOC(h->partials, (size_t)F * 2 * 16 * 28);
-    ALLOC(h->partialsGrid, (size_t)2 * 1024 * 28 + (size_t)1024 * 512 * 8);   // + profile dump area (FBPR_LM_PROFILE builds)
+    ALLOC(h->partialsGrid, (size_t)2 * 1024 * 28);
     h->lmGridBlocks = fbpr_lm_grid_blocks(device);
     if (h->lmGridBlocks > 1024) h->lmGridBlocks = 1024;
     h->lmWholeGpu = params->lm_single_frame_mode == 0;
@@ -456,7 +456,8 @@ static LmArgs lm_args(fbpr_handle* h, int first) {
     LmArgs a = {};
     a.meta = h->meta; a.cornerDS = h->cornerDS; a.cornerCap = h->cornerCap; a.surfDS = h->surfDS; a.surfCap = h->P;
     a.gsegs = h->d_gridSegs; a.first = first;
-    a.knnPos = h->knnPos; a.qCap = h->cornerCap + h->P; a.partials = h->partials; a.teamMax = 16; a.partialsGrid = h->partialsGrid; a.gridMax = 1024;
+    a.qhist = h->qhist; a.qCap = h->cornerCap + h->P; a.firstRadius = h->p.knn_first_radius > 0 ? h->p.knn_first_radius : 0.5f;
+    a.partials = h->partials; a.teamMax = 16; a.partialsGrid = h->partialsGrid; a.gridMax = 1024;
     a.edgeMin = h->p.edgeFeatureMinValidNum; a.surfMin = h->p.surfFeatureMinValidNum;
     a.z_tol = h->p.z_tollerance; a.rot_tol = h->p.rotation_tollerance;
     a.debug_iter = (h->debugIter >= 0 && first + 0 < h->dbgSlots) ? h->debugIter : -1;
@@ -681,14 +682,6 @@ int fbpr_get_stage_ms(fbpr_handle* h, float ms[FBPR_STAGE_COUNT], int32_t calls[
     return 0;
 }
 
-// profile builds only (-DFBPR_LM_PROFILE): copies the per-thread phase clocks of the last lm_kernel launch
-extern "C" __attribute__((visibility("default"))) int fbpr_debug_lm_profile(fbpr_handle* h, long long* out, int ctas) {
-    cudaSetDevice(h->device);
-    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
-    FBPR_CUDA_OK(cudaMemcpy(out, h->partialsGrid + 2 * 1024 * 28, sizeof(long long) * (size_t)ctas * 512 * 8, cudaMemcpyDeviceToHost));
-    return 0;
-}
-
 int fbpr_set_debug_iteration(fbpr_handle* h, int iter) {
     if (!h) return fbpr_fail_msg("null handle");
     cudaSetDevice(h->device);
@@ -795,6 +788,13 @@ int fbpr_voxel_grid(fbpr_handle* h, const float* xyzi, int n, float leaf, float*
     return m;
 }
 
+int fbpr_knn5_first_radius(fbpr_handle* h, int cells) {
+    if (!h) return fbpr_fail_msg("null handle");
+    if (cells < 1 || cells > 64) return fbpr_fail_msg("first radius must be 1..64 cells");
+    h->knnRad0 = cells;
+    return 0;
+}
+
 int fbpr_knn5(fbpr_handle* h, const float* map_xyzi, int n_map, float cell, const float* q_xyz, int nq, int32_t* idx, float* d2, int mem) {
     if (!h) return fbpr_fail_msg("null handle");
     if (n_map < 0 || nq < 0) return fbpr_fail_msg("bad sizes");
@@ -825,7 +825,7 @@ int fbpr_knn5(fbpr_handle* h, const float* map_xyzi, int n_map, float cell, cons
     FBPR_CUDA_OK(cudaMallocAsync(&d_idx, sizeof(int) * 5 * (size_t)(nq + 1), h->stream));
     FBPR_CUDA_OK(cudaMallocAsync(&d_d2, sizeof(float) * 5 * (size_t)(nq + 1), h->stream));
     if (nq) FBPR_CUDA_OK(cudaMemcpyAsync(d_q, q_xyz, sizeof(float) * 3 * (size_t)nq, cudaMemcpyHostToDevice, h->stream));
-    fbpr_launch_knn5(h->d_soloGrid, d_q, nq, d_idx, d_d2, 0, h->stream, &h->launches);
+    fbpr_launch_knn5(h->d_soloGrid, d_q, nq, d_idx, d_d2, h->knnRad0, h->stream, &h->launches);
     if (nq) {
         FBPR_CUDA_OK(cudaMemcpyAsync(idx, d_idx, sizeof(int) * 5 * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));
         FBPR_CUDA_OK(cudaMemcpyAsync(d2, d_d2, sizeof(float) * 5 * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));

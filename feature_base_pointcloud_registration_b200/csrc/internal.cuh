@@ -123,7 +123,8 @@ struct LmArgs {
     const float4* cornerDS; int cornerCap;
     const float4* surfDS; int surfCap;
     const GridSeg* gsegs;         // [2*slot + kind]
-    int* knnPos; int qCap;        // [slot][qCap][5] neighbour positions of the current iteration (L2-resident scratch)
+    float4* qhist; int qCap;      // [slot][qCap] per feature point: map-frame position and 5th-NN d^2 of its last search
+    float firstRadius;            // metres the first iteration's search cube must cover
     double* partials; int teamMax;     // [slot][2][teamMax][28] per-CTA partial sums, double-buffered by iteration parity
     double* partialsGrid; int gridMax; // [2][gridMax][28] same for the whole-GPU single-frame variant
     int first;

@@ -4,16 +4,17 @@
 // cornerOptimization (:1002-1124), surfOptimization (:1126-1215), combineOptimizationCoeffs
 // (:1218-1243), LMOptimization (:1246-1401) and transformUpdate (:1444-1479).
 //
-// B200 mapping: one thread-block CLUSTER per frame.  Every thread owns feature points
-// (transform -> exact 5-NN in the grid index -> line / plane fit -> coefficient -> Jacobian row)
-// and accumulates the 21+6 unique entries of J^T J / J^T r in f64; a warp-shuffle + shared-memory
-// block reduce produces one partial per CTA; after ONE hardware cluster barrier every CTA pulls
-// all partials through distributed shared memory in rank order and redundantly solves the 6x6
-// system (QR, degeneracy projection at iteration 0, pose update, convergence test), so a frame
-// needs one cluster.sync() per iteration and no grid-wide or host synchronisation at all.
-// Independent frames are independent clusters (blockIdx.x / cluster size).
+// B200 mapping: one thread-block CLUSTER per frame.  Warps own chunks of 32 feature points
+// (transform -> exact 5-NN in the grid index, warp-cooperative -> line / plane fit, coefficient and
+// Jacobian row, one thread per point); rows are staged in shared memory and folded warp-wise into the 21+6 unique entries of J^T J / J^T r
+// in f64; a shared-memory block reduce produces one partial per CTA; after ONE hardware cluster
+// barrier every CTA reads all partials in rank order and redundantly solves the 6x6 system (QR,
+// degeneracy projection at iteration 0, pose update, convergence test), so a frame needs one
+// cluster.sync() per iteration and no grid-wide or host synchronisation at all.
+// Independent frames are independent clusters (blockIdx.x / cluster size); a single frame can
+// instead take the whole GPU as one cooperative grid (grid.sync() per iteration).
 //
-// Bound: latency (<= 30 dependent iterations) and L2 gathers of map cells; never tensor cores
+// Bound: latency (<= 30 dependent iterations) and L1/L2 gathers of map cells; never tensor cores
 // (contractions are K=3 and 6x6).  Compulsory traffic per iteration: 16 B per feature point +
 // 5 x 16 B neighbours (B_iter = 96 * (n_c + n_s)).
 #include <cooperative_groups.h>
@@ -27,10 +28,10 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-#ifndef FBPR_LM_TPB
-#define FBPR_LM_TPB 512
-#endif
-constexpr int LM_TPB = FBPR_LM_TPB;
+// Launch shapes.  Batched calls: one cluster per frame, 256-thread CTAs (3 resident per SM).
+// Single-frame calls: one 768-thread CTA per SM over the whole GPU.
+constexpr int LM_TPB_CLUSTER = 256, LM_CTAS_CLUSTER = 3;
+constexpr int LM_TPB_GRID = 768, LM_CTAS_GRID = 1;
 constexpr int NACC = 28;          // 21 (upper triangle of A^T A) + 6 (A^T b) + 1 (row count)
 
 __device__ __forceinline__ void transform_point(const float* T, float4 p, float& x, float& y, float& z) {
@@ -40,10 +41,10 @@ __device__ __forceinline__ void transform_point(const float* T, float4 p, float&
 }
 
 // cornerOptimization body for one point (mapOptmization.h:1026-1121)
-__device__ inline bool corner_fit(const float4* __restrict__ mpts, const int* pos, float x0, float y0, float z0, float4& coeff) {
+__device__ __forceinline__ bool corner_fit(const float4 (&nb)[5], float x0, float y0, float z0, float4& coeff) {
     float px[5], py[5], pz[5];
     #pragma unroll
-    for (int j = 0; j < 5; j++) { float4 m = mpts[pos[j]]; px[j] = m.x; py[j] = m.y; pz[j] = m.z; }
+    for (int j = 0; j < 5; j++) { px[j] = nb[j].x; py[j] = nb[j].y; pz[j] = nb[j].z; }
     float cx = 0, cy = 0, cz = 0;
     #pragma unroll
     for (int j = 0; j < 5; j++) { cx += px[j]; cy += py[j]; cz += pz[j]; }
@@ -83,10 +84,10 @@ __device__ inline bool corner_fit(const float4* __restrict__ mpts, const int* po
 }
 
 // surfOptimization body for one point (mapOptmization.h:1153-1212)
-__device__ inline bool surf_fit(const float4* __restrict__ mpts, const int* pos, float x0, float y0, float z0, float4& coeff) {
+__device__ __forceinline__ bool surf_fit(const float4 (&nb)[5], float x0, float y0, float z0, float4& coeff) {
     float A0[15];
     #pragma unroll
-    for (int j = 0; j < 5; j++) { float4 m = mpts[pos[j]]; A0[3 * j] = m.x; A0[3 * j + 1] = m.y; A0[3 * j + 2] = m.z; }
+    for (int j = 0; j < 5; j++) { A0[3 * j] = nb[j].x; A0[3 * j + 1] = nb[j].y; A0[3 * j + 2] = nb[j].z; }
     float X0[3];
     dev_plane_solve(A0, X0);
     float pa = X0[0], pb = X0[1], pc = X0[2], pd = 1;
@@ -141,7 +142,7 @@ __device__ inline void q_get_rpy(const double q[4], double& roll, double& pitch,
 }
 __device__ inline float clampf(float v, float lim) { if (v < -lim) v = -lim; if (v > lim) v = lim; return v; }
 
-__device__ inline void transform_update(float* pose, long long imuAvailable, float imuRollInit, float imuPitchInit, float rot_tol, float z_tol) {
+__device__ __noinline__ void transform_update(float* pose, long long imuAvailable, float imuRollInit, float imuPitchInit, float rot_tol, float z_tol) {
     if (imuAvailable == 1 && fabs((double)imuPitchInit) < 1.4) {
         double q0[4], q1[4], qm[4], r, p, y;
         q_set_rpy((double)pose[0], 0, 0, q0); q_set_rpy((double)imuRollInit, 0, 0, q1);
@@ -158,7 +159,7 @@ __device__ inline void transform_update(float* pose, long long imuAvailable, flo
 
 // LMOptimization after the reduction (mapOptmization.h:1336-1400), one thread.
 // Returns 1 when converged.  matP is the reference's LOCAL zero-initialised matrix (:1278).
-__device__ inline int lm_solve_step(const float* AtA, const float* AtB, int iter, int& isDegenerate, float* pose, float* Xout) {
+__device__ __noinline__ int lm_solve_step(const float* AtA, const float* AtB, int iter, int& isDegenerate, float* pose, float* Xout) {
     float Aw[36], bw[6], X[6];
     for (int k = 0; k < 36; k++) Aw[k] = AtA[k];
     for (int k = 0; k < 6; k++) bw[k] = AtB[k];
@@ -203,12 +204,18 @@ __device__ inline int lm_solve_step(const float* AtA, const float* AtB, int iter
     return ((double)deltaR < 0.05 && (double)deltaT < 0.05) ? 1 : 0;
 }
 
-// One LM iteration = phase A (warp per query: exact 5-NN) -> phase B (thread per query: fit,
-// Jacobian row, f64 accumulation) -> CTA reduce -> team barrier -> every CTA sums all partials
-// in a fixed order and solves redundantly.  The TEAM of one frame is a thread-block cluster
-// (GRID = false, many frames per launch) or the whole cooperative grid (GRID = true, one frame).
+// One LM iteration = association (a warp takes 32 consecutive feature points: transform, then the exact 5-NN
+// of each point on the grid index by the WHOLE WARP, one point after the other (mapgrid.cuh), then ONE
+// THREAD per point: line / plane fit -> coefficient -> Jacobian row, staged as f64 in shared memory) -> every
+// warp folds its 32 staged rows into the 27 unique entries of J^T J / J^T r (+ the row count), one
+// entry per lane, f64 -> CTA reduce in fixed warp order -> one partial per CTA -> team barrier ->
+// every CTA sums all partials in the same fixed order and solves redundantly.
+// The TEAM of one frame is a thread-block cluster (GRID = false, many frames per launch) or the whole
+// cooperative grid (GRID = true, one frame).  A warp takes 32 CONSECUTIVE points of the scan (voxel order),
+// so successive queries touch neighbouring map cells and find their candidates in L1.
 template <bool GRID>
-__global__ void __launch_bounds__(LM_TPB, 1) lm_kernel(LmArgs a) {
+__global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM_CTAS_GRID : LM_CTAS_CLUSTER) lm_kernel(LmArgs a) {
+    constexpr int LM_TPB = GRID ? LM_TPB_GRID : LM_TPB_CLUSTER;
     cg::cluster_group cluster = cg::this_cluster();
     cg::grid_group grid = cg::this_grid();
     const int C = GRID ? (int)gridDim.x : (int)cluster.num_blocks();        // CTAs in the team
@@ -218,8 +225,11 @@ __global__ void __launch_bounds__(LM_TPB, 1) lm_kernel(LmArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int WPB = LM_TPB / 32;
 
+    // per-warp staging of the 32 Jacobian rows (6) and -residual (1) of the warp's current 32 points, as f64
+    __shared__ double s_rows[WPB][32][7];
     __shared__ double wred[WPB][NACC];
     __shared__ double sh_tot[NACC];
+    __shared__ GridDesc sh_gd[2];
     __shared__ float sh_pose[6], sh_T[12], sh_trig[6], sh_AtA[36], sh_AtB[6];
     __shared__ int sh_stop, sh_nsel;
 
@@ -230,27 +240,26 @@ __global__ void __launch_bounds__(LM_TPB, 1) lm_kernel(LmArgs a) {
     }
     const int nQ = nC + nS;
     const GridSeg gc = a.gsegs[2 * slot], gs = a.gsegs[2 * slot + 1];
-    const GridDesc gdc = *gc.desc, gds = *gs.desc;
     const float4* cpts = a.cornerDS + (size_t)slot * a.cornerCap;
     const float4* spts = a.surfDS + (size_t)slot * a.surfCap;
-    int* knn = a.knnPos + (size_t)slot * a.qCap * 5;
     double* part = GRID ? a.partialsGrid : a.partials + (size_t)slot * 2 * a.teamMax * NACC;
     const int teamStride = GRID ? a.gridMax : a.teamMax;
     if (tid < 6) sh_pose[tid] = M.pose[tid];
+    if (tid == 32) sh_gd[0] = *gc.desc;
+    if (tid == 64) sh_gd[1] = *gs.desc;
+    // the accumulator entry this lane owns: 0..20 = upper triangle (ei <= ej), 21..26 = (ei, 6) = A^T b, 27 = row count
+    int ei = 0, ej = 6;
+    if (lane < 21) { int rr = 0, qx = lane; while (qx >= 6 - rr) { qx -= 6 - rr; rr++; } ei = rr; ej = rr + qx; }
+    else if (lane < 27) ei = lane - 21;
     __syncthreads();
 
+    KnnMaps maps; maps.gd = sh_gd; maps.cell_start[0] = gc.cell_start; maps.cell_start[1] = gs.cell_start; maps.pts[0] = gc.sorted; maps.pts[1] = gs.sorted;
+    // points per warp chunk: 32 when the team has fewer warps than chunks (batched calls); when a whole GPU works
+    // on one frame there are more warps than that, so chunks shrink until every warp has a few points to search
+    int CS = 32;
+    while (CS > 1 && nQ <= (CS / 2) * C * WPB) CS >>= 1;
     unsigned flags = 0; int isDegenerate = 0; int iters = 0;
-#ifdef FBPR_LM_PROFILE
-    long long pf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; long long pc = 0;
-    long long kq[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-#define PF_START() pc = clock64()
-#define PF_MARK(i) { long long now_ = clock64(); pf[i] += now_ - pc; pc = now_; }
-#else
-#define PF_START()
-#define PF_MARK(i)
-#endif
     for (int iter = 0; iter < FBPR_MAX_ITERS; iter++) {
-        PF_START();
         // --- pose -> rigid transform + the six sines/cosines LMOptimization needs (:1259-1264)
         if (tid < 6) {
             float ang = sh_pose[tid % 3];            // 0 roll, 1 pitch, 2 yaw
@@ -266,127 +275,111 @@ __global__ void __launch_bounds__(LM_TPB, 1) lm_kernel(LmArgs a) {
             sh_T[8] = -D;     sh_T[9] = Cc * F;         sh_T[10] = Cc * E;         sh_T[11] = sh_pose[5];
         }
         __syncthreads();
-        float T[12];
-        #pragma unroll
-        for (int k = 0; k < 12; k++) T[k] = sh_T[k];
         const bool cap = iter == a.debug_iter;
-        PF_MARK(0);
 
-        // --- phase A: one warp per query, exact 5-NN inside the 1 m ball on the grid index
-        const int nW = C * WPB;
-#ifdef FBPR_KNN_PROFILE
-        long long kqt = clock64();
-#endif
-        for (int q = rank * WPB + warp; q < nQ; q += nW) {
+        // --- association: one thread per feature point
+        double acc = 0.0;
+        // chunks of CS consecutive points are dealt round-robin over the team's CTAs, so the (more expensive)
+        // corner chunks at the front of the index range spread evenly instead of loading one CTA
+        for (int chunk = warp * C + rank; chunk * CS < nQ; chunk += WPB * C) {
+            const int q = chunk * CS + lane;
+            bool ok = false;
+            // corners occupy [0, nC), surface points follow; each lane searches the map of its own kind
+            const bool inRange = lane < CS && q < nQ;
             const bool isCorner = q < nC;
             const int li = isCorner ? q : q - nC;
-            const float4 pOri = isCorner ? cpts[li] : spts[li];
-            float x0, y0, z0;
-            transform_point(T, pOri, x0, y0, z0);
-            WarpKnn5 r;
-            bool ok;
-#ifdef FBPR_KNN_PROFILE
-            { long long n_ = clock64(); pf[0] += 0; kq[6] += n_ - kqt; kqt = n_; }
-            if (isCorner) ok = gdc.n >= 5 && warp_knn5(gdc, gc.cell_start, gc.cell_cursor, gc.sorted, x0, y0, z0, r, kq);
-            else          ok = gds.n >= 5 && warp_knn5(gds, gs.cell_start, gs.cell_cursor, gs.sorted, x0, y0, z0, r, kq);
-            kqt = clock64(); kq[7] += 1;
-#else
-            if (isCorner) ok = gdc.n >= 5 && warp_knn5(gdc, gc.cell_start, gc.cell_cursor, gc.sorted, x0, y0, z0, r);
-            else          ok = gds.n >= 5 && warp_knn5(gds, gs.cell_start, gs.cell_cursor, gs.sorted, x0, y0, z0, r);
-#endif
-            if (lane < 5) {
-                int v = r.pos[0];
-                if (lane == 1) v = r.pos[1]; else if (lane == 2) v = r.pos[2]; else if (lane == 3) v = r.pos[3]; else if (lane == 4) v = r.pos[4];
-                knn[(size_t)q * 5 + lane] = ok ? v : -1;
+            float4 pOri = make_float4(0, 0, 0, 0);
+            float x0 = 0.f, y0 = 0.f, z0 = 0.f;
+            if (inRange) { pOri = isCorner ? cpts[li] : spts[li]; transform_point(sh_T, pOri, x0, y0, z0); }
+            // search radius: exact bound from this point's previous search (old 5th-NN distance + how far it moved);
+            // on the first iteration the configured cover of the initial-guess error
+            const int kind = isCorner ? 0 : 1;
+            const bool active = inRange && sh_gd[kind].n >= 5;
+            float4* hist = a.qhist + (size_t)slot * a.qCap + q;
+            int rad0 = 1;
+            if (active) {
+                if (iter == 0) rad0 = max(1, (int)ceilf(a.firstRadius / (sh_gd[kind].h * 0.9995f)));
+                else {
+                    const float4 hp = *hist;
+                    const float mx = x0 - hp.x, my = y0 - hp.y, mz = z0 - hp.z;
+                    rad0 = knn5_radius_from_history(sh_gd[kind], hp.w, sqrtf(mx * mx + my * my + mz * mz));
+                }
+            }
+            ThreadKnn5 r;
+            ok = warp_knn5(maps, kind, x0, y0, z0, rad0, active, r);
+            if (active) *hist = make_float4(x0, y0, z0, knn_d5(r));
+            if (inRange) {
+                const GridDesc& gd = sh_gd[isCorner ? 0 : 1];
                 if (cap) {
-                    unsigned long long kk = r.key[0];
-                    if (lane == 1) kk = r.key[1]; else if (lane == 2) kk = r.key[2]; else if (lane == 3) kk = r.key[3]; else if (lane == 4) kk = r.key[4];
-                    const bool have = (isCorner ? gdc.n : gds.n) >= 5;
-                    size_t o = isCorner ? (size_t)slot * a.cornerCap + li : (size_t)slot * a.surfCap + li;
+                    const size_t o = isCorner ? (size_t)slot * a.cornerCap + li : (size_t)slot * a.surfCap + li;
                     int* kd = isCorner ? a.knnC : a.knnS; float* dd = isCorner ? a.d2C : a.d2S;
-                    kd[5 * o + lane] = ok ? (int)(unsigned)(kk & 0xffffffffu) : -1;
-                    dd[5 * o + lane] = have ? __uint_as_float((unsigned)(kk >> 32)) : 3.0e38f;
-                }
-            }
-        }
-        PF_MARK(1);
-        __syncthreads();                             // this CTA's phase-B threads consume what its own warps produced
-        PF_MARK(2);
-
-        // --- phase B: one thread per query: line / plane fit, coefficient, Jacobian row, f64 accumulation
-        const float srz = sh_trig[0], srx = sh_trig[1], sry = sh_trig[2], crz = sh_trig[3], crx = sh_trig[4], cry = sh_trig[5];
-        double acc[NACC];
-        #pragma unroll
-        for (int k = 0; k < NACC; k++) acc[k] = 0.0;
-        for (int j = tid; ; j += LM_TPB) {
-            const int q = rank * WPB + (j % WPB) + (j / WPB) * nW;      // the j-th query this CTA's warps handled
-            if (q >= nQ) break;
-            int pos[5];
-            #pragma unroll
-            for (int k = 0; k < 5; k++) pos[k] = knn[(size_t)q * 5 + k];
-            const bool isCorner = q < nC;
-            const int li = isCorner ? q : q - nC;
-            float4 coeff = make_float4(0, 0, 0, 0);
-            bool ok = pos[4] >= 0;
-            const float4 pOri = isCorner ? cpts[li] : spts[li];
-            if (ok) {
-                float x0, y0, z0;
-                transform_point(T, pOri, x0, y0, z0);
-                ok = isCorner ? corner_fit(gc.sorted, pos, x0, y0, z0, coeff) : surf_fit(gs.sorted, pos, x0, y0, z0, coeff);
-            }
-            if (cap) {
-                if (isCorner) { size_t o = (size_t)slot * a.cornerCap + li; a.coeffC[o] = coeff; a.flagC[o] = ok ? 1 : 0; }
-                else          { size_t o = (size_t)slot * a.surfCap + li;   a.coeffS[o] = coeff; a.flagS[o] = ok ? 1 : 0; }
-            }
-            if (ok) {
-                // Jacobian row, lidar -> "camera" axis permutation (mapOptmization.h:1286-1332)
-                const float ox = pOri.y, oy = pOri.z, oz = pOri.x;
-                const float kx = coeff.y, ky = coeff.z, kz = coeff.x;
-                float arx = (crx * sry * srz * ox + crx * crz * sry * oy - srx * sry * oz) * kx
-                          + (-srx * srz * ox - crz * srx * oy - crx * oz) * ky
-                          + (crx * cry * srz * ox + crx * cry * crz * oy - cry * srx * oz) * kz;
-                float ary = ((cry * srx * srz - crz * sry) * ox
-                          + (sry * srz + cry * crz * srx) * oy + crx * cry * oz) * kx
-                          + ((-cry * crz - srx * sry * srz) * ox
-                          + (cry * srz - crz * srx * sry) * oy - crx * sry * oz) * kz;
-                float arz = ((crz * srx * sry - cry * srz) * ox + (-cry * crz - srx * sry * srz) * oy) * kx
-                          + (crx * crz * ox - crx * srz * oy) * ky
-                          + ((sry * srz + cry * crz * srx) * ox + (crz * sry - cry * srx * srz) * oy) * kz;
-                const double row[6] = { (double)arz, (double)arx, (double)ary, (double)kz, (double)kx, (double)ky };
-                const double b = (double)(-coeff.w);
-                int qq = 0;
-                #pragma unroll
-                for (int rr = 0; rr < 6; rr++) {
                     #pragma unroll
-                    for (int cc = rr; cc < 6; cc++) acc[qq++] += row[rr] * row[cc];
+                    for (int k = 0; k < 5; k++) {
+                        kd[5 * o + k] = ok ? (int)(unsigned)(r.key[k] & 0xffffffffu) : -1;
+                        dd[5 * o + k] = (gd.n >= 5 && r.key[k] != ~0ull) ? __uint_as_float((unsigned)(r.key[k] >> 32)) : 3.0e38f;
+                    }
                 }
-                #pragma unroll
-                for (int rr = 0; rr < 6; rr++) acc[21 + rr] += row[rr] * b;
-                acc[27] += 1.0;
+                float4 coeff = make_float4(0, 0, 0, 0);
+                if (ok) {
+                    // the five neighbours' coordinates, by original map index (mapOptmization.h:1028-1036, :1157-1163)
+                    const float4* mo = isCorner ? gc.pts : gs.pts;
+                    float4 nb[5];
+                    #pragma unroll
+                    for (int k = 0; k < 5; k++) nb[k] = __ldg(mo + knn_index(r, k));
+                    ok = isCorner ? corner_fit(nb, x0, y0, z0, coeff) : surf_fit(nb, x0, y0, z0, coeff);
+                }
+                if (cap) {
+                    if (isCorner) { size_t o = (size_t)slot * a.cornerCap + li; a.coeffC[o] = coeff; a.flagC[o] = ok ? 1 : 0; }
+                    else          { size_t o = (size_t)slot * a.surfCap + li;   a.coeffS[o] = coeff; a.flagS[o] = ok ? 1 : 0; }
+                }
+                if (ok) {
+                    // Jacobian row, lidar -> "camera" axis permutation (mapOptmization.h:1286-1332)
+                    const float srz = sh_trig[0], srx = sh_trig[1], sry = sh_trig[2], crz = sh_trig[3], crx = sh_trig[4], cry = sh_trig[5];
+                    const float ox = pOri.y, oy = pOri.z, oz = pOri.x;
+                    const float kx = coeff.y, ky = coeff.z, kz = coeff.x;
+                    float arx = (crx * sry * srz * ox + crx * crz * sry * oy - srx * sry * oz) * kx
+                              + (-srx * srz * ox - crz * srx * oy - crx * oz) * ky
+                              + (crx * cry * srz * ox + crx * cry * crz * oy - cry * srx * oz) * kz;
+                    float ary = ((cry * srx * srz - crz * sry) * ox
+                              + (sry * srz + cry * crz * srx) * oy + crx * cry * oz) * kx
+                              + ((-cry * crz - srx * sry * srz) * ox
+                              + (cry * srz - crz * srx * sry) * oy - crx * sry * oz) * kz;
+                    float arz = ((crz * srx * sry - cry * srz) * ox + (-cry * crz - srx * sry * srz) * oy) * kx
+                              + (crx * crz * ox - crx * srz * oy) * ky
+                              + ((sry * srz + cry * crz * srx) * ox + (crz * sry - cry * srx * srz) * oy) * kz;
+                    double* row = s_rows[warp][lane];
+                    row[0] = (double)arz; row[1] = (double)arx; row[2] = (double)ary;
+                    row[3] = (double)kz;  row[4] = (double)kx;  row[5] = (double)ky;
+                    row[6] = (double)(-coeff.w);
+                }
             }
+            // fold the warp's staged rows into the lane-owned entries (rows in point order, f64)
+            unsigned m = __ballot_sync(0xffffffffu, ok);
+            __syncwarp();
+            if (lane == 27) acc += (double)__popc(m);
+            else if (lane < 27) {
+                while (m) {
+                    const int rr = __ffs(m) - 1; m &= m - 1;
+                    acc += s_rows[warp][rr][ei] * s_rows[warp][rr][ej];
+                }
+            }
+            __syncwarp();
         }
-        PF_MARK(3);
-        // --- CTA reduce (warp shuffles, then shared memory in fixed warp order) -> one partial per CTA in global memory
-        #pragma unroll
-        for (int k = 0; k < NACC; k++) {
-            double v = acc[k];
-            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) wred[warp][k] = v;
-        }
+        // --- CTA reduce (shared memory, fixed warp order) -> one partial per CTA in global memory
+        if (lane < NACC) wred[warp][lane] = acc;
         __syncthreads();
         const int buf = iter & 1;
         double* mypart = part + ((size_t)buf * teamStride + rank) * NACC;
         if (tid < NACC) {
             double v = 0.0;
+            #pragma unroll
             for (int w = 0; w < WPB; w++) v += wred[w][tid];
             mypart[tid] = v;
             __threadfence();
         }
-        PF_MARK(4);
         if (GRID) grid.sync(); else cluster.sync();
-        PF_MARK(5);
         // --- every CTA sums all partials in the same fixed order (bitwise identical everywhere), then solves redundantly
-        if (tid < NACC * 8) {
+        if (tid < NACC * 8) {                        // 224 threads <= LM_TPB in both shapes
             const int v = tid >> 3, s8 = tid & 7;
             double sum = 0.0;
             const double* base = part + (size_t)buf * teamStride * NACC + v;
@@ -412,7 +405,6 @@ __global__ void __launch_bounds__(LM_TPB, 1) lm_kernel(LmArgs a) {
             }
         }
         __syncthreads();
-        PF_MARK(6);
         if (tid == 0) {
             int stop = 0;
             iters = iter + 1;
@@ -435,19 +427,8 @@ __global__ void __launch_bounds__(LM_TPB, 1) lm_kernel(LmArgs a) {
             sh_stop = stop;
         }
         __syncthreads();
-        PF_MARK(7);
         if (sh_stop) break;
     }
-#ifdef FBPR_LM_PROFILE
-    if (slot == a.first && a.partialsGrid) {        // profile dump: [rank][thread][8] after the partial buffers
-        long long* out = reinterpret_cast<long long*>(a.partialsGrid + 2 * (size_t)a.gridMax * NACC);
-#ifdef FBPR_KNN_PROFILE
-        for (int k = 0; k < 8; k++) if (tid < 512) out[((size_t)rank * 512 + tid) * 8 + k] = kq[k];
-#else
-        for (int k = 0; k < 8; k++) if (tid < 512) out[((size_t)rank * 512 + tid) * 8 + k] = pf[k];
-#endif
-    }
-#endif
     if (rank == 0 && tid == 0) {
         float pose[6];
         for (int k = 0; k < 6; k++) pose[k] = sh_pose[k];
@@ -475,7 +456,7 @@ int fbpr_lm_grid_blocks(int device) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
     int per = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lm_kernel<true>, LM_TPB, 0) != cudaSuccess || per < 1) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lm_kernel<true>, LM_TPB_GRID, 0) != cudaSuccess || per < 1) return 0;
     return sms;
 }
 
@@ -488,18 +469,19 @@ int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blo
         configured = 1;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(LM_TPB);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e;
     if (count == 1 && grid_blocks > 0) {           // one frame: the whole GPU cooperates, grid-wide barrier per iteration
+        cfg.blockDim = dim3(LM_TPB_GRID);
         cfg.gridDim = dim3((unsigned)grid_blocks);
         attr[0].id = cudaLaunchAttributeCooperative;
         attr[0].val.cooperative = 1;
         e = cudaLaunchKernelEx(&cfg, lm_kernel<true>, args);
     } else {                                        // many frames: one cluster per frame, hardware cluster barrier per iteration
+        cfg.blockDim = dim3(LM_TPB_CLUSTER);
         cfg.gridDim = dim3((unsigned)(count * cluster_size));
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

@@ -180,36 +180,24 @@ __global__ void __launch_bounds__(TPB) grid_scatter(const GridSeg* segs) {
     }
 }
 
-// stand-alone query kernel behind fbpr_knn5 (parity tests of the index itself): one warp per query
-__global__ void __launch_bounds__(128) knn5_query(const GridSeg* segs, const float* __restrict__ q, int nq, int* idx, float* d2) {
+// stand-alone query kernel behind fbpr_knn5 (parity tests of the index itself): the same routine the LM kernel
+// uses; rad0 = first cube radius in cells (the LM kernel derives it per point from the previous iteration)
+__global__ void __launch_bounds__(128) knn5_query(const GridSeg* segs, const float* __restrict__ q, int nq, int rad0, int* idx, float* d2) {
+    __shared__ GridDesc gd[2];
     const GridSeg& s = segs[0];
-    const GridDesc g = *s.desc;
-    const int lane = threadIdx.x & 31;
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= nq) return;
-    WarpKnn5 r;
-    #pragma unroll
-    for (int k = 0; k < 5; k++) { r.key[k] = ~0ull; r.pos[k] = -1; }
-        bool ok = g.n >= 5 && warp_knn5(g, s.cell_start, s.cell_cursor, s.sorted, q[3 * i], q[3 * i + 1], q[3 * i + 2], r);
-    if (lane == 0)
-        for (int k = 0; k < 5; k++) {
-            idx[5 * i + k] = ok ? (int)(unsigned)(r.key[k] & 0xffffffffu) : -1;
-            d2[5 * i + k] = r.key[k] == ~0ull ? 3.0e38f : __uint_as_float((unsigned)(r.key[k] >> 32));
-        }
-}
-
-// same query through the thread-per-query path
-__global__ void __launch_bounds__(128) knn5_query_thread(const GridSeg* segs, const float* __restrict__ q, int nq, int* idx, float* d2) {
-    const GridSeg& s = segs[0];
-    const GridDesc g = *s.desc;
+    if (threadIdx.x == 0) { gd[0] = *s.desc; gd[1] = gd[0]; }
+    __syncthreads();
+    KnnMaps M; M.gd = gd; M.cell_start[0] = M.cell_start[1] = s.cell_start; M.pts[0] = M.pts[1] = s.sorted;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
+    const bool active = i < nq && gd[0].n >= 5;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) { qx = q[3 * i]; qy = q[3 * i + 1]; qz = q[3 * i + 2]; }
     ThreadKnn5 r;
+    const bool ok = warp_knn5(M, 0, qx, qy, qz, rad0, active, r);
+    if (i >= nq) return;
     #pragma unroll
-    for (int k = 0; k < 5; k++) { r.key[k] = ~0ull; r.pos[k] = -1; }
-    bool ok = g.n >= 5 && thread_knn5(g, s.cell_start, s.cell_cursor, s.sorted, q[3 * i], q[3 * i + 1], q[3 * i + 2], r);
     for (int k = 0; k < 5; k++) {
-        idx[5 * i + k] = ok ? (int)(unsigned)(r.key[k] & 0xffffffffu) : -1;
+        idx[5 * i + k] = ok ? knn_index(r, k) : -1;
         d2[5 * i + k] = r.key[k] == ~0ull ? 3.0e38f : __uint_as_float((unsigned)(r.key[k] >> 32));
     }
 }
@@ -233,9 +221,8 @@ void fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cel
     if (launches) *launches += 8;
 }
 
-void fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, int thread_mode, cudaStream_t st, long long* launches) {
+void fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, int rad0, cudaStream_t st, long long* launches) {
     if (nq <= 0) return;
-    if (thread_mode) knn5_query_thread<<<(nq + 127) / 128, 128, 0, st>>>(d_seg, d_q, nq, d_idx, d_d2);
-    else knn5_query<<<(nq + 3) / 4, 128, 0, st>>>(d_seg, d_q, nq, d_idx, d_d2);
+    knn5_query<<<(nq + 127) / 128, 128, 0, st>>>(d_seg, d_q, nq, rad0, d_idx, d_d2);
     if (launches) *launches += 1;
 }

@@ -6,246 +6,180 @@
 // the 1 m ball or "reject".  Distance is ((dx*dx)+(dy*dy))+(dz*dz) in f32 without FMA (the
 // library is built with -fmad=false) so ordering and the < 1.0 gate match the reference; ties
 // are broken by the original point index.
+//
+// ONE WARP per query, 32 queries per warp taken one after the other.  The map is stored
+// cell-contiguous (counting sort, mapgrid.cu) with x the fastest cell axis, so the (2R+1)^3 cells
+// around a query are (2R+1)^2 contiguous ranges of the sorted array ("rows"):
+//   - the lanes fetch the bounds of up to 32 rows at once and prefix-sum their lengths;
+//   - the concatenated candidates are walked 64 at a time: consecutive lanes read consecutive
+//     float4 points (coalesced), every load of a trip is issued before any is consumed, each lane
+//     keeps a private sorted top-5 of packed keys in registers (compare-exchange chain, no local
+//     memory), and five redux.sync rounds merge the 32 private lists;
+//   - the search radius R (in cells) of a query is chosen by the caller.  The LM kernel derives it
+//     from the previous iteration: the old 5 neighbours lie within sqrt(d5_old) + |p_new - p_old| of
+//     the new position, so a cube covering that radius contains the new exact 5-NN and ONE pass is
+//     enough.  If the covered ball does not yet certify the result (first iteration, R too small)
+//     the cube is doubled and only the cells it ADDS are scanned.
+// A query therefore costs two or three dependent memory round trips whatever its candidate count
+// (25 for a surface point in a dense map, ~1000 for a corner point next to several edges).
+// Ranking key = (d^2 bits as u32) << 32 | original index: the (d^2, index) total order of the oracle
+// (d^2 >= 0, so the f32 bit pattern is monotonic).
 #pragma once
 #include "internal.cuh"
 
-struct Knn5 {
-    float d[5];
-    int id[5];     // original map index
-    int pos[5];    // position in the cell-sorted array (to re-fetch coordinates)
+// the (up to) two map indices a warp's queries may refer to: kind 0 = corner map, kind 1 = surface map
+struct KnnMaps {
+    const GridDesc* gd;           // [2], usually in shared memory
+    const int* cell_start[2];     // [ncells + 1] exclusive prefix of the cell populations
+    const float4* pts[2];         // cell-sorted copies (w = original index bits)
 };
 
-__device__ __forceinline__ bool knn_better(float dd, int ii, float d, int i) { return dd < d || (dd == d && ii < i); }
-
-__device__ __forceinline__ void knn_offer(Knn5& r, float dd, int ii, int pp) {
-    if (!knn_better(dd, ii, r.d[4], r.id[4])) return;
-    // insertion keeping (d, id) ascending; fully unrolled so the set stays in registers
-    #pragma unroll
-    for (int k = 4; k >= 0; k--) {
-        if (k > 0 && knn_better(dd, ii, r.d[k - 1], r.id[k - 1])) { r.d[k] = r.d[k - 1]; r.id[k] = r.id[k - 1]; r.pos[k] = r.pos[k - 1]; }
-        else { r.d[k] = dd; r.id[k] = ii; r.pos[k] = pp; break; }
-    }
-}
-
-// Returns true when 5 neighbours with d^2 < 1.0 exist (then r is exact and sorted).
-// When false, r holds whatever was found inside the covered ball (exact for every entry < 1.0).
-__device__ inline bool grid_knn5(const GridDesc& g, const int* __restrict__ cell_start, const int* __restrict__ cell_end,
-                                 const float4* __restrict__ pts, float qx, float qy, float qz, Knn5& r) {
-    const int cx = (int)floorf((qx - g.ox) * g.inv_h);
-    const int cy = (int)floorf((qy - g.oy) * g.inv_h);
-    const int cz = (int)floorf((qz - g.oz) * g.inv_h);
-    int rad = 1;
-    while (true) {
-        #pragma unroll
-        for (int k = 0; k < 5; k++) { r.d[k] = 3.0e38f; r.id[k] = 0x7fffffff; r.pos[k] = -1; }
-        const int x0 = max(cx - rad, 0), x1 = min(cx + rad, g.dx - 1);
-        const int y0 = max(cy - rad, 0), y1 = min(cy + rad, g.dy - 1);
-        const int z0 = max(cz - rad, 0), z1 = min(cz + rad, g.dz - 1);
-        if (x0 <= x1) {
-            for (int z = z0; z <= z1; z++) {
-                for (int y = y0; y <= y1; y++) {
-                    const int row = (z * g.dy + y) * g.dx;
-                    const int a = cell_start[row + x0], b = cell_end[row + x1];   // x-adjacent cells are contiguous
-                    for (int p = a; p < b; p++) {
-                        const float4 m = pts[p];
-                        const float ddx = qx - m.x, ddy = qy - m.y, ddz = qz - m.z;
-                        float dd = ddx * ddx; dd += ddy * ddy; dd += ddz * ddz;
-                        knn_offer(r, dd, __float_as_int(m.w), p);
-                    }
-                }
-            }
-        }
-        // every point closer than rad*h (minus a rounding guard) has been seen
-        const float guard = (float)rad * g.h * 0.9995f;
-        if (r.d[4] < guard * guard) break;          // exact 5-NN found inside the covered ball
-        if (rad >= g.rmax) break;                   // the whole 1 m ball is covered
-        rad = min(rad * 2, g.rmax);
-    }
-    return r.d[4] < 1.0f;
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Warp-cooperative form of the same query: ONE WARP per query point.
-//   - lanes fetch the (start, end) bounds of up to 32 cell rows at once (x-adjacent cells are
-//     contiguous in the cell-sorted array, so a row of the search cube is one range);
-//   - the concatenated candidates of those rows are walked 32 at a time: consecutive lanes read
-//     consecutive float4 points (coalesced 512 B), compute d^2 and keep a private sorted top-5;
-//   - five rounds of warp-min over packed (d^2 bits, index) keys merge the 32 private lists.
-// Every global load of a batch is independent, so a query costs two or three memory round trips
-// instead of one per candidate.  Ranking key = (d^2 as ordered u32) << 32 | original index: the
-// (d^2, index) total order of the oracle.  Result is replicated in all lanes.
-struct WarpKnn5 {
-    unsigned long long key[5];   // ascending; 0xffff... = empty
-    int pos[5];                  // position in the cell-sorted array
+struct ThreadKnn5 {
+    unsigned long long key[5];   // ascending; 0xffff... = empty.  Only ever indexed with compile-time constants (registers).
 };
 
-__device__ __forceinline__ void lane_insert5(unsigned long long* k, int* ps, unsigned long long key, int pos) {
-    if (key >= k[4]) return;
-    #pragma unroll
-    for (int i = 4; i >= 0; i--) {
-        if (i > 0 && key < k[i - 1]) { k[i] = k[i - 1]; ps[i] = ps[i - 1]; }
-        else { k[i] = key; ps[i] = pos; break; }
-    }
+__device__ __forceinline__ void knn_cswap(unsigned long long& lo, unsigned long long& hi) {   // order a pair
+    const unsigned long long a = lo, b = hi;
+    const bool sw = b < a;
+    lo = sw ? b : a; hi = sw ? a : b;
 }
 
-__device__ inline bool warp_knn5(const GridDesc& g, const int* __restrict__ cell_start, const int* __restrict__ cell_end,
-                                 const float4* __restrict__ pts, float qx, float qy, float qz, WarpKnn5& out) {
+__device__ __forceinline__ void knn_offer(ThreadKnn5& r, const float4 m, float qx, float qy, float qz) {
+    const float ddx = qx - m.x, ddy = qy - m.y, ddz = qz - m.z;
+    float dd = ddx * ddx; dd += ddy * ddy; dd += ddz * ddz;
+    if (__float_as_uint(dd) > (unsigned)(r.key[4] >> 32)) return;          // cannot enter the top-5 (the common case)
+    const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)__float_as_int(m.w);
+    if (key >= r.key[4]) return;
+    r.key[4] = key;                                                         // replace the worst, then bubble it down
+    knn_cswap(r.key[3], r.key[4]); knn_cswap(r.key[2], r.key[3]); knn_cswap(r.key[1], r.key[2]); knn_cswap(r.key[0], r.key[1]);
+}
+
+__device__ __forceinline__ float knn_d5(const ThreadKnn5& r) {      // 5th-best squared distance (huge when fewer than 5 were found)
+    return r.key[4] == ~0ull ? 3.0e38f : __uint_as_float((unsigned)(r.key[4] >> 32));
+}
+__device__ __forceinline__ int knn_index(const ThreadKnn5& r, int k) { return (int)(unsigned)(r.key[k] & 0xffffffffu); }   // original map index
+
+// Merge the private sorted lists of the 32 lanes into the warp's top-5, replicated in every lane.  Keys are unique
+// (the low word is the map index), so in each of the five rounds exactly one lane owns the minimum and pops it.
+__device__ __forceinline__ void knn5_merge_warp(ThreadKnn5& p, ThreadKnn5& m) {
     const unsigned FULL = 0xffffffffu;
+    #pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const unsigned hi = (unsigned)(p.key[0] >> 32), lo = (unsigned)p.key[0];
+        const unsigned mhi = __reduce_min_sync(FULL, hi);
+        const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
+        m.key[k] = ((unsigned long long)mhi << 32) | mlo;
+        if (hi == mhi && lo == mlo && m.key[k] != ~0ull) { p.key[0] = p.key[1]; p.key[1] = p.key[2]; p.key[2] = p.key[3]; p.key[3] = p.key[4]; p.key[4] = ~0ull; }
+    }
+}
+
+// Stream the concatenation of 32 ranges (lane i owns [a, a + len)) through the lanes' private top-5 lists:
+// 64 candidates per trip, consecutive lanes on consecutive points, both loads of a trip issued before use.
+__device__ __forceinline__ void knn5_scan_ranges(ThreadKnn5& p, const float4* __restrict__ pts, int a, int len, float qx, float qy, float qz) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int incl = len;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    const int excl = incl - len;
+    for (int t0 = 0; t0 < total; t0 += 64) {
+        float4 m[2]; bool v[2];
+        #pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int t = t0 + u * 32 + lane;
+            int j = 0;                                  // the last lane whose exclusive offset is <= t owns candidate t
+            #pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const int e = __shfl_sync(FULL, excl, (j + s) & 31);
+                if (e <= t) j += s;
+            }
+            const int aj = __shfl_sync(FULL, a, j), ej = __shfl_sync(FULL, excl, j);
+            v[u] = t < total;
+            if (v[u]) m[u] = __ldg(pts + aj + (t - ej));
+        }
+        #pragma unroll
+        for (int u = 0; u < 2; u++) if (v[u]) knn_offer(p, m[u], qx, qy, qz);
+    }
+}
+
+// Exact 5-NN of ONE query by the whole warp (all lanes pass the same query).  rad0 = first cube radius in cells.
+// r (replicated) = exact sorted 5-NN among all map points within the covered ball; the caller rejects when
+// knn_d5(r) >= 1.0.  Exactness: every point closer than rad * h (minus a rounding guard) lies in the cube, so the
+// result is final once the 5th distance is inside that ball or the cube covers the whole 1 m ball (rad = rmax).
+__device__ __forceinline__ void warp_query_knn5(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ pts,
+                                                float qx, float qy, float qz, int rad0, ThreadKnn5& r) {
     const int lane = threadIdx.x & 31;
     const int cx = (int)floorf((qx - g.ox) * g.inv_h);
     const int cy = (int)floorf((qy - g.oy) * g.inv_h);
     const int cz = (int)floorf((qz - g.oz) * g.inv_h);
-    int rad = 1;
+    ThreadKnn5 p;
+    #pragma unroll
+    for (int i = 0; i < 5; i++) p.key[i] = ~0ull;
+    int prev = -1, rad = min(max(rad0, 1), g.rmax);          // prev = radius of the cube already scanned (-1: none)
     while (true) {
-        unsigned long long k[5]; int ps[5];
-        #pragma unroll
-        for (int i = 0; i < 5; i++) { k[i] = ~0ull; ps[i] = -1; }
         const int x0 = max(cx - rad, 0), x1 = min(cx + rad, g.dx - 1);
         const int y0 = max(cy - rad, 0), y1 = min(cy + rad, g.dy - 1);
         const int z0 = max(cz - rad, 0), z1 = min(cz + rad, g.dz - 1);
+        const int px0 = max(cx - prev, 0), px1 = min(cx + prev, g.dx - 1);   // x extent of the cube already scanned
+        const bool havePrev = prev >= 0 && px0 <= px1;
         const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
         const int nrows = (x0 <= x1 && ny > 0 && nz > 0) ? ny * nz : 0;
         for (int rbase = 0; rbase < nrows; rbase += 32) {
-            const int rr = rbase + lane;
-            int a = 0, len = 0;
-            if (rr < nrows) {
-                const int zz = z0 + rr / ny, yy = y0 + rr % ny;
+            const int i = rbase + lane;
+            int a0 = 0, l0 = 0, a1 = 0, l1 = 0;
+            bool anyRight = false;
+            if (i < nrows) {
+                const int zz = z0 + i / ny, yy = y0 + i % ny;
                 const int row = (zz * g.dy + yy) * g.dx;
-                a = cell_start[row + x0];
-                len = cell_end[row + x1] - a;
+                const bool inner = havePrev && abs(zz - cz) <= prev && abs(yy - cy) <= prev;
+                // left part [x0, lx1] and right part [rx0, x1]; a row outside the old footprint is all "left"
+                const int lx1 = inner ? px0 - 1 : x1;
+                const int rx0 = inner ? px1 + 1 : x1 + 1;
+                if (x0 <= lx1) { a0 = __ldg(cell_start + row + x0); l0 = __ldg(cell_start + row + lx1 + 1) - a0; }
+                if (rx0 <= x1) { a1 = __ldg(cell_start + row + rx0); l1 = __ldg(cell_start + row + x1 + 1) - a1; anyRight = true; }
             }
-            int incl = len;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-            const int total = __shfl_sync(FULL, incl, 31);
-            const int excl = incl - len;
-            // four batches of 32 candidates per trip: all 128 loads are in flight before any is consumed
-            for (int t0 = 0; t0 < total; t0 += 128) {
-                float4 m[4]; int p[4]; bool v[4];
-                #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int t = t0 + u * 32 + lane;
-                    int j = 0;
-                    #pragma unroll
-                    for (int s = 16; s >= 1; s >>= 1) {
-                        const int cand = j + s;
-                        const int e = __shfl_sync(FULL, excl, cand & 31);
-                        if (e <= t) j = cand;
-                    }
-                    const int aj = __shfl_sync(FULL, a, j), ej = __shfl_sync(FULL, excl, j);
-                    v[u] = t < total;
-                    p[u] = aj + (t - ej);
-                    if (v[u]) m[u] = pts[p[u]];
-                }
-                #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (v[u]) {
-                        const float ddx = qx - m[u].x, ddy = qy - m[u].y, ddz = qz - m[u].z;
-                        float dd = ddx * ddx; dd += ddy * ddy; dd += ddz * ddz;
-                        lane_insert5(k, ps, ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)__float_as_int(m[u].w), p[u]);
-                    }
-                }
-            }
+            knn5_scan_ranges(p, pts, a0, l0, qx, qy, qz);
+            if (__any_sync(0xffffffffu, anyRight)) knn5_scan_ranges(p, pts, a1, l1, qx, qy, qz);
         }
-        // merge the 32 private lists: five rounds of (hardware warp-min on d^2 bits, then on the index among the ties)
-        #pragma unroll
-        for (int r = 0; r < 5; r++) {
-            const unsigned hi = (unsigned)(k[0] >> 32), lo = (unsigned)k[0];
-            const unsigned mhi = __reduce_min_sync(FULL, hi);
-            const unsigned mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
-            const unsigned who = __ballot_sync(FULL, hi == mhi && lo == mlo);
-            const int src = __ffs(who) - 1;
-            out.key[r] = ((unsigned long long)mhi << 32) | mlo;
-            out.pos[r] = __shfl_sync(FULL, ps[0], src);
-            if (lane == src) {
-                k[0] = k[1]; k[1] = k[2]; k[2] = k[3]; k[3] = k[4]; k[4] = ~0ull;
-                ps[0] = ps[1]; ps[1] = ps[2]; ps[2] = ps[3]; ps[3] = ps[4]; ps[4] = -1;
-            }
-        }
-        const float d5 = __uint_as_float((unsigned)(out.key[4] >> 32));
-        const bool have5 = out.key[4] != ~0ull;
+        knn5_merge_warp(p, r);
         const float guard = (float)rad * g.h * 0.9995f;
-        if (have5 && d5 < guard * guard) break;      // exact 5-NN found inside the covered ball
-        if (rad >= g.rmax) break;                    // the whole 1 m ball is covered
-        rad = min(rad * 2, g.rmax);
+        if (knn_d5(r) < guard * guard || rad >= g.rmax) break;
+        #pragma unroll
+        for (int i = 0; i < 5; i++) p.key[i] = lane == 0 ? r.key[i] : ~0ull;   // keep what was found, scan only the added cells
+        prev = rad; rad = min(rad * 2, g.rmax);
     }
-    return out.key[4] != ~0ull && __uint_as_float((unsigned)(out.key[4] >> 32)) < 1.0f;
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// Thread-per-query form with memory-level parallelism: ONE THREAD per query point.
-// The bounds of up to 9 cell rows (18 loads) are issued together, then the concatenated candidates
-// are fetched eight at a time (8 independent 16-byte loads in flight) before any is consumed, so a
-// query costs ~2 + T/8 memory round trips instead of one per candidate, and a warp keeps 32 queries
-// in flight.  Used where the map is sparse around the query (planar points); dense linear features
-// go through warp_knn5.  Every array index below is a compile-time constant after unrolling.
-struct ThreadKnn5 {
-    unsigned long long key[5];
-    int pos[5];
-};
-
-__device__ inline bool thread_knn5(const GridDesc& g, const int* __restrict__ cell_start, const int* __restrict__ cell_end,
-                                   const float4* __restrict__ pts, float qx, float qy, float qz, ThreadKnn5& out) {
-    constexpr int RC = 9;        // rows per chunk
-    constexpr int GB = 8;        // candidates per batch
-    const int cx = (int)floorf((qx - g.ox) * g.inv_h);
-    const int cy = (int)floorf((qy - g.oy) * g.inv_h);
-    const int cz = (int)floorf((qz - g.oz) * g.inv_h);
-    int rad = 1;
-    while (true) {
-        #pragma unroll
-        for (int i = 0; i < 5; i++) { out.key[i] = ~0ull; out.pos[i] = -1; }
-        const int x0 = max(cx - rad, 0), x1 = min(cx + rad, g.dx - 1);
-        const int y0 = max(cy - rad, 0), y1 = min(cy + rad, g.dy - 1);
-        const int z0 = max(cz - rad, 0), z1 = min(cz + rad, g.dz - 1);
-        const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
-        const int nrows = (x0 <= x1 && ny > 0 && nz > 0) ? ny * nz : 0;
-        for (int rbase = 0; rbase < nrows; rbase += RC) {
-            int a[RC], b[RC];
-            int yy = y0 + rbase % ny, zz = z0 + rbase / ny;
+// Exact 5-NN of the 32 queries of a warp, one query per lane (`active` = this lane has a query, `kind` = which of
+// the two maps it searches, `rad0` = its first cube radius in cells); must be called by all 32 lanes.
+// Returns true when 5 neighbours with d^2 < 1.0 exist (then r is exact and sorted ascending by (d^2, index)).
+// When false, r holds whatever was found inside the covered ball (exact for every entry < 1.0).
+__device__ __forceinline__ bool warp_knn5(const KnnMaps& M, int kind, float qx, float qy, float qz, int rad0, bool active, ThreadKnn5& r) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    #pragma unroll
+    for (int i = 0; i < 5; i++) r.key[i] = ~0ull;
+    unsigned todo = __ballot_sync(FULL, active);
+    while (todo) {
+        const int src = __ffs(todo) - 1; todo &= todo - 1;
+        const float bx = __shfl_sync(FULL, qx, src), by = __shfl_sync(FULL, qy, src), bz = __shfl_sync(FULL, qz, src);
+        const int bk = __shfl_sync(FULL, kind, src), br = __shfl_sync(FULL, rad0, src);
+        ThreadKnn5 m;
+        warp_query_knn5(M.gd[bk], bk ? M.cell_start[1] : M.cell_start[0], bk ? M.pts[1] : M.pts[0], bx, by, bz, br, m);
+        if (lane == src) {
             #pragma unroll
-            for (int r = 0; r < RC; r++) {
-                a[r] = 0; b[r] = 0;
-                if (rbase + r < nrows) {
-                    const int row = (zz * g.dy + yy) * g.dx;
-                    a[r] = cell_start[row + x0];
-                    b[r] = cell_end[row + x1];
-                }
-                if (++yy > y1) { yy = y0; zz++; }
-            }
-            int s[RC];                                // exclusive prefix of the row lengths
-            int T = 0;
-            #pragma unroll
-            for (int r = 0; r < RC; r++) { s[r] = T; T += b[r] - a[r]; }
-            for (int t0 = 0; t0 < T; t0 += GB) {
-                float4 m[GB]; int p[GB];
-                #pragma unroll
-                for (int u = 0; u < GB; u++) {
-                    const int t = t0 + u;
-                    int ar = a[0], sr = 0;
-                    #pragma unroll
-                    for (int r = 1; r < RC; r++) if (t >= s[r]) { ar = a[r]; sr = s[r]; }
-                    p[u] = ar + (t - sr);
-                    if (t < T) m[u] = pts[p[u]];
-                }
-                #pragma unroll
-                for (int u = 0; u < GB; u++) {
-                    if (t0 + u < T) {
-                        const float ddx = qx - m[u].x, ddy = qy - m[u].y, ddz = qz - m[u].z;
-                        float dd = ddx * ddx; dd += ddy * ddy; dd += ddz * ddz;
-                        lane_insert5(out.key, out.pos, ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)__float_as_int(m[u].w), p[u]);
-                    }
-                }
-            }
+            for (int i = 0; i < 5; i++) r.key[i] = m.key[i];
         }
-        const float d5 = __uint_as_float((unsigned)(out.key[4] >> 32));
-        const bool have5 = out.key[4] != ~0ull;
-        const float guard = (float)rad * g.h * 0.9995f;
-        if (have5 && d5 < guard * guard) break;
-        if (rad >= g.rmax) break;
-        rad = min(rad * 2, g.rmax);
     }
-    return out.key[4] != ~0ull && __uint_as_float((unsigned)(out.key[4] >> 32)) < 1.0f;
+    return active && knn_d5(r) < 1.0f;
+}
+
+// First cube radius (cells) that certainly contains the exact 5-NN of a point that moved by `moved` since a search
+// that found the 5th neighbour at squared distance d5_old: the old neighbours are within sqrt(d5_old) + moved.
+__device__ __forceinline__ int knn5_radius_from_history(const GridDesc& g, float d5_old, float moved) {
+    if (!(d5_old < 1.0e30f)) return g.rmax;                  // fewer than 5 found last time: cover the whole 1 m ball
+    const float rho = (sqrtf(d5_old) + moved) * 1.001f + 1.0e-5f;
+    const float cells = rho / (g.h * 0.9995f);
+    return cells >= (float)g.rmax ? g.rmax : max(1, (int)ceilf(cells));
 }

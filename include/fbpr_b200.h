@@ -74,6 +74,8 @@ typedef struct fbpr_params {
     int32_t grid_cells_surf;                 /*   edge is doubled until the map's bounding box fits the budget        */
     int32_t lm_cluster_size;                 /* CTAs cooperating on one frame's LM loop in batched calls: 1,2,4,8,16 (0 = 8) */
     int32_t lm_single_frame_mode;            /* count == 1 calls: 0 = whole GPU cooperates (grid barrier), 1 = one cluster   */
+    float   knn_first_radius;                /* metres the FIRST LM iteration's neighbour search must cover around each point (0 = 0.5):
+                                                about the expected error of the initial guess; later iterations derive it exactly */
 } fbpr_params;
 
 /* one frame's outcome: transformTobeMapped after transformUpdate, iterations executed, FBPR_FLAG_* */
@@ -225,6 +227,9 @@ FBPR_API int fbpr_voxel_grid(fbpr_handle* h, const float* xyzi, int n, float lea
    inside the 1 m ball, entries whose 5th distance is >= 1 m^2 are marked by idx = -1. */
 FBPR_API int fbpr_knn5(fbpr_handle* h, const float* map_xyzi, int n_map, float cell, const float* q_xyz,
                        int nq, int32_t* idx, float* d2, int mem);
+/* first search-cube radius (grid cells) fbpr_knn5 starts from (default 1).  Results do not depend on it; the LM
+   kernel derives the radius per point from the previous iteration, and the knob lets tests pin several starts. */
+FBPR_API int fbpr_knn5_first_radius(fbpr_handle* h, int cells);
 
 #ifdef __cplusplus
 }

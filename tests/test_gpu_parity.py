@@ -51,8 +51,9 @@ def test_voxel_grid_overflow_path(fb):
 
 
 # ------------------------------------------------------------------ exact 5-NN on the grid index
+@pytest.mark.parametrize("first_radius", [1, 2, 5])
 @pytest.mark.parametrize("cell", [0.25, 0.5, 1.0])
-def test_knn5_index_sets_bit_exact(fb, cell):
+def test_knn5_index_sets_bit_exact(fb, cell, first_radius):
     fr = synth.make_frame(1, 5)
     m = fr["map_surf"]
     rng = np.random.default_rng(3)
@@ -60,7 +61,7 @@ def test_knn5_index_sets_bit_exact(fb, cell):
     q[:500] += rng.uniform(-3, 3, (500, 3)).astype(np.float32)    # some far from any surface
     q[500:700] = m[1000:1200, :3]                                 # exactly on map points
     r = _reg(fb, fr["params"])
-    idx, d2 = r.knn5(m, q, cell=cell)
+    idx, d2 = r.knn5(m, q, cell=cell, first_radius=first_radius)
     ridx, rd2 = oracle.knn5(m, q)
     accept = rd2[:, 4] < 1.0
     assert accept.sum() > 15000
@@ -69,16 +70,17 @@ def test_knn5_index_sets_bit_exact(fb, cell):
     assert np.all(idx[~accept] == -1)
 
 
-def test_knn5_ties_and_tiny_maps(fb):
+@pytest.mark.parametrize("first_radius", [1, 3])
+def test_knn5_ties_and_tiny_maps(fb, first_radius):
     rng = np.random.default_rng(4)
     m = np.concatenate([rng.uniform(-2, 2, (3000, 3)), np.zeros((3000, 1))], 1).astype(np.float32)
     m[1500:1700] = m[100:300]                                     # duplicates -> distance ties broken by index
     q = m[100:300, :3].copy()
     r = _reg(fb, synth.params_for(1))
-    idx, d2 = r.knn5(m, q, cell=0.25)
+    idx, d2 = r.knn5(m, q, cell=0.25, first_radius=first_radius)
     ridx, rd2 = oracle.knn5(m, q, brute=True)
     assert np.array_equal(idx, ridx) and np.array_equal(d2, rd2)
-    idx, _ = r.knn5(m[:4], q[:10], cell=0.25)                     # fewer than 5 map points: reject
+    idx, _ = r.knn5(m[:4], q[:10], cell=0.25, first_radius=first_radius)                     # fewer than 5 map points: reject
     assert np.all(idx == -1)
 
 
