@@ -60,7 +60,7 @@ struct fbpr_handle {
     int *picked = nullptr, *label = nullptr, *ringCorner = nullptr, *cornerStage = nullptr, *ringSurf = nullptr, *ringSurfDS = nullptr, *cornerIndex = nullptr;
     float4 *mapCorner = nullptr, *mapSurf = nullptr;
     float* poseTrace = nullptr;
-    float4* qhist = nullptr; double* partials = nullptr; double* partialsGrid = nullptr; int lmGridBlocks = 0; bool lmWholeGpu = true;
+    float4* qanchor = nullptr; int* qcache = nullptr; double* partials = nullptr; double* partialsGrid = nullptr; int lmGridBlocks = 0; bool lmWholeGpu = true;
     // descriptors
     VoxSeg* d_scanSegs = nullptr;      // [2F]  downsampleCurrentScan
     GridSeg* d_gridSegs = nullptr;     // [2F]  map index
@@ -177,7 +177,8 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     ALLOC(h->corner, (size_t)F * h->cornerCap); ALLOC(h->cornerDS, (size_t)F * h->cornerCap); ALLOC(h->cornerIndex, (size_t)F * h->cornerCap);
     ALLOC(h->mapCorner, (size_t)F * h->mapCornerCap); ALLOC(h->mapSurf, (size_t)F * h->mapSurfCap);
     ALLOC(h->poseTrace, (size_t)F * FBPR_MAX_ITERS * 6);
-    ALLOC(h->qhist, (size_t)F * (h->cornerCap + P));
+    ALLOC(h->qanchor, (size_t)F * (h->cornerCap + P));
+    ALLOC(h->qcache, (size_t)F * (h->cornerCap + P) * 16);
     ALLOC(h->partials, (size_t)F * 2 * 16 * 28);
     ALLOC(h->partialsGrid, (size_t)2 * 1024 * 28);
     h->lmGridBlocks = fbpr_lm_grid_blocks(device);
@@ -456,7 +457,7 @@ static LmArgs lm_args(fbpr_handle* h, int first) {
     LmArgs a = {};
     a.meta = h->meta; a.cornerDS = h->cornerDS; a.cornerCap = h->cornerCap; a.surfDS = h->surfDS; a.surfCap = h->P;
     a.gsegs = h->d_gridSegs; a.first = first;
-    a.qhist = h->qhist; a.qCap = h->cornerCap + h->P; a.firstRadius = h->p.knn_first_radius > 0 ? h->p.knn_first_radius : 0.5f;
+    a.qanchor = h->qanchor; a.qcache = h->qcache; a.qCap = h->cornerCap + h->P; a.firstRadius = h->p.knn_first_radius > 0 ? h->p.knn_first_radius : 0.5f;
     a.partials = h->partials; a.teamMax = 16; a.partialsGrid = h->partialsGrid; a.gridMax = 1024;
     a.edgeMin = h->p.edgeFeatureMinValidNum; a.surfMin = h->p.surfFeatureMinValidNum;
     a.z_tol = h->p.z_tollerance; a.rot_tol = h->p.rotation_tollerance;

@@ -123,7 +123,7 @@ struct LmArgs {
     const float4* cornerDS; int cornerCap;
     const float4* surfDS; int surfCap;
     const GridSeg* gsegs;         // [2*slot + kind]
-    float4* qhist; int qCap;      // [slot][qCap] per feature point: map-frame position and 5th-NN d^2 of its last search
+    float4* qanchor; int* qcache; int qCap;   // [slot][qCap] per feature point: position + bound of its last full search, [..][16] cached map indices
     float firstRadius;            // metres the first iteration's search cube must cover
     double* partials; int teamMax;     // [slot][2][teamMax][28] per-CTA partial sums, double-buffered by iteration parity
     double* partialsGrid; int gridMax; // [2][gridMax][28] same for the whole-GPU single-frame variant

@@ -291,23 +291,48 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             float4 pOri = make_float4(0, 0, 0, 0);
             float x0 = 0.f, y0 = 0.f, z0 = 0.f;
             if (inRange) { pOri = isCorner ? cpts[li] : spts[li]; transform_point(sh_T, pOri, x0, y0, z0); }
-            // search radius: exact bound from this point's previous search (old 5th-NN distance + how far it moved);
-            // on the first iteration the configured cover of the initial-guess error
             const int kind = isCorner ? 0 : 1;
             const bool active = inRange && sh_gd[kind].n >= 5;
-            float4* hist = a.qhist + (size_t)slot * a.qCap + q;
+            float4* anchor = a.qanchor + (size_t)slot * a.qCap + q;
+            int* cache = a.qcache + ((size_t)slot * a.qCap + q) * FBPR_KNN_CACHE;
+            const float4* mo = isCorner ? gc.pts : gs.pts;   // the map in original order (XYZI)
+            ThreadKnn5 r;
+            #pragma unroll
+            for (int k = 0; k < 5; k++) r.key[k] = ~0ull;
+            // (1) candidate cache of this point's last full search: re-rank the cached map points (one thread); the
+            //     result is the exact 5-NN when every uncached map point is provably farther (mapgrid.cuh)
+            bool need = active;
             int rad0 = 1;
             if (active) {
                 if (iter == 0) rad0 = max(1, (int)ceilf(a.firstRadius / (sh_gd[kind].h * 0.9995f)));
                 else {
-                    const float4 hp = *hist;
-                    const float mx = x0 - hp.x, my = y0 - hp.y, mz = z0 - hp.z;
-                    rad0 = knn5_radius_from_history(sh_gd[kind], hp.w, sqrtf(mx * mx + my * my + mz * mz));
+                    const float4 an = *anchor;
+                    if (an.w > 0.f) {
+                        const int4* c4 = reinterpret_cast<const int4*>(cache);
+                        #pragma unroll
+                        for (int half = 0; half < FBPR_KNN_CACHE / 8; half++) {     // 8 independent gathers in flight
+                            const int4 va = c4[2 * half], vb = c4[2 * half + 1];
+                            const int ci[8] = { va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w };
+                            float4 cm[8];
+                            #pragma unroll
+                            for (int k = 0; k < 8; k++) if (ci[k] >= 0) cm[k] = __ldg(mo + ci[k]);
+                            #pragma unroll
+                            for (int k = 0; k < 8; k++) if (ci[k] >= 0) knn_offer_idx(r, cm[k].x, cm[k].y, cm[k].z, ci[k], x0, y0, z0);
+                        }
+                        const float mx = x0 - an.x, my = y0 - an.y, mz = z0 - an.z;
+                        const float moved = sqrtf(mx * mx + my * my + mz * mz);
+                        const float lim = an.w * 0.9999f - moved * 1.0001f - 1.0e-5f;     // every uncached point is farther than this
+                        const float lim2 = lim > 0.f ? lim * lim * 0.9999f : 0.f;
+                        need = !(knn_d5(r) < lim2 || lim2 >= 1.0f);                       // 2nd case: the cache decides the whole 1 m ball
+                        rad0 = knn5_radius_from_bound(sh_gd[kind], knn_d5(r));
+                    } else {
+                        rad0 = sh_gd[kind].rmax;
+                    }
                 }
             }
-            ThreadKnn5 r;
-            ok = warp_knn5(maps, kind, x0, y0, z0, rad0, active, r);
-            if (active) *hist = make_float4(x0, y0, z0, knn_d5(r));
+            // (2) full search by the whole warp for the points that need one; it refreshes their cache
+            warp_knn5(maps, kind, x0, y0, z0, rad0, need, r, anchor, cache);
+            ok = active && knn_d5(r) < 1.0f;
             if (inRange) {
                 const GridDesc& gd = sh_gd[isCorner ? 0 : 1];
                 if (cap) {
@@ -322,7 +347,6 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
                 float4 coeff = make_float4(0, 0, 0, 0);
                 if (ok) {
                     // the five neighbours' coordinates, by original map index (mapOptmization.h:1028-1036, :1157-1163)
-                    const float4* mo = isCorner ? gc.pts : gs.pts;
                     float4 nb[5];
                     #pragma unroll
                     for (int k = 0; k < 5; k++) nb[k] = __ldg(mo + knn_index(r, k));

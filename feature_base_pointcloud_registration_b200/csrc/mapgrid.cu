@@ -193,7 +193,10 @@ __global__ void __launch_bounds__(128) knn5_query(const GridSeg* segs, const flo
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (active) { qx = q[3 * i]; qy = q[3 * i + 1]; qz = q[3 * i + 2]; }
     ThreadKnn5 r;
-    const bool ok = warp_knn5(M, 0, qx, qy, qz, rad0, active, r);
+    #pragma unroll
+    for (int k = 0; k < 5; k++) r.key[k] = ~0ull;
+    warp_knn5(M, 0, qx, qy, qz, rad0, active, r, nullptr, nullptr);
+    const bool ok = active && knn_d5(r) < 1.0f;
     if (i >= nq) return;
     #pragma unroll
     for (int k = 0; k < 5; k++) {

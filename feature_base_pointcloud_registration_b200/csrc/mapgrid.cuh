@@ -20,6 +20,12 @@
 //     the new position, so a cube covering that radius contains the new exact 5-NN and ONE pass is
 //     enough.  If the covered ball does not yet certify the result (first iteration, R too small)
 //     the cube is doubled and only the cells it ADDS are scanned.
+//   - temporal coherence across LM iterations: a full search also leaves a CANDIDATE CACHE for the point -- up
+//     to 16 map indices and a radius tau such that every map point NOT in the cache is at least tau away from
+//     the search position.  At the next iteration the point has moved by delta, so every uncached map point
+//     is at least tau - delta away; one thread re-ranks the cached candidates, and if their 5th distance is
+//     below tau - delta (or tau - delta covers the whole 1 m ball) that is the exact 5-NN and no search is
+//     needed.  Otherwise the warp searches again, inside the radius the cached 5th distance bounds.
 // A query therefore costs two or three dependent memory round trips whatever its candidate count
 // (25 for a surface point in a dense map, ~1000 for a corner point next to several edges).
 // Ranking key = (d^2 bits as u32) << 32 | original index: the (d^2, index) total order of the oracle
@@ -52,6 +58,10 @@ __device__ __forceinline__ void knn_offer(ThreadKnn5& r, const float4 m, float q
     if (key >= r.key[4]) return;
     r.key[4] = key;                                                         // replace the worst, then bubble it down
     knn_cswap(r.key[3], r.key[4]); knn_cswap(r.key[2], r.key[3]); knn_cswap(r.key[1], r.key[2]); knn_cswap(r.key[0], r.key[1]);
+}
+
+__device__ __forceinline__ void knn_offer_idx(ThreadKnn5& r, float mx, float my, float mz, int idx, float qx, float qy, float qz) {
+    knn_offer(r, make_float4(mx, my, mz, __int_as_float(idx)), qx, qy, qz);
 }
 
 __device__ __forceinline__ float knn_d5(const ThreadKnn5& r) {      // 5th-best squared distance (huge when fewer than 5 were found)
@@ -103,20 +113,26 @@ __device__ __forceinline__ void knn5_scan_ranges(ThreadKnn5& p, const float4* __
     }
 }
 
+#define FBPR_KNN_CACHE 16           // cached candidates per feature point
+
 // Exact 5-NN of ONE query by the whole warp (all lanes pass the same query).  rad0 = first cube radius in cells.
 // r (replicated) = exact sorted 5-NN among all map points within the covered ball; the caller rejects when
 // knn_d5(r) >= 1.0.  Exactness: every point closer than rad * h (minus a rounding guard) lies in the cube, so the
 // result is final once the 5th distance is inside that ball or the cube covers the whole 1 m ball (rad = rmax).
-__device__ __forceinline__ void warp_query_knn5(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ pts,
-                                                float qx, float qy, float qz, int rad0, ThreadKnn5& r) {
+// cache (may be null) receives up to 16 original indices (-1 = unused slot); the return value is tau (metres):
+// every map point whose index is not in the cache is at distance >= tau from the query (0 = cache not usable).
+__device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ pts,
+                                                 float qx, float qy, float qz, int rad0, ThreadKnn5& r, int* cache) {
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int cx = (int)floorf((qx - g.ox) * g.inv_h);
     const int cy = (int)floorf((qy - g.oy) * g.inv_h);
     const int cz = (int)floorf((qz - g.oz) * g.inv_h);
-    ThreadKnn5 p;
+    ThreadKnn5 p;                                            // private list, kept across widening passes
     #pragma unroll
     for (int i = 0; i < 5; i++) p.key[i] = ~0ull;
     int prev = -1, rad = min(max(rad0, 1), g.rmax);          // prev = radius of the cube already scanned (-1: none)
+    float guard;
     while (true) {
         const int x0 = max(cx - rad, 0), x1 = min(cx + rad, g.dx - 1);
         const int y0 = max(cy - rad, 0), y1 = min(cy + rad, g.dy - 1);
@@ -140,46 +156,80 @@ __device__ __forceinline__ void warp_query_knn5(const GridDesc& g, const int* __
                 if (rx0 <= x1) { a1 = __ldg(cell_start + row + rx0); l1 = __ldg(cell_start + row + x1 + 1) - a1; anyRight = true; }
             }
             knn5_scan_ranges(p, pts, a0, l0, qx, qy, qz);
-            if (__any_sync(0xffffffffu, anyRight)) knn5_scan_ranges(p, pts, a1, l1, qx, qy, qz);
+            if (__any_sync(FULL, anyRight)) knn5_scan_ranges(p, pts, a1, l1, qx, qy, qz);
         }
-        knn5_merge_warp(p, r);
-        const float guard = (float)rad * g.h * 0.9995f;
-        if (knn_d5(r) < guard * guard || rad >= g.rmax) break;
+        ThreadKnn5 pm;                                       // the merge consumes a copy; the private lists live on
         #pragma unroll
-        for (int i = 0; i < 5; i++) p.key[i] = lane == 0 ? r.key[i] : ~0ull;   // keep what was found, scan only the added cells
+        for (int i = 0; i < 5; i++) pm.key[i] = p.key[i];
+        knn5_merge_warp(pm, r);
+        guard = (float)rad * g.h * 0.9995f;
+        if (knn_d5(r) < guard * guard || rad >= g.rmax) break;
         prev = rad; rad = min(rad * 2, g.rmax);
     }
+    if (!cache) return 0.f;
+    // ---- candidate cache.  Points outside it are: never scanned (>= guard away), pushed out of a full private
+    // list (>= that list's last key), or kept but >= the threshold chosen below.
+    const unsigned d5b = (unsigned)(r.key[4] >> 32);                                  // 0xffffffff when fewer than 5 exist
+    unsigned tb = __float_as_uint(guard * guard);                                     // threshold on d^2 bits, exclusive
+    tb = min(tb, __reduce_min_sync(FULL, (unsigned)(p.key[4] >> 32)));                // tails of the full lists (empty = 0xffffffff)
+    int count = 0;
+    for (int tries = 0; tries < 8; tries++) {
+        const unsigned long long tk = (unsigned long long)tb << 32;
+        int c = 0;
+        #pragma unroll
+        for (int i = 0; i < 5; i++) c += p.key[i] < tk ? 1 : 0;
+        count = __reduce_add_sync(FULL, c);
+        if (count <= FBPR_KNN_CACHE) break;
+        // too many: shrink towards the 5th distance in proportion to the surplus (point counts grow ~ with d^2)
+        const float t2 = __uint_as_float(tb), d5f = __uint_as_float(d5b);
+        tb = __float_as_uint(d5f + (t2 - d5f) * (13.0f / (float)count));
+    }
+    const bool usable = count <= FBPR_KNN_CACHE && (d5b == 0xffffffffu || tb > d5b);   // must hold the whole top-5
+    {
+        const unsigned long long tk = usable ? (unsigned long long)tb << 32 : 0ull;
+        int c = 0;
+        #pragma unroll
+        for (int i = 0; i < 5; i++) c += p.key[i] < tk ? 1 : 0;
+        int incl = c;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(FULL, incl, 31);
+        int off = incl - c;
+        #pragma unroll
+        for (int i = 0; i < 5; i++) if (p.key[i] < tk) cache[off++] = (int)(unsigned)(p.key[i] & 0xffffffffu);
+        if (lane >= total && lane < FBPR_KNN_CACHE) cache[lane] = -1;
+    }
+    return usable ? sqrtf(__uint_as_float(tb)) : 0.f;
 }
 
-// Exact 5-NN of the 32 queries of a warp, one query per lane (`active` = this lane has a query, `kind` = which of
-// the two maps it searches, `rad0` = its first cube radius in cells); must be called by all 32 lanes.
-// Returns true when 5 neighbours with d^2 < 1.0 exist (then r is exact and sorted ascending by (d^2, index)).
-// When false, r holds whatever was found inside the covered ball (exact for every entry < 1.0).
-__device__ __forceinline__ bool warp_knn5(const KnnMaps& M, int kind, float qx, float qy, float qz, int rad0, bool active, ThreadKnn5& r) {
+// Full searches for the lanes of a warp that `need` one (one query per lane; `kind` = which of the two maps it
+// searches, `rad0` = its first cube radius in cells); must be called by all 32 lanes.  A lane that does not need a
+// search keeps its r.  anchor / cache (per lane: this lane's record, may be null) receive the candidate cache.
+__device__ __forceinline__ void warp_knn5(const KnnMaps& M, int kind, float qx, float qy, float qz, int rad0, bool need, ThreadKnn5& r,
+                                          float4* anchor, int* cache) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    #pragma unroll
-    for (int i = 0; i < 5; i++) r.key[i] = ~0ull;
-    unsigned todo = __ballot_sync(FULL, active);
+    unsigned todo = __ballot_sync(FULL, need);
     while (todo) {
         const int src = __ffs(todo) - 1; todo &= todo - 1;
         const float bx = __shfl_sync(FULL, qx, src), by = __shfl_sync(FULL, qy, src), bz = __shfl_sync(FULL, qz, src);
         const int bk = __shfl_sync(FULL, kind, src), br = __shfl_sync(FULL, rad0, src);
+        int* bc = reinterpret_cast<int*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(cache), src));
         ThreadKnn5 m;
-        warp_query_knn5(M.gd[bk], bk ? M.cell_start[1] : M.cell_start[0], bk ? M.pts[1] : M.pts[0], bx, by, bz, br, m);
+        const float tau = warp_query_knn5(M.gd[bk], bk ? M.cell_start[1] : M.cell_start[0], bk ? M.pts[1] : M.pts[0], bx, by, bz, br, m, bc);
         if (lane == src) {
             #pragma unroll
             for (int i = 0; i < 5; i++) r.key[i] = m.key[i];
+            if (anchor) *anchor = make_float4(qx, qy, qz, tau);
         }
     }
-    return active && knn_d5(r) < 1.0f;
 }
 
-// First cube radius (cells) that certainly contains the exact 5-NN of a point that moved by `moved` since a search
-// that found the 5th neighbour at squared distance d5_old: the old neighbours are within sqrt(d5_old) + moved.
-__device__ __forceinline__ int knn5_radius_from_history(const GridDesc& g, float d5_old, float moved) {
-    if (!(d5_old < 1.0e30f)) return g.rmax;                  // fewer than 5 found last time: cover the whole 1 m ball
-    const float rho = (sqrtf(d5_old) + moved) * 1.001f + 1.0e-5f;
+// First cube radius (cells) that certainly contains the exact 5-NN when 5 map points are known to lie within
+// squared distance d5_known of the query (huge = unknown: cover the whole 1 m ball).
+__device__ __forceinline__ int knn5_radius_from_bound(const GridDesc& g, float d5_known) {
+    if (!(d5_known < 1.0e30f)) return g.rmax;
+    const float rho = sqrtf(d5_known) * 1.001f + 1.0e-5f;
     const float cells = rho / (g.h * 0.9995f);
     return cells >= (float)g.rmax ? g.rmax : max(1, (int)ceilf(cells));
 }
