@@ -30,7 +30,7 @@ namespace {
 
 // Launch shapes.  Batched calls: one cluster per frame, 256-thread CTAs (3 resident per SM).
 // Single-frame calls: one 768-thread CTA per SM over the whole GPU.
-constexpr int LM_TPB_CLUSTER = 256, LM_CTAS_CLUSTER = 3;
+constexpr int LM_TPB_CLUSTER = 256, LM_CTAS_CLUSTER = 4;
 constexpr int LM_TPB_GRID = 768, LM_CTAS_GRID = 1;
 constexpr int NACC = 28;          // 21 (upper triangle of A^T A) + 6 (A^T b) + 1 (row count)
 
