@@ -231,6 +231,13 @@ class Registration:
     def set_frames(self, first, frame_inputs, mem=MEM_HOST):
         self._ck(self.lib.fbpr_set_frames(self.h, first, len(frame_inputs), frame_inputs, mem))
 
+    def register_frames(self, first, frame_inputs, chunk_frames=0):
+        """Upload (host buffers), run the whole path and fetch the results of len(frame_inputs) independent frames,
+        with the uploads of one chunk overlapping the kernels of the previous one."""
+        out = np.zeros(len(frame_inputs), RESULT_DTYPE)
+        self._ck(self.lib.fbpr_register_frames(self.h, first, len(frame_inputs), frame_inputs, int(chunk_frames), _vp(out)))
+        return out
+
     def enable_stage_timing(self, on=True): self._ck(self.lib.fbpr_enable_stage_timing(self.h, int(on)))
 
     def get_stage_ms(self, reset=True):

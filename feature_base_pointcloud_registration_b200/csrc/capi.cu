@@ -82,6 +82,7 @@ struct fbpr_handle {
     int globalCornerN = -1, globalSurfN = 0;   // resident global maps (fbpr_set_global_map)
     // batched input staging (pinned) + stage timing
     FrameMeta* h_metaStage = nullptr; double* h_imuStage = nullptr; cudaEvent_t stageDone = nullptr; bool stagePending = false;
+    cudaStream_t copyStream = nullptr; std::vector<cudaEvent_t> pipeEvents;      // fbpr_register_frames: uploads overlap compute
     bool timing = false;
     struct TimedSpan { int stage; cudaEvent_t a, b; };
     std::vector<TimedSpan> spans; size_t spansUsed = 0;
@@ -246,6 +247,8 @@ void fbpr_destroy(fbpr_handle* h) {
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     if (h->stageDone) cudaEventDestroy(h->stageDone);
+    for (auto& e : h->pipeEvents) cudaEventDestroy(e);
+    if (h->copyStream) cudaStreamDestroy(h->copyStream);
     if (h->h_metaStage) cudaFreeHost(h->h_metaStage);
     if (h->h_imuStage) cudaFreeHost(h->h_imuStage);
     for (void* p : h->allocs) cudaFree(p);
@@ -341,22 +344,17 @@ int fbpr_set_local_map(fbpr_handle* h, int slot, const float* corner, int nC, co
 
 int fbpr_set_pose(fbpr_handle* h, int slot, const float pose6[6]) { return fbpr_set_poses(h, slot, 1, pose6, FBPR_MEM_HOST); }
 
-int fbpr_set_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input* fr, int mem) {
-    int rc = check_range(h, first, count); if (rc) return rc;
-    if (count == 0) return 0;
-    if (!fr) return fbpr_fail_msg("null frames");
-    cudaSetDevice(h->device);
+// validate `count` frames and stage their scalars (and IMU ramps) in pinned memory; *anyImu reports whether ramps were staged
+static int stage_frames(fbpr_handle* h, int count, const fbpr_frame_input* fr, bool* anyImu) {
     if (!h->h_metaStage) {
         FBPR_CUDA_OK(cudaHostAlloc((void**)&h->h_metaStage, sizeof(FrameMeta) * (size_t)h->F, cudaHostAllocDefault));
         FBPR_CUDA_OK(cudaHostAlloc((void**)&h->h_imuStage, sizeof(double) * 4 * (size_t)h->F * FBPR_IMU_CAP, cudaHostAllocDefault));
         FBPR_CUDA_OK(cudaEventCreateWithFlags(&h->stageDone, cudaEventDisableTiming));
     }
     if (h->stagePending) { FBPR_CUDA_OK(cudaEventSynchronize(h->stageDone)); h->stagePending = false; }
-    bool anyImu = false;
-    const cudaMemcpyKind k = kind_in(mem);
+    *anyImu = false;
     for (int i = 0; i < count; i++) {
         const fbpr_frame_input& f = fr[i];
-        const int slot = first + i;
         if (f.n_raw < 0 || f.n_raw > h->rawCap) return fbpr_fail_msg("raw scan larger than max_raw_points");
         if (f.n_map_corner < 0 || f.n_map_corner > h->mapCornerCap || f.n_map_surf < 0 || f.n_map_surf > h->mapSurfCap)
             return fbpr_fail_msg("local map exceeds max_map_corner / max_map_surf");
@@ -372,19 +370,41 @@ int fbpr_set_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input
             const size_t nb = (size_t)(f.imuPointerCur + 1) * sizeof(double);
             const double* src[4] = { f.imuTime, f.imuRotX, f.imuRotY, f.imuRotZ };
             for (int a = 0; a < 4; a++) memcpy(h->h_imuStage + ((size_t)a * count + i) * FBPR_IMU_CAP, src[a], nb);
-            anyImu = true;
+            *anyImu = true;
         }
-        if (m.n_raw) FBPR_CUDA_OK(cudaMemcpyAsync(h->raw + (size_t)slot * h->rawCap, f.raw, (size_t)m.n_raw * sizeof(fbpr_raw_point), k, h->stream));
-        if (m.n_map_corner) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapCorner + (size_t)slot * h->mapCornerCap, f.map_corner_xyzi, (size_t)m.n_map_corner * sizeof(float4), k, h->stream));
-        if (m.n_map_surf) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapSurf + (size_t)slot * h->mapSurfCap, f.map_surf_xyzi, (size_t)m.n_map_surf * sizeof(float4), k, h->stream));
     }
-    FBPR_CUDA_OK(cudaMemcpyAsync(h->meta + first, h->h_metaStage, sizeof(FrameMeta) * (size_t)count, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+// enqueue the copies of the staged scalars / IMU ramps of `count` frames starting at slot `first`
+static int upload_staged(fbpr_handle* h, int first, int count, bool anyImu, cudaStream_t st) {
+    FBPR_CUDA_OK(cudaMemcpyAsync(h->meta + first, h->h_metaStage, sizeof(FrameMeta) * (size_t)count, cudaMemcpyHostToDevice, st));
     if (anyImu) {
         double* dst[4] = { h->imuTime, h->imuRotX, h->imuRotY, h->imuRotZ };
         for (int a = 0; a < 4; a++)
             FBPR_CUDA_OK(cudaMemcpyAsync(dst[a] + (size_t)first * FBPR_IMU_CAP, h->h_imuStage + (size_t)a * count * FBPR_IMU_CAP,
-                                         sizeof(double) * (size_t)count * FBPR_IMU_CAP, cudaMemcpyHostToDevice, h->stream));
+                                         sizeof(double) * (size_t)count * FBPR_IMU_CAP, cudaMemcpyHostToDevice, st));
     }
+    return 0;
+}
+
+int fbpr_set_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input* fr, int mem) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    if (count == 0) return 0;
+    if (!fr) return fbpr_fail_msg("null frames");
+    cudaSetDevice(h->device);
+    bool anyImu = false;
+    rc = stage_frames(h, count, fr, &anyImu); if (rc) return rc;
+    const cudaMemcpyKind k = kind_in(mem);
+    for (int i = 0; i < count; i++) {
+        const fbpr_frame_input& f = fr[i];
+        const FrameMeta& m = h->h_metaStage[i];
+        const int slot = first + i;
+        if (m.n_raw) FBPR_CUDA_OK(cudaMemcpyAsync(h->raw + (size_t)slot * h->rawCap, f.raw, (size_t)m.n_raw * sizeof(fbpr_raw_point), k, h->stream));
+        if (m.n_map_corner) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapCorner + (size_t)slot * h->mapCornerCap, f.map_corner_xyzi, (size_t)m.n_map_corner * sizeof(float4), k, h->stream));
+        if (m.n_map_surf) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapSurf + (size_t)slot * h->mapSurfCap, f.map_surf_xyzi, (size_t)m.n_map_surf * sizeof(float4), k, h->stream));
+    }
+    rc = upload_staged(h, first, count, anyImu, h->stream); if (rc) return rc;
     FBPR_CUDA_OK(cudaEventRecord(h->stageDone, h->stream));
     h->stagePending = true;
     return 0;
@@ -545,6 +565,57 @@ int fbpr_run_frames(fbpr_handle* h, int first, int count, int with_projection, i
         if (!r) r = enqueue_scan2map(h, first, count);
         return r;
     });
+}
+
+int fbpr_register_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input* fr, int chunk_frames, fbpr_result* out) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    if (count == 0) return 0;
+    if (!fr || !out) return fbpr_fail_msg("null frames / results");
+    if (fbpr_feat_ring_smem(feat_args(h, first)) > 200 * 1024) return fbpr_fail_msg("Horizon_SCAN too large for the per-ring shared-memory kernel");
+    cudaSetDevice(h->device);
+    const int chunk = chunk_frames > 0 ? chunk_frames : 32;
+    const int nchunks = (count + chunk - 1) / chunk;
+    if (!h->copyStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+    while ((int)h->pipeEvents.size() < 2 * nchunks + 2) {
+        cudaEvent_t e; FBPR_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->pipeEvents.push_back(e);
+    }
+    bool anyImu = false;
+    rc = stage_frames(h, count, fr, &anyImu); if (rc) return rc;
+    // the upload stream starts after everything already queued on the compute stream (earlier operators may still read the slots)
+    cudaEvent_t evStart = h->pipeEvents[2 * nchunks], evMeta = h->pipeEvents[2 * nchunks + 1];
+    FBPR_CUDA_OK(cudaEventRecord(evStart, h->stream));
+    FBPR_CUDA_OK(cudaStreamWaitEvent(h->copyStream, evStart, 0));
+    rc = upload_staged(h, first, count, anyImu, h->copyStream); if (rc) return rc;
+    FBPR_CUDA_OK(cudaEventRecord(evMeta, h->copyStream));
+    FBPR_CUDA_OK(cudaEventRecord(h->stageDone, h->copyStream));
+    h->stagePending = true;
+    // uploads: raw sweeps of chunk k, then its local maps; compute: front-end of chunk k as soon as its sweeps are in HBM,
+    // map index + LM as soon as its maps are -- so the PCIe copies of chunk k+1 run under the kernels of chunk k
+    for (int c = 0; c < nchunks; c++) {
+        const int lo = c * chunk, hi = lo + chunk < count ? lo + chunk : count;
+        for (int i = lo; i < hi; i++) {
+            const FrameMeta& m = h->h_metaStage[i];
+            if (m.n_raw) FBPR_CUDA_OK(cudaMemcpyAsync(h->raw + (size_t)(first + i) * h->rawCap, fr[i].raw, (size_t)m.n_raw * sizeof(fbpr_raw_point), cudaMemcpyHostToDevice, h->copyStream));
+        }
+        FBPR_CUDA_OK(cudaEventRecord(h->pipeEvents[2 * c], h->copyStream));
+        for (int i = lo; i < hi; i++) {
+            const FrameMeta& m = h->h_metaStage[i];
+            if (m.n_map_corner) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapCorner + (size_t)(first + i) * h->mapCornerCap, fr[i].map_corner_xyzi, (size_t)m.n_map_corner * sizeof(float4), cudaMemcpyHostToDevice, h->copyStream));
+            if (m.n_map_surf) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapSurf + (size_t)(first + i) * h->mapSurfCap, fr[i].map_surf_xyzi, (size_t)m.n_map_surf * sizeof(float4), cudaMemcpyHostToDevice, h->copyStream));
+        }
+        FBPR_CUDA_OK(cudaEventRecord(h->pipeEvents[2 * c + 1], h->copyStream));
+    }
+    FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, evMeta, 0));
+    for (int c = 0; c < nchunks; c++) {
+        const int lo = first + c * chunk, n = (c + 1) * chunk <= count ? chunk : count - c * chunk;
+        FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, h->pipeEvents[2 * c], 0));
+        rc = enqueue_project(h, lo, n); if (rc) return rc;
+        rc = enqueue_features(h, lo, n); if (rc) return rc;
+        rc = enqueue_downsample(h, lo, n); if (rc) return rc;
+        FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, h->pipeEvents[2 * c + 1], 0));
+        rc = enqueue_scan2map(h, lo, n); if (rc) return rc;
+    }
+    return fbpr_get_results(h, first, count, out, FBPR_MEM_HOST);
 }
 
 int fbpr_extract_surrounding_keyframes(fbpr_handle* h, int slot, int K, const float* key_poses6,

@@ -189,6 +189,14 @@ FBPR_API int fbpr_registration(fbpr_handle* h, int slot, const float* corner_glo
 /* the whole per-frame path in one call: project -> feature_extract -> downsample -> scan2map */
 FBPR_API int fbpr_run_frames(fbpr_handle* h, int first, int count, int with_projection, int with_features);
 
+/* the batch form of the caller's per-frame loop (cloudHandler -> featureExtra -> registration, imageProjection.cpp:182-226)
+   for `count` INDEPENDENT frames given in HOST memory (pinned for full PCIe speed): uploads are issued in chunks of
+   `chunk_frames` (0 = 32) on a second stream, so the copies of chunk k+1 run under the kernels of chunk k; the whole path
+   (projection, features, downsample, map index, LM, transformUpdate) runs per chunk; results land in `out` (host) and the
+   call returns when they are there. */
+FBPR_API int fbpr_register_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input* frames, int chunk_frames,
+                                  fbpr_result* out);
+
 /* ---- results ----------------------------------------------------------------------------- */
 FBPR_API int fbpr_get_pose(fbpr_handle* h, int slot, float pose6[6], int32_t* iters, uint32_t* flags);
 FBPR_API int fbpr_get_results(fbpr_handle* h, int first, int count, fbpr_result* out, int mem);

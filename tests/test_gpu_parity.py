@@ -299,3 +299,28 @@ def test_end_to_end_pose_and_batch_equals_single(fb, config):
             r.run_frames(s, 1)
         again = r.get_results(0, 3)
         assert np.array_equal(again["pose"], res["pose"]) and np.array_equal(again["iters"], res["iters"])
+
+
+def test_pipelined_register_frames_equals_plain_batch(fb):
+    """fbpr_register_frames (chunked uploads on a second stream) must give exactly what set_frames + run_frames gives."""
+    F = 5
+    frames = [synth.make_frame(1, 20 + i) for i in range(F)]
+    r = fb.Registration(frames[0]["params"], max_frames=F, max_map_corner=16384, max_map_surf=65536)
+    raws = [fb.api.pack_raw(fr["scan"]) for fr in frames]
+    fin = r.make_frame_inputs([dict(raw_ptr=raw.ctypes.data, n_raw=len(raw), imu=fr["imu"], imu_available=fr["imu_available"],
+                                    map_corner_ptr=fr["map_corner"].ctypes.data, n_map_corner=len(fr["map_corner"]),
+                                    map_surf_ptr=fr["map_surf"].ctypes.data, n_map_surf=len(fr["map_surf"]), pose=fr["guess"])
+                               for fr, raw in zip(frames, raws)])
+    r.set_frames(0, fin); r.run_frames(0, F)
+    want = r.get_results(0, F)
+    for chunk in (1, 2, 32):
+        got = r.register_frames(0, fin, chunk)
+        assert np.array_equal(got["pose"], want["pose"]) and np.array_equal(got["iters"], want["iters"]) and np.array_equal(got["flags"], want["flags"])
+    for s_, fr in enumerate(frames[:2]):                      # and both equal the oracle
+        ci = oracle.project(fr["params"], fr["scan"], fr["imu"], fr["imu_available"]); fe = oracle.extract_features(fr["params"], ci)
+        mo = oracle.MapOptimization(fr["params"]); mo.set_imu(fr["imu_available"], 0.0, 0.0)
+        mo.set_scan(fe["corner"], fe["surface"]); mo.set_map(fr["map_corner"], fr["map_surf"]); mo.downsample()
+        pw, iw, fw, _ = mo.scan2map(fr["guess"])
+        assert iw == int(want[s_]["iters"]) and fw == int(want[s_]["flags"])
+        assert np.max(np.abs(pw - want[s_]["pose"])) <= 1e-4
+    r.close()
