@@ -359,7 +359,7 @@ def run_b200(args, rank, world, local_rank):
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": "configs[3]/[2]: synthetic HDL-64E-like 64x2048 frames, each vs its own 200k-pt corner/surf local map, "
                                   "projection+deskew, features, VoxelGrid, <=30 LM iterations",
-                      "frames_per_gpu": F, "frames_per_step": world * F, "lm_cluster_size": reg.params.lm_cluster_size or 8,
+                      "frames_per_gpu": F, "frames_per_step": world * F, "lm_cluster_size": reg.params.lm_cluster_size or "auto",
                       "l2": "inputs larger than L2: %.0f MB of scans+maps per GPU per step" % (h2d / 1e6)},
            "ms_per_frame": ms_total / args.steps / F,
            "latency_ms_per_frame": lat,

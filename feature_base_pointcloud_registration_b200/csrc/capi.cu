@@ -46,7 +46,7 @@ struct fbpr_handle {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     int F = 0, P = 0, rawCap = 0, cornerCap = 0, mapCornerCap = 0, mapSurfCap = 0, kfCap = 0;
-    int tilesCap = 0, cellsCorner = 0, cellsSurf = 0, cluster = 8;
+    int tilesCap = 0, cellsCorner = 0, cellsSurf = 0, cluster = 0;
     float cellCorner = 0.5f, cellSurf = 0.25f;
     std::vector<void*> allocs;
     size_t bytes = 0;
@@ -159,8 +159,8 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     h->cellSurf = params->knn_cell_surf > 0 ? params->knn_cell_surf : 0.25f;
     h->cellsCorner = params->grid_cells_corner > 0 ? params->grid_cells_corner : 262144;
     h->cellsSurf = params->grid_cells_surf > 0 ? params->grid_cells_surf : 1048576;
-    h->cluster = params->lm_cluster_size > 0 ? params->lm_cluster_size : 8;
-    if (h->cluster != 1 && h->cluster != 2 && h->cluster != 4 && h->cluster != 8 && h->cluster != 16) return fbpr_fail_msg("lm_cluster_size must be 1,2,4,8 or 16");
+    h->cluster = params->lm_cluster_size;              // 0 = chosen per call from the batch size
+    if (h->cluster != 0 && h->cluster != 1 && h->cluster != 2 && h->cluster != 4 && h->cluster != 8 && h->cluster != 16) return fbpr_fail_msg("lm_cluster_size must be 0 (auto),1,2,4,8 or 16");
     int maxVox = P; if (h->kfCap > maxVox) maxVox = h->kfCap;
     h->tilesCap = (maxVox + fbpr_voxel_tile() - 1) / fbpr_voxel_tile() + 1;
 

@@ -484,6 +484,39 @@ int fbpr_lm_grid_blocks(int device) {
     return sms;
 }
 
+// co-resident clusters of `c` CTAs of the batched variant (0 if the size cannot be launched)
+static int lm_max_active_clusters(int c) {
+    static int cached[17] = { 0 }, known[17] = { 0 };
+    if (c < 1 || c > 16) return 0;
+    if (!known[c]) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(LM_TPB_CLUSTER); cfg.gridDim = dim3((unsigned)(c * 64)); cfg.dynamicSmemBytes = 0;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, lm_kernel<false>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+        cached[c] = n; known[c] = 1;
+    }
+    return cached[c];
+}
+
+// cluster size for a batch of `count` frames: the time of the launch is ~ waves / (CTAs per frame), so take the size
+// that minimises it (a small batch gets big clusters to fill the GPU, a big batch small ones for fewer waves);
+// ties go to the smaller cluster (cheaper barrier, fewer redundant solves)
+int fbpr_lm_auto_cluster(int count) {
+    const int sizes[5] = { 1, 2, 4, 8, 16 };
+    int best = 8; double bestScore = 1e30;
+    for (int k = 0; k < 5; k++) {
+        const int c = sizes[k], n = lm_max_active_clusters(c);
+        if (n <= 0) continue;
+        const double score = (double)((count + n - 1) / n) / (double)c;
+        if (score < bestScore * 0.999) { bestScore = score; best = c; }
+    }
+    return best;
+}
+
 int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blocks, cudaStream_t st, long long* launches) {
     if (count <= 0) return 0;
     static int configured = 0;
@@ -505,6 +538,7 @@ int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blo
         attr[0].val.cooperative = 1;
         e = cudaLaunchKernelEx(&cfg, lm_kernel<true>, args);
     } else {                                        // many frames: one cluster per frame, hardware cluster barrier per iteration
+        if (cluster_size <= 0) cluster_size = fbpr_lm_auto_cluster(count);
         cfg.blockDim = dim3(LM_TPB_CLUSTER);
         cfg.gridDim = dim3((unsigned)(count * cluster_size));
         attr[0].id = cudaLaunchAttributeClusterDimension;
