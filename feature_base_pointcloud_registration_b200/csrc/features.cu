@@ -79,7 +79,8 @@ __device__ inline int block_excl_scan(int v, int* total, int* ws) {
     return off + incl - v;
 }
 
-// bitonic network over `count` keys made of aligned blocks of `blk` (pow2); every block ends ascending
+// bitonic network over `count` keys made of aligned blocks of `blk` (pow2); every block ends ascending.
+// Generic shared-memory form (any sizes); the register forms below are used for the common shapes.
 __device__ inline void bitonic_blocks(unsigned long long* keys, int count, int blk) {
     for (int k = 2; k <= blk; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -96,9 +97,116 @@ __device__ inline void bitonic_blocks(unsigned long long* keys, int count, int b
     }
 }
 
+__device__ __forceinline__ void key_cswap(unsigned long long& a, unsigned long long& b, bool asc) {
+    const unsigned long long x = a, y = b;
+    const bool sw = (x > y) == asc;
+    a = sw ? y : x; b = sw ? x : y;
+}
+
+// One WARP sorts 32 * IPT keys ascending, IPT keys per lane in registers (element e = lane * IPT + i): strides below
+// IPT are register-to-register compare-exchanges, the others one shuffle per key.  No shared memory, no barriers.
+template <int IPT>
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&k)[IPT], int lane) {
+    #pragma unroll
+    for (int kk = 2; kk <= 32 * IPT; kk <<= 1) {
+        #pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= IPT) {
+                const int lj = j / IPT;
+                const bool up = ((lane * IPT) & kk) == 0 || kk == 32 * IPT;
+                const bool keepMin = ((lane & lj) == 0) == up;
+                #pragma unroll
+                for (int i = 0; i < IPT; i++) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[i], lj);
+                    const bool less = o < k[i];
+                    k[i] = (less == keepMin) ? o : k[i];
+                }
+            } else {
+                #pragma unroll
+                for (int i = 0; i < IPT; i++) {
+                    if ((i & j) == 0) {
+                        const bool up = (((lane * IPT + i) & kk) == 0) || kk == 32 * IPT;
+                        key_cswap(k[i], k[i | j], up);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// The whole CTA (RING_TPB threads) sorts RING_TPB * IPT keys of shared memory ascending, IPT keys per thread in
+// registers (element e = tid * IPT + i); only the strides that cross warps go through shared memory.
+template <int IPT>
+__device__ __forceinline__ void cta_bitonic_sort(unsigned long long* keys) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int N = RING_TPB * IPT;
+    unsigned long long k[IPT];
+    #pragma unroll
+    for (int i = 0; i < IPT; i++) k[i] = keys[tid * IPT + i];
+    #pragma unroll
+    for (int kk = 2; kk <= N; kk <<= 1) {
+        #pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= 32 * IPT) {                     // partner in another warp: exchange through shared memory
+                __syncthreads();
+                #pragma unroll
+                for (int i = 0; i < IPT; i++) keys[tid * IPT + i] = k[i];
+                __syncthreads();
+                const int tj = j / IPT;
+                const bool up = ((tid * IPT) & kk) == 0 || kk == N;
+                const bool keepMin = ((tid & tj) == 0) == up;
+                #pragma unroll
+                for (int i = 0; i < IPT; i++) {
+                    const unsigned long long o = keys[(tid ^ tj) * IPT + i];
+                    const bool less = o < k[i];
+                    k[i] = (less == keepMin) ? o : k[i];
+                }
+            } else if (j >= IPT) {
+                const int lj = j / IPT;
+                const bool up = ((tid * IPT) & kk) == 0 || kk == N;
+                const bool keepMin = ((lane & lj) == 0) == up;
+                #pragma unroll
+                for (int i = 0; i < IPT; i++) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[i], lj);
+                    const bool less = o < k[i];
+                    k[i] = (less == keepMin) ? o : k[i];
+                }
+            } else {
+                #pragma unroll
+                for (int i = 0; i < IPT; i++) {
+                    if ((i & j) == 0) {
+                        const bool up = (((tid * IPT + i) & kk) == 0) || kk == N;
+                        key_cswap(k[i], k[i | j], up);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int i = 0; i < IPT; i++) keys[tid * IPT + i] = k[i];
+    __syncthreads();
+}
+
+// the six segment sorts: warp w < 6 sorts keys [w * segPad, (w + 1) * segPad) in registers
+template <int IPT>
+__device__ __forceinline__ void segment_sorts(unsigned long long* keys) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (w < FBPR_SEGS) {
+        unsigned long long k[IPT];
+        unsigned long long* base = keys + w * 32 * IPT;
+        #pragma unroll
+        for (int i = 0; i < IPT; i++) k[i] = base[lane * IPT + i];
+        warp_bitonic_sort<IPT>(k, lane);
+        #pragma unroll
+        for (int i = 0; i < IPT; i++) base[lane * IPT + i] = k[i];
+    }
+    __syncthreads();
+}
+
 enum : unsigned char { ST_NONE = 0, ST_UNDECIDED = 1, ST_PICKED = 2, ST_DEAD = 3 };
 
-__global__ void __launch_bounds__(RING_TPB) feat_ring(FeatArgs a) {
+__global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
     extern __shared__ unsigned char smem_raw[];
     const int slot = a.first + blockIdx.y, ring = blockIdx.x;
     const int n = a.meta[slot].n_valid;
@@ -176,7 +284,10 @@ __global__ void __launch_bounds__(RING_TPB) feat_ring(FeatArgs a) {
             s_keys[t] = key;
         }
         __syncthreads();
-        bitonic_blocks(s_keys, FBPR_SEGS * a.segPad, a.segPad);
+        if (a.segPad == 512) segment_sorts<16>(s_keys);
+        else if (a.segPad == 256) segment_sorts<8>(s_keys);
+        else if (a.segPad == 128) segment_sorts<4>(s_keys);
+        else bitonic_blocks(s_keys, FBPR_SEGS * a.segPad, a.segPad);
 
         for (int j = 0; j < FBPR_SEGS; j++) {
             const int sp = s_sp[j], ep = s_ep[j];
@@ -344,7 +455,10 @@ __global__ void __launch_bounds__(RING_TPB) feat_ring(FeatArgs a) {
                 s_keys[t] = key;
             }
             __syncthreads();
-            bitonic_blocks(s_keys, a.voxPad, a.voxPad);
+            if (a.voxPad == 4 * RING_TPB) cta_bitonic_sort<4>(s_keys);
+            else if (a.voxPad == 2 * RING_TPB) cta_bitonic_sort<2>(s_keys);
+            else if (a.voxPad == 8 * RING_TPB) cta_bitonic_sort<8>(s_keys);
+            else bitonic_blocks(s_keys, a.voxPad, a.voxPad);
             int carry = 0;
             for (int base = 0; base < nsurf; base += RING_TPB) {
                 int t = base + tid;
