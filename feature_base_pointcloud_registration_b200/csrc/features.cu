@@ -218,12 +218,11 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
     float* s_curv = reinterpret_cast<float*>(s_keys + keyCount);
     int* s_col = reinterpret_cast<int*>(s_curv + a.wcap);
     int* s_list = s_col + a.wcap;                         // surface candidate list (global indices)
-    unsigned short* s_rank = reinterpret_cast<unsigned short*>(s_list + a.wcap);
-    unsigned char* s_picked = reinterpret_cast<unsigned char*>(s_rank + a.wcap);
+    unsigned* s_meta = reinterpret_cast<unsigned*>(s_list + a.wcap);          // rank << 16 | forward reach << 8 | backward reach
+    unsigned char* s_picked = reinterpret_cast<unsigned char*>(s_meta + a.wcap);
     signed char* s_label = reinterpret_cast<signed char*>(s_picked + a.wcap);
-    unsigned char* s_state = reinterpret_cast<unsigned char*>(s_label + a.wcap);
-    unsigned char* s_fwd = s_state + a.wcap;
-    unsigned char* s_bwd = s_fwd + a.wcap;
+    unsigned char* s_state0 = reinterpret_cast<unsigned char*>(s_label + a.wcap);   // flat-loop state, double-buffered by round
+    unsigned char* s_state1 = s_state0 + a.wcap;
     __shared__ int s_corner[CORNERS_PER_RING];
     __shared__ int s_ncorner, s_ws[RING_TPB / 32];
     __shared__ int s_sp[FBPR_SEGS], s_ep[FBPR_SEGS];
@@ -253,7 +252,7 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
         for (int t = tid; t < W; t += RING_TPB) {
             int g = w0 + t;
             s_curv[t] = g_curv[g]; s_col[t] = g_col[g];
-            s_picked[t] = (unsigned char)(g_picked[g] != 0); s_label[t] = 0; s_state[t] = ST_NONE;
+            s_picked[t] = (unsigned char)(g_picked[g] != 0); s_label[t] = 0; s_state0[t] = ST_NONE; s_state1[t] = ST_NONE;
         }
         __syncthreads();
         // static suppression reach of every index (featureExtraction.h:226-240)
@@ -269,7 +268,7 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
                 if (abs(s_col[q - w0] - s_col[q + 1 - w0]) > 10) break;
                 b = -l;
             }
-            s_fwd[t] = (unsigned char)f; s_bwd[t] = (unsigned char)b;
+            s_meta[t] = ((unsigned)f << 8) | (unsigned)b;
         }
         // sort keys of all six segments: cloudSmoothness[k] = {curv[k], k} inside [5, n-5), else {0.0f, 0}
         for (int t = tid; t < FBPR_SEGS * a.segPad; t += RING_TPB) {
@@ -309,7 +308,7 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
                         if (cnt <= FBPR_CORNERS_PER_SEG) { s_label[ind - w0] = 1; s_corner[s_ncorner++] = ind; }
                         else break;
                         s_picked[ind - w0] = 1;
-                        int f = s_fwd[ind - w0], b = s_bwd[ind - w0];
+                        int f = (s_meta[ind - w0] >> 8) & 0xff, b = s_meta[ind - w0] & 0xff;
                         for (int l = 1; l <= f; l++) s_picked[ind + l - w0] = 1;
                         for (int l = 1; l <= b; l++) s_picked[ind - l - w0] = 1;
                     }
@@ -320,7 +319,7 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
                 if (len > 0 && (ind0 < sp || ind0 > ep) && ind0 >= w0 && ind0 <= w1) {
                     if (s_picked[ind0 - w0] == 0 && s_curv[ind0 - w0] < a.surfThreshold) {
                         s_label[ind0 - w0] = -1; s_picked[ind0 - w0] = 1;
-                        int f = s_fwd[ind0 - w0], b = s_bwd[ind0 - w0];
+                        int f = (s_meta[ind0 - w0] >> 8) & 0xff, b = s_meta[ind0 - w0] & 0xff;
                         for (int l = 1; l <= f; l++) s_picked[ind0 + l - w0] = 1;
                         for (int l = 1; l <= b; l++) s_picked[ind0 - l - w0] = 1;
                     }
@@ -331,52 +330,50 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
             for (int v = tid; v <= len; v += RING_TPB) {
                 int ind = v == len ? ((ep >= 5 && ep < n - 5) ? ep : 0) : (int)(unsigned)(keys[v] & 0xffffffffu);
                 if (ind < sp || ind > ep) continue;
-                s_rank[ind - w0] = (unsigned short)v;
+                s_meta[ind - w0] = (s_meta[ind - w0] & 0xffffu) | ((unsigned)v << 16);
                 unsigned char st = ST_NONE;
                 if (s_curv[ind - w0] < a.surfThreshold) st = s_picked[ind - w0] ? ST_DEAD : ST_UNDECIDED;
-                s_state[ind - w0] = st;
+                s_state0[ind - w0] = st;
             }
             __syncthreads();
+            // rounds: every element of [sp, ep] is re-written into the other buffer each round, so one barrier per round
+            unsigned char* cur = s_state0; unsigned char* nxt = s_state1;
             while (true) {
-                // phase 1: decide from a consistent snapshot
-                unsigned char newst[(4096 + RING_TPB - 1) / RING_TPB];
-                int pending = 0, slotk = 0;
-                for (int g = sp + tid; g <= ep; g += RING_TPB, slotk++) {
-                    unsigned char st = s_state[g - w0];
-                    newst[slotk] = st;
-                    if (st != ST_UNDECIDED) continue;
-                    const unsigned short rk = s_rank[g - w0];
-                    bool dead = false, wait = false;
-                    const int qlo = max(g - 5, sp), qhi = min(g + 5, ep);
-                    for (int q = qlo; q <= qhi; q++) {
-                        if (q == g) continue;
-                        unsigned char sq = s_state[q - w0];
-                        if (sq != ST_PICKED && sq != ST_UNDECIDED) continue;
-                        if (s_rank[q - w0] >= rk) continue;
-                        bool covers = q < g ? (g - q <= s_fwd[q - w0]) : (q - g <= s_bwd[q - w0]);
-                        if (!covers) continue;
-                        if (sq == ST_PICKED) dead = true; else wait = true;
+                int pending = 0;
+                for (int g = sp + tid; g <= ep; g += RING_TPB) {
+                    unsigned char st = cur[g - w0];
+                    if (st == ST_UNDECIDED) {
+                        const unsigned rk = s_meta[g - w0] >> 16;
+                        bool dead = false, wait = false;
+                        const int qlo = max(g - 5, sp), qhi = min(g + 5, ep);
+                        for (int q = qlo; q <= qhi; q++) {
+                            if (q == g) continue;
+                            const unsigned char sq = cur[q - w0];
+                            if (sq != ST_PICKED && sq != ST_UNDECIDED) continue;
+                            const unsigned mq = s_meta[q - w0];
+                            if ((mq >> 16) >= rk) continue;
+                            const bool covers = q < g ? (g - q <= (int)((mq >> 8) & 0xff)) : (q - g <= (int)(mq & 0xff));
+                            if (!covers) continue;
+                            if (sq == ST_PICKED) dead = true; else wait = true;
+                        }
+                        if (dead) st = ST_DEAD;
+                        else if (!wait) st = ST_PICKED;
+                        else pending = 1;
                     }
-                    if (dead) newst[slotk] = ST_DEAD;
-                    else if (!wait) newst[slotk] = ST_PICKED;
-                    else pending = 1;
+                    nxt[g - w0] = st;
                 }
-                __syncthreads();
-                slotk = 0;
-                for (int g = sp + tid; g <= ep; g += RING_TPB, slotk++) s_state[g - w0] = newst[slotk];
+                unsigned char* t_ = cur; cur = nxt; nxt = t_;
                 if (!__syncthreads_or(pending)) break;
             }
             // apply picks: label -1, mark self and reach
             for (int g = sp + tid; g <= ep; g += RING_TPB) {
-                if (s_state[g - w0] == ST_PICKED) {
+                if (cur[g - w0] == ST_PICKED) {
                     s_label[g - w0] = -1; s_picked[g - w0] = 1;
-                    int f = s_fwd[g - w0], b = s_bwd[g - w0];
+                    const int f = (s_meta[g - w0] >> 8) & 0xff, b = s_meta[g - w0] & 0xff;
                     for (int l = 1; l <= f; l++) s_picked[g + l - w0] = 1;
                     for (int l = 1; l <= b; l++) s_picked[g - l - w0] = 1;
                 }
             }
-            __syncthreads();
-            for (int g = sp + tid; g <= ep; g += RING_TPB) s_state[g - w0] = ST_NONE;
             __syncthreads();
         }
         // ---- write back labels / marks (1s only: neighbouring rings' windows overlap)
@@ -514,7 +511,7 @@ __global__ void __launch_bounds__(256) feat_gather(FeatArgs a) {
 
 size_t fbpr_feat_ring_smem(const FeatArgs& a) {
     size_t keyCount = (size_t)(FBPR_SEGS * a.segPad > a.voxPad ? FBPR_SEGS * a.segPad : a.voxPad);
-    return keyCount * 8 + (size_t)a.wcap * (4 + 4 + 4 + 2 + 1 + 1 + 1 + 1 + 1) + 64;
+    return keyCount * 8 + (size_t)a.wcap * (4 + 4 + 4 + 4 + 1 + 1 + 1 + 1) + 64;
 }
 
 int fbpr_launch_features(const FeatArgs& a, int count, cudaStream_t st, long long* launches) {
