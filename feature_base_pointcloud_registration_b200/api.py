@@ -262,10 +262,17 @@ class Registration:
         self._ck(self.lib.fbpr_extract_surrounding_keyframes(self.h, slot, K, _vp(kp), _vp(call), _vp(coff), _vp(sall), _vp(soff), _vp(lk), MEM_HOST))
         self.sync()
 
-    def registration(self, slot, corner_global, surf_global, pose12):
+    def set_global_map(self, corner_global, surf_global):
         c = _f32(corner_global).reshape(-1, 4); s = _f32(surf_global).reshape(-1, 4)
+        self._ck(self.lib.fbpr_set_global_map(self.h, _vp(c), len(c), _vp(s), len(s), MEM_HOST))
+
+    def registration(self, slot, corner_global, surf_global, pose12):
         T = _f32(pose12).reshape(-1).copy()
-        self._ck(self.lib.fbpr_registration(self.h, slot, _vp(c), len(c), _vp(s), len(s), MEM_HOST, _vp(T)))
+        if corner_global is None and surf_global is None:       # use the maps made resident by set_global_map
+            self._ck(self.lib.fbpr_registration(self.h, slot, None, 0, None, 0, MEM_DEVICE, _vp(T)))
+        else:
+            c = _f32(corner_global).reshape(-1, 4); s = _f32(surf_global).reshape(-1, 4)
+            self._ck(self.lib.fbpr_registration(self.h, slot, _vp(c), len(c), _vp(s), len(s), MEM_HOST, _vp(T)))
         return T.reshape(3, 4)
 
     def run_frames(self, first=0, count=1, with_projection=True, with_features=True):

@@ -324,3 +324,89 @@ def test_pipelined_register_frames_equals_plain_batch(fb):
         assert iw == int(want[s_]["iters"]) and fw == int(want[s_]["flags"])
         assert np.max(np.abs(pw - want[s_]["pose"])) <= 1e-4
     r.close()
+
+
+# ------------------------------------------------------------------ operators around the path
+def _registration_case():
+    fr = synth.make_frame(1, 4, small=(16, 600, 3000, 12000))
+    P = fr["params"]
+    ci = oracle.project(P, fr["scan"], fr["imu"], 0)
+    fe = oracle.extract_features(P, ci)
+    rng = np.random.default_rng(0)
+    clutter = np.concatenate([rng.uniform(100, 200, (500, 3)), np.zeros((500, 1))], 1).astype(np.float32)
+    gc = np.concatenate([fr["map_corner"], clutter]); gs = np.concatenate([clutter, fr["map_surf"]])
+    T0 = oracle.get_transformation(fr["guess"])
+    mo = oracle.MapOptimization(P)
+    mo.set_scan(fe["corner"], fe["surface"])
+    T, iters, flags = mo.registration(gc, gs, T0)
+    return fr, P, ci, fe, gc, gs, T0, T, iters, flags
+
+
+def test_registration_entry_cropbox_matches_oracle(fb):
+    """fbpr_registration = mapOptimization::registration (mapOptmization.h:263-343): CropBox, pose decompose, downsample, LM, recompose."""
+    fr, P, ci, fe, gc, gs, T0, T, iters, flags = _registration_case()
+    r = _reg(fb, P)
+    r.set_feature_clouds(0, fe["corner"], fe["surface"])
+    got = r.registration(0, gc, gs, T0)
+    pose, it, fl = r.get_pose(0)
+    assert (it, fl) == (iters, flags)
+    assert np.max(np.abs(got[:, 3] - T[:, 3])) <= POSE_TOL_T and np.max(np.abs(got[:, :3] - T[:, :3])) <= POSE_TOL_R
+    c = r.get_counts(0)
+    keep_c = oracle.crop_box(gc, T0[:, 3] - [30, 30, 10], T0[:, 3] + [30, 30, 10])
+    keep_s = oracle.crop_box(gs, T0[:, 3] - [30, 30, 10], T0[:, 3] + [30, 30, 10])
+    assert c["n_map_corner"] == len(keep_c) and c["n_map_surf"] == len(keep_s)
+    assert np.array_equal(r.get_buffer(0, "MAP_CORNER").reshape(-1, 4), keep_c)      # inclusive AABB, order preserved
+    # resident global map: same answer with NULL maps
+    r.set_global_map(gc, gs)
+    r.set_feature_clouds(0, fe["corner"], fe["surface"])
+    got2 = r.registration(0, None, None, T0)
+    assert np.array_equal(got2, got)
+    r.close()
+
+
+def test_extract_surrounding_keyframes_matches_oracle(fb):
+    """extractCloud (mapOptmization.h:909-955): distance re-check, per-keyframe rigid transform, concat in list order, VoxelGrid x2."""
+    rng = np.random.default_rng(1)
+    P = synth.params_for(1)
+    K = 4
+    poses = np.concatenate([rng.uniform(-0.2, 0.2, (K, 3)), rng.uniform(-5, 5, (K, 3))], 1).astype(np.float32)
+    poses[3, 3:] += 100.0                                        # farther than surroundingKeyframeSearchRadius from the last key pose
+    cf = [np.concatenate([rng.uniform(-10, 10, (n, 3)), np.full((n, 1), k)], 1).astype(np.float32) for k, n in enumerate((50, 70, 30, 40))]
+    sf = [np.concatenate([rng.uniform(-10, 10, (n, 3)), np.full((n, 1), k)], 1).astype(np.float32) for k, n in enumerate((500, 700, 300, 400))]
+    mo = oracle.MapOptimization(P)
+    counts = mo.extract_cloud(poses, cf, sf, poses[0, 3:])
+    r = _reg(fb, P, max_keyframe_points=4096)
+    r.extractSurroundingKeyFrames(0, poses, cf, sf, poses[0, 3:])
+    c = r.get_counts(0)
+    assert (c["n_map_corner"], c["n_map_surf"]) == (int(counts[2]), int(counts[3]))
+    assert np.array_equal(r.get_buffer(0, "MAP_CORNER").reshape(-1, 4), mo.get_cloud(2))
+    assert np.array_equal(r.get_buffer(0, "MAP_SURF").reshape(-1, 4), mo.get_cloud(3))
+    r.close()
+
+
+@pytest.mark.parametrize("share", [0, 1])
+def test_cpp_host_classes_cloud_handler(fb, share, tmp_path):
+    """The C++ host layer (host/feature_matching.hpp: FeatureExtraction::featureExtra + mapOptimization::registration with the
+    reference's names) driven the way ImageProjection::cloudHandler drives the reference (imageProjection.cpp:203, :218)."""
+    import ctypes as C
+    import os
+    fr, P, ci, fe, gc, gs, T0, T, iters, flags = _registration_case()
+    so = os.path.join(os.path.dirname(fb.__file__), "host", "libfeature_matching_b200.so")
+    lib = C.CDLL(so)
+    y = tmp_path / "params.yaml"
+    y.write_text("".join(f"{k}: {P[k]}\n" for k in ("edgeThreshold", "surfThreshold", "edgeFeatureMinValidNum", "surfFeatureMinValidNum",
+                                                      "odometrySurfLeafSize", "mappingCornerLeafSize", "mappingSurfLeafSize",
+                                                      "z_tollerance", "rotation_tollerance", "numberOfCores")))
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    sr, er, col, rng_, cloud = i32(ci["startRingIndex"]), i32(ci["endRingIndex"]), i32(ci["pointColInd"]), f32(ci["pointRange"]), f32(ci["cloud_deskewed"])
+    gcf, gsf = f32(gc), f32(gs)
+    pose = f32(T0).reshape(-1).copy()
+    it = C.c_int(0); fl = C.c_uint(0); counts = (C.c_int * 4)(); err = C.create_string_buffer(512)
+    rc = lib.fm_cloud_handler(str(y).encode(), int(P["N_SCAN"]), int(P["Horizon_SCAN"]), vp(sr), vp(er), vp(col), vp(rng_), vp(cloud), len(col),
+                              vp(gcf), len(gcf), vp(gsf), len(gsf), vp(pose), int(share), C.byref(it), C.byref(fl), counts, err, 512)
+    assert rc == 0, err.value.decode()
+    assert (it.value, fl.value) == (iters, flags)
+    got = pose.reshape(3, 4)
+    assert np.max(np.abs(got[:, 3] - T[:, 3])) <= POSE_TOL_T and np.max(np.abs(got[:, :3] - T[:, :3])) <= POSE_TOL_R
