@@ -32,6 +32,7 @@ namespace {
 // Single-frame calls: one 768-thread CTA per SM over the whole GPU.
 constexpr int LM_TPB_CLUSTER = 256, LM_CTAS_CLUSTER = 4;
 constexpr int LM_TPB_GRID = 768, LM_CTAS_GRID = 1;
+constexpr int LM_PART_SLOTS = 64;      // chunks of one CTA whose partial sums have their own shared-memory slot
 constexpr int NACC = 28;          // 21 (upper triangle of A^T A) + 6 (A^T b) + 1 (row count)
 
 __device__ __forceinline__ void transform_point(const float* T, float4 p, float& x, float& y, float& z) {
@@ -225,9 +226,14 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int WPB = LM_TPB / 32;
 
-    // per-warp staging of the 32 Jacobian rows (6) and -residual (1) of the warp's current 32 points, as f64
-    __shared__ double s_rows[WPB][32][7];
-    __shared__ double wred[WPB][NACC];
+    // per-warp staging of the 32 Jacobian rows (6) and -residual (1) of the warp's current 32 points, as f64 (dynamic shared memory)
+    extern __shared__ double s_dyn[];
+    double (*s_rows)[32][7] = reinterpret_cast<double (*)[32][7]>(s_dyn);
+    // one 28-double partial per CHUNK (dynamic dispatch, summed in chunk order: the result does not depend on which warp
+    // took which chunk) or, when this CTA has more chunks than slots, one per WARP (static dispatch)
+    constexpr int SLOTS = LM_PART_SLOTS > WPB ? LM_PART_SLOTS : WPB;
+    __shared__ double s_part[SLOTS][NACC];
+    __shared__ int s_next;
     __shared__ double sh_tot[NACC];
     __shared__ GridDesc sh_gd[2];
     __shared__ float sh_pose[6], sh_T[12], sh_trig[6], sh_AtA[36], sh_AtB[6];
@@ -247,6 +253,7 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
     if (tid < 6) sh_pose[tid] = M.pose[tid];
     if (tid == 32) sh_gd[0] = *gc.desc;
     if (tid == 64) sh_gd[1] = *gs.desc;
+    if (tid == 0) s_next = 0;
     // the accumulator entry this lane owns: 0..20 = upper triangle (ei <= ej), 21..26 = (ei, 6) = A^T b, 27 = row count
     int ei = 0, ej = 6;
     if (lane < 21) { int rr = 0, qx = lane; while (qx >= 6 - rr) { qx -= 6 - rr; rr++; } ei = rr; ej = rr + qx; }
@@ -258,6 +265,9 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
     // on one frame there are more warps than that, so chunks shrink until every warp has a few points to search
     int CS = 32;
     while (CS > 1 && nQ <= (CS / 2) * C * WPB) CS >>= 1;
+    const int nChunks = (nQ + CS - 1) / CS;
+    const int myChunks = rank < nChunks ? (nChunks - rank + C - 1) / C : 0;      // chunks k * C + rank of this CTA
+    const bool dynamic = myChunks <= LM_PART_SLOTS;
     unsigned flags = 0; int isDegenerate = 0; int iters = 0;
     for (int iter = 0; iter < FBPR_MAX_ITERS; iter++) {
         // --- pose -> rigid transform + the six sines/cosines LMOptimization needs (:1259-1264)
@@ -279,9 +289,13 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
 
         // --- association: one thread per feature point
         double acc = 0.0;
-        // chunks of CS consecutive points are dealt round-robin over the team's CTAs, so the (more expensive)
-        // corner chunks at the front of the index range spread evenly instead of loading one CTA
-        for (int chunk = warp * C + rank; chunk * CS < nQ; chunk += WPB * C) {
+        // chunks of CS consecutive points are dealt round-robin over the team's CTAs (chunk = k * C + rank), so the (more
+        // expensive) corner chunks at the front of the index range spread evenly; inside the CTA the warps take the
+        // CTA's chunks from a shared counter, because a chunk costs anything between 0 and 32 full searches
+        int k = warp;
+        if (dynamic) { if (lane == 0) k = atomicAdd(&s_next, 1); k = __shfl_sync(0xffffffffu, k, 0); }
+        while (k < myChunks) {
+            const int chunk = k * C + rank;
             const int q = chunk * CS + lane;
             bool ok = false;
             // corners occupy [0, nC), surface points follow; each lane searches the map of its own kind
@@ -388,19 +402,28 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
                 }
             }
             __syncwarp();
+            if (dynamic) {
+                if (lane < NACC) s_part[k][lane] = acc;
+                acc = 0.0;
+                if (lane == 0) k = atomicAdd(&s_next, 1);
+                k = __shfl_sync(0xffffffffu, k, 0);
+            } else {
+                k += WPB;
+            }
         }
-        // --- CTA reduce (shared memory, fixed warp order) -> one partial per CTA in global memory
-        if (lane < NACC) wred[warp][lane] = acc;
+        // --- CTA reduce (shared memory, fixed order) -> one partial per CTA in global memory
+        if (!dynamic && lane < NACC) s_part[warp][lane] = acc;
         __syncthreads();
         const int buf = iter & 1;
         double* mypart = part + ((size_t)buf * teamStride + rank) * NACC;
         if (tid < NACC) {
             double v = 0.0;
-            #pragma unroll
-            for (int w = 0; w < WPB; w++) v += wred[w][tid];
+            const int nslots = dynamic ? myChunks : WPB;
+            for (int w = 0; w < nslots; w++) v += s_part[w][tid];
             mypart[tid] = v;
             __threadfence();
         }
+        if (tid == 0) s_next = 0;                    // next iteration's dispatch counter (ordered by the barriers below)
         if (GRID) grid.sync(); else cluster.sync();
         // --- every CTA sums all partials in the same fixed order (bitwise identical everywhere), then solves redundantly
         if (tid < NACC * 8) {                        // 224 threads <= LM_TPB in both shapes
@@ -475,12 +498,27 @@ __global__ void transform_update_kernel(FrameMeta* meta, int first, int count, f
 
 }  // namespace
 
+static size_t lm_dyn_smem(int tpb) { return (size_t)(tpb / 32) * 32 * 7 * sizeof(double); }    // s_rows
+
+// one-time function attributes of both variants (cluster sizes above 8, dynamic shared memory above the default limit)
+static int lm_configure() {
+    static int configured = 0;
+    if (configured) return 0;
+    cudaError_t e = cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(NonPortableClusterSizeAllowed)", __FILE__, __LINE__);
+    e = cudaFuncSetAttribute(lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dyn_smem(LM_TPB_GRID));
+    if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", __FILE__, __LINE__);
+    configured = 1;
+    return 0;
+}
+
 int fbpr_lm_grid_blocks(int device) {
     // co-resident CTAs of the cooperative (one frame on the whole GPU) variant: one per SM
+    if (lm_configure()) return 0;
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
     int per = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lm_kernel<true>, LM_TPB_GRID, 0) != cudaSuccess || per < 1) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lm_kernel<true>, LM_TPB_GRID, lm_dyn_smem(LM_TPB_GRID)) != cudaSuccess || per < 1) return 0;
     return sms;
 }
 
@@ -490,7 +528,7 @@ static int lm_max_active_clusters(int c) {
     if (c < 1 || c > 16) return 0;
     if (!known[c]) {
         cudaLaunchConfig_t cfg = {};
-        cfg.blockDim = dim3(LM_TPB_CLUSTER); cfg.gridDim = dim3((unsigned)(c * 64)); cfg.dynamicSmemBytes = 0;
+        cfg.blockDim = dim3(LM_TPB_CLUSTER); cfg.gridDim = dim3((unsigned)(c * 64)); cfg.dynamicSmemBytes = lm_dyn_smem(LM_TPB_CLUSTER);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -519,20 +557,15 @@ int fbpr_lm_auto_cluster(int count) {
 
 int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blocks, cudaStream_t st, long long* launches) {
     if (count <= 0) return 0;
-    static int configured = 0;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(NonPortableClusterSizeAllowed)", __FILE__, __LINE__);
-        configured = 1;
-    }
+    { int rc = lm_configure(); if (rc) return rc; }
     cudaLaunchConfig_t cfg = {};
-    cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e;
     if (count == 1 && grid_blocks > 0) {           // one frame: the whole GPU cooperates, grid-wide barrier per iteration
         cfg.blockDim = dim3(LM_TPB_GRID);
+        cfg.dynamicSmemBytes = lm_dyn_smem(LM_TPB_GRID);
         cfg.gridDim = dim3((unsigned)grid_blocks);
         attr[0].id = cudaLaunchAttributeCooperative;
         attr[0].val.cooperative = 1;
@@ -540,6 +573,7 @@ int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blo
     } else {                                        // many frames: one cluster per frame, hardware cluster barrier per iteration
         if (cluster_size <= 0) cluster_size = fbpr_lm_auto_cluster(count);
         cfg.blockDim = dim3(LM_TPB_CLUSTER);
+        cfg.dynamicSmemBytes = lm_dyn_smem(LM_TPB_CLUSTER);
         cfg.gridDim = dim3((unsigned)(count * cluster_size));
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
