@@ -10,6 +10,9 @@
 
 #include "internal.cuh"
 
+int fbpr_knn_cache_slots();
+#define FBPR_KNN_CACHE_SLOTS fbpr_knn_cache_slots()
+
 // ---- kernel-side argument blocks and launchers (defined in the other translation units) ----
 void fbpr_launch_projection(const ProjArgs& a, int count, cudaStream_t st, long long* launches);
 int fbpr_launch_features(const FeatArgs& a, int count, cudaStream_t st, long long* launches);
@@ -179,7 +182,7 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     ALLOC(h->mapCorner, (size_t)F * h->mapCornerCap); ALLOC(h->mapSurf, (size_t)F * h->mapSurfCap);
     ALLOC(h->poseTrace, (size_t)F * FBPR_MAX_ITERS * 6);
     ALLOC(h->qanchor, (size_t)F * (h->cornerCap + P));
-    ALLOC(h->qcache, (size_t)F * (h->cornerCap + P) * 16);
+    ALLOC(h->qcache, (size_t)F * (h->cornerCap + P) * FBPR_KNN_CACHE_SLOTS);
     ALLOC(h->partials, (size_t)F * 2 * 16 * 28);
     ALLOC(h->partialsGrid, (size_t)2 * 1024 * 28);
     h->lmGridBlocks = fbpr_lm_grid_blocks(device);

@@ -512,6 +512,8 @@ static int lm_configure() {
     return 0;
 }
 
+int fbpr_knn_cache_slots() { return FBPR_KNN_CACHE; }
+
 int fbpr_lm_grid_blocks(int device) {
     // co-resident CTAs of the cooperative (one frame on the whole GPU) variant: one per SM
     if (lm_configure()) return 0;

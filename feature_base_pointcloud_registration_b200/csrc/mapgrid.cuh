@@ -21,7 +21,7 @@
 //     enough.  If the covered ball does not yet certify the result (first iteration, R too small)
 //     the cube is doubled and only the cells it ADDS are scanned.
 //   - temporal coherence across LM iterations: a full search also leaves a CANDIDATE CACHE for the point -- up
-//     to 16 map indices and a radius tau such that every map point NOT in the cache is at least tau away from
+//     to FBPR_KNN_CACHE (16) map indices and a radius tau such that every map point NOT in the cache is at least tau away from
 //     the search position.  At the next iteration the point has moved by delta, so every uncached map point
 //     is at least tau - delta away; one thread re-ranks the cached candidates, and if their 5th distance is
 //     below tau - delta (or tau - delta covers the whole 1 m ball) that is the exact 5-NN and no search is
@@ -113,13 +113,15 @@ __device__ __forceinline__ void knn5_scan_ranges(ThreadKnn5& p, const float4* __
     }
 }
 
-#define FBPR_KNN_CACHE 16           // cached candidates per feature point
+#ifndef FBPR_KNN_CACHE
+#define FBPR_KNN_CACHE 16           // cached candidates per feature point (multiple of 8, <= 32; 16 measured best: 8 -> 6.1 ms, 16 -> 5.9, 24 -> 6.2, 32 -> 6.7 per 128 frames)
+#endif
 
 // Exact 5-NN of ONE query by the whole warp (all lanes pass the same query).  rad0 = first cube radius in cells.
 // r (replicated) = exact sorted 5-NN among all map points within the covered ball; the caller rejects when
 // knn_d5(r) >= 1.0.  Exactness: every point closer than rad * h (minus a rounding guard) lies in the cube, so the
 // result is final once the 5th distance is inside that ball or the cube covers the whole 1 m ball (rad = rmax).
-// cache (may be null) receives up to 16 original indices (-1 = unused slot); the return value is tau (metres):
+// cache (may be null) receives up to FBPR_KNN_CACHE original indices (-1 = unused slot); the return value is tau (metres):
 // every map point whose index is not in the cache is at distance >= tau from the query (0 = cache not usable).
 __device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ pts,
                                                  float qx, float qy, float qz, int rad0, ThreadKnn5& r, int* cache) {
@@ -182,7 +184,7 @@ __device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* _
         if (count <= FBPR_KNN_CACHE) break;
         // too many: shrink towards the 5th distance in proportion to the surplus (point counts grow ~ with d^2)
         const float t2 = __uint_as_float(tb), d5f = __uint_as_float(d5b);
-        tb = __float_as_uint(d5f + (t2 - d5f) * (13.0f / (float)count));
+        tb = __float_as_uint(d5f + (t2 - d5f) * ((float)(FBPR_KNN_CACHE - 3) / (float)count));
     }
     const bool usable = count <= FBPR_KNN_CACHE && (d5b == 0xffffffffu || tb > d5b);   // must hold the whole top-5
     {
