@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <utility>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -85,7 +86,7 @@ struct fbpr_handle {
     int globalCornerN = -1, globalSurfN = 0;   // resident global maps (fbpr_set_global_map)
     // batched input staging (pinned) + stage timing
     FrameMeta* h_metaStage = nullptr; double* h_imuStage = nullptr; cudaEvent_t stageDone = nullptr; bool stagePending = false;
-    cudaStream_t copyStream = nullptr; std::vector<cudaEvent_t> pipeEvents;      // fbpr_register_frames: uploads overlap compute
+    cudaStream_t copyStream = nullptr, lmStream = nullptr; std::vector<cudaEvent_t> pipeEvents;      // fbpr_register_frames: uploads overlap compute
     bool timing = false;
     struct TimedSpan { int stage; cudaEvent_t a, b; };
     std::vector<TimedSpan> spans; size_t spansUsed = 0;
@@ -252,6 +253,7 @@ void fbpr_destroy(fbpr_handle* h) {
     if (h->stageDone) cudaEventDestroy(h->stageDone);
     for (auto& e : h->pipeEvents) cudaEventDestroy(e);
     if (h->copyStream) cudaStreamDestroy(h->copyStream);
+    if (h->lmStream) cudaStreamDestroy(h->lmStream);
     if (h->h_metaStage) cudaFreeHost(h->h_metaStage);
     if (h->h_imuStage) cudaFreeHost(h->h_imuStage);
     for (void* p : h->allocs) cudaFree(p);
@@ -579,45 +581,57 @@ int fbpr_register_frames(fbpr_handle* h, int first, int count, const fbpr_frame_
     const int chunk = chunk_frames > 0 ? chunk_frames : 32;
     const int nchunks = (count + chunk - 1) / chunk;
     if (!h->copyStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
-    while ((int)h->pipeEvents.size() < 2 * nchunks + 2) {
+    if (!h->lmStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->lmStream, cudaStreamNonBlocking));
+    while ((int)h->pipeEvents.size() < 3 * nchunks + 3) {
         cudaEvent_t e; FBPR_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->pipeEvents.push_back(e);
     }
     bool anyImu = false;
     rc = stage_frames(h, count, fr, &anyImu); if (rc) return rc;
     // the upload stream starts after everything already queued on the compute stream (earlier operators may still read the slots)
-    cudaEvent_t evStart = h->pipeEvents[2 * nchunks], evMeta = h->pipeEvents[2 * nchunks + 1];
+    cudaEvent_t evStart = h->pipeEvents[3 * nchunks], evMeta = h->pipeEvents[3 * nchunks + 1], evLmDone = h->pipeEvents[3 * nchunks + 2];
     FBPR_CUDA_OK(cudaEventRecord(evStart, h->stream));
     FBPR_CUDA_OK(cudaStreamWaitEvent(h->copyStream, evStart, 0));
+    FBPR_CUDA_OK(cudaStreamWaitEvent(h->lmStream, evStart, 0));
     rc = upload_staged(h, first, count, anyImu, h->copyStream); if (rc) return rc;
     FBPR_CUDA_OK(cudaEventRecord(evMeta, h->copyStream));
     FBPR_CUDA_OK(cudaEventRecord(h->stageDone, h->copyStream));
     h->stagePending = true;
-    // uploads: raw sweeps of chunk k, then its local maps; compute: front-end of chunk k as soon as its sweeps are in HBM,
-    // map index + LM as soon as its maps are -- so the PCIe copies of chunk k+1 run under the kernels of chunk k
+    // three streams.  Upload: raw sweeps of chunk k, then its local maps.  Front-end (the handle's stream): projection, features
+    // and downsample of chunk k as soon as its sweeps are in HBM.  Registration (second compute stream): map index + LM of chunk k
+    // as soon as its maps are in HBM and its front-end is done -- so the PCIe copies of chunk k+1 and the front-end of chunk k+1
+    // run under the latency-bound LM kernel of chunk k.
     for (int c = 0; c < nchunks; c++) {
         const int lo = c * chunk, hi = lo + chunk < count ? lo + chunk : count;
         for (int i = lo; i < hi; i++) {
             const FrameMeta& m = h->h_metaStage[i];
             if (m.n_raw) FBPR_CUDA_OK(cudaMemcpyAsync(h->raw + (size_t)(first + i) * h->rawCap, fr[i].raw, (size_t)m.n_raw * sizeof(fbpr_raw_point), cudaMemcpyHostToDevice, h->copyStream));
         }
-        FBPR_CUDA_OK(cudaEventRecord(h->pipeEvents[2 * c], h->copyStream));
+        FBPR_CUDA_OK(cudaEventRecord(h->pipeEvents[3 * c], h->copyStream));
         for (int i = lo; i < hi; i++) {
             const FrameMeta& m = h->h_metaStage[i];
             if (m.n_map_corner) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapCorner + (size_t)(first + i) * h->mapCornerCap, fr[i].map_corner_xyzi, (size_t)m.n_map_corner * sizeof(float4), cudaMemcpyHostToDevice, h->copyStream));
             if (m.n_map_surf) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapSurf + (size_t)(first + i) * h->mapSurfCap, fr[i].map_surf_xyzi, (size_t)m.n_map_surf * sizeof(float4), cudaMemcpyHostToDevice, h->copyStream));
         }
-        FBPR_CUDA_OK(cudaEventRecord(h->pipeEvents[2 * c + 1], h->copyStream));
+        FBPR_CUDA_OK(cudaEventRecord(h->pipeEvents[3 * c + 1], h->copyStream));
     }
     FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, evMeta, 0));
+    FBPR_CUDA_OK(cudaStreamWaitEvent(h->lmStream, evMeta, 0));
     for (int c = 0; c < nchunks; c++) {
         const int lo = first + c * chunk, n = (c + 1) * chunk <= count ? chunk : count - c * chunk;
-        FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, h->pipeEvents[2 * c], 0));
+        FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, h->pipeEvents[3 * c], 0));
         rc = enqueue_project(h, lo, n); if (rc) return rc;
         rc = enqueue_features(h, lo, n); if (rc) return rc;
         rc = enqueue_downsample(h, lo, n); if (rc) return rc;
-        FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, h->pipeEvents[2 * c + 1], 0));
-        rc = enqueue_scan2map(h, lo, n); if (rc) return rc;
+        FBPR_CUDA_OK(cudaEventRecord(h->pipeEvents[3 * c + 2], h->stream));
+        FBPR_CUDA_OK(cudaStreamWaitEvent(h->lmStream, h->pipeEvents[3 * c + 2], 0));
+        FBPR_CUDA_OK(cudaStreamWaitEvent(h->lmStream, h->pipeEvents[3 * c + 1], 0));
+        std::swap(h->stream, h->lmStream);                       // enqueue_* launch on h->stream
+        rc = enqueue_scan2map(h, lo, n);
+        std::swap(h->stream, h->lmStream);
+        if (rc) return rc;
     }
+    FBPR_CUDA_OK(cudaEventRecord(evLmDone, h->lmStream));
+    FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, evLmDone, 0));
     return fbpr_get_results(h, first, count, out, FBPR_MEM_HOST);
 }
 
