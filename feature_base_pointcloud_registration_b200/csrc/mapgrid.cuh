@@ -143,12 +143,14 @@ __device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* _
         const bool havePrev = prev >= 0 && px0 <= px1;
         const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
         const int nrows = (x0 <= x1 && ny > 0 && nz > 0) ? ny * nz : 0;
+        const float inv_ny = 1.0f / (float)max(ny, 1);
         for (int rbase = 0; rbase < nrows; rbase += 32) {
             const int i = rbase + lane;
             int a0 = 0, l0 = 0, a1 = 0, l1 = 0;
             bool anyRight = false;
             if (i < nrows) {
-                const int zz = z0 + i / ny, yy = y0 + i % ny;
+                const int zi = (int)(((float)i + 0.5f) * inv_ny);            // i / ny for the small integers involved
+                const int zz = z0 + zi, yy = y0 + (i - zi * ny);
                 const int row = (zz * g.dy + yy) * g.dx;
                 const bool inner = havePrev && abs(zz - cz) <= prev && abs(yy - cy) <= prev;
                 // left part [x0, lx1] and right part [rx0, x1]; a row outside the old footprint is all "left"
@@ -174,10 +176,10 @@ __device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* _
     const unsigned d5b = (unsigned)(r.key[4] >> 32);                                  // 0xffffffff when fewer than 5 exist
     unsigned tb = __float_as_uint(guard * guard);                                     // threshold on d^2 bits, exclusive
     tb = min(tb, __reduce_min_sync(FULL, (unsigned)(p.key[4] >> 32)));                // tails of the full lists (empty = 0xffffffff)
-    int count = 0;
+    int count = 0, c = 0;                                                             // c = this lane's cached entries at the final threshold
     for (int tries = 0; tries < 8; tries++) {
         const unsigned long long tk = (unsigned long long)tb << 32;
-        int c = 0;
+        c = 0;
         #pragma unroll
         for (int i = 0; i < 5; i++) c += p.key[i] < tk ? 1 : 0;
         count = __reduce_add_sync(FULL, c);
@@ -188,17 +190,14 @@ __device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* _
     }
     const bool usable = count <= FBPR_KNN_CACHE && (d5b == 0xffffffffu || tb > d5b);   // must hold the whole top-5
     {
-        const unsigned long long tk = usable ? (unsigned long long)tb << 32 : 0ull;
-        int c = 0;
-        #pragma unroll
-        for (int i = 0; i < 5; i++) c += p.key[i] < tk ? 1 : 0;
+        if (!usable) c = 0;
         int incl = c;
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
         const int total = __shfl_sync(FULL, incl, 31);
         int off = incl - c;
         #pragma unroll
-        for (int i = 0; i < 5; i++) if (p.key[i] < tk) cache[off++] = (int)(unsigned)(p.key[i] & 0xffffffffu);
+        for (int i = 0; i < 5; i++) if (i < c) cache[off++] = (int)(unsigned)(p.key[i] & 0xffffffffu);   // the list is sorted: its first c keys qualify
         if (lane >= total && lane < FBPR_KNN_CACHE) cache[lane] = -1;
     }
     return usable ? sqrtf(__uint_as_float(tb)) : 0.f;
