@@ -170,7 +170,7 @@ def _oracle_scan2map(fr, debug_iter=0):
     return fe, mo, pose, iters, flags
 
 
-@pytest.mark.parametrize("config,frame,debug_iter", [(1, 0, 0), (1, 1, 2), (2, 0, 1), (3, 1, 0), (0, 0, 0)])
+@pytest.mark.parametrize("config,frame,debug_iter", [(1, 0, 0), (1, 1, 2), (2, 0, 1), (3, 1, 0), (3, 2, 3), (4, 5, 4), (0, 0, 0)])
 def test_scan2map_matches_oracle(fb, config, frame, debug_iter):
     fr = synth.make_frame(config, frame)
     fe, mo, pose_w, iters_w, flags_w = _oracle_scan2map(fr, debug_iter)
@@ -410,3 +410,41 @@ def test_cpp_host_classes_cloud_handler(fb, share, tmp_path):
     assert (it.value, fl.value) == (iters, flags)
     got = pose.reshape(3, 4)
     assert np.max(np.abs(got[:, 3] - T[:, 3])) <= POSE_TOL_T and np.max(np.abs(got[:, :3] - T[:, :3])) <= POSE_TOL_R
+
+
+# ------------------------------------------------------------------ BASELINE configs[4]: 128-beam scan vs 2 M-point map
+def test_dense_map_stress_config5(fb):
+    """OS1-128-like 128 x 2048 scan against a raw-dense 2 M-point map (0.2 m surface leaf): feature indices, the scan
+    VoxelGrids, the kNN sets / coefficients of iterations 0 and 3 and the final pose against the oracle."""
+    fr = synth.make_frame(5, 0)
+    P = fr["params"]
+    cap = dict(max_map_corner=len(fr["map_corner"]) + 64, max_map_surf=len(fr["map_surf"]) + 64)
+    ci = oracle.project(P, fr["scan"], fr["imu"], fr["imu_available"])
+    fe = oracle.extract_features(P, ci)
+    r = _reg(fb, P, **cap)
+    r.set_raw_scan(0, fb.api.pack_raw(fr["scan"]), imu=fr["imu"], imu_available=fr["imu_available"])
+    r.project(0, 1); r.featureExtra(0, 1); r.sync()
+    assert np.array_equal(r.get_buffer(0, "CORNER_INDEX"), fe["corner_index"])
+    assert np.array_equal(r.get_buffer(0, "SURF"), fe["surface"])
+    for debug_iter in (0, 3):
+        mo = oracle.MapOptimization(P)
+        mo.set_imu(fr["imu_available"], 0.0, 0.0)
+        mo.set_scan(fe["corner"], fe["surface"]); mo.set_map(fr["map_corner"], fr["map_surf"]); mo.downsample()
+        pose_w, iters_w, flags_w, _ = mo.scan2map(fr["guess"], debug_iter)
+        dbg = mo.debug()
+        r.set_local_map(0, fr["map_corner"], fr["map_surf"])
+        r.set_pose(0, fr["guess"])
+        r.set_debug_iteration(debug_iter)
+        r.downsampleCurrentScan(0, 1); r.scan2MapOptimization(0, 1); r.sync()
+        assert np.array_equal(r.get_buffer(0, "SURF_DS"), mo.get_cloud(1))
+        pose, iters, flags = r.get_pose(0)
+        assert (iters, flags) == (iters_w, flags_w)
+        assert np.max(np.abs(pose[3:] - pose_w[3:])) <= POSE_TOL_T and np.max(np.abs(pose[:3] - pose_w[:3])) <= POSE_TOL_R
+        if dbg["iter"] == debug_iter:
+            for kind, K in (("CORNER", "corner"), ("SURF", "surf")):
+                knn = r.get_buffer(0, "KNN_" + kind); d2 = r.get_buffer(0, "KNN_D2_" + kind)
+                accept = dbg[K + "D2"][:, 4] < 1.0
+                assert np.array_equal(knn[accept], dbg[K + "Knn"][accept]), kind
+                assert np.array_equal(d2[accept], dbg[K + "D2"][accept])
+                assert np.array_equal(r.get_buffer(0, "FLAG_" + kind), dbg[K + "Flag"]), kind
+    r.close()
