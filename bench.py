@@ -27,7 +27,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "scan-to-map frames/sec/box (64-beam synthetic)"
+METRIC = "ms/frame scan-to-map (64-beam synthetic); frames/sec/box at 1/2/4/8 GPUs"   # BASELINE.json; `value` is the frames/sec/box half
 CONFIG = 4   # synth config id: HDL-64E-like 64x2048 scan, own 200k map per frame
 
 
@@ -322,10 +322,19 @@ def run_b200(args, rank, world, local_rank):
     kernel_names = dict(project="proj_scatter+proj_compact", features="feat_ring", downsample="rs_scatter (radix-sort VoxelGrid)",
                         map_index="grid_count+grid_scatter", lm="lm_kernel")
     ach = stages[dom]["alg_GBps"] or 0.0
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r01_traffic.json), scaled per frame
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tj.get("kernel") == kernel_names[dom]:
+            traffic = float(tj["dram_bytes_per_frame"]) * F
+    except Exception:
+        pass
     roofline = dict(bound="hbm", kernel=kernel_names[dom], stage=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
-                    traffic=None, peak_source=peak_src,
+                    traffic=traffic, peak_source=peak_src,
                     note="achieved = SURVEY 8(d) algorithmic bytes of this stage for the F frames of one step / its CUDA-event time; "
-                         "the LM loop is latency/L2-gather bound by design (<=30 dependent iterations), see DESIGN.md")
+                         "the LM loop is latency/L2-gather bound by design (<=30 dependent iterations), see DESIGN.md; "
+                         "traffic = dram read+write bytes of one launch from profiles/ (ncu --set full at the same batch size)")
     whole = sum(alg.values())
     frame_GBps = whole / (ms_total / args.steps * 1e-3) / 1e9
 
