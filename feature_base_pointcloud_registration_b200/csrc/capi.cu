@@ -189,6 +189,7 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     h->lmGridBlocks = fbpr_lm_grid_blocks(device);
     if (h->lmGridBlocks > 1024) h->lmGridBlocks = 1024;
     h->lmWholeGpu = params->lm_single_frame_mode == 0;
+    if (h->lmWholeGpu && h->lmGridBlocks <= 0) return fbpr_fail_msg("the cooperative single-frame LM kernel cannot be made resident on this device (set lm_single_frame_mode = 1 to use one cluster)");
     ALLOC(h->regPose, 16);
 
     // downsampleCurrentScan segments: (slot, corner), (slot, surf)
