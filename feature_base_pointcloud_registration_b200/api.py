@@ -71,6 +71,10 @@ class CloudInfoView(C.Structure):
                 ("imuAvailable", C.c_int64), ("imuRollInit", C.c_float), ("imuPitchInit", C.c_float), ("imuYawInit", C.c_float)]
 
 
+class Pc2Layout(C.Structure):                                # fbpr_pc2_layout
+    _fields_ = [(k, C.c_int32) for k in ("point_step", "off_x", "off_y", "off_z", "off_intensity", "off_ring", "ring_bytes", "off_time")]
+
+
 class FrameInput(C.Structure):
     _fields_ = [("raw", C.c_void_p), ("n_raw", C.c_int32), ("deskewFlag", C.c_int32), ("imuAvailable", C.c_int64),
                 ("timeScanCur", C.c_double), ("imuTime", C.c_void_p), ("imuRotX", C.c_void_p), ("imuRotY", C.c_void_p), ("imuRotZ", C.c_void_p),
@@ -168,6 +172,43 @@ class Registration:
         self._ck(self.lib.fbpr_set_raw_scan(self.h, slot, _vp(raw), len(raw), MEM_HOST, C.c_int64(imu_available), C.c_int(deskew_flag),
                                             *args, C.c_float(imu_roll_init), C.c_float(imu_pitch_init)))
         self._keep = [raw]
+
+    def set_raw_scan_pc2(self, slot, data, n, layout, imu=None, imu_available=0, imu_roll_init=0.0, imu_pitch_init=0.0):
+        """sensor_msgs/PointCloud2 payload bytes (any point_step / field offsets) -> the slot's raw scan, repacked on the device.
+        layout: dict(point_step, off_x, off_y, off_z, off_intensity, off_ring, ring_bytes, off_time)."""
+        buf = np.ascontiguousarray(np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data.view(np.uint8).reshape(-1))
+        L = Pc2Layout(*[int(layout[k]) for k, _ in Pc2Layout._fields_])
+        if imu is not None and imu_available:
+            args = (C.c_double(imu["timeScanCur"]), _vp(imu["imuTime"]), _vp(imu["imuRotX"]), _vp(imu["imuRotY"]), _vp(imu["imuRotZ"]),
+                    C.c_int(int(imu["imuPointerCur"])))
+        else:
+            args = (C.c_double(0.0), None, None, None, None, C.c_int(0))
+        self._ck(self.lib.fbpr_set_raw_scan_pc2(self.h, slot, _vp(buf), int(n), C.byref(L), MEM_HOST, C.c_int64(imu_available), *args,
+                                                C.c_float(imu_roll_init), C.c_float(imu_pitch_init)))
+
+    def set_clouds_xyzi32(self, slot, kind, corner32, surf32):
+        """32-byte pcl::PointXYZI records ([n,8] f32) as the slot's feature clouds (kind 0) or local map (kind 1)."""
+        c = _f32(corner32).reshape(-1, 8); s = _f32(surf32).reshape(-1, 8)
+        self._ck(self.lib.fbpr_set_clouds_xyzi32(self.h, slot, int(kind), _vp(c), len(c), _vp(s), len(s)))
+
+    def get_buffer_xyzi32(self, slot, name):
+        cap = max(self.params.N_SCAN * self.params.Horizon_SCAN, self.params.max_map_corner, self.params.max_map_surf, 65536) * 32 + 1024
+        buf = np.zeros(cap, np.uint8)
+        self.lib.fbpr_get_buffer_xyzi32.restype = C.c_int64
+        self.lib.fbpr_get_buffer_xyzi32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64]
+        nb = self._ck(self.lib.fbpr_get_buffer_xyzi32(self.h, slot, BUF[name], _vp(buf), cap))
+        return buf[:nb].view(np.float32).reshape(-1, 8).copy()
+
+    def extractCloud(self, slot, key_poses6, check_xyz, corner_frames, surf_frames, last_key_xyz):
+        """fbpr_extract_cloud: extractCloud with explicit re-check positions (entry i re-checked at check_xyz[i])."""
+        K = len(corner_frames)
+        kp = _f32(key_poses6).reshape(K, 6); ck = _f32(check_xyz).reshape(K, 3) if check_xyz is not None else None
+        coff = np.zeros(K + 1, np.int32); soff = np.zeros(K + 1, np.int32)
+        coff[1:] = np.cumsum([len(c) for c in corner_frames]); soff[1:] = np.cumsum([len(s) for s in surf_frames])
+        call = _f32(np.concatenate(corner_frames)).reshape(-1, 4); sall = _f32(np.concatenate(surf_frames)).reshape(-1, 4)
+        lk = _f32(last_key_xyz)
+        self._ck(self.lib.fbpr_extract_cloud(self.h, slot, K, _vp(kp), _vp(ck), _vp(call), _vp(coff), _vp(sall), _vp(soff), _vp(lk), MEM_HOST))
+        self.sync()
 
     def set_raw_scan_device(self, slot, dev_ptr, n, imu=None, imu_available=0, deskew_flag=1):
         if imu is not None and imu_available:

@@ -26,12 +26,14 @@ int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blo
 int fbpr_lm_grid_blocks(int device);
 void fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float rot_tol, float z_tol, cudaStream_t st, long long* launches);
 void fbpr_launch_keyframe_transform(const float* d_poses6, int K, const float4* d_in, const int* d_off, float4* d_out, int* d_n_out,
-                                    const float* d_last_xyz, float radius, int max_pts, int* d_outoff, float* d_T,
+                                    const float* d_last_xyz, float radius, const float* d_check_xyz, int max_pts, int* d_outoff, float* d_T,
                                     cudaStream_t st, long long* launches);
 void fbpr_launch_crop_box(const float4* d_in, int n, const float* d_pose12, float4* d_out, int cap, int* d_n_out, int* d_tile,
                           cudaStream_t st, long long* launches);
 void fbpr_launch_pose_decompose(const float* d_pose12, FrameMeta* meta, int slot, cudaStream_t st, long long* launches);
 void fbpr_launch_pose_compose(const FrameMeta* meta, int slot, float* d_pose12, cudaStream_t st, long long* launches);
+void fbpr_launch_pc2_to_raw(const unsigned char* d_src, int n, const fbpr_pc2_layout& L, fbpr_raw_point* d_dst, cudaStream_t st, long long* launches);
+void fbpr_launch_xyzi_repack(const float4* d_in, int n, float4* d_out, int to32, cudaStream_t st, long long* launches);
 
 // ---- error reporting -------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -86,6 +88,7 @@ struct fbpr_handle {
     int globalCornerN = -1, globalSurfN = 0;   // resident global maps (fbpr_set_global_map)
     // batched input staging (pinned) + stage timing
     FrameMeta* h_metaStage = nullptr; double* h_imuStage = nullptr; cudaEvent_t stageDone = nullptr; bool stagePending = false;
+    unsigned char* wireStage = nullptr; size_t wireStageBytes = 0;          // PointCloud2 / 32-byte PCL staging (grown on demand)
     cudaStream_t copyStream = nullptr, lmStream = nullptr; std::vector<cudaEvent_t> pipeEvents;      // fbpr_register_frames: uploads overlap compute
     bool timing = false;
     struct TimedSpan { int stage; cudaEvent_t a, b; };
@@ -253,6 +256,7 @@ void fbpr_destroy(fbpr_handle* h) {
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     if (h->stageDone) cudaEventDestroy(h->stageDone);
     for (auto& e : h->pipeEvents) cudaEventDestroy(e);
+    if (h->wireStage) cudaFree(h->wireStage);
     if (h->copyStream) cudaStreamDestroy(h->copyStream);
     if (h->lmStream) cudaStreamDestroy(h->lmStream);
     if (h->h_metaStage) cudaFreeHost(h->h_metaStage);
@@ -301,6 +305,67 @@ int fbpr_set_raw_scan(fbpr_handle* h, int slot, const fbpr_raw_point* pts, int n
     FBPR_CUDA_OK(cudaMemcpyAsync(base + offsetof(FrameMeta, n_raw), &m.n_raw, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     FBPR_CUDA_OK(cudaMemcpyAsync(base + offsetof(FrameMeta, deskewFlag), &m.deskewFlag,
                                  offsetof(FrameMeta, pose) - offsetof(FrameMeta, deskewFlag), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+static int wire_stage(fbpr_handle* h, size_t bytes) {
+    if (bytes <= h->wireStageBytes) return 0;
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (h->wireStage) cudaFree(h->wireStage);
+    h->wireStage = nullptr; h->wireStageBytes = 0;
+    FBPR_CUDA_OK(cudaMalloc((void**)&h->wireStage, bytes + 4096));
+    h->wireStageBytes = bytes + 4096;
+    return 0;
+}
+
+int fbpr_set_raw_scan_pc2(fbpr_handle* h, int slot, const void* data, int n, const fbpr_pc2_layout* L, int mem,
+                          int64_t imuAvailable, double timeScanCur,
+                          const double* imuTime, const double* imuRotX, const double* imuRotY, const double* imuRotZ,
+                          int imuPointerCur, float imuRollInit, float imuPitchInit) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    if (!L || (!data && n > 0)) return fbpr_fail_msg("null PointCloud2 data / layout");
+    if (n < 0 || n > h->rawCap) return fbpr_fail_msg("raw scan larger than max_raw_points");
+    if (L->ring_bytes != 1 && L->ring_bytes != 2 && L->ring_bytes != 4)
+        return fbpr_fail_msg("Point cloud ring channel not available (imageProjection.cpp:262-280)");
+    const int step = L->point_step;
+    auto inside = [&](int off, int sz) { return off >= 0 && off + sz <= step; };
+    if (step <= 0 || !inside(L->off_x, 4) || !inside(L->off_y, 4) || !inside(L->off_z, 4) || !inside(L->off_ring, L->ring_bytes) ||
+        (L->off_intensity >= 0 && !inside(L->off_intensity, 4)) || (L->off_time >= 0 && !inside(L->off_time, 4)))
+        return fbpr_fail_msg("PointCloud2 field offsets outside point_step");
+    cudaSetDevice(h->device);
+    const unsigned char* d_src = reinterpret_cast<const unsigned char*>(data);
+    if (mem == FBPR_MEM_HOST && n > 0) {
+        rc = wire_stage(h, (size_t)n * step); if (rc) return rc;
+        FBPR_CUDA_OK(cudaMemcpyAsync(h->wireStage, data, (size_t)n * step, cudaMemcpyHostToDevice, h->stream));
+        d_src = h->wireStage;
+    }
+    const int deskewFlag = L->off_time >= 0 ? 1 : -1;          // imageProjection.cpp:283-297
+    rc = fbpr_set_raw_scan(h, slot, nullptr, 0, FBPR_MEM_DEVICE, imuAvailable, deskewFlag, timeScanCur, imuTime, imuRotX, imuRotY, imuRotZ,
+                           imuPointerCur, imuRollInit, imuPitchInit);
+    if (rc) return rc;
+    fbpr_launch_pc2_to_raw(d_src, n, *L, h->raw + (size_t)slot * h->rawCap, h->stream, &h->launches);
+    FBPR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->meta + slot) + offsetof(FrameMeta, n_raw), &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));            // `n` lives on the caller's stack
+    return 0;
+}
+
+int fbpr_set_clouds_xyzi32(fbpr_handle* h, int slot, int kind, const void* corner32, int nC, const void* surf32, int nS) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    if (kind != 0 && kind != 1) return fbpr_fail_msg("kind must be 0 (feature clouds) or 1 (local map)");
+    const int capC = kind == 0 ? h->cornerCap : h->mapCornerCap, capS = kind == 0 ? h->P : h->mapSurfCap;
+    if (nC < 0 || nC > capC || nS < 0 || nS > capS) return fbpr_fail_msg("cloud exceeds capacity");
+    cudaSetDevice(h->device);
+    rc = wire_stage(h, ((size_t)nC + (size_t)nS) * 32); if (rc) return rc;
+    float4* dC = kind == 0 ? h->corner + (size_t)slot * h->cornerCap : h->mapCorner + (size_t)slot * h->mapCornerCap;
+    float4* dS = kind == 0 ? h->surf + (size_t)slot * h->P : h->mapSurf + (size_t)slot * h->mapSurfCap;
+    if (nC) FBPR_CUDA_OK(cudaMemcpyAsync(h->wireStage, corner32, (size_t)nC * 32, cudaMemcpyHostToDevice, h->stream));
+    if (nS) FBPR_CUDA_OK(cudaMemcpyAsync(h->wireStage + (size_t)nC * 32, surf32, (size_t)nS * 32, cudaMemcpyHostToDevice, h->stream));
+    fbpr_launch_xyzi_repack(reinterpret_cast<const float4*>(h->wireStage), nC, dC, 0, h->stream, &h->launches);
+    fbpr_launch_xyzi_repack(reinterpret_cast<const float4*>(h->wireStage + (size_t)nC * 32), nS, dS, 0, h->stream, &h->launches);
+    int v[2] = { nC, nS };
+    const size_t off = kind == 0 ? offsetof(FrameMeta, n_corner) : offsetof(FrameMeta, n_map_corner);
+    FBPR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->meta + slot) + off, v, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -640,6 +705,13 @@ int fbpr_extract_surrounding_keyframes(fbpr_handle* h, int slot, int K, const fl
                                        const float* corner_xyzi, const int32_t* corner_off,
                                        const float* surf_xyzi, const int32_t* surf_off,
                                        const float last_key_xyz[3], int mem) {
+    return fbpr_extract_cloud(h, slot, K, key_poses6, nullptr, corner_xyzi, corner_off, surf_xyzi, surf_off, last_key_xyz, mem);
+}
+
+int fbpr_extract_cloud(fbpr_handle* h, int slot, int K, const float* key_poses6, const float* check_xyz,
+                       const float* corner_xyzi, const int32_t* corner_off,
+                       const float* surf_xyzi, const int32_t* surf_off,
+                       const float last_key_xyz[3], int mem) {
     int rc = check_range(h, slot, 1); if (rc) return rc;
     if (h->kfCap <= 0) return fbpr_fail_msg("handle created with max_keyframe_points = 0");
     if (mem != FBPR_MEM_HOST) return fbpr_fail_msg("extract_surrounding_keyframes takes host buffers");
@@ -655,6 +727,11 @@ int fbpr_extract_surrounding_keyframes(fbpr_handle* h, int slot, int K, const fl
     FBPR_CUDA_OK(cudaMallocAsync(&d_cin, sizeof(float4) * (nc + 1), h->stream));
     FBPR_CUDA_OK(cudaMallocAsync(&d_sin, sizeof(float4) * (ns + 1), h->stream));
     FBPR_CUDA_OK(cudaMallocAsync(&d_last, sizeof(float) * 4, h->stream));
+    float* d_check = nullptr;
+    if (check_xyz && K) {
+        FBPR_CUDA_OK(cudaMallocAsync(&d_check, sizeof(float) * 3 * K, h->stream));
+        FBPR_CUDA_OK(cudaMemcpyAsync(d_check, check_xyz, sizeof(float) * 3 * K, cudaMemcpyHostToDevice, h->stream));
+    }
     int* d_outoff = nullptr; float* d_T = nullptr;
     FBPR_CUDA_OK(cudaMallocAsync(&d_outoff, sizeof(int) * (K + 2), h->stream));
     FBPR_CUDA_OK(cudaMallocAsync(&d_T, sizeof(float) * 12 * (K + 1), h->stream));
@@ -667,13 +744,14 @@ int fbpr_extract_surrounding_keyframes(fbpr_handle* h, int slot, int K, const fl
     }
     FBPR_CUDA_OK(cudaMemcpyAsync(d_last, last_key_xyz, sizeof(float) * 3, cudaMemcpyHostToDevice, h->stream));
     fbpr_launch_keyframe_transform(d_poses, K, d_cin, d_coff, h->kfCorner + (size_t)slot * h->kfCap, h->kfCount + 2 * slot,
-                                   d_last, h->p.surroundingKeyframeSearchRadius, nc, d_outoff, d_T, h->stream, &h->launches);
+                                   d_last, h->p.surroundingKeyframeSearchRadius, d_check, nc, d_outoff, d_T, h->stream, &h->launches);
     fbpr_launch_keyframe_transform(d_poses, K, d_sin, d_soff, h->kfSurf + (size_t)slot * h->kfCap, h->kfCount + 2 * slot + 1,
-                                   d_last, h->p.surroundingKeyframeSearchRadius, ns, d_outoff, d_T, h->stream, &h->launches);
+                                   d_last, h->p.surroundingKeyframeSearchRadius, d_check, ns, d_outoff, d_T, h->stream, &h->launches);
     fbpr_launch_voxel(h->d_kfSegs + 2 * (size_t)slot, 2, h->kfCap, h->tilesCap, h->stream, &h->launches);
     cudaFreeAsync(d_poses, h->stream); cudaFreeAsync(d_coff, h->stream); cudaFreeAsync(d_soff, h->stream);
     cudaFreeAsync(d_cin, h->stream); cudaFreeAsync(d_sin, h->stream); cudaFreeAsync(d_last, h->stream);
     cudaFreeAsync(d_outoff, h->stream); cudaFreeAsync(d_T, h->stream);
+    if (d_check) cudaFreeAsync(d_check, h->stream);
     return 0;
 }
 
@@ -833,6 +911,34 @@ int64_t fbpr_get_buffer(fbpr_handle* h, int slot, int which, void* dst, int64_t 
     if (!src) return fbpr_fail_msg("buffer not available (unknown id, or debug capture not enabled for this slot)");
     if ((int64_t)bytes > cap_bytes) return fbpr_fail_msg("destination too small");
     if (bytes) FBPR_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return (int64_t)bytes;
+}
+
+int64_t fbpr_get_buffer_xyzi32(fbpr_handle* h, int slot, int which, void* dst, int64_t cap_bytes) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    cudaSetDevice(h->device);
+    FrameMeta m;
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    FBPR_CUDA_OK(cudaMemcpy(&m, h->meta + slot, sizeof(m), cudaMemcpyDeviceToHost));
+    const size_t P = h->P, CC = h->cornerCap;
+    const float4* src = nullptr; int n = 0;
+    switch (which) {
+    case FBPR_BUF_CLOUD: src = h->cloud + slot * P; n = m.n_valid; break;
+    case FBPR_BUF_CORNER: src = h->corner + slot * CC; n = m.n_corner; break;
+    case FBPR_BUF_SURF: src = h->surf + slot * P; n = m.n_surf; break;
+    case FBPR_BUF_CORNER_DS: src = h->cornerDS + slot * CC; n = m.n_corner_ds; break;
+    case FBPR_BUF_SURF_DS: src = h->surfDS + slot * P; n = m.n_surf_ds; break;
+    case FBPR_BUF_MAP_CORNER: src = h->mapCorner + (size_t)slot * h->mapCornerCap; n = m.n_map_corner; break;
+    case FBPR_BUF_MAP_SURF: src = h->mapSurf + (size_t)slot * h->mapSurfCap; n = m.n_map_surf; break;
+    default: return fbpr_fail_msg("not a point-cloud buffer");
+    }
+    const size_t bytes = (size_t)n * 32;
+    if ((int64_t)bytes > cap_bytes) return fbpr_fail_msg("destination too small");
+    if (n == 0) return 0;
+    rc = wire_stage(h, bytes); if (rc) return rc;
+    fbpr_launch_xyzi_repack(src, n, reinterpret_cast<float4*>(h->wireStage), 1, h->stream, &h->launches);
+    FBPR_CUDA_OK(cudaMemcpyAsync(dst, h->wireStage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
     return (int64_t)bytes;
 }
 

@@ -14,7 +14,9 @@ constexpr int TILE = 2048;
 constexpr int IPT = TILE / TPB;
 
 // one CTA: keep flags (distance re-check, :924), output offsets, one 3x4 transform per keyframe
-__global__ void kf_prepare(const float* poses6, int K, const int* off, const float* last_xyz, float radius,
+// check_xyz (may be null) = the positions the re-check looks at when they differ from the keyframes' own poses: after
+// extractNearby they are the VoxelGrid-averaged key poses, whose averaged intensity picks the keyframe (:927)
+__global__ void kf_prepare(const float* poses6, int K, const int* off, const float* last_xyz, float radius, const float* check_xyz,
                            int* outoff, float* T, int* n_out) {
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
         const float* p = poses6 + 6 * i;
@@ -24,7 +26,7 @@ __global__ void kf_prepare(const float* poses6, int K, const int* off, const flo
     if (threadIdx.x == 0) {
         int run = 0;
         for (int i = 0; i < K; i++) {
-            const float* p = poses6 + 6 * i;
+            const float* p = check_xyz ? check_xyz + 3 * i - 3 : poses6 + 6 * i;       // p[3..5] = position
             float ddx = p[3] - last_xyz[0], ddy = p[4] - last_xyz[1], ddz = p[5] - last_xyz[2];
             bool keep = !(sqrtf(ddx * ddx + ddy * ddy + ddz * ddz) > radius);
             outoff[i] = keep ? run : -1;
@@ -126,12 +128,62 @@ __global__ void pose_compose(const FrameMeta* meta, int slot, float* T) {
     for (int k = 0; k < 12; k++) T[k] = t[k];
 }
 
+// ---- wire formats -----------------------------------------------------------------------------
+// sensor_msgs/PointCloud2 records of any point_step / field offsets (the Velodyne driver's 22-byte x,y,z,intensity,ring,time
+// or pcl::toROSMsg's padded 32-byte PointXYZIRT, imageProjection.cpp:8-21, :252) -> the packed 24-byte record of the projection
+__device__ __forceinline__ unsigned load_u32_unaligned(const unsigned char* p) {
+    return (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+}
+__global__ void __launch_bounds__(TPB) pc2_to_raw(const unsigned char* __restrict__ src, int n, fbpr_pc2_layout L, fbpr_raw_point* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char* r = src + (size_t)i * L.point_step;
+    fbpr_raw_point o;
+    o.x = __uint_as_float(load_u32_unaligned(r + L.off_x));
+    o.y = __uint_as_float(load_u32_unaligned(r + L.off_y));
+    o.z = __uint_as_float(load_u32_unaligned(r + L.off_z));
+    o.intensity = L.off_intensity >= 0 ? __uint_as_float(load_u32_unaligned(r + L.off_intensity)) : 0.f;
+    int ring = 0;
+    if (L.ring_bytes == 1) ring = r[L.off_ring];
+    else if (L.ring_bytes == 2) ring = (int)r[L.off_ring] | ((int)r[L.off_ring + 1] << 8);
+    else if (L.ring_bytes == 4) ring = (int)load_u32_unaligned(r + L.off_ring);
+    o.ring = ring;
+    o.time = L.off_time >= 0 ? __uint_as_float(load_u32_unaligned(r + L.off_time)) : 0.f;
+    dst[i] = o;
+}
+// float4 XYZI <-> the 32-byte pcl::PointXYZI of pcl::toROSMsg / fromROSMsg (x,y,z,pad | intensity,pad,pad,pad; utility.h:55, :255-264)
+__global__ void __launch_bounds__(TPB) xyzi16_to_32(const float4* __restrict__ in, int n, float4* __restrict__ out2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = in[i];
+    out2[2 * i] = make_float4(p.x, p.y, p.z, 1.0f);          // PCL initialises the padding word data[3] to 1
+    out2[2 * i + 1] = make_float4(p.w, 0.f, 0.f, 0.f);
+}
+__global__ void __launch_bounds__(TPB) xyzi32_to_16(const float4* __restrict__ in2, int n, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = in2[2 * i], b = in2[2 * i + 1];
+    out[i] = make_float4(a.x, a.y, a.z, b.x);
+}
+
 }  // namespace
 
+void fbpr_launch_pc2_to_raw(const unsigned char* d_src, int n, const fbpr_pc2_layout& L, fbpr_raw_point* d_dst, cudaStream_t st, long long* launches) {
+    if (n <= 0) return;
+    pc2_to_raw<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(d_src, n, L, d_dst);
+    if (launches) *launches += 1;
+}
+void fbpr_launch_xyzi_repack(const float4* d_in, int n, float4* d_out, int to32, cudaStream_t st, long long* launches) {
+    if (n <= 0) return;
+    if (to32) xyzi16_to_32<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(d_in, n, d_out);
+    else xyzi32_to_16<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(d_in, n, d_out);
+    if (launches) *launches += 1;
+}
+
 void fbpr_launch_keyframe_transform(const float* d_poses6, int K, const float4* d_in, const int* d_off, float4* d_out, int* d_n_out,
-                                    const float* d_last_xyz, float radius, int max_pts, int* d_outoff, float* d_T,
+                                    const float* d_last_xyz, float radius, const float* d_check_xyz, int max_pts, int* d_outoff, float* d_T,
                                     cudaStream_t st, long long* launches) {
-    kf_prepare<<<1, 256, 0, st>>>(d_poses6, K, d_off, d_last_xyz, radius, d_outoff, d_T, d_n_out);
+    kf_prepare<<<1, 256, 0, st>>>(d_poses6, K, d_off, d_last_xyz, radius, d_check_xyz, d_outoff, d_T, d_n_out);
     if (max_pts > 0 && K > 0) kf_transform<<<(max_pts + TPB - 1) / TPB, TPB, 0, st>>>(K, d_in, d_off, d_outoff, d_T, d_out, max_pts);
     if (launches) *launches += (max_pts > 0 && K > 0) ? 2 : 1;
 }

@@ -3,6 +3,7 @@
 // reference keeps on the host.  Every numeric step is a call into libfbpr_b200.so.
 #include "feature_matching.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -41,6 +42,7 @@ bool ParamServer::loadYaml(const std::string& path) {
         else if (key == "z_tollerance") is >> z_tollerance; else if (key == "rotation_tollerance") is >> rotation_tollerance;
         else if (key == "numberOfCores") is >> numberOfCores; else if (key == "mappingProcessInterval") is >> mappingProcessInterval;
         else if (key == "surroundingKeyframeSearchRadius") is >> surroundingKeyframeSearchRadius;
+        else if (key == "surroundingKeyframeDensity") is >> surroundingKeyframeDensity;
         else if (key == "loopClosureEnableFlag") loopClosureEnableFlag = (val == "true" || val == "True" || val == "1");
     }
     return true;
@@ -60,6 +62,131 @@ fbpr_params ParamServer::toAbi(int max_frames, int max_map_corner, int max_map_s
 static void download(fbpr_handle* h, int which, int n, PointCloud& out) {
     out.resize((size_t)(n > 0 ? n : 0));
     if (n > 0) check((int)fbpr_get_buffer(h, 0, which, out.data(), (int64_t)out.size() * sizeof(PointType)), "fbpr_get_buffer");
+}
+
+// ------------------------------------------------------------------ PCD IO
+bool loadPCDFile(const std::string& path, PointCloud& cloud, std::string* error) {
+    auto fail = [&](const char* m) { if (error) *error = m; return false; };
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return fail("cannot open file");
+    std::vector<std::string> fields; std::vector<int> sizes, counts; std::vector<char> types;
+    long long points = -1, width = -1, height = 1; std::string data;
+    std::string line;
+    while (std::getline(f, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty() || line[0] == '#') continue;
+        std::istringstream is(line); std::string key; is >> key;
+        if (key == "FIELDS") { std::string v; while (is >> v) fields.push_back(v); }
+        else if (key == "SIZE") { int v; while (is >> v) sizes.push_back(v); }
+        else if (key == "TYPE") { char v; while (is >> v) types.push_back(v); }
+        else if (key == "COUNT") { int v; while (is >> v) counts.push_back(v); }
+        else if (key == "WIDTH") is >> width; else if (key == "HEIGHT") is >> height; else if (key == "POINTS") is >> points;
+        else if (key == "DATA") { is >> data; break; }
+    }
+    if (points < 0) points = width * height;
+    if (fields.empty() || sizes.size() != fields.size() || types.size() != fields.size() || points < 0) return fail("bad PCD header");
+    if (counts.empty()) counts.assign(fields.size(), 1);
+    int ix = -1, iy = -1, iz = -1, ii = -1; std::vector<int> off(fields.size()); int step = 0, col = 0; std::vector<int> colOf(fields.size());
+    for (size_t k = 0; k < fields.size(); k++) {
+        off[k] = step; colOf[k] = col; step += sizes[k] * counts[k]; col += counts[k];
+        if (fields[k] == "x") ix = (int)k; else if (fields[k] == "y") iy = (int)k; else if (fields[k] == "z") iz = (int)k; else if (fields[k] == "intensity") ii = (int)k;
+    }
+    if (ix < 0 || iy < 0 || iz < 0) return fail("PCD has no x y z fields");
+    for (int k : { ix, iy, iz, ii }) if (k >= 0 && !(types[k] == 'F' && sizes[k] == 4)) return fail("x y z intensity must be 4-byte floats");
+    cloud.assign((size_t)points, PointType{ 0, 0, 0, 0 });
+    if (data == "ascii") {
+        std::vector<double> row(col);
+        for (long long n = 0; n < points; n++) {
+            if (!std::getline(f, line)) return fail("PCD ascii data truncated");
+            std::istringstream is(line);
+            for (int c = 0; c < col; c++) { std::string tok; if (!(is >> tok)) return fail("PCD ascii row too short"); row[c] = std::strtod(tok.c_str(), nullptr); }
+            PointType& p = cloud[(size_t)n];
+            p.x = (float)row[colOf[ix]]; p.y = (float)row[colOf[iy]]; p.z = (float)row[colOf[iz]]; p.intensity = ii >= 0 ? (float)row[colOf[ii]] : 0.f;
+        }
+    } else if (data == "binary") {
+        std::vector<char> buf((size_t)points * step);
+        f.read(buf.data(), (std::streamsize)buf.size());
+        if ((size_t)f.gcount() != buf.size()) return fail("PCD binary data truncated");
+        for (long long n = 0; n < points; n++) {
+            const char* r = buf.data() + (size_t)n * step; PointType& p = cloud[(size_t)n];
+            std::memcpy(&p.x, r + off[ix], 4); std::memcpy(&p.y, r + off[iy], 4); std::memcpy(&p.z, r + off[iz], 4);
+            if (ii >= 0) std::memcpy(&p.intensity, r + off[ii], 4);
+        }
+    } else return fail("unsupported PCD DATA mode (ascii and binary are supported)");
+    return true;
+}
+
+static void pcd_header(std::ostream& o, size_t n, const char* mode) {
+    o << "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\n"
+      << "WIDTH " << n << "\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS " << n << "\nDATA " << mode << "\n";
+}
+bool savePCDFileASCII(const std::string& path, const PointCloud& cloud) {
+    std::ofstream f(path, std::ios::binary);
+    if (!f) return false;
+    pcd_header(f, cloud.size(), "ascii");
+    char buf[128];
+    for (const PointType& p : cloud) {          // PCL writes 8 significant digits
+        int len = std::snprintf(buf, sizeof(buf), "%.8g %.8g %.8g %.8g\n", (double)p.x, (double)p.y, (double)p.z, (double)p.intensity);
+        f.write(buf, len);
+    }
+    return (bool)f;
+}
+bool savePCDFileBinary(const std::string& path, const PointCloud& cloud) {
+    std::ofstream f(path, std::ios::binary);
+    if (!f) return false;
+    pcd_header(f, cloud.size(), "binary");
+    f.write(reinterpret_cast<const char*>(cloud.data()), (std::streamsize)(cloud.size() * sizeof(PointType)));
+    return (bool)f;
+}
+
+// ------------------------------------------------------------------ IMU deskew inputs
+static void quat_to_rpy(double x, double y, double z, double w, double& roll, double& pitch, double& yaw) {   // tf::Matrix3x3(q).getRPY
+    double d = x * x + y * y + z * z + w * w;
+    if (std::fabs(d - 1.0) > 0.1) {                            // tf::quaternionMsgToTF normalises (with a warning) beyond QUATERNION_TOLERANCE
+        const double l = std::sqrt(d); x /= l; y /= l; z /= l; w /= l; d = x * x + y * y + z * z + w * w;
+    }
+    const double s = 2.0 / d;
+    const double xs = x * s, ys = y * s, zs = z * s, wx = w * xs, wy = w * ys, wz = w * zs;
+    const double xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
+    const double m00 = 1.0 - (yy + zz), m01 = xy - wz, m02 = xz + wy, m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+    if (std::fabs(m20) >= 1) {
+        yaw = 0; const double delta = std::atan2(m01, m02);
+        if (m20 < 0) { pitch = M_PI / 2.0; roll = delta; } else { pitch = -M_PI / 2.0; roll = delta; }
+    } else {
+        pitch = -std::asin(m20);
+        roll = std::atan2(m21 / std::cos(pitch), m22 / std::cos(pitch));
+        yaw = std::atan2(m10 / std::cos(pitch), m00 / std::cos(pitch));
+    }
+}
+
+ImuDeskewInfo imuDeskewInfo(std::vector<ImuSample>& q, double timeScanCur, double timeScanNext, int capacity) {
+    ImuDeskewInfo r;                                                        // imuAvailable = false (:325)
+    size_t drop = 0;
+    while (drop < q.size() && q[drop].time < timeScanCur - 0.01) drop++;    // :328-335
+    q.erase(q.begin(), q.begin() + (long)drop);
+    if (q.empty()) return r;
+    r.imuTime.assign((size_t)capacity, 0.0); r.imuRotX.assign((size_t)capacity, 0.0); r.imuRotY.assign((size_t)capacity, 0.0); r.imuRotZ.assign((size_t)capacity, 0.0);
+    int cur = 0;
+    for (size_t i = 0; i < q.size() && cur < capacity; i++) {
+        const ImuSample& s = q[i];
+        if (s.time <= timeScanCur) {                                        // :354-355
+            double ro, pi, ya; quat_to_rpy(s.qx, s.qy, s.qz, s.qw, ro, pi, ya);
+            r.imuRollInit = (float)ro; r.imuPitchInit = (float)pi; r.imuYawInit = (float)ya;
+        }
+        if (s.time > timeScanNext + 0.01) break;                            // :358-359
+        if (cur == 0) { r.imuRotX[0] = r.imuRotY[0] = r.imuRotZ[0] = 0; r.imuTime[0] = s.time; ++cur; continue; }
+        const double dt = s.time - r.imuTime[(size_t)cur - 1];              // :376-381
+        r.imuRotX[(size_t)cur] = r.imuRotX[(size_t)cur - 1] + s.gx * dt;
+        r.imuRotY[(size_t)cur] = r.imuRotY[(size_t)cur - 1] + s.gy * dt;
+        r.imuRotZ[(size_t)cur] = r.imuRotZ[(size_t)cur - 1] + s.gz * dt;
+        r.imuTime[(size_t)cur] = s.time;
+        ++cur;
+    }
+    --cur;                                                                  // :385
+    r.imuPointerCur = cur;
+    if (cur <= 0) return r;
+    r.imuAvailable = true;
+    return r;
 }
 
 // ------------------------------------------------------------------ FeatureExtraction
@@ -130,16 +257,53 @@ void mapOptimization::registration(const cloud_info& cloud_info_, Affine3f& pose
     }
 }
 
+std::vector<int> mapOptimization::extractNearby() {                                            // :872-907
+    std::vector<int> out;
+    const int n = (int)cloudKeyPoses6D.size();
+    if (n == 0) return out;
+    const PointTypePose& last = cloudKeyPoses6D.back();
+    // radiusSearch(cloudKeyPoses3D->back(), radius): FLANN L2_Simple d^2 < (float)(r*r), sorted ascending (ties by index)
+    std::vector<std::pair<float, int>> hit;
+    const float r2 = (float)((double)surroundingKeyframeSearchRadius * (double)surroundingKeyframeSearchRadius);
+    for (int i = 0; i < n; i++) {
+        const PointTypePose& p = cloudKeyPoses6D[i];
+        const float dx = last.x - p.x, dy = last.y - p.y, dz = last.z - p.z;
+        float d = dx * dx; d += dy * dy; d += dz * dz;
+        if (d < r2) hit.push_back({ d, i });                    // flann::RadiusResultSet::addPoint: strictly inside
+    }
+    std::sort(hit.begin(), hit.end());
+    // VoxelGrid(surroundingKeyframeDensity) of the XYZI key poses (intensity = keyframe index, cloudKeyPoses3D): on the device
+    std::vector<float> in(hit.size() * 4), ds(hit.size() * 4);
+    for (size_t k = 0; k < hit.size(); k++) {
+        const PointTypePose& p = cloudKeyPoses6D[hit[k].second];
+        in[4 * k] = p.x; in[4 * k + 1] = p.y; in[4 * k + 2] = p.z; in[4 * k + 3] = p.intensity;
+    }
+    int m = 0;
+    if (!hit.empty()) {
+        m = fbpr_voxel_grid(ctx_->h, in.data(), (int)hit.size(), surroundingKeyframeDensity, ds.data(), nullptr, nullptr, FBPR_MEM_HOST);
+        check(m, "fbpr_voxel_grid(key poses)");
+    }
+    surroundingKeyPosesDS.clear();
+    for (int k = 0; k < m; k++) surroundingKeyPosesDS.push_back(PointType{ ds[4 * k], ds[4 * k + 1], ds[4 * k + 2], ds[4 * k + 3] });
+    // key poses of the last 10 s, newest first (:897-904)
+    for (int i = n - 1; i >= 0; --i) {
+        if (timeLaserCloudInfoLast - cloudKeyPoses6D[i].time < 10.0) {
+            const PointTypePose& p = cloudKeyPoses6D[i];
+            surroundingKeyPosesDS.push_back(PointType{ p.x, p.y, p.z, p.intensity });
+        } else break;
+    }
+    for (const PointType& p : surroundingKeyPosesDS) out.push_back((int)p.intensity);           // thisKeyInd = (int)intensity (:927)
+    return out;
+}
+
 void mapOptimization::extractSurroundingKeyFrames() {                                          // :964-978
     if (cloudKeyPoses6D.empty()) return;
     const PointTypePose& last = cloudKeyPoses6D.back();
     std::vector<int> sel = surroundingKeyframeIndices;
+    std::vector<PointType> selPoses;                          // positions the distance re-check of extractCloud (:924) looks at
     if (sel.empty()) {
-        for (int i = 0; i < (int)cloudKeyPoses6D.size(); i++) {
-            const PointTypePose& p = cloudKeyPoses6D[i];
-            float dx = p.x - last.x, dy = p.y - last.y, dz = p.z - last.z;
-            if (std::sqrt(dx * dx + dy * dy + dz * dz) <= surroundingKeyframeSearchRadius) sel.push_back(i);
-        }
+        sel = extractNearby();
+        selPoses = surroundingKeyPosesDS;
     }
     std::vector<float> poses; std::vector<int32_t> coff(1, 0), soff(1, 0); PointCloud call, sall;
     for (int i : sel) {
@@ -151,9 +315,12 @@ void mapOptimization::extractSurroundingKeyFrames() {                           
         coff.push_back((int32_t)call.size()); soff.push_back((int32_t)sall.size());
     }
     const float lk[3] = { last.x, last.y, last.z };
-    check(fbpr_extract_surrounding_keyframes(ctx_->h, 0, (int)sel.size(), poses.data(), reinterpret_cast<const float*>(call.data()), coff.data(),
-                                             reinterpret_cast<const float*>(sall.data()), soff.data(), lk, FBPR_MEM_HOST),
-          "fbpr_extract_surrounding_keyframes");
+    std::vector<float> chk;
+    for (const PointType& p : selPoses) { chk.push_back(p.x); chk.push_back(p.y); chk.push_back(p.z); }
+    check(fbpr_extract_cloud(ctx_->h, 0, (int)sel.size(), poses.data(), chk.empty() ? nullptr : chk.data(),
+                             reinterpret_cast<const float*>(call.data()), coff.data(),
+                             reinterpret_cast<const float*>(sall.data()), soff.data(), lk, FBPR_MEM_HOST),
+          "fbpr_extract_cloud");
     check(fbpr_sync(ctx_->h), "fbpr_sync");
     int32_t c[8]; check(fbpr_get_counts(ctx_->h, 0, c), "fbpr_get_counts");
     laserCloudCornerFromMapDSNum = c[6]; laserCloudSurfFromMapDSNum = c[7];
@@ -225,4 +392,68 @@ int fm_cloud_handler(const char* params_yaml, int N_SCAN, int Horizon_SCAN,
         if (err && errlen > 0) { std::strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
         return -1;
     }
+}
+
+// extractSurroundingKeyFrames with the class's own extractNearby (mapOptmization.h:872-955) over a keyframe store given as
+// CSR arrays; returns surroundingKeyPosesDS and the resulting local map sizes (the maps stay in slot 0 of the handle).
+extern "C" __attribute__((visibility("default")))
+int fm_extract_surrounding(const char* params_yaml, int N_SCAN, int Horizon_SCAN, const float* keyPoses6, const double* keyTime, int nKeys,
+                           double timeLaserCloudInfoLast, const float* corner_all, const int32_t* corner_off, const float* surf_all, const int32_t* surf_off,
+                           float* ds_out, int ds_cap, int* n_ds, float* map_corner, int capC, float* map_surf, int capS, int* counts2, char* err, int errlen) {
+    try {
+        ParamServer ps;
+        if (params_yaml && params_yaml[0] && !ps.loadYaml(params_yaml)) throw std::runtime_error("cannot read params yaml");
+        ps.N_SCAN = N_SCAN; ps.Horizon_SCAN = Horizon_SCAN;
+        auto ctx = std::make_shared<DeviceContext>(ps.toAbi(1, capC + 64, capS + 64, corner_off[nKeys] + surf_off[nKeys] + 64), 0);
+        mapOptimization m(ps, ctx);
+        for (int i = 0; i < nKeys; i++) {
+            PointTypePose p{}; p.roll = keyPoses6[6 * i]; p.pitch = keyPoses6[6 * i + 1]; p.yaw = keyPoses6[6 * i + 2];
+            p.x = keyPoses6[6 * i + 3]; p.y = keyPoses6[6 * i + 4]; p.z = keyPoses6[6 * i + 5]; p.intensity = (float)i; p.time = keyTime[i];
+            m.cloudKeyPoses6D.push_back(p);
+            const PointType* c = reinterpret_cast<const PointType*>(corner_all); const PointType* s = reinterpret_cast<const PointType*>(surf_all);
+            m.cornerCloudKeyFrames.emplace_back(c + corner_off[i], c + corner_off[i + 1]);
+            m.surfCloudKeyFrames.emplace_back(s + surf_off[i], s + surf_off[i + 1]);
+        }
+        m.timeLaserCloudInfoLast = timeLaserCloudInfoLast;
+        m.extractSurroundingKeyFrames();
+        m.syncHostClouds();
+        *n_ds = (int)m.surroundingKeyPosesDS.size();
+        for (int i = 0; i < *n_ds && i < ds_cap; i++) std::memcpy(ds_out + 4 * i, &m.surroundingKeyPosesDS[i], 16);
+        counts2[0] = (int)m.laserCloudCornerFromMapDS.size(); counts2[1] = (int)m.laserCloudSurfFromMapDS.size();
+        if (counts2[0] > capC || counts2[1] > capS) throw std::runtime_error("output capacity too small");
+        std::memcpy(map_corner, m.laserCloudCornerFromMapDS.data(), 16 * (size_t)counts2[0]);
+        std::memcpy(map_surf, m.laserCloudSurfFromMapDS.data(), 16 * (size_t)counts2[1]);
+        return 0;
+    } catch (const std::exception& e) {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
+        return -1;
+    }
+}
+
+// imuDeskewInfo over a queue given as 8 doubles per sample (stamp, gyro xyz, orientation xyzw); out5 = imuAvailable,
+// imuPointerCur, roll, pitch, yaw; returns how many samples were popped from the front
+extern "C" __attribute__((visibility("default")))
+int fm_imu_deskew_info(const double* q8, int nq, double timeScanCur, double timeScanNext, int capacity,
+                       double* imuTime, double* imuRotX, double* imuRotY, double* imuRotZ, double* out5) {
+    std::vector<ImuSample> q((size_t)nq);
+    for (int i = 0; i < nq; i++) { const double* m = q8 + 8 * i; q[(size_t)i] = ImuSample{ m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7] }; }
+    ImuDeskewInfo r = imuDeskewInfo(q, timeScanCur, timeScanNext, capacity);
+    for (size_t i = 0; i < r.imuTime.size(); i++) { imuTime[i] = r.imuTime[i]; imuRotX[i] = r.imuRotX[i]; imuRotY[i] = r.imuRotY[i]; imuRotZ[i] = r.imuRotZ[i]; }
+    out5[0] = r.imuAvailable ? 1 : 0; out5[1] = r.imuPointerCur; out5[2] = r.imuRollInit; out5[3] = r.imuPitchInit; out5[4] = r.imuYawInit;
+    return nq - (int)q.size();
+}
+
+// PCD IO hooks: mode 0 = ascii, 1 = binary
+extern "C" __attribute__((visibility("default")))
+int fm_save_pcd(const char* path, const float* xyzi, int n, int mode) {
+    PointCloud c(reinterpret_cast<const PointType*>(xyzi), reinterpret_cast<const PointType*>(xyzi) + n);
+    return (mode ? savePCDFileBinary(path, c) : savePCDFileASCII(path, c)) ? 0 : -1;
+}
+extern "C" __attribute__((visibility("default")))
+int fm_load_pcd(const char* path, float* xyzi, int cap, char* err, int errlen) {
+    PointCloud c; std::string e;
+    if (!loadPCDFile(path, c, &e)) { if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; } return -1; }
+    if ((int)c.size() > cap) return -2;
+    std::memcpy(xyzi, c.data(), 16 * c.size());
+    return (int)c.size();
 }

@@ -48,6 +48,23 @@ struct cloud_info {                                           // msg/cloud_info.
     uint64_t device_token = 0;
 };
 
+// ---- PCD map IO (pcl::io::loadPCDFile / savePCDFileASCII of PointXYZI clouds; mapOptmization.h:247-257, :495-519) ----------
+// FIELDS x y z intensity, SIZE 4 4 4 4, TYPE F F F F; DATA ascii (8 significant digits, as PCL writes) or binary.
+bool loadPCDFile(const std::string& path, PointCloud& cloud, std::string* error = nullptr);
+bool savePCDFileASCII(const std::string& path, const PointCloud& cloud);
+bool savePCDFileBinary(const std::string& path, const PointCloud& cloud);
+
+// ---- IMU-side deskew inputs (ImageProjection::imuDeskewInfo, imageProjection.cpp:323-393) ----------------------------------
+struct ImuSample { double time; double gx, gy, gz; double qx, qy, qz, qw; };   // stamp, angular velocity, orientation (already in the lidar frame)
+struct ImuDeskewInfo {
+    bool imuAvailable = false;
+    float imuRollInit = 0, imuPitchInit = 0, imuYawInit = 0;   // attitude of the last sample at or before the sweep start (imuRPY2rosRPY, utility.h:293-303)
+    int imuPointerCur = 0;                                     // index of the last valid entry of the ramps
+    std::vector<double> imuTime, imuRotX, imuRotY, imuRotZ;    // integrated rotation since the first kept sample
+};
+// queue: IMU samples in time order; entries older than timeScanCur - 0.01 are popped from its front, as the reference does
+ImuDeskewInfo imuDeskewInfo(std::vector<ImuSample>& queue, double timeScanCur, double timeScanNext, int capacity = 2000);
+
 class DeviceContext {                                         // one fbpr handle (one GPU, one stream), shared by both stages
 public:
     DeviceContext(const fbpr_params& p, int device);
@@ -66,6 +83,7 @@ public:
     int numberOfCores = 2;
     double mappingProcessInterval = 0.15;
     float surroundingKeyframeSearchRadius = 50.0f;
+    float surroundingKeyframeDensity = 1.0f;                  // utility.h:197 (params.yaml: 2.0)
     bool loopClosureEnableFlag = false;
     ParamServer() {}
     explicit ParamServer(const std::string& params_yaml) { loadYaml(params_yaml); }
@@ -92,7 +110,13 @@ public:
     PointCloud corner_GlobalMap, surf_GlobalMap;              // the fork's pre-built feature maps (mapOptmization.h:245-260)
     std::vector<PointTypePose> cloudKeyPoses6D;               // keyframe store for extractSurroundingKeyFrames
     std::vector<PointCloud> cornerCloudKeyFrames, surfCloudKeyFrames;
-    std::vector<int> surroundingKeyframeIndices;              // optional caller-side selection
+    std::vector<int> surroundingKeyframeIndices;              // optional caller-side selection (overrides extractNearby)
+    PointCloud surroundingKeyPosesDS;                         // what extractNearby hands to extractCloud (positions + averaged index)
+    // mapOptimization::extractNearby (mapOptmization.h:872-907): key poses within surroundingKeyframeSearchRadius of the last one
+    // (ascending distance, ties by index), VoxelGrid(surroundingKeyframeDensity) of those poses INCLUDING the averaged intensity
+    // that the reference then truncates to a keyframe index (:927), plus the key poses of the last 10 s, newest first.
+    // Returns the keyframe index of every selected entry, in extractCloud's order.
+    std::vector<int> extractNearby();
     float transformTobeMapped[6] = { 0, 0, 0, 0, 0, 0 };
     bool isDegenerate = false;
     int laserCloudCornerFromMapDSNum = 0, laserCloudSurfFromMapDSNum = 0, laserCloudCornerLastDSNum = 0, laserCloudSurfLastDSNum = 0;

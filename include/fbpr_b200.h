@@ -123,6 +123,22 @@ FBPR_API int fbpr_set_raw_scan(fbpr_handle* h, int slot, const fbpr_raw_point* p
                                const double* imuTime, const double* imuRotX, const double* imuRotY,
                                const double* imuRotZ, int imuPointerCur,
                                float imuRollInit, float imuPitchInit);
+/* byte layout of one sensor_msgs/PointCloud2 record (the fields cachePointCloud checks, imageProjection.cpp:262-297) */
+typedef struct fbpr_pc2_layout {
+    int32_t point_step;                      /* bytes per point (22 for the Velodyne driver, 32 for pcl::toROSMsg<PointXYZIRT>) */
+    int32_t off_x, off_y, off_z;             /* float32 fields                                                                  */
+    int32_t off_intensity;                   /* float32, -1 = absent (0 is used)                                                */
+    int32_t off_ring, ring_bytes;            /* unsigned ring: 1, 2 or 4 bytes; ring_bytes = 0 means absent (the reference refuses such clouds) */
+    int32_t off_time;                        /* float32 seconds since sweep start, -1 = absent (deskew disabled, deskewFlag = -1) */
+} fbpr_pc2_layout;
+/* replaces: pcl::fromROSMsg(currentCloudMsg, *laserCloudIn) + the field checks of cachePointCloud (imageProjection.cpp:252-297):
+   the message bytes are uploaded as they are and repacked on the device.  Other arguments as fbpr_set_raw_scan
+   (deskewFlag is derived: 1 with a time field, -1 without). */
+FBPR_API int fbpr_set_raw_scan_pc2(fbpr_handle* h, int slot, const void* data, int n, const fbpr_pc2_layout* layout, int mem,
+                                   int64_t imuAvailable, double timeScanCur,
+                                   const double* imuTime, const double* imuRotX, const double* imuRotY,
+                                   const double* imuRotZ, int imuPointerCur,
+                                   float imuRollInit, float imuPitchInit);
 /* replaces: the cloud_info message handed to featureExtra() (featureExtraction.h:79-92). */
 FBPR_API int fbpr_set_cloud_info(fbpr_handle* h, int slot, const fbpr_cloud_info_view* ci, int mem);
 /* replaces: fromROSMsg(cloud_corner / cloud_surface) into laserCloud{Corner,Surf}Last (mapOptmization.h:272-273). */
@@ -167,6 +183,13 @@ FBPR_API int fbpr_extract_surrounding_keyframes(fbpr_handle* h, int slot, int K,
                                                 const float* corner_xyzi, const int32_t* corner_off,
                                                 const float* surf_xyzi, const int32_t* surf_off,
                                                 const float last_key_xyz[3], int mem);
+/* the same with explicit positions for the distance re-check of extractCloud (mapOptmization.h:924): after extractNearby
+   (:872-907) entry i of the list is a VoxelGrid-averaged key pose at check_xyz[3i..3i+2] whose truncated averaged intensity
+   names the keyframe whose pose (key_poses6) and clouds are used.  check_xyz = NULL: the keyframes' own positions. */
+FBPR_API int fbpr_extract_cloud(fbpr_handle* h, int slot, int K, const float* key_poses6, const float* check_xyz,
+                                const float* corner_xyzi, const int32_t* corner_off,
+                                const float* surf_xyzi, const int32_t* surf_off,
+                                const float last_key_xyz[3], int mem);
 /* replaces: mapOptimization::downsampleCurrentScan (mapOptmization.h:981-993). */
 FBPR_API int fbpr_downsample_current_scan(fbpr_handle* h, int first, int count);
 /* replaces: mapOptimization::scan2MapOptimization (mapOptmization.h:1403-1442) including the two
@@ -222,6 +245,12 @@ enum {
 };
 /* copies buffer `which` of `slot` to dst (at most cap_bytes); returns the byte count, < 0 on error */
 FBPR_API int64_t fbpr_get_buffer(fbpr_handle* h, int slot, int which, void* dst, int64_t cap_bytes);
+/* buffer `which` (a point cloud: CLOUD, CORNER, SURF, *_DS, MAP_*) as 32-byte pcl::PointXYZI records, the payload of the
+   PointCloud2 that publishCloud / pcl::toROSMsg produce (utility.h:255-264); repacked on the device.  Returns bytes. */
+FBPR_API int64_t fbpr_get_buffer_xyzi32(fbpr_handle* h, int slot, int which, void* dst, int64_t cap_bytes);
+/* the inverse for inputs: 32-byte pcl::PointXYZI records (pcl::fromROSMsg, mapOptmization.h:272-273; a loaded PCD map) as the
+   slot's feature clouds / local map.  kind: 0 = feature clouds (corner, surf), 1 = local map (corner, surf). */
+FBPR_API int fbpr_set_clouds_xyzi32(fbpr_handle* h, int slot, int kind, const void* corner32, int n_corner, const void* surf32, int n_surf);
 /* capture per-point kNN / coefficients / AtA / AtB / X of LM iteration `iter` on the next scan2map (-1 = off) */
 FBPR_API int fbpr_set_debug_iteration(fbpr_handle* h, int iter);
 

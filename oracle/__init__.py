@@ -166,6 +166,20 @@ def extract_features(params, ci):
 
 
 # ------------------------------------------------------------------ mapOptimization
+def imu_deskew_info(queue8, time_scan_cur, time_scan_next, queue_length=2000):
+    """ImageProjection::imuDeskewInfo (imageProjection.cpp:323-393).  queue8: [n,8] f64 rows (stamp, gyro xyz, orientation xyzw).
+    Returns dict(popped, imuAvailable, imuPointerCur, imuRollInit, imuPitchInit, imuYawInit, imuTime, imuRotX, imuRotY, imuRotZ)."""
+    q = np.ascontiguousarray(queue8, np.float64).reshape(-1, 8)
+    t, rx, ry, rz = (np.zeros(queue_length, np.float64) for _ in range(4))
+    out = np.zeros(5, np.float64)
+    fn = lib().orc_imu_deskew_info
+    fn.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double, C.c_int] + [C.POINTER(C.c_double)] * 5
+    fn.restype = C.c_int
+    popped = fn(_d(q), len(q), float(time_scan_cur), float(time_scan_next), int(queue_length), _d(t), _d(rx), _d(ry), _d(rz), _d(out))
+    return dict(popped=popped, imuAvailable=int(out[0]), imuPointerCur=int(out[1]), imuRollInit=np.float32(out[2]),
+                imuPitchInit=np.float32(out[3]), imuYawInit=np.float32(out[4]), imuTime=t, imuRotX=rx, imuRotY=ry, imuRotZ=rz)
+
+
 class MapOptimization:
     """Oracle counterpart of the reference's mapOptimization operator surface."""
 
@@ -201,6 +215,23 @@ class MapOptimization:
         counts = np.zeros(4, np.int32); lk = f32(last_key_xyz)
         lib().orc_mo_extract_cloud(self.h, _f(kp), K, _f(call), _i(coff), _f(sall), _i(soff), _f(lk), _i(counts))
         return counts
+
+    def extract_surrounding(self, key_poses6_all, key_times, density, time_last, corner_frames, surf_frames):
+        """extractNearby + extractCloud over the whole keyframe store (mapOptmization.h:872-955).
+        Returns (surroundingKeyPosesDS [m,4], counts[4])."""
+        n = len(corner_frames)
+        kp = f32(key_poses6_all).reshape(n, 6); kt = np.ascontiguousarray(key_times, np.float64)
+        coff = np.zeros(n + 1, np.int32); soff = np.zeros(n + 1, np.int32)
+        coff[1:] = np.cumsum([len(c) for c in corner_frames]); soff[1:] = np.cumsum([len(s) for s in surf_frames])
+        call = f32(np.concatenate(corner_frames)).reshape(-1, 4); sall = f32(np.concatenate(surf_frames)).reshape(-1, 4)
+        counts = np.zeros(4, np.int32); ds = np.zeros((2 * n + 8, 4), np.float32)
+        fn = lib().orc_mo_extract_surrounding
+        fn.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int, C.c_float, C.c_double,
+                       C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int),
+                       C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
+        fn.restype = C.c_int
+        m = fn(self.h, _f(kp), _d(kt), n, float(density), float(time_last), _f(call), _i(coff), _f(sall), _i(soff), _f(ds), len(ds), _i(counts))
+        return ds[:m].copy(), counts
 
     def downsample(self):
         counts = np.zeros(2, np.int32)

@@ -157,6 +157,35 @@ void orc_mo_extract_cloud(orc_mo* h, const float* keyPoses6, int K, const float*
     counts[0] = (int)h->mo.laserCloudCornerFromMap.size(); counts[1] = (int)h->mo.laserCloudSurfFromMap.size();
     counts[2] = (int)h->mo.laserCloudCornerFromMapDS.size(); counts[3] = (int)h->mo.laserCloudSurfFromMapDS.size();
 }
+// extractSurroundingKeyFrames as the reference runs it: extractNearby (:872-907) + extractCloud (:909-955) over the whole
+// keyframe store (key pose i = row i of keyPoses6All, cloudKeyPoses3D[i].intensity = i).  ds_out = surroundingKeyPosesDS.
+int orc_mo_extract_surrounding(orc_mo* h, const float* keyPoses6All, const double* keyTime, int nKeys, float density, double timeLast,
+                               const float* corner_all, const int* corner_off, const float* surf_all, const int* surf_off,
+                               float* ds_out, int ds_cap, int* counts) {
+    std::vector<P4> k3(nKeys);
+    for (int i = 0; i < nKeys; i++) k3[i] = P4{ keyPoses6All[6 * i + 3], keyPoses6All[6 * i + 4], keyPoses6All[6 * i + 5], (float)i };
+    std::vector<P4> ds;
+    MapOptimization::extractNearby(k3.data(), keyTime, nKeys, h->mo.P.surroundingKeyframeSearchRadius, density, timeLast, ds);
+    std::vector<const P4*> cf(nKeys), sf(nKeys); std::vector<int> cn(nKeys), sn(nKeys);
+    for (int i = 0; i < nKeys; i++) {
+        cf[i] = reinterpret_cast<const P4*>(corner_all) + corner_off[i]; cn[i] = corner_off[i + 1] - corner_off[i];
+        sf[i] = reinterpret_cast<const P4*>(surf_all) + surf_off[i];     sn[i] = surf_off[i + 1] - surf_off[i];
+    }
+    h->mo.extractCloudIndexed(ds, keyPoses6All, nKeys, cf.data(), cn.data(), sf.data(), sn.data());
+    counts[0] = (int)h->mo.laserCloudCornerFromMap.size(); counts[1] = (int)h->mo.laserCloudSurfFromMap.size();
+    counts[2] = (int)h->mo.laserCloudCornerFromMapDS.size(); counts[3] = (int)h->mo.laserCloudSurfFromMapDS.size();
+    const int m = (int)ds.size();
+    for (int i = 0; i < m && i < ds_cap; i++) std::memcpy(ds_out + 4 * i, &ds[i], 16);
+    return m;
+}
+// ImageProjection::imuDeskewInfo (imageProjection.cpp:323-393); out5 = imuAvailable, imuPointerCur, roll, pitch, yaw
+int orc_imu_deskew_info(const double* q8, int nq, double timeScanCur, double timeScanNext, int queueLength,
+                        double* imuTime, double* imuRotX, double* imuRotY, double* imuRotZ, double* out5) {
+    ImuDeskewOut o;
+    int popped = imu_deskew_info(q8, nq, timeScanCur, timeScanNext, queueLength, imuTime, imuRotX, imuRotY, imuRotZ, &o);
+    out5[0] = (double)o.imuAvailable; out5[1] = o.imuPointerCur; out5[2] = o.roll; out5[3] = o.pitch; out5[4] = o.yaw;
+    return popped;
+}
 void orc_mo_downsample(orc_mo* h, int* counts) {
     h->mo.downsampleCurrentScan();
     counts[0] = (int)h->mo.laserCloudCornerLastDS.size(); counts[1] = (int)h->mo.laserCloudSurfLastDS.size();

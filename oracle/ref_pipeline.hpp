@@ -147,6 +147,55 @@ static inline void project(const Params& P, const RawScan& raw, int64_t imuAvail
     }
 }
 
+// ImageProjection::imuDeskewInfo  imageProjection.cpp:323-393 (queue of sensor_msgs::Imu as 8 doubles per sample:
+// stamp, angular velocity xyz, orientation xyzw).  Returns how many samples the reference pops from the queue front.
+struct ImuDeskewOut { int64_t imuAvailable = 0; int imuPointerCur = 0; float roll = 0, pitch = 0, yaw = 0; };
+static inline void tf_msg_quat_rpy(double x, double y, double z, double w, double* roll, double* pitch, double* yaw) {
+    // tf::quaternionMsgToTF (normalise when |len^2 - 1| > 0.1) + tf::Matrix3x3(q).getRPY  (utility.h:293-303)
+    double l2 = x * x + y * y + z * z + w * w;
+    if (std::fabs(l2 - 1.0) > 0.1) { double l = std::sqrt(l2); x /= l; y /= l; z /= l; w /= l; l2 = x * x + y * y + z * z + w * w; }
+    const double s = 2.0 / l2;
+    const double xs = x * s, ys = y * s, zs = z * s, wx = w * xs, wy = w * ys, wz = w * zs;
+    const double xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
+    const double m00 = 1.0 - (yy + zz), m01 = xy - wz, m02 = xz + wy, m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+    if (std::fabs(m20) >= 1) {
+        *yaw = 0; *roll = std::atan2(m01, m02); *pitch = m20 < 0 ? M_PI / 2.0 : -M_PI / 2.0;
+    } else {
+        *pitch = -std::asin(m20);
+        *roll = std::atan2(m21 / std::cos(*pitch), m22 / std::cos(*pitch));
+        *yaw = std::atan2(m10 / std::cos(*pitch), m00 / std::cos(*pitch));
+    }
+}
+static inline int imu_deskew_info(const double* q8, int nq, double timeScanCur, double timeScanNext, int queueLength,
+                                  double* imuTime, double* imuRotX, double* imuRotY, double* imuRotZ, ImuDeskewOut* out) {
+    *out = ImuDeskewOut();
+    int popped = 0;
+    while (popped < nq) { if (q8[8 * popped] < timeScanCur - 0.01) ++popped; else break; }
+    if (popped == nq) return popped;
+    int cur = 0;
+    for (int i = popped; i < nq && cur < queueLength; ++i) {
+        const double* m = q8 + 8 * i;
+        const double t = m[0];
+        if (t <= timeScanCur) {
+            double r, p, y; tf_msg_quat_rpy(m[4], m[5], m[6], m[7], &r, &p, &y);
+            out->roll = (float)r; out->pitch = (float)p; out->yaw = (float)y;
+        }
+        if (t > timeScanNext + 0.01) break;
+        if (cur == 0) { imuRotX[0] = 0; imuRotY[0] = 0; imuRotZ[0] = 0; imuTime[0] = t; ++cur; continue; }
+        const double timeDiff = t - imuTime[cur - 1];
+        imuRotX[cur] = imuRotX[cur - 1] + m[1] * timeDiff;
+        imuRotY[cur] = imuRotY[cur - 1] + m[2] * timeDiff;
+        imuRotZ[cur] = imuRotZ[cur - 1] + m[3] * timeDiff;
+        imuTime[cur] = t;
+        ++cur;
+    }
+    --cur;
+    out->imuPointerCur = cur;
+    if (cur <= 0) return popped;
+    out->imuAvailable = 1;
+    return popped;
+}
+
 // ===================================================================== features
 struct FeatureOut {
     std::vector<P4> cornerCloud, surfaceCloud;        // surfaceCloud = per-ring VoxelGrid output, rings concatenated
@@ -302,6 +351,56 @@ public:
             float T[12]; get_transformation(kp[3], kp[4], kp[5], kp[0], kp[1], kp[2], T);
             transformPointCloud(cornerFrames[i], cornerN[i], T, cv[i]);
             transformPointCloud(surfFrames[i], surfN[i], T, sv[i]);
+        }
+        laserCloudCornerFromMap.clear(); laserCloudSurfFromMap.clear();
+        for (int i = 0; i < K; ++i) {
+            laserCloudCornerFromMap.insert(laserCloudCornerFromMap.end(), cv[i].begin(), cv[i].end());
+            laserCloudSurfFromMap.insert(laserCloudSurfFromMap.end(), sv[i].begin(), sv[i].end());
+        }
+        voxel_grid(laserCloudCornerFromMap.data(), (int)laserCloudCornerFromMap.size(), P.mappingCornerLeafSize, laserCloudCornerFromMapDS);
+        voxel_grid(laserCloudSurfFromMap.data(), (int)laserCloudSurfFromMap.size(), P.mappingSurfLeafSize, laserCloudSurfFromMapDS);
+    }
+    // extractNearby  mapOptmization.h:872-907.  cloudKeyPoses3D[i] = (x, y, z, intensity = i); radiusSearch is FLANN's
+    // RadiusResultSet: d^2 < (float)(r*r) (strict, from memory of flann/util/result_set.h), sorted by (d^2, index);
+    // VoxelGrid(surroundingKeyframeDensity) averages xyz AND the intensity; then the key poses of the last 10 s, newest first.
+    static void extractNearby(const P4* cloudKeyPoses3D, const double* keyTime, int n, float searchRadius, float density,
+                              double timeLaserCloudInfoLast, std::vector<P4>& surroundingKeyPosesDS) {
+        surroundingKeyPosesDS.clear();
+        if (n <= 0) return;
+        const P4& q = cloudKeyPoses3D[n - 1];
+        const float r2 = (float)((double)searchRadius * (double)searchRadius);
+        std::vector<std::pair<float, int>> hit;
+        for (int i = 0; i < n; ++i) {
+            const float dx = q.x - cloudKeyPoses3D[i].x, dy = q.y - cloudKeyPoses3D[i].y, dz = q.z - cloudKeyPoses3D[i].z;
+            float d = dx * dx; d += dy * dy; d += dz * dz;                       // L2_Simple, x, y, z order
+            if (d < r2) hit.push_back({ d, i });
+        }
+        std::sort(hit.begin(), hit.end());
+        std::vector<P4> surroundingKeyPoses;
+        for (auto& h : hit) surroundingKeyPoses.push_back(cloudKeyPoses3D[h.second]);
+        voxel_grid(surroundingKeyPoses.data(), (int)surroundingKeyPoses.size(), density, surroundingKeyPosesDS);
+        for (int i = n - 1; i >= 0; --i) {
+            if (timeLaserCloudInfoLast - keyTime[i] < 10.0) surroundingKeyPosesDS.push_back(cloudKeyPoses3D[i]);
+            else break;
+        }
+    }
+    // extractCloud as the reference calls it (:909-955): entry i of cloudToExtract is re-checked at ITS OWN position (:924) and
+    // names keyframe (int)intensity (:927), whose pose and clouds are used
+    void extractCloudIndexed(const std::vector<P4>& cloudToExtract, const float* keyPoses6All, int nKeys,
+                             const P4* const* cornerFramesAll, const int* cornerNAll,
+                             const P4* const* surfFramesAll, const int* surfNAll) {
+        const int K = (int)cloudToExtract.size();
+        std::vector<std::vector<P4>> cv(K), sv(K);
+        const float* lk = keyPoses6All + 6 * (nKeys - 1) + 3;                    // cloudKeyPoses3D->back()
+        #pragma omp parallel for num_threads(P.numberOfCores)
+        for (int i = 0; i < K; ++i) {
+            const P4& c = cloudToExtract[i];
+            if (std::sqrt((c.x - lk[0]) * (c.x - lk[0]) + (c.y - lk[1]) * (c.y - lk[1]) + (c.z - lk[2]) * (c.z - lk[2])) > P.surroundingKeyframeSearchRadius) continue;
+            const int thisKeyInd = (int)c.i;
+            const float* kp = keyPoses6All + 6 * thisKeyInd;
+            float T[12]; get_transformation(kp[3], kp[4], kp[5], kp[0], kp[1], kp[2], T);
+            transformPointCloud(cornerFramesAll[thisKeyInd], cornerNAll[thisKeyInd], T, cv[i]);
+            transformPointCloud(surfFramesAll[thisKeyInd], surfNAll[thisKeyInd], T, sv[i]);
         }
         laserCloudCornerFromMap.clear(); laserCloudSurfFromMap.clear();
         for (int i = 0; i < K; ++i) {

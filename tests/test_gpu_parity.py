@@ -448,3 +448,130 @@ def test_dense_map_stress_config5(fb):
                 assert np.array_equal(d2[accept], dbg[K + "D2"][accept])
                 assert np.array_equal(r.get_buffer(0, "FLAG_" + kind), dbg[K + "Flag"]), kind
     r.close()
+
+
+# ------------------------------------------------------------------ keyframe selection, wire formats
+def _keyframe_store(rng, n, spread, npts=(40, 300)):
+    poses = np.concatenate([rng.uniform(-0.2, 0.2, (n, 3)), np.cumsum(rng.uniform(0, spread, (n, 3)) * [1, 0.3, 0.02], 0)], 1).astype(np.float32)
+    cf = [np.concatenate([rng.uniform(-10, 10, (npts[0] + k, 3)), np.full((npts[0] + k, 1), k)], 1).astype(np.float32) for k in range(n)]
+    sf = [np.concatenate([rng.uniform(-10, 10, (npts[1] + 3 * k, 3)), np.full((npts[1] + 3 * k, 1), k)], 1).astype(np.float32) for k in range(n)]
+    return poses, cf, sf
+
+
+def test_extract_cloud_with_averaged_key_poses_matches_oracle(fb):
+    """fbpr_extract_cloud with the re-check positions of extractNearby's VoxelGrid-averaged key poses (mapOptmization.h:924-927)."""
+    rng = np.random.default_rng(5)
+    P = dict(synth.params_for(1)); P["surroundingKeyframeSearchRadius"] = 12.0
+    n = 40
+    poses, cf, sf = _keyframe_store(rng, n, 1.2)
+    times = np.arange(n) * 0.7
+    mo = oracle.MapOptimization(P)
+    ds, counts = mo.extract_surrounding(poses, times, 2.0, times[-1] + 0.1, cf, sf)
+    sel = ds[:, 3].astype(np.int32)                              # (int)intensity (:927)
+    assert np.any(ds[:, 3] != sel)                               # averaged indices really occur
+    r = _reg(fb, P, max_keyframe_points=1 << 16, max_map_corner=1 << 15, max_map_surf=1 << 16)
+    r.extractCloud(0, poses[sel], ds[:, :3], [cf[i] for i in sel], [sf[i] for i in sel], poses[-1, 3:])
+    c = r.get_counts(0)
+    assert (c["n_map_corner"], c["n_map_surf"]) == (int(counts[2]), int(counts[3]))
+    assert np.array_equal(r.get_buffer(0, "MAP_CORNER").reshape(-1, 4), mo.get_cloud(2))
+    assert np.array_equal(r.get_buffer(0, "MAP_SURF").reshape(-1, 4), mo.get_cloud(3))
+    r.close()
+
+
+def test_cpp_host_extract_nearby_matches_oracle(fb, tmp_path):
+    """mapOptimization::extractSurroundingKeyFrames of the C++ host layer with its own extractNearby (radius search, key-pose
+    VoxelGrid on the device, last-10 s append) against the oracle's restatement of mapOptmization.h:872-955."""
+    import ctypes as C
+    import os
+    rng = np.random.default_rng(9)
+    P = dict(synth.params_for(1)); P["surroundingKeyframeSearchRadius"] = 15.0
+    n = 60
+    poses, cf, sf = _keyframe_store(rng, n, 1.0)
+    times = np.arange(n) * 0.5
+    tlast = float(times[-1] + 0.05)
+    mo = oracle.MapOptimization(P)
+    ds_w, counts_w = mo.extract_surrounding(poses, times, 2.0, tlast, cf, sf)
+    y = tmp_path / "params.yaml"
+    y.write_text("".join(f"{k}: {P[k]}\n" for k in ("mappingCornerLeafSize", "mappingSurfLeafSize", "surroundingKeyframeSearchRadius")) + "surroundingKeyframeDensity: 2.0\n")
+    lib = C.CDLL(os.path.join(os.path.dirname(fb.__file__), "host", "libfeature_matching_b200.so"))
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    coff = np.zeros(n + 1, np.int32); soff = np.zeros(n + 1, np.int32)
+    coff[1:] = np.cumsum([len(c) for c in cf]); soff[1:] = np.cumsum([len(s) for s in sf])
+    call, sall = f32(np.concatenate(cf)), f32(np.concatenate(sf))
+    ds = np.zeros((4 * n, 4), np.float32); nds = C.c_int(0); counts = (C.c_int * 2)(); err = C.create_string_buffer(512)
+    capC, capS = int(coff[-1]) * 2 + 64, int(soff[-1]) * 2 + 64
+    mc = np.zeros((capC, 4), np.float32); ms = np.zeros((capS, 4), np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    kt = np.ascontiguousarray(times, np.float64); kp = f32(poses)
+    rc = lib.fm_extract_surrounding(str(y).encode(), int(P["N_SCAN"]), int(P["Horizon_SCAN"]), vp(kp), vp(kt), n, C.c_double(tlast),
+                                    vp(call), vp(coff), vp(sall), vp(soff), vp(ds), len(ds), C.byref(nds), vp(mc), capC, vp(ms), capS, counts, err, 512)
+    assert rc == 0, err.value.decode()
+    assert nds.value == len(ds_w) and np.array_equal(ds[:nds.value], ds_w)
+    assert (counts[0], counts[1]) == (int(counts_w[2]), int(counts_w[3]))
+    assert np.array_equal(mc[:counts[0]], mo.get_cloud(2)) and np.array_equal(ms[:counts[1]], mo.get_cloud(3))
+
+
+@pytest.mark.parametrize("layout", ["velodyne22", "pcl32", "no_time_ring8"])
+def test_pointcloud2_wire_format_projection(fb, layout):
+    """fbpr_set_raw_scan_pc2: PointCloud2 payload bytes of the layouts cachePointCloud accepts (imageProjection.cpp:252-297)
+    -> the same projection as the packed records / the oracle; a cloud without a time field disables deskew (deskewFlag -1)."""
+    fr = synth.make_frame(3, 1, small=(16, 900, 2000, 8000))
+    P = fr["params"]; sc = fr["scan"]; n = int(sc["n"])
+    if layout == "velodyne22":
+        dt = np.dtype({"names": ["x", "y", "z", "intensity", "ring", "time"], "formats": ["<f4", "<f4", "<f4", "<f4", "<u2", "<f4"],
+                       "offsets": [0, 4, 8, 12, 16, 18], "itemsize": 22})
+        L = dict(point_step=22, off_x=0, off_y=4, off_z=8, off_intensity=12, off_ring=16, ring_bytes=2, off_time=18)
+    elif layout == "pcl32":                                      # pcl::toROSMsg<PointXYZIRT>: EIGEN_ALIGN16 struct, 32 bytes
+        dt = np.dtype({"names": ["x", "y", "z", "intensity", "ring", "time"], "formats": ["<f4", "<f4", "<f4", "<f4", "<u2", "<f4"],
+                       "offsets": [0, 4, 8, 16, 20, 24], "itemsize": 32})
+        L = dict(point_step=32, off_x=0, off_y=4, off_z=8, off_intensity=16, off_ring=20, ring_bytes=2, off_time=24)
+    else:
+        dt = np.dtype({"names": ["x", "y", "z", "intensity", "ring"], "formats": ["<f4", "<f4", "<f4", "<f4", "u1"],
+                       "offsets": [0, 4, 8, 12, 17], "itemsize": 19})
+        L = dict(point_step=19, off_x=0, off_y=4, off_z=8, off_intensity=12, off_ring=17, ring_bytes=1, off_time=-1)
+    msg = np.zeros(n, dt)
+    for k in dt.names:
+        msg[k] = sc[k][:n]
+    deskew = 1 if L["off_time"] >= 0 else -1
+    ci = oracle.project(P, sc, fr["imu"], fr["imu_available"], deskew_flag=deskew)
+    r = _reg(fb, P)
+    r.set_raw_scan_pc2(0, msg.tobytes(), n, L, imu=fr["imu"], imu_available=fr["imu_available"])
+    r.project(0, 1); r.sync()
+    assert r.get_counts(0)["n_valid"] == len(ci["pointRange"])
+    assert np.array_equal(r.get_buffer(0, "COL_IND"), ci["pointColInd"])
+    assert np.array_equal(r.get_buffer(0, "RANGE"), ci["pointRange"])
+    assert np.array_equal(r.get_buffer(0, "CLOUD").reshape(-1, 4), ci["cloud_deskewed"])
+    # refused layouts: no ring channel (the reference shuts down, :262-280), offsets outside the record
+    bad = dict(L); bad["ring_bytes"] = 0
+    with pytest.raises(fb.FbprError, match="ring"):
+        r.set_raw_scan_pc2(0, msg.tobytes(), n, bad)
+    bad = dict(L); bad["off_z"] = L["point_step"] - 2
+    with pytest.raises(fb.FbprError, match="point_step"):
+        r.set_raw_scan_pc2(0, msg.tobytes(), n, bad)
+    r.close()
+
+
+def test_pcl_xyzi32_wire_roundtrip(fb):
+    """32-byte pcl::PointXYZI records (the PointCloud2 payload of cloud_corner / cloud_surface and of a loaded PCD map,
+    utility.h:255-264, mapOptmization.h:272-273): device repack in both directions, then the same registration."""
+    fr = synth.make_frame(1, 2, small=(16, 900, 4000, 20000))
+    P = fr["params"]
+    ci = oracle.project(P, fr["scan"], fr["imu"], fr["imu_available"]); fe = oracle.extract_features(P, ci)
+    wide = lambda a: np.concatenate([a[:, :3], np.ones((len(a), 1), np.float32), a[:, 3:4], np.zeros((len(a), 3), np.float32)], 1).astype(np.float32)
+    r = _reg(fb, P, max_map_corner=8192, max_map_surf=32768)
+    r.set_clouds_xyzi32(0, 0, wide(fe["corner"]), wide(fe["surface"]))
+    r.set_clouds_xyzi32(0, 1, wide(fr["map_corner"]), wide(fr["map_surf"]))
+    assert np.array_equal(r.get_buffer(0, "CORNER").reshape(-1, 4), fe["corner"]) and np.array_equal(r.get_buffer(0, "MAP_SURF").reshape(-1, 4), fr["map_surf"])
+    assert np.array_equal(r.get_buffer_xyzi32(0, "SURF"), wide(fe["surface"]))
+    assert np.array_equal(r.get_buffer_xyzi32(0, "MAP_CORNER"), wide(fr["map_corner"]))
+    r.set_pose(0, fr["guess"])
+    r.downsampleCurrentScan(0, 1); r.scan2MapOptimization(0, 1); r.sync()
+    mo = oracle.MapOptimization(P)
+    mo.set_imu(0, 0.0, 0.0)
+    mo.set_scan(fe["corner"], fe["surface"]); mo.set_map(fr["map_corner"], fr["map_surf"]); mo.downsample()
+    pose_w, iters_w, flags_w, _ = mo.scan2map(fr["guess"])
+    pose, iters, flags = r.get_pose(0)
+    assert (iters, flags) == (iters_w, flags_w)
+    assert np.max(np.abs(pose[3:] - pose_w[3:])) <= POSE_TOL_T and np.max(np.abs(pose[:3] - pose_w[:3])) <= POSE_TOL_R
+    assert np.array_equal(r.get_buffer_xyzi32(0, "SURF_DS")[:, [0, 1, 2, 4]], mo.get_cloud(1))
+    r.close()

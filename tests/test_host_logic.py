@@ -116,3 +116,120 @@ def test_world_size_2_gloo_gather(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GATHER_OK" in out.stdout
+
+
+# ------------------------------------------------------------------ wire formats and IMU deskew inputs (host side)
+def _host_lib():
+    import feature_base_pointcloud_registration_b200 as fb
+    return ctypes.CDLL(os.path.join(os.path.dirname(fb.__file__), "host", "libfeature_matching_b200.so"))
+
+
+def _imu_queue(rng, t0, n, hz=500.0, unnormalised=False):
+    t = t0 + np.arange(n) / hz
+    gyro = rng.normal(0, 0.3, (n, 3))
+    q = rng.normal(0, 1, (n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    if unnormalised:
+        q *= 1.5
+    return np.concatenate([t[:, None], gyro, q], 1)
+
+
+@pytest.mark.parametrize("case", ["normal", "all_old", "one_sample", "capacity", "unnormalised"])
+def test_imu_deskew_info_host_equals_oracle(case):
+    """imuDeskewInfo (imageProjection.cpp:323-393): queue pruning, attitude of the last sample before the sweep,
+    gyro integration into imuTime / imuRotX,Y,Z, imuPointerCur and the imuAvailable gate -- C++ host vs the oracle."""
+    import oracle
+    lib = _host_lib()
+    rng = np.random.default_rng(7)
+    cur, nxt, cap = 100.0, 100.1, 2000
+    if case == "normal":
+        q = _imu_queue(rng, 99.9, 150)
+    elif case == "all_old":
+        q = _imu_queue(rng, 90.0, 50)
+    elif case == "one_sample":
+        q = _imu_queue(rng, 100.2, 5)              # first sample already past timeScanNext + 0.01 -> imuPointerCur 0, unavailable
+    elif case == "capacity":
+        q = _imu_queue(rng, 99.995, 200, hz=2000.0); cap = 64
+    else:
+        q = _imu_queue(rng, 99.9, 150, unnormalised=True)
+    want = oracle.imu_deskew_info(q, cur, nxt, cap)
+    t, rx, ry, rz = (np.zeros(cap) for _ in range(4)); out = np.zeros(5)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    lib.fm_imu_deskew_info.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int] + [ctypes.POINTER(ctypes.c_double)] * 5
+    qq = np.ascontiguousarray(q)
+    popped = lib.fm_imu_deskew_info(dp(qq), len(qq), cur, nxt, cap, dp(t), dp(rx), dp(ry), dp(rz), dp(out))
+    assert popped == want["popped"]
+    assert int(out[0]) == want["imuAvailable"]
+    if case == "all_old":
+        assert want["imuAvailable"] == 0 and popped == len(q)
+        return
+    assert int(out[1]) == want["imuPointerCur"]
+    assert np.float32(out[2]) == want["imuRollInit"] and np.float32(out[3]) == want["imuPitchInit"] and np.float32(out[4]) == want["imuYawInit"]
+    n = want["imuPointerCur"] + 1
+    for a, k in ((t, "imuTime"), (rx, "imuRotX"), (ry, "imuRotY"), (rz, "imuRotZ")):
+        assert np.array_equal(a[:n], want[k][:n])
+    if case == "normal":
+        assert want["imuAvailable"] == 1 and popped == 45        # stamps < 99.99 are dropped
+        # the integrated ramp is the running sum of gyro * dt from the first kept sample
+        kept = q[popped:]
+        last = np.searchsorted(kept[:, 0], nxt + 0.01, side="right")          # first stamp > timeScanNext + 0.01 breaks the loop
+        assert want["imuPointerCur"] == last - 1
+        ref = np.concatenate([[0.0], np.cumsum(kept[1:last, 1] * np.diff(kept[:last, 0]))])
+        assert np.allclose(want["imuRotX"][:last], ref, rtol=0, atol=1e-12)
+    if case == "one_sample":
+        assert want["imuAvailable"] == 0 and want["imuPointerCur"] == -1
+
+
+def test_pcd_io_roundtrip_and_pcl_layout(tmp_path):
+    """PCD map IO (pcl::io::loadPCDFile / savePCDFileASCII, mapOptmization.h:247-257, :495-519): binary round trip is
+    bit-exact, ASCII keeps 8 significant digits (PCL's precision) and a file in PCL's own header layout (extra fields,
+    COUNT, VIEWPOINT) is read field by field."""
+    lib = _host_lib()
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([rng.uniform(-50, 50, (1000, 3)), rng.uniform(0, 255, (1000, 1))], 1).astype(np.float32)
+    fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    for mode in (0, 1):
+        path = str(tmp_path / f"m{mode}.pcd").encode()
+        assert lib.fm_save_pcd(path, fp(pts), len(pts), mode) == 0
+        got = np.zeros_like(pts); err = ctypes.create_string_buffer(256)
+        n = lib.fm_load_pcd(path, fp(got), len(got), err, 256)
+        assert n == len(pts), err.value
+        if mode == 1:
+            assert np.array_equal(got, pts)
+        else:
+            assert np.allclose(got, pts, rtol=2e-8 * 10, atol=0)          # %.8g
+            head = open(path.decode()).read().split("DATA ascii")[0]
+            assert "FIELDS x y z intensity" in head and "SIZE 4 4 4 4" in head and "TYPE F F F F" in head and f"POINTS {len(pts)}" in head
+    # a PCL-written ASCII file with a different field set (PointXYZINormal-like) and CRLF line ends
+    body = "\r\n".join(["# .PCD v0.7 - Point Cloud Data file format", "VERSION 0.7", "FIELDS x y z intensity normal_x curvature", "SIZE 4 4 4 4 4 4",
+                        "TYPE F F F F F F", "COUNT 1 1 1 1 3 1", "WIDTH 2", "HEIGHT 1", "VIEWPOINT 0 0 0 1 0 0 0", "POINTS 2", "DATA ascii",
+                        "1.5 -2.25 3 7 0 0 1 0.5", "nan 4 5e-1 9 1 0 0 0.25", ""])
+    f = tmp_path / "pcl.pcd"; f.write_bytes(body.encode())
+    got = np.zeros((2, 4), np.float32); err = ctypes.create_string_buffer(256)
+    assert lib.fm_load_pcd(str(f).encode(), fp(got), 2, err, 256) == 2, err.value
+    assert np.array_equal(got[0], np.float32([1.5, -2.25, 3, 7])) and np.isnan(got[1, 0]) and np.array_equal(got[1, 1:], np.float32([4, 0.5, 9]))
+    # errors are reported, not swallowed
+    bad = tmp_path / "bad.pcd"; bad.write_text("FIELDS x y\nSIZE 4 4\nTYPE F F\nCOUNT 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA ascii\n1 2\n")
+    assert lib.fm_load_pcd(str(bad).encode(), fp(got), 2, err, 256) == -1 and b"x y z" in err.value
+    assert lib.fm_load_pcd(str(tmp_path / "missing.pcd").encode(), fp(got), 2, err, 256) == -1
+
+
+def test_oracle_extract_nearby_semantics():
+    """extractNearby (mapOptmization.h:872-907) in the oracle: radius hits sorted by distance, VoxelGrid averages the key
+    index with the position, the last-10 s poses are appended newest first, and extractCloud truncates the averaged index."""
+    import oracle
+    import synth
+    P = dict(synth.params_for(1)); P["surroundingKeyframeSearchRadius"] = 10.0
+    # key poses on a line, 0.6 m apart; density 2 m => ~3 poses per voxel; the far ones (> 10 m) are outside the radius
+    n = 30
+    poses = np.zeros((n, 6), np.float32); poses[:, 3] = np.arange(n)[::-1] * 0.6
+    times = np.arange(n) * 1.0                                   # 1 s apart; last 10 s = keys 20..29 (time_last = 29.5)
+    cf = [np.float32([[0, 0, 0, k]]) for k in range(n)]; sf = [np.float32([[1, 0, 0, k]]) for k in range(n)]
+    mo = oracle.MapOptimization(P)
+    ds, counts = mo.extract_surrounding(poses, times, 2.0, 29.5, cf, sf)
+    inside = np.where(poses[:, 3] ** 2 < 100.0)[0]              # strict
+    vox = oracle.voxel_grid(np.concatenate([poses[inside][::-1][:, 3:], inside[::-1, None].astype(np.float32)], 1), 2.0)["points"]
+    assert np.array_equal(ds[:len(vox)], vox)                    # hits ascending by distance = keys 29, 28, ...
+    recent = ds[len(vox):]
+    assert np.array_equal(recent[:, 3], np.arange(29, 19, -1, dtype=np.float32))      # 29.5 - t < 10 -> t > 19.5
+    assert np.any(ds[:len(vox), 3] != np.floor(ds[:len(vox), 3]))                      # averaged (non-integer) indices exist
+    assert counts[0] == len(ds) and counts[1] == len(ds)        # one corner + one surf point per selected entry, none re-check-rejected
