@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--cluster", type=int, default=0, help="lm_cluster_size override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-frames", type=int, default=48)
-    ap.add_argument("--e2e-chunk", type=int, default=32, help="frames per upload chunk of the pipelined e2e call")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="frames per upload chunk of the pipelined e2e call (0 = 32)")
     return ap.parse_args()
 
 
@@ -180,7 +180,7 @@ def run_b200(args, rank, world, local_rank):
     cfg = synth.CONFIGS[CONFIG]
     params = synth.params_for(CONFIG)
     frames = [synth.make_frame(CONFIG, rank * F + i) for i in range(F)]
-    extra = dict(max_frames=F, max_map_corner=cfg["map_corner"] + 64, max_map_surf=cfg["map_surf"] + 64)
+    extra = dict(max_frames=2 * F, max_map_corner=cfg["map_corner"] + 64, max_map_surf=cfg["map_surf"] + 64)   # 2F slots: e2e double-buffers
     if args.cluster:
         extra["lm_cluster_size"] = args.cluster
     reg = fb.Registration(params, device=local_rank, **extra)
@@ -253,25 +253,50 @@ def run_b200(args, rank, world, local_rank):
     value = world * F * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: host buffers in, host results out, every step
-    def step_e2e():
-        # host (pinned) buffers in, host results out: chunked uploads overlap the kernels of the previous chunk
-        return reg.register_frames(0, fin, args.e2e_chunk)   # H2D + whole path + D2H + sync
+    # (a) streaming form: fbpr_register_frames_begin / _end, two batches in flight on disjoint slot ranges, so the uploads of
+    #     step k+1 run under the last kernels of step k (every step still uploads all its inputs and downloads its results);
+    # (b) one synchronous fbpr_register_frames call per step, for comparison.
+    def run_e2e_stream(nsteps):
+        last = None
+        t = reg.register_frames_begin(0, fin, args.e2e_chunk)
+        for s_ in range(nsteps):
+            tn = reg.register_frames_begin(F * ((s_ + 1) % 2), fin, args.e2e_chunk) if s_ + 1 < nsteps else None
+            last = reg.register_frames_end(t)
+            t = tn
+        return last
 
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    barrier()
-    e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    t_host0 = time.perf_counter()
-    for _ in range(args.steps):
-        res_e2e = step_e2e()
-    e3.record(stream)
-    reg.sync()
-    t_host = (time.perf_counter() - t_host0) * 1e3
-    barrier()
-    ms_e2e = max_over_ranks(max(e2.elapsed_time(e3), t_host))
+    def run_e2e_sync(nsteps):
+        last = None
+        for _ in range(nsteps):
+            last = reg.register_frames(0, fin, args.e2e_chunk)   # H2D + whole path + D2H + sync
+        return last
+
+    e2e_ms = {}
+    for name, fn in (("sync", run_e2e_sync), ("stream", run_e2e_stream)):
+        fn(max(2, args.warmup // 2))
+        barrier()
+        t_host0 = time.perf_counter()
+        res_e2e = fn(args.steps)
+        reg.sync()
+        t_host = (time.perf_counter() - t_host0) * 1e3         # host wall clock around the calls (they block until results are on the host)
+        barrier()
+        e2e_ms[name] = max_over_ranks(t_host)
+        assert np.array_equal(res_e2e["iters"], res["iters"])
+    ms_e2e = e2e_ms["stream"]
     e2e_value = world * F * args.steps / (ms_e2e * 1e-3)
-    assert np.array_equal(res_e2e["iters"], res["iters"])
+
+    # PCIe floor: the same host buffers copied with no compute at all
+    dev_scratch = [torch.empty(t_.numel(), dtype=torch.uint8, device="cuda") for t_ in pin]
+    with torch.cuda.stream(stream):
+        for rep in range(2):
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for src, dst in zip(pin, dev_scratch):
+                dst.copy_(src, non_blocking=True)
+            b.record(stream)
+            reg.sync()
+            h2d_only_ms = a.elapsed_time(b)
+    del dev_scratch
 
     # ---- single-frame latency (rank 0 reports; one frame at a time, CUDA-graph replay)
     lat = None
@@ -373,7 +398,11 @@ def run_b200(args, rank, world, local_rank):
            "ms_per_frame": ms_total / args.steps / F,
            "latency_ms_per_frame": lat,
            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": ms_e2e / args.steps, "api": "fbpr_register_frames", "chunk_frames": args.e2e_chunk},
+                   "ms_per_step": ms_e2e / args.steps, "api": "fbpr_register_frames_begin/_end, 2 batches in flight (double-buffered slots)",
+                   "chunk_frames": args.e2e_chunk or 32, "timer": "host wall clock around the blocking calls, max over ranks",
+                   "sync_call": {"value": world * F * args.steps / (e2e_ms["sync"] * 1e-3), "ms_per_step": e2e_ms["sync"] / args.steps,
+                                 "api": "fbpr_register_frames (one blocking call per step)"},
+                   "h2d_only_ms_per_step": h2d_only_ms},
            "gpu_launches": int(launches),
            "clocks": clocks,
            "roofline": roofline,

@@ -279,6 +279,18 @@ class Registration:
         self._ck(self.lib.fbpr_register_frames(self.h, first, len(frame_inputs), frame_inputs, int(chunk_frames), _vp(out)))
         return out
 
+    def register_frames_begin(self, first, frame_inputs, chunk_frames=0):
+        """Enqueue uploads + the whole path of one batch; returns a ticket.  Batches on disjoint slot ranges may overlap."""
+        t = self._ck(self.lib.fbpr_register_frames_begin(self.h, first, len(frame_inputs), frame_inputs, int(chunk_frames)))
+        self._tickets = getattr(self, "_tickets", {}); self._tickets[t] = (len(frame_inputs), frame_inputs)
+        return t
+
+    def register_frames_end(self, ticket):
+        n, _ = self._tickets.pop(ticket)
+        out = np.zeros(n, RESULT_DTYPE)
+        self._ck(self.lib.fbpr_register_frames_end(self.h, int(ticket), _vp(out)))
+        return out
+
     def enable_stage_timing(self, on=True): self._ck(self.lib.fbpr_enable_stage_timing(self.h, int(on)))
 
     def get_stage_ms(self, reset=True):

@@ -90,6 +90,8 @@ struct fbpr_handle {
     FrameMeta* h_metaStage = nullptr; double* h_imuStage = nullptr; cudaEvent_t stageDone = nullptr; bool stagePending = false;
     unsigned char* wireStage = nullptr; size_t wireStageBytes = 0;          // PointCloud2 / 32-byte PCL staging (grown on demand)
     cudaStream_t copyStream = nullptr, lmStream = nullptr; std::vector<cudaEvent_t> pipeEvents;      // fbpr_register_frames: uploads overlap compute
+    struct Ticket { bool busy = false; int first = 0, count = 0; cudaEvent_t done = nullptr; fbpr_result* h_res = nullptr; int cap = 0; };
+    Ticket tickets[FBPR_MAX_TICKETS];                                       // batches between _begin and _end
     bool timing = false;
     struct TimedSpan { int stage; cudaEvent_t a, b; };
     std::vector<TimedSpan> spans; size_t spansUsed = 0;
@@ -256,6 +258,7 @@ void fbpr_destroy(fbpr_handle* h) {
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     if (h->stageDone) cudaEventDestroy(h->stageDone);
     for (auto& e : h->pipeEvents) cudaEventDestroy(e);
+    for (auto& t : h->tickets) { if (t.done) cudaEventDestroy(t.done); if (t.h_res) cudaFreeHost(t.h_res); }
     if (h->wireStage) cudaFree(h->wireStage);
     if (h->copyStream) cudaStreamDestroy(h->copyStream);
     if (h->lmStream) cudaStreamDestroy(h->lmStream);
@@ -638,14 +641,41 @@ int fbpr_run_frames(fbpr_handle* h, int first, int count, int with_projection, i
     });
 }
 
-int fbpr_register_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input* fr, int chunk_frames, fbpr_result* out) {
-    int rc = check_range(h, first, count); if (rc) return rc;
-    if (count == 0) return 0;
-    if (!fr || !out) return fbpr_fail_msg("null frames / results");
-    if (fbpr_feat_ring_smem(feat_args(h, first)) > 200 * 1024) return fbpr_fail_msg("Horizon_SCAN too large for the per-ring shared-memory kernel");
-    cudaSetDevice(h->device);
+// chunk schedule of the pipelined call: uniform chunks of `chunk_frames` (0 = 32).  A tapered tail (.., 16, 8, 8) was measured
+// and is slower (20.6 vs 19.3 ms per 128 frames for a lone call: small LM batches cost more than the shorter tail saves) and
+// makes no difference once two batches are in flight (16.8 ms, 97 % of the PCIe floor).
+static void chunk_schedule(int count, int chunk_frames, std::vector<int>& bounds) {
     const int chunk = chunk_frames > 0 ? chunk_frames : 32;
-    const int nchunks = (count + chunk - 1) / chunk;
+    bounds.assign(1, 0);
+    for (int lo = 0; lo < count; lo += chunk) bounds.push_back(lo + chunk < count ? lo + chunk : count);
+}
+
+int fbpr_register_frames_begin(fbpr_handle* h, int first, int count, const fbpr_frame_input* fr, int chunk_frames) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    if (!fr && count > 0) return fbpr_fail_msg("null frames");
+    if (count > 0 && fbpr_feat_ring_smem(feat_args(h, first)) > 200 * 1024) return fbpr_fail_msg("Horizon_SCAN too large for the per-ring shared-memory kernel");
+    cudaSetDevice(h->device);
+    int ticket = -1;
+    for (int t = 0; t < FBPR_MAX_TICKETS; t++) if (!h->tickets[t].busy) { ticket = t; break; }
+    if (ticket < 0) return fbpr_fail_msg("too many fbpr_register_frames_begin calls in flight (call fbpr_register_frames_end first)");
+    for (int t = 0; t < FBPR_MAX_TICKETS; t++) {
+        const auto& o = h->tickets[t];
+        if (o.busy && first < o.first + o.count && o.first < first + count) return fbpr_fail_msg("slot range overlaps a batch that is still in flight");
+    }
+    fbpr_handle::Ticket& tk = h->tickets[ticket];
+    if (!tk.done) FBPR_CUDA_OK(cudaEventCreateWithFlags(&tk.done, cudaEventDisableTiming));
+    if (tk.cap < count) {
+        if (tk.h_res) cudaFreeHost(tk.h_res);
+        tk.h_res = nullptr; tk.cap = 0;
+        FBPR_CUDA_OK(cudaHostAlloc((void**)&tk.h_res, sizeof(fbpr_result) * (size_t)(count > 0 ? count : 1), cudaHostAllocDefault));
+        tk.cap = count;
+    }
+    tk.first = first; tk.count = count;
+    int inflight = 0;
+    for (int t = 0; t < FBPR_MAX_TICKETS; t++) inflight += h->tickets[t].busy ? 1 : 0;
+    if (count == 0) { tk.busy = true; FBPR_CUDA_OK(cudaEventRecord(tk.done, h->stream)); return ticket; }
+    std::vector<int> bounds; chunk_schedule(count, chunk_frames, bounds);
+    const int nchunks = (int)bounds.size() - 1;
     if (!h->copyStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
     if (!h->lmStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->lmStream, cudaStreamNonBlocking));
     while ((int)h->pipeEvents.size() < 3 * nchunks + 3) {
@@ -653,11 +683,15 @@ int fbpr_register_frames(fbpr_handle* h, int first, int count, const fbpr_frame_
     }
     bool anyImu = false;
     rc = stage_frames(h, count, fr, &anyImu); if (rc) return rc;
-    // the upload stream starts after everything already queued on the compute stream (earlier operators may still read the slots)
-    cudaEvent_t evStart = h->pipeEvents[3 * nchunks], evMeta = h->pipeEvents[3 * nchunks + 1], evLmDone = h->pipeEvents[3 * nchunks + 2];
-    FBPR_CUDA_OK(cudaEventRecord(evStart, h->stream));
-    FBPR_CUDA_OK(cudaStreamWaitEvent(h->copyStream, evStart, 0));
-    FBPR_CUDA_OK(cudaStreamWaitEvent(h->lmStream, evStart, 0));
+    cudaEvent_t evStart = h->pipeEvents[3 * nchunks], evMeta = h->pipeEvents[3 * nchunks + 1];
+    if (inflight == 0) {
+        // nothing pipelined is pending: the upload stream starts after everything already queued on the compute stream
+        // (earlier operators may still read these slots).  With another batch in flight (on DISJOINT slots, whose previous
+        // occupants were drained by fbpr_register_frames_end) the copies may start at once, under that batch's kernels.
+        FBPR_CUDA_OK(cudaEventRecord(evStart, h->stream));
+        FBPR_CUDA_OK(cudaStreamWaitEvent(h->copyStream, evStart, 0));
+        FBPR_CUDA_OK(cudaStreamWaitEvent(h->lmStream, evStart, 0));
+    }
     rc = upload_staged(h, first, count, anyImu, h->copyStream); if (rc) return rc;
     FBPR_CUDA_OK(cudaEventRecord(evMeta, h->copyStream));
     FBPR_CUDA_OK(cudaEventRecord(h->stageDone, h->copyStream));
@@ -667,7 +701,7 @@ int fbpr_register_frames(fbpr_handle* h, int first, int count, const fbpr_frame_
     // as soon as its maps are in HBM and its front-end is done -- so the PCIe copies of chunk k+1 and the front-end of chunk k+1
     // run under the latency-bound LM kernel of chunk k.
     for (int c = 0; c < nchunks; c++) {
-        const int lo = c * chunk, hi = lo + chunk < count ? lo + chunk : count;
+        const int lo = bounds[c], hi = bounds[c + 1];
         for (int i = lo; i < hi; i++) {
             const FrameMeta& m = h->h_metaStage[i];
             if (m.n_raw) FBPR_CUDA_OK(cudaMemcpyAsync(h->raw + (size_t)(first + i) * h->rawCap, fr[i].raw, (size_t)m.n_raw * sizeof(fbpr_raw_point), cudaMemcpyHostToDevice, h->copyStream));
@@ -683,7 +717,7 @@ int fbpr_register_frames(fbpr_handle* h, int first, int count, const fbpr_frame_
     FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, evMeta, 0));
     FBPR_CUDA_OK(cudaStreamWaitEvent(h->lmStream, evMeta, 0));
     for (int c = 0; c < nchunks; c++) {
-        const int lo = first + c * chunk, n = (c + 1) * chunk <= count ? chunk : count - c * chunk;
+        const int lo = first + bounds[c], n = bounds[c + 1] - bounds[c];
         FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, h->pipeEvents[3 * c], 0));
         rc = enqueue_project(h, lo, n); if (rc) return rc;
         rc = enqueue_features(h, lo, n); if (rc) return rc;
@@ -696,9 +730,37 @@ int fbpr_register_frames(fbpr_handle* h, int first, int count, const fbpr_frame_
         std::swap(h->stream, h->lmStream);
         if (rc) return rc;
     }
-    FBPR_CUDA_OK(cudaEventRecord(evLmDone, h->lmStream));
-    FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, evLmDone, 0));
-    return fbpr_get_results(h, first, count, out, FBPR_MEM_HOST);
+    // results: packed D2H on the registration stream, right behind the last LM kernel (the front-end stream stays free for the next batch)
+    FBPR_CUDA_OK(cudaMemcpy2DAsync(tk.h_res, sizeof(fbpr_result), reinterpret_cast<char*>(h->meta + first) + offsetof(FrameMeta, pose), sizeof(FrameMeta),
+                                   sizeof(fbpr_result), count, cudaMemcpyDeviceToHost, h->lmStream));
+    FBPR_CUDA_OK(cudaEventRecord(tk.done, h->lmStream));
+    tk.busy = true;
+    return ticket;
+}
+
+int fbpr_register_frames_end(fbpr_handle* h, int ticket, fbpr_result* out) {
+    if (!h) return fbpr_fail_msg("null handle");
+    if (ticket < 0 || ticket >= FBPR_MAX_TICKETS || !h->tickets[ticket].busy) return fbpr_fail_msg("no such batch in flight");
+    cudaSetDevice(h->device);
+    fbpr_handle::Ticket& tk = h->tickets[ticket];
+    FBPR_CUDA_OK(cudaEventSynchronize(tk.done));
+    tk.busy = false;
+    FBPR_CUDA_OK(cudaGetLastError());
+    if (out && tk.count > 0) memcpy(out, tk.h_res, sizeof(fbpr_result) * (size_t)tk.count);
+    bool any = false;
+    for (int t = 0; t < FBPR_MAX_TICKETS; t++) any = any || h->tickets[t].busy;
+    if (!any) {                                                  // later operators on the handle's stream see the finished slots
+        FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, tk.done, 0));
+    }
+    return tk.count;
+}
+
+int fbpr_register_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input* fr, int chunk_frames, fbpr_result* out) {
+    if (count > 0 && !out) return fbpr_fail_msg("null frames / results");
+    const int ticket = fbpr_register_frames_begin(h, first, count, fr, chunk_frames);
+    if (ticket < 0) return ticket;
+    const int rc = fbpr_register_frames_end(h, ticket, out);
+    return rc < 0 ? rc : 0;
 }
 
 int fbpr_extract_surrounding_keyframes(fbpr_handle* h, int slot, int K, const float* key_poses6,

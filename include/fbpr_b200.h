@@ -219,6 +219,15 @@ FBPR_API int fbpr_run_frames(fbpr_handle* h, int first, int count, int with_proj
    call returns when they are there. */
 FBPR_API int fbpr_register_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input* frames, int chunk_frames,
                                   fbpr_result* out);
+/* the same call split in two so that a caller streaming batches keeps PCIe busy: _begin enqueues the uploads and the whole
+   path of `count` frames into slots [first, first+count) and returns a ticket (>= 0) at once; _end blocks until that batch's
+   results are on the host, copies them to `out` and returns the frame count.  Up to FBPR_MAX_TICKETS batches may be in flight
+   on DISJOINT slot ranges (double buffering: the uploads of batch k+1 run under the last kernels of batch k); the frames'
+   host buffers must stay valid until _end.  No other operator may touch those slots between _begin and _end.
+   chunk_frames: frames per upload chunk; 0 = 32. */
+#define FBPR_MAX_TICKETS 4
+FBPR_API int fbpr_register_frames_begin(fbpr_handle* h, int first, int count, const fbpr_frame_input* frames, int chunk_frames);
+FBPR_API int fbpr_register_frames_end(fbpr_handle* h, int ticket, fbpr_result* out);
 
 /* ---- results ----------------------------------------------------------------------------- */
 FBPR_API int fbpr_get_pose(fbpr_handle* h, int slot, float pose6[6], int32_t* iters, uint32_t* flags);

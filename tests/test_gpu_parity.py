@@ -313,9 +313,31 @@ def test_pipelined_register_frames_equals_plain_batch(fb):
                                for fr, raw in zip(frames, raws)])
     r.set_frames(0, fin); r.run_frames(0, F)
     want = r.get_results(0, F)
-    for chunk in (1, 2, 32):
+    for chunk in (0, 1, 2, 32):
         got = r.register_frames(0, fin, chunk)
         assert np.array_equal(got["pose"], want["pose"]) and np.array_equal(got["iters"], want["iters"]) and np.array_equal(got["flags"], want["flags"])
+    # split form, two batches in flight on disjoint slot ranges (double buffering), three rounds
+    r2 = fb.Registration(frames[0]["params"], max_frames=2 * F, max_map_corner=16384, max_map_surf=65536)
+    fin2 = r2.make_frame_inputs([dict(raw_ptr=raw.ctypes.data, n_raw=len(raw), imu=fr["imu"], imu_available=fr["imu_available"],
+                                      map_corner_ptr=fr["map_corner"].ctypes.data, n_map_corner=len(fr["map_corner"]),
+                                      map_surf_ptr=fr["map_surf"].ctypes.data, n_map_surf=len(fr["map_surf"]), pose=fr["guess"])
+                                 for fr, raw in zip(frames, raws)])
+    t = r2.register_frames_begin(0, fin2, 2)
+    for rnd in range(3):
+        t_next = r2.register_frames_begin(F * ((rnd + 1) % 2), fin2, 0)
+        got = r2.register_frames_end(t)
+        assert np.array_equal(got["pose"], want["pose"]) and np.array_equal(got["iters"], want["iters"]) and np.array_equal(got["flags"], want["flags"])
+        t = t_next
+    with pytest.raises(fb.FbprError, match="overlaps"):
+        r2.register_frames_begin(F * (3 % 2), fin2, 0)           # the same slots while that batch is still in flight
+    got = r2.register_frames_end(t)
+    assert np.array_equal(got["pose"], want["pose"])
+    with pytest.raises(fb.FbprError, match="no such batch"):
+        r2.lib.fbpr_register_frames_end.restype = int
+        r2._ck(r2.lib.fbpr_register_frames_end(r2.h, 0, None))
+    r2.set_frames(0, fin2); r2.run_frames(0, F)                   # ordinary operators work again after _end
+    assert np.array_equal(r2.get_results(0, F)["iters"], want["iters"])
+    r2.close()
     for s_, fr in enumerate(frames[:2]):                      # and both equal the oracle
         ci = oracle.project(fr["params"], fr["scan"], fr["imu"], fr["imu_available"]); fe = oracle.extract_features(fr["params"], ci)
         mo = oracle.MapOptimization(fr["params"]); mo.set_imu(fr["imu_available"], 0.0, 0.0)
