@@ -590,17 +590,22 @@ static int enqueue_downsample(fbpr_handle* h, int first, int count) {
     StageTimer t(h, FBPR_STAGE_DOWNSAMPLE);
     fbpr_launch_voxel(h->d_scanSegs + 2 * (size_t)first, 2 * count, h->P, h->tilesCap, h->stream, &h->launches); return 0;
 }
-static int enqueue_scan2map(fbpr_handle* h, int first, int count) {
+static int enqueue_map_index(fbpr_handle* h, int first, int count) {
     int maxMap = h->mapCornerCap > h->mapSurfCap ? h->mapCornerCap : h->mapSurfCap;
     int maxCells = h->cellsCorner > h->cellsSurf ? h->cellsCorner : h->cellsSurf;
-    {
-        StageTimer t(h, FBPR_STAGE_MAP_INDEX);
-        fbpr_launch_grid_build(h->d_gridSegs + 2 * (size_t)first, 2 * count, maxMap, maxCells, h->stream, &h->launches);
-    }
+    StageTimer t(h, FBPR_STAGE_MAP_INDEX);
+    fbpr_launch_grid_build(h->d_gridSegs + 2 * (size_t)first, 2 * count, maxMap, maxCells, h->stream, &h->launches);
+    return 0;
+}
+static int enqueue_lm(fbpr_handle* h, int first, int count) {
     LmArgs a = lm_args(h, first);
     if (a.debug_iter >= 0 && first + count > h->dbgSlots) return fbpr_fail_msg("debug capture only covers the first slots");
     StageTimer t(h, FBPR_STAGE_LM);
     return fbpr_launch_lm(a, count, h->cluster, h->lmWholeGpu ? h->lmGridBlocks : 0, h->stream, &h->launches);
+}
+static int enqueue_scan2map(fbpr_handle* h, int first, int count) {
+    int rc = enqueue_map_index(h, first, count);
+    return rc ? rc : enqueue_lm(h, first, count);
 }
 
 extern "C" {

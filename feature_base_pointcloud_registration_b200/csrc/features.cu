@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
     __shared__ int s_sp[FBPR_SEGS], s_ep[FBPR_SEGS];
     __shared__ unsigned s_bb[6];
     __shared__ int s_vox[8];          // overflow, min_b[3], m1, m2
+    __shared__ unsigned s_ubits[2][RING_TPB / 32], s_pbits[2][RING_TPB / 32];   // flat loop: undecided / picked bit per element, by round parity
     __shared__ float s_inv;
 
     const float* g_curv = a.curv + (size_t)slot * a.P;
@@ -336,6 +337,64 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
                 s_state0[ind - w0] = st;
             }
             __syncthreads();
+            if (len + 1 <= RING_TPB) {
+                // One thread per element g = sp + tid.  The candidates that can decide g ("dominators": undecided at the start,
+                // ranked before g, and covering g with their reach) never change, so they are found once as an 11-bit mask over
+                // g-5..g+5; a round is then two bit-window tests against the picked / undecided bit vectors of the segment
+                // (one word per warp, written with a ballot, double-buffered so a round needs one barrier).
+                const int g = sp + tid, w = tid >> 5, l = tid & 31;
+                const bool mine = g <= ep;
+                bool und = mine && s_state0[g - w0] == ST_UNDECIDED, pk = false;
+                unsigned dom = 0;
+                if (und) {
+                    const unsigned rk = s_meta[g - w0] >> 16;
+                    const int qlo = max(g - 5, sp), qhi = min(g + 5, ep);
+                    for (int q = qlo; q <= qhi; q++) {
+                        if (q == g || s_state0[q - w0] != ST_UNDECIDED) continue;
+                        const unsigned mq = s_meta[q - w0];
+                        if ((mq >> 16) >= rk) continue;
+                        const bool covers = q < g ? (g - q <= (int)((mq >> 8) & 0xff)) : (q - g <= (int)(mq & 0xff));
+                        if (covers) dom |= 1u << (q - g + 5);
+                    }
+                }
+                int cur = 0;
+                {
+                    const unsigned bu = __ballot_sync(0xffffffffu, und);
+                    if (l == 0) { s_ubits[0][w] = bu; s_pbits[0][w] = 0u; }
+                }
+                __syncthreads();
+                while (true) {
+                    int pending = 0;
+                    if (und) {
+                        // bits g-5 .. g+5 of both vectors (bit 5 = g itself)
+                        const unsigned ulo = w > 0 ? s_ubits[cur][w - 1] : 0u, umid = s_ubits[cur][w], uhi = w + 1 < RING_TPB / 32 ? s_ubits[cur][w + 1] : 0u;
+                        const unsigned plo = w > 0 ? s_pbits[cur][w - 1] : 0u, pmid = s_pbits[cur][w], phi = w + 1 < RING_TPB / 32 ? s_pbits[cur][w + 1] : 0u;
+                        unsigned uw, pw;
+                        if (l >= 5) {
+                            uw = (unsigned)((((unsigned long long)uhi << 32) | umid) >> (l - 5));
+                            pw = (unsigned)((((unsigned long long)phi << 32) | pmid) >> (l - 5));
+                        } else {
+                            uw = (unsigned)((((unsigned long long)umid << 32) | ulo) >> (l + 27));
+                            pw = (unsigned)((((unsigned long long)pmid << 32) | plo) >> (l + 27));
+                        }
+                        if (pw & dom) und = false;                         // a dominator was picked: suppressed
+                        else if (!(uw & dom)) { und = false; pk = true; }  // every dominator is decided and none picked: picked
+                        else pending = 1;
+                    }
+                    const unsigned bu = __ballot_sync(0xffffffffu, und), bp = __ballot_sync(0xffffffffu, pk);
+                    if (l == 0) { s_ubits[cur ^ 1][w] = bu; s_pbits[cur ^ 1][w] = bp; }
+                    cur ^= 1;
+                    if (!__syncthreads_or(pending)) break;
+                }
+                if (pk) {                                                  // apply picks: label -1, mark self and reach
+                    s_label[g - w0] = -1; s_picked[g - w0] = 1;
+                    const int f = (s_meta[g - w0] >> 8) & 0xff, bb = s_meta[g - w0] & 0xff;
+                    for (int q = 1; q <= f; q++) s_picked[g + q - w0] = 1;
+                    for (int q = 1; q <= bb; q++) s_picked[g - q - w0] = 1;
+                }
+                __syncthreads();
+                continue;
+            }
             // rounds: every element of [sp, ep] is re-written into the other buffer each round, so one barrier per round
             unsigned char* cur = s_state0; unsigned char* nxt = s_state1;
             while (true) {
@@ -456,22 +515,27 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
             else if (a.voxPad == 2 * RING_TPB) cta_bitonic_sort<2>(s_keys);
             else if (a.voxPad == 8 * RING_TPB) cta_bitonic_sort<8>(s_keys);
             else bitonic_blocks(s_keys, a.voxPad, a.voxPad);
+            // runs of equal voxel index: list the run heads (s_col is free by now), then ONE THREAD PER RUN sums its points in
+            // sorted order (sequential f32 sums, as pcl::VoxelGrid does) -- whole warps stay busy instead of the few head lanes
+            int* s_run = s_col;
             int carry = 0;
             for (int base = 0; base < nsurf; base += RING_TPB) {
                 int t = base + tid;
                 int flag = (t < nsurf) && (t == 0 || (s_keys[t] >> 32) != (s_keys[t - 1] >> 32));
                 int tot, off = block_excl_scan(flag, &tot, s_ws);
-                if (flag) {
-                    unsigned kk = (unsigned)(s_keys[t] >> 32);
-                    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int c = 0;
-                    for (int q = t; q < nsurf && (unsigned)(s_keys[q] >> 32) == kk; q++) {
-                        float4 p = g_cloud[s_list[(unsigned)(s_keys[q] & 0xffffffffu)]];
-                        sx += p.x; sy += p.y; sz += p.z; si += p.w; c++;
-                    }
-                    float fc = (float)c;
-                    stage[carry + off] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
-                }
+                if (flag) s_run[carry + off] = t;
                 carry += tot;
+            }
+            __syncthreads();
+            for (int r = tid; r < carry; r += RING_TPB) {
+                const int t = s_run[r], end = r + 1 < carry ? s_run[r + 1] : nsurf;
+                float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+                for (int q = t; q < end; q++) {
+                    const float4 p = g_cloud[s_list[(unsigned)(s_keys[q] & 0xffffffffu)]];
+                    sx += p.x; sy += p.y; sz += p.z; si += p.w;
+                }
+                const float fc = (float)(end - t);
+                stage[r] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
             }
             nout = carry;
         }
