@@ -222,7 +222,7 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
                 g.h0 = k == 0 ? h->cellCorner : h->cellSurf;
                 g.pts = (k == 0 ? h->mapCorner + (size_t)f * h->mapCornerCap : h->mapSurf + (size_t)f * h->mapSurfCap);
                 g.n = k == 0 ? &h->meta[f].n_map_corner : &h->meta[f].n_map_surf;
-                ALLOC(g.sorted, g.cap); ALLOC(g.cell_start, g.cells_cap + 2); ALLOC(g.cell_cursor, g.cells_cap + 2);
+                ALLOC(g.sorted, g.cap); ALLOC(g.cell_start, g.cells_cap + 2);
                 ALLOC(g.cell_of, g.cap); ALLOC(g.tile_sum, g.cells_cap / 4096 + 4); ALLOC(g.bbox, 8); ALLOC(g.desc, 1);
                 h->h_gridSegs[2 * f + k] = g;
             }
@@ -1073,7 +1073,7 @@ int fbpr_knn5(fbpr_handle* h, const float* map_xyzi, int n_map, float cell, cons
         GridSeg g = {};
         FBPR_CUDA_OK(A((void**)&h->soloMap, sizeof(float4) * cap)); FBPR_CUDA_OK(A((void**)&h->soloMapN, 16));
         FBPR_CUDA_OK(A((void**)&g.sorted, sizeof(float4) * cap)); FBPR_CUDA_OK(A((void**)&g.cell_start, 4 * (size_t)(cells + 2)));
-        FBPR_CUDA_OK(A((void**)&g.cell_cursor, 4 * (size_t)(cells + 2))); FBPR_CUDA_OK(A((void**)&g.cell_of, 4 * (size_t)cap));
+        FBPR_CUDA_OK(A((void**)&g.cell_of, 4 * (size_t)cap));
         FBPR_CUDA_OK(A((void**)&g.tile_sum, 4 * (size_t)(cells / 4096 + 4))); FBPR_CUDA_OK(A((void**)&g.bbox, 32)); FBPR_CUDA_OK(A((void**)&g.desc, sizeof(GridDesc)));
         FBPR_CUDA_OK(A((void**)&h->d_soloGrid, sizeof(GridSeg)));
         g.pts = h->soloMap; g.n = h->soloMapN; g.cap = cap; g.cells_cap = cells; g.h0 = cell;

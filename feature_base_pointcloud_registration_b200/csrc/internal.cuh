@@ -78,8 +78,7 @@ struct GridSeg {                  // host-built descriptor of one map-index segm
     const int* n;                 // device pointer to count
     float4* sorted;               // cell-contiguous copy, w = original index bits
     int* cell_start;              // [cells_cap+1]
-    int* cell_cursor;             // [cells_cap+1] fill cursor, ends up = cell end
-    int* cell_of;                 // [cap] cell id per point
+    int* cell_of;                 // [cap] rank of the point inside its cell (the value its counting atomic returned)
     int* tile_sum;                // scan scratch
     unsigned* bbox;               // 6 encoded floats
     GridDesc* desc;

@@ -5,8 +5,8 @@
 // histogram (atomics) -> exclusive scan over cells -> scatter into cell-contiguous order
 // (counting sort).  Order inside a cell is arbitrary; exactness of the k-NN does not depend on
 // it because candidates are ranked by (d^2, original index).
-// HBM-bound: reads each map point twice (16 B) and writes it once; the cell arrays are
-// L2-resident.  blockIdx.y = segment (2 maps x frame slots).
+// HBM-bound: reads each map point three times (16 B: bbox, count, scatter) and writes it once; the cell array costs
+// 16 B per cell (zero, sum, scan in place).  blockIdx.y = segment (2 maps x frame slots).
 #include "internal.cuh"
 #include "mapgrid.cuh"
 
@@ -90,6 +90,8 @@ __device__ inline int cell_of_point(const GridDesc& g, float4 p) {
     return (cz * g.dy + cy) * g.dx + cx;
 }
 
+// histogram of the cells; the value the atomic returns is the point's rank inside its cell, which makes the scatter
+// below atomic-free (position = cell_start[cell] + rank)
 __global__ void __launch_bounds__(TPB) grid_count(const GridSeg* segs) {
     const GridSeg& s = segs[blockIdx.y];
     const GridDesc g = *s.desc;
@@ -97,19 +99,49 @@ __global__ void __launch_bounds__(TPB) grid_count(const GridSeg* segs) {
     if (base >= g.n) return;
     for (int k = 0; k < IPT; k++) {
         int i = base + k * TPB + threadIdx.x;
-        if (i < g.n) { int c = cell_of_point(g, s.pts[i]); s.cell_of[i] = c; atomicAdd(&s.cell_start[c], 1); }
+        if (i < g.n) { int c = cell_of_point(g, s.pts[i]); s.cell_of[i] = atomicAdd(&s.cell_start[c], 1); }
     }
 }
 
-// three-phase exclusive scan over the cells of every segment
-__global__ void __launch_bounds__(1024) grid_scan_tiles(const GridSeg* segs) {
+// exclusive scan over the cells of every segment in two passes (12 B of traffic per cell): per-tile sums, then every
+// tile adds up the sums of the tiles before it (at most cells_cap / SCAN_TILE values) and scans itself in place
+__device__ inline int block_sum_1024(int v, int* ws) {
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (l == 0) ws[w] = v;
+    __syncthreads();
+    int t = ws[l];
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    return t;
+}
+__global__ void __launch_bounds__(1024) grid_tile_sums(const GridSeg* segs) {
     const GridSeg& s = segs[blockIdx.y];
     const int nc = s.desc->ncells + 1;
     int base = blockIdx.x * SCAN_TILE;
     if (base >= nc) return;
-    int v[4], sum = 0;
-    for (int k = 0; k < 4; k++) { int c = base + threadIdx.x * 4 + k; v[k] = c < nc ? s.cell_start[c] : 0; sum += v[k]; }
     __shared__ int ws[32];
+    int sum = 0;
+    const int c0 = base + threadIdx.x * 4;
+    if (c0 + 3 < nc) { const int4 v = *reinterpret_cast<const int4*>(s.cell_start + c0); sum = v.x + v.y + v.z + v.w; }
+    else for (int k = 0; k < 4; k++) if (c0 + k < nc) sum += s.cell_start[c0 + k];
+    sum = block_sum_1024(sum, ws);
+    if (threadIdx.x == 0) s.tile_sum[blockIdx.x] = sum;
+}
+__global__ void __launch_bounds__(1024) grid_scan_apply(const GridSeg* segs) {
+    const GridSeg& s = segs[blockIdx.y];
+    const int nc = s.desc->ncells + 1;
+    int base = blockIdx.x * SCAN_TILE;
+    if (base >= nc) return;
+    __shared__ int ws[32];
+    int before = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += 1024) before += s.tile_sum[t];
+    before = block_sum_1024(before, ws);
+    int v[4] = { 0, 0, 0, 0 }, sum = 0;
+    const int c0 = base + threadIdx.x * 4;
+    if (c0 + 3 < nc) { const int4 q = *reinterpret_cast<const int4*>(s.cell_start + c0); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+    else for (int k = 0; k < 4; k++) if (c0 + k < nc) v[k] = s.cell_start[c0 + k];
+    sum = v[0] + v[1] + v[2] + v[3];
     int incl = sum, l = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
     if (l == 31) ws[w] = incl;
@@ -118,63 +150,24 @@ __global__ void __launch_bounds__(1024) grid_scan_tiles(const GridSeg* segs) {
         int a = ws[l], ia = a;
         for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, ia, o); if (l >= o) ia += u; }
         ws[l] = ia - a;
-        if (l == 31) s.tile_sum[blockIdx.x] = ia;
     }
     __syncthreads();
-    int run = ws[w] + incl - sum;
-    for (int k = 0; k < 4; k++) { int c = base + threadIdx.x * 4 + k; if (c < nc) { s.cell_start[c] = run; run += v[k]; } }
-}
-
-__global__ void __launch_bounds__(1024) grid_scan_sums(const GridSeg* segs) {
-    const GridSeg& s = segs[blockIdx.x];
-    const int nt = (s.desc->ncells + 1 + SCAN_TILE - 1) / SCAN_TILE;
-    __shared__ int ws[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int b = 0; b < nt; b += 1024) {
-        int e = b + threadIdx.x;
-        int v = e < nt ? s.tile_sum[e] : 0;
-        int incl = v, l = threadIdx.x & 31, w = threadIdx.x >> 5;
-        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
-        if (l == 31) ws[w] = incl;
-        __syncthreads();
-        if (w == 0) {
-            int a = ws[l], ia = a;
-            for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, ia, o); if (l >= o) ia += u; }
-            ws[l] = ia - a;
-        }
-        __syncthreads();
-        int excl = carry + ws[w] + incl - v;
-        if (e < nt) s.tile_sum[e] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(1024) grid_scan_add(const GridSeg* segs) {
-    const GridSeg& s = segs[blockIdx.y];
-    const int nc = s.desc->ncells + 1;
-    int base = blockIdx.x * SCAN_TILE;
-    if (base >= nc) return;
-    int add = s.tile_sum[blockIdx.x];
-    for (int k = 0; k < 4; k++) {
-        int c = base + threadIdx.x * 4 + k;
-        if (c < nc) { int v = s.cell_start[c] + add; s.cell_start[c] = v; s.cell_cursor[c] = v; }
-    }
+    int run = before + ws[w] + incl - sum;
+    int4 o4; o4.x = run; o4.y = run + v[0]; o4.z = o4.y + v[1]; o4.w = o4.z + v[2];
+    if (c0 + 3 < nc) *reinterpret_cast<int4*>(s.cell_start + c0) = o4;
+    else { const int o[4] = { o4.x, o4.y, o4.z, o4.w }; for (int k = 0; k < 4; k++) if (c0 + k < nc) s.cell_start[c0 + k] = o[k]; }
 }
 
 __global__ void __launch_bounds__(TPB) grid_scatter(const GridSeg* segs) {
     const GridSeg& s = segs[blockIdx.y];
-    const int n = s.desc->n;
+    const GridDesc g = *s.desc;
     int base = blockIdx.x * TILE;
-    if (base >= n) return;
+    if (base >= g.n) return;
     for (int k = 0; k < IPT; k++) {
         int i = base + k * TPB + threadIdx.x;
-        if (i < n) {
+        if (i < g.n) {
             float4 p = s.pts[i];
-            int pos = atomicAdd(&s.cell_cursor[s.cell_of[i]], 1);
+            int pos = __ldg(s.cell_start + cell_of_point(g, p)) + s.cell_of[i];
             s.sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
         }
     }
@@ -217,11 +210,10 @@ void fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cel
     int zb = (cells_cap + TPB * 8) / (TPB * 8); if (zb > 1024) zb = 1024;
     grid_setup_zero<<<dim3(zb, nsegs), TPB, 0, st>>>(d_segs);
     grid_count<<<g, TPB, 0, st>>>(d_segs);
-    grid_scan_tiles<<<gs, 1024, 0, st>>>(d_segs);
-    grid_scan_sums<<<nsegs, 1024, 0, st>>>(d_segs);
-    grid_scan_add<<<gs, 1024, 0, st>>>(d_segs);
+    grid_tile_sums<<<gs, 1024, 0, st>>>(d_segs);
+    grid_scan_apply<<<gs, 1024, 0, st>>>(d_segs);
     grid_scatter<<<g, TPB, 0, st>>>(d_segs);
-    if (launches) *launches += 8;
+    if (launches) *launches += 7;
 }
 
 void fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, int rad0, cudaStream_t st, long long* launches) {
