@@ -159,10 +159,14 @@ __host__ __device__ inline float ord2f(unsigned u) {
 // f32 trig contract
 __device__ inline float sinf_c(float x) { return (float)sin((double)x); }
 __device__ inline float cosf_c(float x) { return (float)cos((double)x); }
+__device__ inline void sincosf_c(float x, float& s, float& c) {      // both at once: one argument reduction instead of two
+    double sd, cd; sincos((double)x, &sd, &cd); s = (float)sd; c = (float)cd;
+}
 
 // pcl::getTransformation(x,y,z,roll,pitch,yaw) -> 3x4 row-major, f32
 __device__ inline void get_transformation(float x, float y, float z, float roll, float pitch, float yaw, float T[12]) {
-    float A = cosf_c(yaw), B = sinf_c(yaw), C = cosf_c(pitch), D = sinf_c(pitch), E = cosf_c(roll), F = sinf_c(roll);
+    float A, B, C, D, E, F;
+    sincosf_c(yaw, B, A); sincosf_c(pitch, D, C); sincosf_c(roll, F, E);
     float DE = D * E, DF = D * F;
     T[0] = A * C; T[1] = A * DF - B * E; T[2]  = B * F + A * DE; T[3]  = x;
     T[4] = B * C; T[5] = A * E + B * DF; T[6]  = B * DE - A * F; T[7]  = y;

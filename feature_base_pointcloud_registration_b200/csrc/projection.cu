@@ -70,9 +70,15 @@ __global__ void __launch_bounds__(TPB) proj_ring_count(ProjArgs a) {
 
 // findRotation (imageProjection.cpp:494-526)
 __device__ inline void find_rotation(const double* imuTime, const double* rX, const double* rY, const double* rZ,
-                                     int imuPointerCur, double pointTime, float& rx, float& ry, float& rz) {
+                                     int imuPointerCur, double pointTime, float& rx, float& ry, float& rz, bool sorted = false) {
     int front = 0;
-    while (front < imuPointerCur) { if (pointTime < imuTime[front]) break; ++front; }
+    if (sorted) {                                            // ascending stamps: the first entry later than pointTime, by bisection
+        int lo = 0, hi = imuPointerCur;                      // answer in [0, imuPointerCur]
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (pointTime < imuTime[mid]) hi = mid; else lo = mid + 1; }
+        front = lo;
+    } else {
+        while (front < imuPointerCur) { if (pointTime < imuTime[front]) break; ++front; }
+    }
     if (pointTime > imuTime[front] || front == 0) {
         rx = (float)rX[front]; ry = (float)rY[front]; rz = (float)rZ[front];
     } else {
@@ -119,6 +125,21 @@ __global__ void __launch_bounds__(TPB) proj_compact(ProjArgs a) {
     __shared__ float s_Tinv[12];
     __shared__ int ws[TPB / 32];
     const bool deskew = !(M.deskewFlag == -1 || M.imuAvailable == 0);
+    // the frame's IMU ramp, staged once per CTA; when its stamps ascend (they do for a real IMU queue) findRotation's linear
+    // scan is replaced by a bisection with the same answer
+    __shared__ double s_imu[4][FBPR_IMU_CAP];
+    bool sortedRamp = false;
+    if (deskew) {
+        const int np = min(max(M.imuPointerCur, 0), FBPR_IMU_CAP - 1) + 1;
+        int bad = 0;
+        for (int i = threadIdx.x; i < np; i += TPB) {
+            const double t = imuTime[i];
+            s_imu[0][i] = t; s_imu[1][i] = rX[i]; s_imu[2][i] = rY[i]; s_imu[3][i] = rZ[i];
+            if (i + 1 < np && !(t <= imuTime[i + 1])) bad = 1;
+        }
+        sortedRamp = !__syncthreads_or(bad);
+        imuTime = s_imu[0]; rX = s_imu[1]; rY = s_imu[2]; rZ = s_imu[3];
+    }
     if (threadIdx.x < 32) {
         // ring base = counts of all previous rings; total = all rings
         int b = 0, t = 0;
@@ -156,7 +177,7 @@ __global__ void __launch_bounds__(TPB) proj_compact(ProjArgs a) {
             float4 out = make_float4(p.x, p.y, p.z, p.intensity);
             if (deskew) {
                 float rx, ry, rz, T[12], Bt[12];
-                find_rotation(imuTime, rX, rY, rZ, M.imuPointerCur, M.timeScanCur + (double)p.time, rx, ry, rz);
+                find_rotation(imuTime, rX, rY, rZ, M.imuPointerCur, M.timeScanCur + (double)p.time, rx, ry, rz, sortedRamp);
                 get_transformation(0.f, 0.f, 0.f, rx, ry, rz, T);
                 affine_mul(s_Tinv, T, Bt);
                 out.x = Bt[0] * p.x + Bt[1] * p.y + Bt[2] * p.z + Bt[3];

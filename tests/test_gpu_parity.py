@@ -108,6 +108,26 @@ def test_projection_matches_oracle(fb, config):
         assert np.array_equal(cloud, want["cloud_deskewed"])
 
 
+def test_projection_unsorted_imu_ramp_uses_the_reference_scan(fb):
+    """findRotation (imageProjection.cpp:494-526) walks the IMU ramp linearly; the device bisects only when the stamps
+    ascend.  A ramp with two stamps swapped (and one repeated) must still give the linear-scan answer."""
+    fr = synth.make_frame(3, 5, small=(16, 900, 2000, 8000))
+    P = fr["params"]
+    imu = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in fr["imu"].items()}
+    n = int(imu["imuPointerCur"])
+    i = n // 2
+    imu["imuTime"][[i, i + 1]] = imu["imuTime"][[i + 1, i]]
+    imu["imuTime"][i + 5] = imu["imuTime"][i + 4]
+    want = oracle.project(P, fr["scan"], imu, 1)
+    r = _reg(fb, P)
+    r.set_raw_scan(0, fb.api.pack_raw(fr["scan"]), imu=imu, imu_available=1)
+    r.project(0, 1); r.sync()
+    cloud = r.get_buffer(0, "CLOUD")
+    assert np.array_equal(r.get_buffer(0, "COL_IND"), want["pointColInd"])
+    assert np.allclose(cloud, want["cloud_deskewed"], rtol=0, atol=2e-5) and np.mean(cloud == want["cloud_deskewed"]) > 0.99
+    r.close()
+
+
 # ------------------------------------------------------------------ features
 @pytest.mark.parametrize("config,frame", [(1, 0), (1, 1), (2, 0), (3, 0), (0, 0)])
 def test_feature_extraction_bit_exact(fb, config, frame):
