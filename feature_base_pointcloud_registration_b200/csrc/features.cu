@@ -204,6 +204,23 @@ __device__ __forceinline__ void segment_sorts(unsigned long long* keys) {
     __syncthreads();
 }
 
+template <int IPT>
+__device__ __forceinline__ void warp_sort_list(unsigned long long* base, int lane) {   // 32 * IPT keys of shared memory, one warp
+    unsigned long long k[IPT];
+    #pragma unroll
+    for (int i = 0; i < IPT; i++) k[i] = base[lane * IPT + i];
+    warp_bitonic_sort<IPT>(k, lane);
+    #pragma unroll
+    for (int i = 0; i < IPT; i++) base[lane * IPT + i] = k[i];
+}
+
+// bits e-5 .. e+5 (bit 5 = e itself) of a bit vector stored one word per warp, for element e = 32 * w + l
+__device__ __forceinline__ unsigned bit_window(const unsigned* words, int w, int l) {
+    const unsigned lo = w > 0 ? words[w - 1] : 0u, mid = words[w], hi = w + 1 < RING_TPB / 32 ? words[w + 1] : 0u;
+    return l >= 5 ? (unsigned)((((unsigned long long)hi << 32) | mid) >> (l - 5))
+                  : (unsigned)((((unsigned long long)mid << 32) | lo) >> (l + 27));
+}
+
 enum : unsigned char { ST_NONE = 0, ST_UNDECIDED = 1, ST_PICKED = 2, ST_DEAD = 3 };
 
 __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
@@ -225,7 +242,7 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
     unsigned char* s_state1 = s_state0 + a.wcap;
     __shared__ int s_corner[CORNERS_PER_RING];
     __shared__ int s_ncorner, s_ws[RING_TPB / 32];
-    __shared__ int s_sp[FBPR_SEGS], s_ep[FBPR_SEGS];
+    __shared__ int s_sp[FBPR_SEGS], s_ep[FBPR_SEGS], s_ccnt[FBPR_SEGS];
     __shared__ unsigned s_bb[6];
     __shared__ int s_vox[8];          // overflow, min_b[3], m1, m2
     __shared__ unsigned s_ubits[2][RING_TPB / 32], s_pbits[2][RING_TPB / 32];   // flat loop: undecided / picked bit per element, by round parity
@@ -271,118 +288,116 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
             }
             s_meta[t] = ((unsigned)f << 8) | (unsigned)b;
         }
-        // sort keys of all six segments: cloudSmoothness[k] = {curv[k], k} inside [5, n-5), else {0.0f, 0}
-        for (int t = tid; t < FBPR_SEGS * a.segPad; t += RING_TPB) {
-            int j = t / a.segPad, q = t - j * a.segPad;
-            int sp = s_sp[j], ep = s_ep[j];
-            unsigned long long key = ~0ull;
-            if (sp < ep && q < ep - sp) {
-                int k = sp + q;
-                if (k >= 5 && k < n - 5) key = ((unsigned long long)__float_as_uint(s_curv[k - w0]) << 32) | (unsigned)k;
-                else key = 0ull;
-            }
-            s_keys[t] = key;
-        }
-        __syncthreads();
-        if (a.segPad == 512) segment_sorts<16>(s_keys);
-        else if (a.segPad == 256) segment_sorts<8>(s_keys);
-        else if (a.segPad == 128) segment_sorts<4>(s_keys);
-        else bitonic_blocks(s_keys, FBPR_SEGS * a.segPad, a.segPad);
-
-        for (int j = 0; j < FBPR_SEGS; j++) {
-            const int sp = s_sp[j], ep = s_ep[j];
-            if (sp >= ep) continue;                                   // uniform across the CTA
-            const int len = ep - sp;
-            const unsigned long long* keys = s_keys + j * a.segPad;
-            // ---- corner loop (:208-242), one thread, early exit once sorted curvature <= edgeThreshold
-            if (tid == 0) {
-                int cnt = 0;
-                for (int v = len; v >= 0; v--) {
-                    int ind; float cv;
-                    if (v == len) { ind = (ep >= 5 && ep < n - 5) ? ep : 0; }
-                    else { ind = (int)(unsigned)(keys[v] & 0xffffffffu); }
-                    cv = (ind >= w0 && ind <= w1) ? s_curv[ind - w0] : 0.f;
-                    if (v < len && !(cv > a.edgeThreshold)) break;   // sorted ascending: nothing below can qualify
-                    if (ind < w0 || ind > w1) continue;
-                    if (s_picked[ind - w0] == 0 && cv > a.edgeThreshold) {
-                        cnt++;
-                        if (cnt <= FBPR_CORNERS_PER_SEG) { s_label[ind - w0] = 1; s_corner[s_ncorner++] = ind; }
-                        else break;
-                        s_picked[ind - w0] = 1;
-                        int f = (s_meta[ind - w0] >> 8) & 0xff, b = s_meta[ind - w0] & 0xff;
-                        for (int l = 1; l <= f; l++) s_picked[ind + l - w0] = 1;
-                        for (int l = 1; l <= b; l++) s_picked[ind - l - w0] = 1;
-                    }
-                }
-                // quirk slot: a sorted entry whose index lies outside the segment (cloudSmoothness slot < 5 -> ind 0)
-                // is ranked first in the flat loop; handle it sequentially before the parallel rounds
-                int ind0 = (int)(unsigned)(keys[0] & 0xffffffffu);
-                if (len > 0 && (ind0 < sp || ind0 > ep) && ind0 >= w0 && ind0 <= w1) {
-                    if (s_picked[ind0 - w0] == 0 && s_curv[ind0 - w0] < a.surfThreshold) {
-                        s_label[ind0 - w0] = -1; s_picked[ind0 - w0] = 1;
-                        int f = (s_meta[ind0 - w0] >> 8) & 0xff, b = s_meta[ind0 - w0] & 0xff;
-                        for (int l = 1; l <= f; l++) s_picked[ind0 + l - w0] = 1;
-                        for (int l = 1; l <= b; l++) s_picked[ind0 - l - w0] = 1;
+        // Two ways through the six segments.  The usual one needs NO full sort of cloudSmoothness (:203): the corner loop only
+        // ever reaches the entries above edgeThreshold (it stops at the first one that is not, :208-242 over an ascending
+        // array walked from the top), so only those few are listed and sorted; and the flat loop's outcome depends only on the
+        // ORDER BETWEEN NEIGHBOURS within the +-5 suppression reach, which is a direct comparison of their
+        // (curvature, index) keys -- slot `ep` is never sorted (:203 sorts [sp, ep)), so it ranks after everything else.
+        const bool sortFree = a.segPad <= RING_TPB && a.segPad >= 32;   // one thread per segment element is possible
+        if (sortFree) {
+            const int warp = tid >> 5, lane = tid & 31;
+            if (tid < FBPR_SEGS) s_ccnt[tid] = 0;
+            __syncthreads();
+            for (int t = tid; t < W; t += RING_TPB) {
+                const int g = w0 + t;
+                if (!(g >= 5 && g < n - 5) || !(s_curv[t] > a.edgeThreshold)) continue;
+                for (int j = 0; j < FBPR_SEGS; j++) {
+                    if (s_sp[j] < s_ep[j] && g >= s_sp[j] && g < s_ep[j]) {
+                        const int pos = atomicAdd(&s_ccnt[j], 1);
+                        s_keys[j * a.segPad + pos] = ((unsigned long long)__float_as_uint(s_curv[t]) << 32) | (unsigned)g;
                     }
                 }
             }
             __syncthreads();
-            // ---- flat loop (:245-276) as parallel lexicographically-first MIS
-            for (int v = tid; v <= len; v += RING_TPB) {
-                int ind = v == len ? ((ep >= 5 && ep < n - 5) ? ep : 0) : (int)(unsigned)(keys[v] & 0xffffffffu);
-                if (ind < sp || ind > ep) continue;
-                s_meta[ind - w0] = (s_meta[ind - w0] & 0xffffu) | ((unsigned)v << 16);
-                unsigned char st = ST_NONE;
-                if (s_curv[ind - w0] < a.surfThreshold) st = s_picked[ind - w0] ? ST_DEAD : ST_UNDECIDED;
-                s_state0[ind - w0] = st;
+            for (int t = tid; t < FBPR_SEGS * a.segPad; t += RING_TPB) {      // pad every list to a power of two with +inf keys
+                const int j = t / a.segPad, q = t - j * a.segPad, c = s_ccnt[j];
+                int pad = 32; while (pad < c) pad <<= 1;
+                if (q >= c && q < pad) s_keys[t] = ~0ull;
             }
             __syncthreads();
-            if (len + 1 <= RING_TPB) {
-                // One thread per element g = sp + tid.  The candidates that can decide g ("dominators": undecided at the start,
-                // ranked before g, and covering g with their reach) never change, so they are found once as an 11-bit mask over
-                // g-5..g+5; a round is then two bit-window tests against the picked / undecided bit vectors of the segment
-                // (one word per warp, written with a ballot, double-buffered so a round needs one barrier).
-                const int g = sp + tid, w = tid >> 5, l = tid & 31;
+            if (warp < FBPR_SEGS && s_ccnt[warp] > 1) {                      // warp j sorts list j ascending, in registers
+                const int c = s_ccnt[warp];
+                unsigned long long* base = s_keys + warp * a.segPad;
+                if (c <= 32) { unsigned long long k[1] = { base[lane] }; warp_bitonic_sort<1>(k, lane); base[lane] = k[0]; }
+                else if (c <= 64) warp_sort_list<2>(base, lane);
+                else if (c <= 128) warp_sort_list<4>(base, lane);
+                else if (c <= 256) warp_sort_list<8>(base, lane);
+                else warp_sort_list<16>(base, lane);
+            }
+            __syncthreads();
+            for (int j = 0; j < FBPR_SEGS; j++) {
+                const int sp = s_sp[j], ep = s_ep[j];
+                if (sp >= ep) continue;                                   // uniform across the CTA
+                const unsigned long long* keys = s_keys + j * a.segPad;
+                const int ncand = s_ccnt[j];
+                // ---- corner loop (:208-242), one thread: slot ep first, then the listed entries from the largest down
+                if (tid == 0) {
+                    int cnt = 0;
+                    for (int v = ncand; v >= 0; v--) {
+                        const int ind = v == ncand ? ((ep >= 5 && ep < n - 5) ? ep : 0) : (int)(unsigned)(keys[v] & 0xffffffffu);
+                        if (ind < w0 || ind > w1) continue;
+                        if (s_picked[ind - w0] == 0 && s_curv[ind - w0] > a.edgeThreshold) {
+                            cnt++;
+                            if (cnt <= FBPR_CORNERS_PER_SEG) { s_label[ind - w0] = 1; s_corner[s_ncorner++] = ind; }
+                            else break;
+                            s_picked[ind - w0] = 1;
+                            int f = (s_meta[ind - w0] >> 8) & 0xff, b = s_meta[ind - w0] & 0xff;
+                            for (int l = 1; l <= f; l++) s_picked[ind + l - w0] = 1;
+                            for (int l = 1; l <= b; l++) s_picked[ind - l - w0] = 1;
+                        }
+                    }
+                    // quirk: a slot of [sp, ep) outside [5, n-5) holds {0.0f, ind 0}; it sorts first, so the flat loop starts at index 0
+                    if ((sp < 5 || ep - 1 >= n - 5) && (0 < sp || 0 > ep) && 0 >= w0 && 0 <= w1) {
+                        if (s_picked[0 - w0] == 0 && s_curv[0 - w0] < a.surfThreshold) {
+                            s_label[0 - w0] = -1; s_picked[0 - w0] = 1;
+                            int f = (s_meta[0 - w0] >> 8) & 0xff, b = s_meta[0 - w0] & 0xff;
+                            for (int l = 1; l <= f; l++) s_picked[0 + l - w0] = 1;
+                            for (int l = 1; l <= b; l++) s_picked[0 - l - w0] = 1;
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- flat loop (:245-276) = the lexicographically-first maximal independent set in visiting order, one thread
+                // per element g = sp + tid.  The elements that can decide g ("dominators": undecided at the start, visited
+                // before g, covering g with their reach) never change, so they are found once as an 11-bit mask over g-5..g+5; a
+                // round is then two bit-window tests against the picked / undecided bit vectors of the segment (one word per
+                // warp, written with a ballot, double-buffered so a round needs one barrier).
+                const int g = sp + tid;
                 const bool mine = g <= ep;
-                bool und = mine && s_state0[g - w0] == ST_UNDECIDED, pk = false;
+                const float cg = mine ? s_curv[g - w0] : 0.f;
+                bool und = mine && g >= 5 && g < n - 5 && cg < a.surfThreshold && s_picked[g - w0] == 0, pk = false;
+                {
+                    const unsigned bu = __ballot_sync(0xffffffffu, und);
+                    if (lane == 0) { s_ubits[0][warp] = bu; s_pbits[0][warp] = 0u; }
+                }
+                __syncthreads();
                 unsigned dom = 0;
                 if (und) {
-                    const unsigned rk = s_meta[g - w0] >> 16;
-                    const int qlo = max(g - 5, sp), qhi = min(g + 5, ep);
-                    for (int q = qlo; q <= qhi; q++) {
-                        if (q == g || s_state0[q - w0] != ST_UNDECIDED) continue;
+                    const unsigned uw0 = bit_window(s_ubits[0], warp, lane) & ~(1u << 5);
+                    const unsigned cgb = __float_as_uint(cg);
+                    #pragma unroll
+                    for (int d = 0; d < 11; d++) {
+                        if (!((uw0 >> d) & 1u)) continue;
+                        const int q = g + d - 5;
+                        const unsigned cqb = __float_as_uint(s_curv[q - w0]);
+                        const bool before = g == ep ? true : (q == ep ? false : (cqb < cgb || (cqb == cgb && q < g)));
+                        if (!before) continue;
                         const unsigned mq = s_meta[q - w0];
-                        if ((mq >> 16) >= rk) continue;
                         const bool covers = q < g ? (g - q <= (int)((mq >> 8) & 0xff)) : (q - g <= (int)(mq & 0xff));
-                        if (covers) dom |= 1u << (q - g + 5);
+                        if (covers) dom |= 1u << d;
                     }
                 }
                 int cur = 0;
-                {
-                    const unsigned bu = __ballot_sync(0xffffffffu, und);
-                    if (l == 0) { s_ubits[0][w] = bu; s_pbits[0][w] = 0u; }
-                }
-                __syncthreads();
                 while (true) {
                     int pending = 0;
                     if (und) {
-                        // bits g-5 .. g+5 of both vectors (bit 5 = g itself)
-                        const unsigned ulo = w > 0 ? s_ubits[cur][w - 1] : 0u, umid = s_ubits[cur][w], uhi = w + 1 < RING_TPB / 32 ? s_ubits[cur][w + 1] : 0u;
-                        const unsigned plo = w > 0 ? s_pbits[cur][w - 1] : 0u, pmid = s_pbits[cur][w], phi = w + 1 < RING_TPB / 32 ? s_pbits[cur][w + 1] : 0u;
-                        unsigned uw, pw;
-                        if (l >= 5) {
-                            uw = (unsigned)((((unsigned long long)uhi << 32) | umid) >> (l - 5));
-                            pw = (unsigned)((((unsigned long long)phi << 32) | pmid) >> (l - 5));
-                        } else {
-                            uw = (unsigned)((((unsigned long long)umid << 32) | ulo) >> (l + 27));
-                            pw = (unsigned)((((unsigned long long)pmid << 32) | plo) >> (l + 27));
-                        }
+                        const unsigned uw = bit_window(s_ubits[cur], warp, lane), pw = bit_window(s_pbits[cur], warp, lane);
                         if (pw & dom) und = false;                         // a dominator was picked: suppressed
                         else if (!(uw & dom)) { und = false; pk = true; }  // every dominator is decided and none picked: picked
                         else pending = 1;
                     }
                     const unsigned bu = __ballot_sync(0xffffffffu, und), bp = __ballot_sync(0xffffffffu, pk);
-                    if (l == 0) { s_ubits[cur ^ 1][w] = bu; s_pbits[cur ^ 1][w] = bp; }
+                    if (lane == 0) { s_ubits[cur ^ 1][warp] = bu; s_pbits[cur ^ 1][warp] = bp; }
                     cur ^= 1;
                     if (!__syncthreads_or(pending)) break;
                 }
@@ -393,47 +408,172 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
                     for (int q = 1; q <= bb; q++) s_picked[g - q - w0] = 1;
                 }
                 __syncthreads();
-                continue;
             }
-            // rounds: every element of [sp, ep] is re-written into the other buffer each round, so one barrier per round
-            unsigned char* cur = s_state0; unsigned char* nxt = s_state1;
-            while (true) {
-                int pending = 0;
-                for (int g = sp + tid; g <= ep; g += RING_TPB) {
-                    unsigned char st = cur[g - w0];
-                    if (st == ST_UNDECIDED) {
+        } else {
+            // sort keys of all six segments: cloudSmoothness[k] = {curv[k], k} inside [5, n-5), else {0.0f, 0}
+            for (int t = tid; t < FBPR_SEGS * a.segPad; t += RING_TPB) {
+                int j = t / a.segPad, q = t - j * a.segPad;
+                int sp = s_sp[j], ep = s_ep[j];
+                unsigned long long key = ~0ull;
+                if (sp < ep && q < ep - sp) {
+                    int k = sp + q;
+                    if (k >= 5 && k < n - 5) key = ((unsigned long long)__float_as_uint(s_curv[k - w0]) << 32) | (unsigned)k;
+                    else key = 0ull;
+                }
+                s_keys[t] = key;
+            }
+            __syncthreads();
+            if (a.segPad == 512) segment_sorts<16>(s_keys);
+            else if (a.segPad == 256) segment_sorts<8>(s_keys);
+            else if (a.segPad == 128) segment_sorts<4>(s_keys);
+            else bitonic_blocks(s_keys, FBPR_SEGS * a.segPad, a.segPad);
+
+            for (int j = 0; j < FBPR_SEGS; j++) {
+                const int sp = s_sp[j], ep = s_ep[j];
+                if (sp >= ep) continue;                                   // uniform across the CTA
+                const int len = ep - sp;
+                const unsigned long long* keys = s_keys + j * a.segPad;
+                // ---- corner loop (:208-242), one thread, early exit once sorted curvature <= edgeThreshold
+                if (tid == 0) {
+                    int cnt = 0;
+                    for (int v = len; v >= 0; v--) {
+                        int ind; float cv;
+                        if (v == len) { ind = (ep >= 5 && ep < n - 5) ? ep : 0; }
+                        else { ind = (int)(unsigned)(keys[v] & 0xffffffffu); }
+                        cv = (ind >= w0 && ind <= w1) ? s_curv[ind - w0] : 0.f;
+                        if (v < len && !(cv > a.edgeThreshold)) break;   // sorted ascending: nothing below can qualify
+                        if (ind < w0 || ind > w1) continue;
+                        if (s_picked[ind - w0] == 0 && cv > a.edgeThreshold) {
+                            cnt++;
+                            if (cnt <= FBPR_CORNERS_PER_SEG) { s_label[ind - w0] = 1; s_corner[s_ncorner++] = ind; }
+                            else break;
+                            s_picked[ind - w0] = 1;
+                            int f = (s_meta[ind - w0] >> 8) & 0xff, b = s_meta[ind - w0] & 0xff;
+                            for (int l = 1; l <= f; l++) s_picked[ind + l - w0] = 1;
+                            for (int l = 1; l <= b; l++) s_picked[ind - l - w0] = 1;
+                        }
+                    }
+                    // quirk slot: a sorted entry whose index lies outside the segment (cloudSmoothness slot < 5 -> ind 0)
+                    // is ranked first in the flat loop; handle it sequentially before the parallel rounds
+                    int ind0 = (int)(unsigned)(keys[0] & 0xffffffffu);
+                    if (len > 0 && (ind0 < sp || ind0 > ep) && ind0 >= w0 && ind0 <= w1) {
+                        if (s_picked[ind0 - w0] == 0 && s_curv[ind0 - w0] < a.surfThreshold) {
+                            s_label[ind0 - w0] = -1; s_picked[ind0 - w0] = 1;
+                            int f = (s_meta[ind0 - w0] >> 8) & 0xff, b = s_meta[ind0 - w0] & 0xff;
+                            for (int l = 1; l <= f; l++) s_picked[ind0 + l - w0] = 1;
+                            for (int l = 1; l <= b; l++) s_picked[ind0 - l - w0] = 1;
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- flat loop (:245-276) as parallel lexicographically-first MIS
+                for (int v = tid; v <= len; v += RING_TPB) {
+                    int ind = v == len ? ((ep >= 5 && ep < n - 5) ? ep : 0) : (int)(unsigned)(keys[v] & 0xffffffffu);
+                    if (ind < sp || ind > ep) continue;
+                    s_meta[ind - w0] = (s_meta[ind - w0] & 0xffffu) | ((unsigned)v << 16);
+                    unsigned char st = ST_NONE;
+                    if (s_curv[ind - w0] < a.surfThreshold) st = s_picked[ind - w0] ? ST_DEAD : ST_UNDECIDED;
+                    s_state0[ind - w0] = st;
+                }
+                __syncthreads();
+                if (len + 1 <= RING_TPB) {
+                    // One thread per element g = sp + tid.  The candidates that can decide g ("dominators": undecided at the start,
+                    // ranked before g, and covering g with their reach) never change, so they are found once as an 11-bit mask over
+                    // g-5..g+5; a round is then two bit-window tests against the picked / undecided bit vectors of the segment
+                    // (one word per warp, written with a ballot, double-buffered so a round needs one barrier).
+                    const int g = sp + tid, w = tid >> 5, l = tid & 31;
+                    const bool mine = g <= ep;
+                    bool und = mine && s_state0[g - w0] == ST_UNDECIDED, pk = false;
+                    unsigned dom = 0;
+                    if (und) {
                         const unsigned rk = s_meta[g - w0] >> 16;
-                        bool dead = false, wait = false;
                         const int qlo = max(g - 5, sp), qhi = min(g + 5, ep);
                         for (int q = qlo; q <= qhi; q++) {
-                            if (q == g) continue;
-                            const unsigned char sq = cur[q - w0];
-                            if (sq != ST_PICKED && sq != ST_UNDECIDED) continue;
+                            if (q == g || s_state0[q - w0] != ST_UNDECIDED) continue;
                             const unsigned mq = s_meta[q - w0];
                             if ((mq >> 16) >= rk) continue;
                             const bool covers = q < g ? (g - q <= (int)((mq >> 8) & 0xff)) : (q - g <= (int)(mq & 0xff));
-                            if (!covers) continue;
-                            if (sq == ST_PICKED) dead = true; else wait = true;
+                            if (covers) dom |= 1u << (q - g + 5);
                         }
-                        if (dead) st = ST_DEAD;
-                        else if (!wait) st = ST_PICKED;
-                        else pending = 1;
                     }
-                    nxt[g - w0] = st;
+                    int cur = 0;
+                    {
+                        const unsigned bu = __ballot_sync(0xffffffffu, und);
+                        if (l == 0) { s_ubits[0][w] = bu; s_pbits[0][w] = 0u; }
+                    }
+                    __syncthreads();
+                    while (true) {
+                        int pending = 0;
+                        if (und) {
+                            // bits g-5 .. g+5 of both vectors (bit 5 = g itself)
+                            const unsigned ulo = w > 0 ? s_ubits[cur][w - 1] : 0u, umid = s_ubits[cur][w], uhi = w + 1 < RING_TPB / 32 ? s_ubits[cur][w + 1] : 0u;
+                            const unsigned plo = w > 0 ? s_pbits[cur][w - 1] : 0u, pmid = s_pbits[cur][w], phi = w + 1 < RING_TPB / 32 ? s_pbits[cur][w + 1] : 0u;
+                            unsigned uw, pw;
+                            if (l >= 5) {
+                                uw = (unsigned)((((unsigned long long)uhi << 32) | umid) >> (l - 5));
+                                pw = (unsigned)((((unsigned long long)phi << 32) | pmid) >> (l - 5));
+                            } else {
+                                uw = (unsigned)((((unsigned long long)umid << 32) | ulo) >> (l + 27));
+                                pw = (unsigned)((((unsigned long long)pmid << 32) | plo) >> (l + 27));
+                            }
+                            if (pw & dom) und = false;                         // a dominator was picked: suppressed
+                            else if (!(uw & dom)) { und = false; pk = true; }  // every dominator is decided and none picked: picked
+                            else pending = 1;
+                        }
+                        const unsigned bu = __ballot_sync(0xffffffffu, und), bp = __ballot_sync(0xffffffffu, pk);
+                        if (l == 0) { s_ubits[cur ^ 1][w] = bu; s_pbits[cur ^ 1][w] = bp; }
+                        cur ^= 1;
+                        if (!__syncthreads_or(pending)) break;
+                    }
+                    if (pk) {                                                  // apply picks: label -1, mark self and reach
+                        s_label[g - w0] = -1; s_picked[g - w0] = 1;
+                        const int f = (s_meta[g - w0] >> 8) & 0xff, bb = s_meta[g - w0] & 0xff;
+                        for (int q = 1; q <= f; q++) s_picked[g + q - w0] = 1;
+                        for (int q = 1; q <= bb; q++) s_picked[g - q - w0] = 1;
+                    }
+                    __syncthreads();
+                    continue;
                 }
-                unsigned char* t_ = cur; cur = nxt; nxt = t_;
-                if (!__syncthreads_or(pending)) break;
-            }
-            // apply picks: label -1, mark self and reach
-            for (int g = sp + tid; g <= ep; g += RING_TPB) {
-                if (cur[g - w0] == ST_PICKED) {
-                    s_label[g - w0] = -1; s_picked[g - w0] = 1;
-                    const int f = (s_meta[g - w0] >> 8) & 0xff, b = s_meta[g - w0] & 0xff;
-                    for (int l = 1; l <= f; l++) s_picked[g + l - w0] = 1;
-                    for (int l = 1; l <= b; l++) s_picked[g - l - w0] = 1;
+                // rounds: every element of [sp, ep] is re-written into the other buffer each round, so one barrier per round
+                unsigned char* cur = s_state0; unsigned char* nxt = s_state1;
+                while (true) {
+                    int pending = 0;
+                    for (int g = sp + tid; g <= ep; g += RING_TPB) {
+                        unsigned char st = cur[g - w0];
+                        if (st == ST_UNDECIDED) {
+                            const unsigned rk = s_meta[g - w0] >> 16;
+                            bool dead = false, wait = false;
+                            const int qlo = max(g - 5, sp), qhi = min(g + 5, ep);
+                            for (int q = qlo; q <= qhi; q++) {
+                                if (q == g) continue;
+                                const unsigned char sq = cur[q - w0];
+                                if (sq != ST_PICKED && sq != ST_UNDECIDED) continue;
+                                const unsigned mq = s_meta[q - w0];
+                                if ((mq >> 16) >= rk) continue;
+                                const bool covers = q < g ? (g - q <= (int)((mq >> 8) & 0xff)) : (q - g <= (int)(mq & 0xff));
+                                if (!covers) continue;
+                                if (sq == ST_PICKED) dead = true; else wait = true;
+                            }
+                            if (dead) st = ST_DEAD;
+                            else if (!wait) st = ST_PICKED;
+                            else pending = 1;
+                        }
+                        nxt[g - w0] = st;
+                    }
+                    unsigned char* t_ = cur; cur = nxt; nxt = t_;
+                    if (!__syncthreads_or(pending)) break;
                 }
+                // apply picks: label -1, mark self and reach
+                for (int g = sp + tid; g <= ep; g += RING_TPB) {
+                    if (cur[g - w0] == ST_PICKED) {
+                        s_label[g - w0] = -1; s_picked[g - w0] = 1;
+                        const int f = (s_meta[g - w0] >> 8) & 0xff, b = s_meta[g - w0] & 0xff;
+                        for (int l = 1; l <= f; l++) s_picked[g + l - w0] = 1;
+                        for (int l = 1; l <= b; l++) s_picked[g - l - w0] = 1;
+                    }
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
         // ---- write back labels / marks (1s only: neighbouring rings' windows overlap)
         for (int t = tid; t < W; t += RING_TPB) {
