@@ -215,10 +215,12 @@ __device__ __forceinline__ void warp_sort_list(unsigned long long* base, int lan
 }
 
 // bits e-5 .. e+5 (bit 5 = e itself) of a bit vector stored one word per warp, for element e = 32 * w + l
-__device__ __forceinline__ unsigned bit_window(const unsigned* words, int w, int l) {
-    const unsigned lo = w > 0 ? words[w - 1] : 0u, mid = words[w], hi = w + 1 < RING_TPB / 32 ? words[w + 1] : 0u;
+__device__ __forceinline__ unsigned bit_window3(unsigned lo, unsigned mid, unsigned hi, int l) {
     return l >= 5 ? (unsigned)((((unsigned long long)hi << 32) | mid) >> (l - 5))
                   : (unsigned)((((unsigned long long)mid << 32) | lo) >> (l + 27));
+}
+__device__ __forceinline__ unsigned bit_window(const unsigned* words, int w, int l) {
+    return bit_window3(w > 0 ? words[w - 1] : 0u, words[w], w + 1 < RING_TPB / 32 ? words[w + 1] : 0u, l);
 }
 
 enum : unsigned char { ST_NONE = 0, ST_UNDECIDED = 1, ST_PICKED = 2, ST_DEAD = 3 };
@@ -330,29 +332,49 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
                 if (sp >= ep) continue;                                   // uniform across the CTA
                 const unsigned long long* keys = s_keys + j * a.segPad;
                 const int ncand = s_ccnt[j];
-                // ---- corner loop (:208-242), one thread: slot ep first, then the listed entries from the largest down
-                if (tid == 0) {
-                    int cnt = 0;
-                    for (int v = ncand; v >= 0; v--) {
-                        const int ind = v == ncand ? ((ep >= 5 && ep < n - 5) ? ep : 0) : (int)(unsigned)(keys[v] & 0xffffffffu);
-                        if (ind < w0 || ind > w1) continue;
-                        if (s_picked[ind - w0] == 0 && s_curv[ind - w0] > a.edgeThreshold) {
-                            cnt++;
-                            if (cnt <= FBPR_CORNERS_PER_SEG) { s_label[ind - w0] = 1; s_corner[s_ncorner++] = ind; }
-                            else break;
-                            s_picked[ind - w0] = 1;
-                            int f = (s_meta[ind - w0] >> 8) & 0xff, b = s_meta[ind - w0] & 0xff;
-                            for (int l = 1; l <= f; l++) s_picked[ind + l - w0] = 1;
-                            for (int l = 1; l <= b; l++) s_picked[ind - l - w0] = 1;
+                // ---- corner loop (:208-242) by warp 0: slot ep first, then the listed entries from the largest down, 32 visiting
+                // positions per batch.  Lanes hold one entry each; the picks happen strictly in visiting order (a uniform loop over
+                // the eligible lanes), every pick marks its reach in the other lanes' registers and in shared memory.
+                if (warp == 0) {
+                    int cnt = 0, nc = s_ncorner;
+                    bool stop = false;
+                    for (int base = 0; base <= ncand && !stop; base += 32) {
+                        const int pos = base + lane;
+                        int ind = -1;
+                        if (pos <= ncand) ind = pos == 0 ? ((ep >= 5 && ep < n - 5) ? ep : 0) : (int)(unsigned)(keys[ncand - pos] & 0xffffffffu);
+                        const bool inwin = ind >= w0 && ind <= w1;
+                        int taken = 1, f = 0, b = 0;
+                        bool elig = false;
+                        if (inwin) {
+                            taken = s_picked[ind - w0];
+                            elig = s_curv[ind - w0] > a.edgeThreshold;
+                            const unsigned m = s_meta[ind - w0];
+                            f = (int)((m >> 8) & 0xff); b = (int)(m & 0xff);
                         }
+                        unsigned todo = __ballot_sync(0xffffffffu, elig);
+                        while (todo) {
+                            const int i = __ffs(todo) - 1; todo &= todo - 1;
+                            if (__shfl_sync(0xffffffffu, taken, i)) continue;
+                            cnt++;
+                            if (cnt > FBPR_CORNERS_PER_SEG) { stop = true; break; }            // the 21st breaks before marking
+                            const int pi = __shfl_sync(0xffffffffu, ind, i), pf = __shfl_sync(0xffffffffu, f, i), pb = __shfl_sync(0xffffffffu, b, i);
+                            if (inwin && ind >= pi - pb && ind <= pi + pf) taken = 1;
+                            if (lane <= pf + pb) s_picked[pi - pb + lane - w0] = 1;
+                            if (lane == 0) { s_label[pi - w0] = 1; s_corner[nc] = pi; }
+                            nc++;
+                        }
+                        __syncwarp();
                     }
-                    // quirk: a slot of [sp, ep) outside [5, n-5) holds {0.0f, ind 0}; it sorts first, so the flat loop starts at index 0
-                    if ((sp < 5 || ep - 1 >= n - 5) && (0 < sp || 0 > ep) && 0 >= w0 && 0 <= w1) {
-                        if (s_picked[0 - w0] == 0 && s_curv[0 - w0] < a.surfThreshold) {
-                            s_label[0 - w0] = -1; s_picked[0 - w0] = 1;
-                            int f = (s_meta[0 - w0] >> 8) & 0xff, b = s_meta[0 - w0] & 0xff;
-                            for (int l = 1; l <= f; l++) s_picked[0 + l - w0] = 1;
-                            for (int l = 1; l <= b; l++) s_picked[0 - l - w0] = 1;
+                    if (lane == 0) {
+                        s_ncorner = nc;
+                        // quirk: a slot of [sp, ep) outside [5, n-5) holds {0.0f, ind 0}; it sorts first, so the flat loop starts at index 0
+                        if ((sp < 5 || ep - 1 >= n - 5) && (0 < sp || 0 > ep) && 0 >= w0 && 0 <= w1) {
+                            if (s_picked[0 - w0] == 0 && s_curv[0 - w0] < a.surfThreshold) {
+                                s_label[0 - w0] = -1; s_picked[0 - w0] = 1;
+                                int f = (s_meta[0 - w0] >> 8) & 0xff, b = s_meta[0 - w0] & 0xff;
+                                for (int l = 1; l <= f; l++) s_picked[0 + l - w0] = 1;
+                                for (int l = 1; l <= b; l++) s_picked[0 - l - w0] = 1;
+                            }
                         }
                     }
                 }
@@ -387,19 +409,27 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
                         if (covers) dom |= 1u << d;
                     }
                 }
+                // A block round: the neighbouring warps' words are read once (they may be stale -- states only move from
+                // undecided to picked / suppressed, so a stale word can delay a decision but never change it), then the warp
+                // iterates on its own fresh ballots until nothing changes; only chains that cross warps need another round.
                 int cur = 0;
                 while (true) {
-                    int pending = 0;
-                    if (und) {
-                        const unsigned uw = bit_window(s_ubits[cur], warp, lane), pw = bit_window(s_pbits[cur], warp, lane);
-                        if (pw & dom) und = false;                         // a dominator was picked: suppressed
-                        else if (!(uw & dom)) { und = false; pk = true; }  // every dominator is decided and none picked: picked
-                        else pending = 1;
+                    const unsigned ulo = warp > 0 ? s_ubits[cur][warp - 1] : 0u, uhi = warp + 1 < RING_TPB / 32 ? s_ubits[cur][warp + 1] : 0u;
+                    const unsigned plo = warp > 0 ? s_pbits[cur][warp - 1] : 0u, phi = warp + 1 < RING_TPB / 32 ? s_pbits[cur][warp + 1] : 0u;
+                    unsigned bu = __ballot_sync(0xffffffffu, und), bp = __ballot_sync(0xffffffffu, pk);
+                    while (bu) {
+                        bool changed = false;
+                        if (und) {
+                            const unsigned uw = bit_window3(ulo, bu, uhi, lane), pw = bit_window3(plo, bp, phi, lane);
+                            if (pw & dom) { und = false; changed = true; }                     // a dominator was picked: suppressed
+                            else if (!(uw & dom)) { und = false; pk = true; changed = true; }  // all dominators decided, none picked
+                        }
+                        if (!__any_sync(0xffffffffu, changed)) break;
+                        bu = __ballot_sync(0xffffffffu, und); bp = __ballot_sync(0xffffffffu, pk);
                     }
-                    const unsigned bu = __ballot_sync(0xffffffffu, und), bp = __ballot_sync(0xffffffffu, pk);
                     if (lane == 0) { s_ubits[cur ^ 1][warp] = bu; s_pbits[cur ^ 1][warp] = bp; }
                     cur ^= 1;
-                    if (!__syncthreads_or(pending)) break;
+                    if (!__syncthreads_or(und ? 1 : 0)) break;
                 }
                 if (pk) {                                                  // apply picks: label -1, mark self and reach
                     s_label[g - w0] = -1; s_picked[g - w0] = 1;
