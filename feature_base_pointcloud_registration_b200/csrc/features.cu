@@ -31,38 +31,61 @@ constexpr int TPB1 = 256;
 constexpr int RING_TPB = 512;
 constexpr int CORNERS_PER_RING = FBPR_SEGS * FBPR_CORNERS_PER_SEG;
 
+// occlusion rule of source position i (featureExtraction.h:142-166): bit 0 = "mark i-5..i", bit 1 = "mark i+1..i+6"
+__device__ __forceinline__ int occlusion_source(const float* __restrict__ r, const int* __restrict__ col, int i, int n) {
+    if (i < 5 || i >= n - 6) return 0;
+    if (abs(col[i + 1] - col[i]) >= 10) return 0;
+    const float d1 = r[i], d2 = r[i + 1];
+    if ((double)(d1 - d2) > 0.3) return 1;
+    if ((double)(d2 - d1) > 0.3) return 2;
+    return 0;
+}
+
+// One tile of TPB1 consecutive points per CTA.  Every source position is evaluated once (plus a 32-point halo on each side),
+// its two flags go into per-warp ballot words, and a point's mark is a bit-window test: any "mark back" source in j..j+5 or
+// any "mark forward" source in j-6..j-1.  No scattered writes, no ordering issue.
 __global__ void __launch_bounds__(TPB1) feat_smooth(FeatArgs a) {
     const int slot = a.first + blockIdx.y;
     const int n = a.meta[slot].n_valid;
+    const int base = blockIdx.x * TPB1;
+    if (base >= n) return;
     const float* r = a.range + (size_t)slot * a.P;
     const int* col = a.colInd + (size_t)slot * a.P;
     float* curv = a.curv + (size_t)slot * a.P;
     int* picked = a.picked + (size_t)slot * a.P;
     int* label = a.label + (size_t)slot * a.P;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        float c = 0.f;
-        if (j >= 5 && j < n - 5) {
-            float d = r[j - 5] + r[j - 4] + r[j - 3] + r[j - 2] + r[j - 1] - r[j] * 10
-                    + r[j + 1] + r[j + 2] + r[j + 3] + r[j + 4] + r[j + 5];
-            c = d * d;
+    constexpr int NW = TPB1 / 32;
+    __shared__ unsigned s_back[NW + 2], s_fwd[NW + 2];          // word 0 = halo before the tile, word NW + 1 = halo after it
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j = base + tid;
+    {
+        const int f = occlusion_source(r, col, j, n);
+        const unsigned wb = __ballot_sync(0xffffffffu, f == 1), wf = __ballot_sync(0xffffffffu, f == 2);
+        if (lane == 0) { s_back[warp + 1] = wb; s_fwd[warp + 1] = wf; }
+        if (warp < 2) {                                           // halos: 32 positions before / after the tile
+            const int i = warp == 0 ? base - 32 + lane : base + TPB1 + lane;
+            const int fh = occlusion_source(r, col, i, n);
+            const unsigned hb = __ballot_sync(0xffffffffu, fh == 1), hf = __ballot_sync(0xffffffffu, fh == 2);
+            if (lane == 0) { const int wd = warp == 0 ? 0 : NW + 1; s_back[wd] = hb; s_fwd[wd] = hf; }
         }
-        int pk = 0;
-        // sources i in [j, j+5] mark i-5..i when depth1 - depth2 > 0.3;  i in [j-6, j-1] mark i+1..i+6 when depth2 - depth1 > 0.3
-        for (int i = j - 6; i <= j + 5; i++) {
-            if (i < 5 || i >= n - 6) continue;
-            int cd = abs(col[i + 1] - col[i]);
-            if (cd >= 10) continue;
-            float d1 = r[i], d2 = r[i + 1];
-            bool A = (double)(d1 - d2) > 0.3;
-            bool B = !A && (double)(d2 - d1) > 0.3;
-            if (i >= j ? A : B) pk = 1;
-        }
-        if (j >= 5 && j < n - 6) {
-            float diff1 = fabsf(r[j - 1] - r[j]), diff2 = fabsf(r[j + 1] - r[j]);
-            if ((double)diff1 > 0.02 * (double)r[j] && (double)diff2 > 0.02 * (double)r[j]) pk = 1;
-        }
-        curv[j] = c; picked[j] = pk; label[j] = 0;
     }
+    __syncthreads();
+    if (j >= n) return;
+    float c = 0.f;
+    if (j >= 5 && j < n - 5) {
+        float d = r[j - 5] + r[j - 4] + r[j - 3] + r[j - 2] + r[j - 1] - r[j] * 10
+                + r[j + 1] + r[j + 2] + r[j + 3] + r[j + 4] + r[j + 5];
+        c = d * d;
+    }
+    // "mark back" sources j .. j+5: bits lane .. lane+5 of (next:this); "mark forward" sources j-6 .. j-1: bits lane+26 .. lane+31 of (this:prev)
+    const unsigned long long backBits = (((unsigned long long)s_back[warp + 2] << 32) | s_back[warp + 1]) >> lane;
+    const unsigned long long fwdBits = (((unsigned long long)s_fwd[warp + 1] << 32) | s_fwd[warp]) >> (lane + 26);
+    int pk = ((backBits & 0x3full) | (fwdBits & 0x3full)) ? 1 : 0;
+    if (j >= 5 && j < n - 6) {
+        float diff1 = fabsf(r[j - 1] - r[j]), diff2 = fabsf(r[j + 1] - r[j]);
+        if ((double)diff1 > 0.02 * (double)r[j] && (double)diff2 > 0.02 * (double)r[j]) pk = 1;
+    }
+    curv[j] = c; picked[j] = pk; label[j] = 0;
 }
 
 // ---- block helpers -----------------------------------------------------------------------
@@ -757,7 +780,7 @@ int fbpr_launch_features(const FeatArgs& a, int count, cudaStream_t st, long lon
         if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(feat_ring smem)", __FILE__, __LINE__);
         configured = smem;
     }
-    int b = (a.P + TPB1 * 2 - 1) / (TPB1 * 2);
+    int b = (a.P + TPB1 - 1) / TPB1;
     feat_smooth<<<dim3(b, count), TPB1, 0, st>>>(a);
     feat_ring<<<dim3(a.N_SCAN, count), RING_TPB, smem, st>>>(a);
     feat_gather<<<dim3(a.N_SCAN, count), 256, 0, st>>>(a);
