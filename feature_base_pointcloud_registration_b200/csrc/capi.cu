@@ -169,7 +169,7 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     h->cellsCorner = params->grid_cells_corner > 0 ? params->grid_cells_corner : 262144;
     h->cellsSurf = params->grid_cells_surf > 0 ? params->grid_cells_surf : 1048576;
     h->cluster = params->lm_cluster_size;              // 0 = chosen per call from the batch size
-    if (h->cluster != 0 && h->cluster != 1 && h->cluster != 2 && h->cluster != 4 && h->cluster != 8 && h->cluster != 16) return fbpr_fail_msg("lm_cluster_size must be 0 (auto),1,2,4,8 or 16");
+    if (h->cluster < 0 || h->cluster > 16) return fbpr_fail_msg("lm_cluster_size must be 0 (auto) or 1..16");
     int maxVox = P; if (h->kfCap > maxVox) maxVox = h->kfCap;
     h->tilesCap = (maxVox + fbpr_voxel_tile() - 1) / fbpr_voxel_tile() + 1;
 

@@ -72,7 +72,7 @@ typedef struct fbpr_params {
     float   knn_cell_surf;
     int32_t grid_cells_corner;               /* dense-grid cell budget per map index (0 = 262144 / 1048576); the cell */
     int32_t grid_cells_surf;                 /*   edge is doubled until the map's bounding box fits the budget        */
-    int32_t lm_cluster_size;                 /* CTAs cooperating on one frame's LM loop in batched calls: 1,2,4,8,16 (0 = per call, from the batch size) */
+    int32_t lm_cluster_size;                 /* CTAs cooperating on one frame's LM loop in batched calls: 1..16 (0 = per call, from the batch size) */
     int32_t lm_single_frame_mode;            /* count == 1 calls: 0 = whole GPU cooperates (grid barrier), 1 = one cluster   */
     float   knn_first_radius;                /* metres the FIRST LM iteration's neighbour search must cover around each point (0 = 0.5):
                                                 about the expected error of the initial guess; later iterations derive it exactly */
