@@ -87,6 +87,11 @@ struct GridSeg {                  // host-built descriptor of one map-index segm
 };
 
 
+// pieces of one dense host span that was uploaded with a single copy and is now scattered to its slots (capi.cu, mapops.cu)
+#define FBPR_SCATTER_MAX 112
+struct ScatterPiece { unsigned long long src_off; void* dst; unsigned long long bytes; };     // offsets / sizes are multiples of 4
+struct ScatterTable { const unsigned char* stage; int n; int pad; ScatterPiece p[FBPR_SCATTER_MAX]; };
+
 // ---- kernel argument blocks (passed by value) ----------------------------------------------
 struct ProjArgs {
     FrameMeta* meta;

@@ -166,7 +166,32 @@ __global__ void __launch_bounds__(TPB) xyzi32_to_16(const float4* __restrict__ i
     out[i] = make_float4(a.x, a.y, a.z, b.x);
 }
 
+// one CTA column per piece (blockIdx.y); 16-byte copies when source and destination allow, 4-byte otherwise
+__global__ void __launch_bounds__(TPB) stage_scatter(const __grid_constant__ ScatterTable t) {
+    const ScatterPiece pc = t.p[blockIdx.y];
+    const unsigned char* src = t.stage + pc.src_off;
+    unsigned char* dst = reinterpret_cast<unsigned char*>(pc.dst);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if ((((size_t)src | (size_t)dst) & 15) == 0) {
+        const size_t n16 = pc.bytes >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src); uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (size_t i = tid; i < n16; i += nth) d4[i] = s4[i];
+        const size_t done = n16 << 4;
+        for (size_t i = done + 4 * tid; i < pc.bytes; i += 4 * nth) *reinterpret_cast<unsigned*>(dst + i) = *reinterpret_cast<const unsigned*>(src + i);
+    } else {
+        const size_t n4 = pc.bytes >> 2;
+        const unsigned* s1 = reinterpret_cast<const unsigned*>(src); unsigned* d1 = reinterpret_cast<unsigned*>(dst);
+        for (size_t i = tid; i < n4; i += nth) d1[i] = s1[i];
+    }
+}
+
 }  // namespace
+
+void fbpr_launch_stage_scatter(const ScatterTable& t, cudaStream_t st, long long* launches) {
+    if (t.n <= 0) return;
+    stage_scatter<<<dim3(24, t.n), TPB, 0, st>>>(t);
+    if (launches) *launches += 1;
+}
 
 void fbpr_launch_pc2_to_raw(const unsigned char* d_src, int n, const fbpr_pc2_layout& L, fbpr_raw_point* d_dst, cudaStream_t st, long long* launches) {
     if (n <= 0) return;

@@ -336,6 +336,26 @@ def test_pipelined_register_frames_equals_plain_batch(fb):
     for chunk in (0, 1, 2, 32):
         got = r.register_frames(0, fin, chunk)
         assert np.array_equal(got["pose"], want["pose"]) and np.array_equal(got["iters"], want["iters"]) and np.array_equal(got["flags"], want["flags"])
+    # the same frames out of ONE pinned arena (all sweeps back to back, then all maps): a densely packed group of buffers is
+    # uploaded as one copy + a scatter kernel, i.e. 2 extra kernel launches per chunk and identical results
+    import torch
+    arrays = list(raws) + [m for fr in frames for m in (fr["map_corner"], fr["map_surf"])]
+    offs = np.concatenate([[0], np.cumsum([(a_.nbytes + 15) // 16 * 16 for a_ in arrays])])
+    arena = torch.empty(int(offs[-1]) + 16, dtype=torch.uint8).pin_memory()
+    ptrs = []
+    for a_, off in zip(arrays, offs[:-1]):
+        arena[int(off):int(off) + a_.nbytes] = torch.from_numpy(np.ascontiguousarray(a_).view(np.uint8).reshape(-1))
+        ptrs.append(arena.data_ptr() + int(off))
+    fin_a = r.make_frame_inputs([dict(raw_ptr=ptrs[i], n_raw=len(raw), imu=fr["imu"], imu_available=fr["imu_available"],
+                                      map_corner_ptr=ptrs[F + 2 * i], n_map_corner=len(fr["map_corner"]),
+                                      map_surf_ptr=ptrs[F + 2 * i + 1], n_map_surf=len(fr["map_surf"]), pose=fr["guess"])
+                                 for i, (fr, raw) in enumerate(zip(frames, raws))])
+    for chunk, nchunks in ((5, 1), (2, 3)):
+        l0 = r.kernel_launches(); r.register_frames(0, fin, chunk); l1 = r.kernel_launches()
+        got = r.register_frames(0, fin_a, chunk); l2 = r.kernel_launches()
+        assert np.array_equal(got["pose"], want["pose"]) and np.array_equal(got["iters"], want["iters"]) and np.array_equal(got["flags"], want["flags"])
+        merged = (l2 - l1) - (l1 - l0)
+        assert merged == 2 * nchunks - (1 if chunk == 2 else 0), merged      # the last chunk of (2, 2, 1) has a single sweep: plain copy
     # split form, two batches in flight on disjoint slot ranges (double buffering), three rounds
     r2 = fb.Registration(frames[0]["params"], max_frames=2 * F, max_map_corner=16384, max_map_surf=65536)
     fin2 = r2.make_frame_inputs([dict(raw_ptr=raw.ctypes.data, n_raw=len(raw), imu=fr["imu"], imu_available=fr["imu_available"],
