@@ -28,7 +28,7 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-// Launch shapes.  Batched calls: one cluster per frame, 256-thread CTAs (3 resident per SM).
+// Launch shapes.  Batched calls: one cluster per frame, 256-thread CTAs (4 resident per SM at 64 registers).
 // Single-frame calls: one 768-thread CTA per SM over the whole GPU.
 constexpr int LM_TPB_CLUSTER = 256, LM_CTAS_CLUSTER = 4;
 constexpr int LM_TPB_GRID = 768, LM_CTAS_GRID = 1;
