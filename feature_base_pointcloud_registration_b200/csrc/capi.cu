@@ -55,7 +55,7 @@ struct fbpr_handle {
     long long launches = 0;
     int F = 0, P = 0, rawCap = 0, cornerCap = 0, mapCornerCap = 0, mapSurfCap = 0, kfCap = 0;
     int tilesCap = 0, cellsCorner = 0, cellsSurf = 0, cluster = 0;
-    float cellCorner = 0.5f, cellSurf = 0.25f;
+    float cellCorner = 0.5f, cellSurf = 0.33f;
     std::vector<void*> allocs;
     size_t bytes = 0;
     // per-slot arrays
@@ -168,7 +168,7 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     h->mapSurfCap = params->max_map_surf > 0 ? params->max_map_surf : 262144;
     h->kfCap = params->max_keyframe_points;
     h->cellCorner = params->knn_cell_corner > 0 ? params->knn_cell_corner : 0.5f;
-    h->cellSurf = params->knn_cell_surf > 0 ? params->knn_cell_surf : 0.25f;
+    h->cellSurf = params->knn_cell_surf > 0 ? params->knn_cell_surf : 0.33f;     // measured on config 3/4 (scripts/knn_param_sweep.py): 0.25 / 0.5 m -> 7.42 ms of map index + LM per 128 frames, 0.33 / 0.3 m -> 6.72
     h->cellsCorner = params->grid_cells_corner > 0 ? params->grid_cells_corner : 262144;
     h->cellsSurf = params->grid_cells_surf > 0 ? params->grid_cells_surf : 1048576;
     h->cluster = params->lm_cluster_size;              // 0 = chosen per call from the batch size
@@ -555,7 +555,7 @@ static LmArgs lm_args(fbpr_handle* h, int first) {
     LmArgs a = {};
     a.meta = h->meta; a.cornerDS = h->cornerDS; a.cornerCap = h->cornerCap; a.surfDS = h->surfDS; a.surfCap = h->P;
     a.gsegs = h->d_gridSegs; a.first = first;
-    a.qanchor = h->qanchor; a.qcache = h->qcache; a.qCap = h->cornerCap + h->P; a.firstRadius = h->p.knn_first_radius > 0 ? h->p.knn_first_radius : 0.5f;
+    a.qanchor = h->qanchor; a.qcache = h->qcache; a.qCap = h->cornerCap + h->P; a.firstRadius = h->p.knn_first_radius > 0 ? h->p.knn_first_radius : 0.3f;
     a.partials = h->partials; a.teamMax = 16; a.partialsGrid = h->partialsGrid; a.gridMax = 1024;
     a.edgeMin = h->p.edgeFeatureMinValidNum; a.surfMin = h->p.surfFeatureMinValidNum;
     a.z_tol = h->p.z_tollerance; a.rot_tol = h->p.rotation_tollerance;
