@@ -115,47 +115,53 @@ __device__ inline int block_sum_1024(int v, int* ws) {
     __syncthreads();
     return t;
 }
+// both scan kernels walk the tiles of their segment with a small fixed number of CTAs: the cell capacity is a worst case
+// (1 M cells) and a launch sized for it would consist mostly of CTAs that find nothing to do
+constexpr int SCAN_CTAS = 16;
 __global__ void __launch_bounds__(1024) grid_tile_sums(const GridSeg* segs) {
     const GridSeg& s = segs[blockIdx.y];
     const int nc = s.desc->ncells + 1;
-    int base = blockIdx.x * SCAN_TILE;
-    if (base >= nc) return;
     __shared__ int ws[32];
-    int sum = 0;
-    const int c0 = base + threadIdx.x * 4;
-    if (c0 + 3 < nc) { const int4 v = *reinterpret_cast<const int4*>(s.cell_start + c0); sum = v.x + v.y + v.z + v.w; }
-    else for (int k = 0; k < 4; k++) if (c0 + k < nc) sum += s.cell_start[c0 + k];
-    sum = block_sum_1024(sum, ws);
-    if (threadIdx.x == 0) s.tile_sum[blockIdx.x] = sum;
+    for (int tile = blockIdx.x; tile * SCAN_TILE < nc; tile += gridDim.x) {
+        const int base = tile * SCAN_TILE;
+        int sum = 0;
+        const int c0 = base + threadIdx.x * 4;
+        if (c0 + 3 < nc) { const int4 v = *reinterpret_cast<const int4*>(s.cell_start + c0); sum = v.x + v.y + v.z + v.w; }
+        else for (int k = 0; k < 4; k++) if (c0 + k < nc) sum += s.cell_start[c0 + k];
+        sum = block_sum_1024(sum, ws);
+        if (threadIdx.x == 0) s.tile_sum[tile] = sum;
+    }
 }
 __global__ void __launch_bounds__(1024) grid_scan_apply(const GridSeg* segs) {
     const GridSeg& s = segs[blockIdx.y];
     const int nc = s.desc->ncells + 1;
-    int base = blockIdx.x * SCAN_TILE;
-    if (base >= nc) return;
     __shared__ int ws[32];
-    int before = 0;
-    for (int t = threadIdx.x; t < (int)blockIdx.x; t += 1024) before += s.tile_sum[t];
-    before = block_sum_1024(before, ws);
-    int v[4] = { 0, 0, 0, 0 }, sum = 0;
-    const int c0 = base + threadIdx.x * 4;
-    if (c0 + 3 < nc) { const int4 q = *reinterpret_cast<const int4*>(s.cell_start + c0); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-    else for (int k = 0; k < 4; k++) if (c0 + k < nc) v[k] = s.cell_start[c0 + k];
-    sum = v[0] + v[1] + v[2] + v[3];
-    int incl = sum, l = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
-    if (l == 31) ws[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-        int a = ws[l], ia = a;
-        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, ia, o); if (l >= o) ia += u; }
-        ws[l] = ia - a;
+    for (int tile = blockIdx.x; tile * SCAN_TILE < nc; tile += gridDim.x) {
+        const int base = tile * SCAN_TILE;
+        int before = 0;
+        for (int t = threadIdx.x; t < tile; t += 1024) before += s.tile_sum[t];
+        before = block_sum_1024(before, ws);
+        int v[4] = { 0, 0, 0, 0 }, sum = 0;
+        const int c0 = base + threadIdx.x * 4;
+        if (c0 + 3 < nc) { const int4 q = *reinterpret_cast<const int4*>(s.cell_start + c0); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+        else for (int k = 0; k < 4; k++) if (c0 + k < nc) v[k] = s.cell_start[c0 + k];
+        sum = v[0] + v[1] + v[2] + v[3];
+        int incl = sum, l = threadIdx.x & 31, w = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
+        if (l == 31) ws[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int a = ws[l], ia = a;
+            for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, ia, o); if (l >= o) ia += u; }
+            ws[l] = ia - a;
+        }
+        __syncthreads();
+        int run = before + ws[w] + incl - sum;
+        int4 o4; o4.x = run; o4.y = run + v[0]; o4.z = o4.y + v[1]; o4.w = o4.z + v[2];
+        if (c0 + 3 < nc) *reinterpret_cast<int4*>(s.cell_start + c0) = o4;
+        else { const int o[4] = { o4.x, o4.y, o4.z, o4.w }; for (int k = 0; k < 4; k++) if (c0 + k < nc) s.cell_start[c0 + k] = o[k]; }
+        __syncthreads();                                  // ws is reused by the next tile
     }
-    __syncthreads();
-    int run = before + ws[w] + incl - sum;
-    int4 o4; o4.x = run; o4.y = run + v[0]; o4.z = o4.y + v[1]; o4.w = o4.z + v[2];
-    if (c0 + 3 < nc) *reinterpret_cast<int4*>(s.cell_start + c0) = o4;
-    else { const int o[4] = { o4.x, o4.y, o4.z, o4.w }; for (int k = 0; k < 4; k++) if (c0 + k < nc) s.cell_start[c0 + k] = o[k]; }
 }
 
 __global__ void __launch_bounds__(TPB) grid_scatter(const GridSeg* segs) {
@@ -204,10 +210,15 @@ void fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cel
     if (nsegs <= 0) return;
     int tiles = (max_n + TILE - 1) / TILE; if (tiles < 1) tiles = 1;
     int stiles = (cells_cap + 1 + SCAN_TILE - 1) / SCAN_TILE;
-    dim3 g(tiles, nsegs), gs(stiles, nsegs);
+    // grid-stride zeroing / scanning with about two waves of CTAs over all segments (every zeroing CTA repeats the serial choice of
+    // the cell size, and the cell capacity is a worst case: a launch sized for it is mostly CTAs that find nothing to do)
+    int zb = (cells_cap + TPB * 8) / (TPB * 8);
+    const int zmax = 24 > 2368 / nsegs ? 24 : 2368 / nsegs;
+    if (zb > zmax) zb = zmax;
+    const int smax = SCAN_CTAS > 592 / nsegs ? SCAN_CTAS : 592 / nsegs;
+    dim3 g(tiles, nsegs), gs(stiles < smax ? stiles : smax, nsegs);
     grid_init<<<nsegs, 32, 0, st>>>(d_segs);
     grid_minmax<<<g, TPB, 0, st>>>(d_segs);
-    int zb = (cells_cap + TPB * 8) / (TPB * 8); if (zb > 1024) zb = 1024;
     grid_setup_zero<<<dim3(zb, nsegs), TPB, 0, st>>>(d_segs);
     grid_count<<<g, TPB, 0, st>>>(d_segs);
     grid_tile_sums<<<gs, 1024, 0, st>>>(d_segs);
