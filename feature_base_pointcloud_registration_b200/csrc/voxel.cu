@@ -35,17 +35,12 @@ __global__ void vox_init(const VoxSeg* segs) {
 __global__ void __launch_bounds__(TPB) vox_minmax(const VoxSeg* segs) {
     const VoxSeg& s = segs[blockIdx.y];
     int n = *s.n_in; if (n > s.cap) n = s.cap;
-    int base = blockIdx.x * TILE;
-    if (base >= n) return;
     unsigned mn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, mx[3] = { 0u, 0u, 0u };
-    for (int k = 0; k < IPT; k++) {
-        int i = base + k * TPB + threadIdx.x;
-        if (i < n) {
-            float4 p = s.in[i];
-            unsigned ex = f2ord(p.x), ey = f2ord(p.y), ez = f2ord(p.z);
-            mn[0] = min(mn[0], ex); mn[1] = min(mn[1], ey); mn[2] = min(mn[2], ez);
-            mx[0] = max(mx[0], ex); mx[1] = max(mx[1], ey); mx[2] = max(mx[2], ez);
-        }
+    for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+        float4 p = s.in[i];
+        unsigned ex = f2ord(p.x), ey = f2ord(p.y), ez = f2ord(p.z);
+        mn[0] = min(mn[0], ex); mn[1] = min(mn[1], ey); mn[2] = min(mn[2], ez);
+        mx[0] = max(mx[0], ex); mx[1] = max(mx[1], ey); mx[2] = max(mx[2], ez);
     }
     __shared__ unsigned sm[6][TPB / 32];
     for (int c = 0; c < 3; c++) { mn[c] = warp_min_u(mn[c]); mx[c] = warp_max_u(mx[c]); }
@@ -89,13 +84,11 @@ __global__ void vox_setup(const VoxSeg* segs) {
 __global__ void __launch_bounds__(TPB) vox_keys(const VoxSeg* segs) {
     const VoxSeg& s = segs[blockIdx.y];
     const VoxDesc d = *s.desc;
-    int base = blockIdx.x * TILE;
-    if (base >= d.n || d.overflow) return;
+    if (d.overflow) return;
     const float inv = d.inv_leaf;
     const int m1 = d.div_b[0], m2 = d.div_b[0] * d.div_b[1];
-    for (int k = 0; k < IPT; k++) {
-        int i = base + k * TPB + threadIdx.x;
-        if (i < d.n) {
+    {
+        for (int i = blockIdx.x * TPB + threadIdx.x; i < d.n; i += gridDim.x * TPB) {
             float4 p = s.in[i];
             int i0 = (int)(floorf(p.x * inv) - (float)d.min_b[0]);
             int i1 = (int)(floorf(p.y * inv) - (float)d.min_b[1]);
@@ -111,20 +104,23 @@ __global__ void __launch_bounds__(TPB) vox_keys(const VoxSeg* segs) {
 __global__ void __launch_bounds__(TPB) rs_hist(const VoxSeg* segs, int pass, int tiles_cap) {
     const VoxSeg& s = segs[blockIdx.y];
     const VoxDesc d = *s.desc;
-    int base = blockIdx.x * TILE;
     int ntiles = (d.n + TILE - 1) / TILE;
     if ((int)blockIdx.x >= ntiles || d.overflow || pass >= d.npass) return;
     __shared__ unsigned hist[256];
-    hist[threadIdx.x] = 0;
-    __syncthreads();
     const unsigned* key = s.key[pass & 1];
     const int shift = pass * 8;
-    for (int k = 0; k < IPT; k++) {
-        int i = base + k * TPB + threadIdx.x;
-        if (i < d.n) atomicAdd(&hist[(key[i] >> shift) & 255u], 1u);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {       // a few CTAs walk the tiles of the segment
+        const int base = tile * TILE;
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (int k = 0; k < IPT; k++) {
+            int i = base + k * TPB + threadIdx.x;
+            if (i < d.n) atomicAdd(&hist[(key[i] >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        s.tile_hist[(size_t)threadIdx.x * tiles_cap + tile] = hist[threadIdx.x];
+        __syncthreads();
     }
-    __syncthreads();
-    s.tile_hist[(size_t)threadIdx.x * tiles_cap + blockIdx.x] = hist[threadIdx.x];
 }
 
 // exclusive scan of tile_hist over (digit-major, tile) order; one CTA per segment
@@ -173,11 +169,12 @@ __global__ void __launch_bounds__(TPB) rs_scatter(const VoxSeg* segs, int pass, 
     unsigned* okey = s.key[(pass + 1) & 1]; unsigned* oval = s.val[(pass + 1) & 1];
     const int shift = pass * 8;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {       // a few CTAs walk the tiles of the segment
     for (int k = threadIdx.x; k < NW * 256; k += TPB) (&wcount[0][0])[k] = 0;
     __syncthreads();
     // each warp owns a contiguous chunk of TILE/NW items, walked in order 32 at a time
     const int chunk = TILE / NW;
-    const int wbase = blockIdx.x * TILE + w * chunk;
+    const int wbase = tile * TILE + w * chunk;
     unsigned mykey[chunk / 32], myval[chunk / 32];
     #pragma unroll
     for (int r = 0; r < chunk / 32; r++) {
@@ -195,7 +192,7 @@ __global__ void __launch_bounds__(TPB) rs_scatter(const VoxSeg* segs, int pass, 
     __syncthreads();
     // digit `threadIdx.x`: exclusive prefix over warps + global base
     {
-        unsigned base = s.tile_hist[(size_t)threadIdx.x * tiles_cap + blockIdx.x];
+        unsigned base = s.tile_hist[(size_t)threadIdx.x * tiles_cap + tile];
         for (int q = 0; q < NW; q++) { unsigned c = wcount[q][threadIdx.x]; wcount[q][threadIdx.x] = base; base += c; }
     }
     __syncthreads();
@@ -215,6 +212,8 @@ __global__ void __launch_bounds__(TPB) rs_scatter(const VoxSeg* segs, int pass, 
         }
         __syncwarp();
     }
+    __syncthreads();
+    }
 }
 
 // ---- runs -> centroids -----------------------------------------------------------------
@@ -224,16 +223,19 @@ __global__ void __launch_bounds__(TPB) vox_runs_count(const VoxSeg* segs) {
     const int ntiles = (d.n + TILE - 1) / TILE;
     if ((int)blockIdx.x >= ntiles || d.overflow) return;
     const unsigned* key = s.key[d.npass & 1];
-    int base = blockIdx.x * TILE, cnt = 0;
-    for (int k = 0; k < IPT; k++) {
-        int i = base + k * TPB + threadIdx.x;
-        if (i < d.n && (i == 0 || key[i] != key[i - 1])) cnt++;
-    }
     __shared__ int ws[TPB / 32];
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < TPB / 32; k++) t += ws[k]; s.run_tile[blockIdx.x] = t; }
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int base = tile * TILE, cnt = 0;
+        for (int k = 0; k < IPT; k++) {
+            int i = base + k * TPB + threadIdx.x;
+            if (i < d.n && (i == 0 || key[i] != key[i - 1])) cnt++;
+        }
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < TPB / 32; k++) t += ws[k]; s.run_tile[tile] = t; }
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(1024) vox_runs_scan(const VoxSeg* segs) {
@@ -267,10 +269,12 @@ __global__ void __launch_bounds__(TPB) vox_emit(const VoxSeg* segs) {
     const VoxDesc d = *s.desc;
     const int ntiles = (d.n + TILE - 1) / TILE;
     if ((int)blockIdx.x >= ntiles) return;
-    int base = blockIdx.x * TILE;
+    __shared__ int ws[TPB / 32];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int base = tile * TILE;
     if (d.overflow) {             // PCL's "leaf size too small" path: output = input
         for (int k = 0; k < IPT; k++) { int i = base + k * TPB + threadIdx.x; if (i < d.n) s.out[i] = s.in[i]; }
-        return;
+        continue;
     }
     const unsigned* key = s.key[d.npass & 1]; const unsigned* val = s.val[d.npass & 1];
     // thread t owns items [base + t*IPT, base + (t+1)*IPT): blocked layout keeps run order
@@ -280,13 +284,12 @@ __global__ void __launch_bounds__(TPB) vox_emit(const VoxSeg* segs) {
         int i = start + k;
         if (i < d.n && (i == 0 || key[i] != key[i - 1])) { flags |= 1 << k; cnt++; }
     }
-    __shared__ int ws[TPB / 32];
     int incl = cnt, l = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += v; }
     if (l == 31) ws[w] = incl;
     __syncthreads();
     int woff = 0; for (int q = 0; q < w; q++) woff += ws[q];
-    int slot = s.run_tile[blockIdx.x] + woff + incl - cnt;
+    int slot = s.run_tile[tile] + woff + incl - cnt;
     for (int k = 0; k < IPT; k++) {
         if (!(flags & (1 << k))) continue;
         int i = start + k;
@@ -301,6 +304,8 @@ __global__ void __launch_bounds__(TPB) vox_emit(const VoxSeg* segs) {
         if (s.out_keys) s.out_keys[slot] = (int)kk;
         slot++;
     }
+    __syncthreads();                                      // ws is reused by the next tile
+    }
 }
 
 }  // namespace
@@ -309,7 +314,10 @@ __global__ void __launch_bounds__(TPB) vox_emit(const VoxSeg* segs) {
 void fbpr_launch_voxel(const VoxSeg* d_segs, int nsegs, int max_n, int tiles_cap, cudaStream_t st, long long* launches) {
     if (nsegs <= 0) return;
     int tiles = (max_n + TILE - 1) / TILE; if (tiles < 1) tiles = 1;
-    dim3 g(tiles, nsegs);
+    // the capacity is a worst case (every pixel a surface point): a few CTAs per segment walk the tiles that exist instead of a
+    // launch that is mostly CTAs with nothing to do; small batches get more CTAs per segment
+    const int gmax = 16 > 2368 / nsegs ? 16 : 2368 / nsegs;
+    dim3 g(tiles < gmax ? tiles : gmax, nsegs);
     vox_init<<<nsegs, 32, 0, st>>>(d_segs);
     vox_minmax<<<g, TPB, 0, st>>>(d_segs);
     vox_setup<<<nsegs, 32, 0, st>>>(d_segs);
