@@ -97,9 +97,19 @@ __global__ void __launch_bounds__(TPB) grid_count(const GridSeg* segs) {
     const GridDesc g = *s.desc;
     int base = blockIdx.x * TILE;
     if (base >= g.n) return;
+    // all loads, then all atomics, then all stores: eight independent L2 round trips in flight per thread instead of one
+    int c[IPT], r[IPT];
+    #pragma unroll
     for (int k = 0; k < IPT; k++) {
-        int i = base + k * TPB + threadIdx.x;
-        if (i < g.n) { int c = cell_of_point(g, s.pts[i]); s.cell_of[i] = atomicAdd(&s.cell_start[c], 1); }
+        const int i = base + k * TPB + threadIdx.x;
+        c[k] = i < g.n ? cell_of_point(g, s.pts[i]) : -1;
+    }
+    #pragma unroll
+    for (int k = 0; k < IPT; k++) r[k] = c[k] >= 0 ? atomicAdd(&s.cell_start[c[k]], 1) : 0;
+    #pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const int i = base + k * TPB + threadIdx.x;
+        if (c[k] >= 0) s.cell_of[i] = r[k];
     }
 }
 
@@ -169,13 +179,18 @@ __global__ void __launch_bounds__(TPB) grid_scatter(const GridSeg* segs) {
     const GridDesc g = *s.desc;
     int base = blockIdx.x * TILE;
     if (base >= g.n) return;
+    float4 p[IPT]; int pos[IPT];
+    #pragma unroll
     for (int k = 0; k < IPT; k++) {
-        int i = base + k * TPB + threadIdx.x;
-        if (i < g.n) {
-            float4 p = s.pts[i];
-            int pos = __ldg(s.cell_start + cell_of_point(g, p)) + s.cell_of[i];
-            s.sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
-        }
+        const int i = base + k * TPB + threadIdx.x;
+        if (i < g.n) { p[k] = s.pts[i]; pos[k] = s.cell_of[i]; } else pos[k] = -1;
+    }
+    #pragma unroll
+    for (int k = 0; k < IPT; k++) if (pos[k] >= 0) pos[k] += __ldg(s.cell_start + cell_of_point(g, p[k]));
+    #pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const int i = base + k * TPB + threadIdx.x;
+        if (pos[k] >= 0) s.sorted[pos[k]] = make_float4(p[k].x, p[k].y, p[k].z, __int_as_float(i));
     }
 }
 
