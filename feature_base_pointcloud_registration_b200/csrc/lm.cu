@@ -226,9 +226,9 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int WPB = LM_TPB / 32;
 
-    // per-warp staging of the 32 Jacobian rows (6) and -residual (1) of the warp's current 32 points, as f64 (dynamic shared memory)
-    extern __shared__ double s_dyn[];
-    double (*s_rows)[32][7] = reinterpret_cast<double (*)[32][7]>(s_dyn);
+    // per-warp staging of the 32 Jacobian rows (6) and -residual (1) of the warp's current 32 points, as f32 -- widened exactly when folded (dynamic shared memory)
+    extern __shared__ float s_dyn[];
+    float (*s_rows)[32][7] = reinterpret_cast<float (*)[32][7]>(s_dyn);      // staged as f32 (what they are); widened exactly when folded
     // one 28-double partial per CHUNK (dynamic dispatch, summed in chunk order: the result does not depend on which warp
     // took which chunk) or, when this CTA has more chunks than slots, one per WARP (static dispatch)
     constexpr int SLOTS = LM_PART_SLOTS > WPB ? LM_PART_SLOTS : WPB;
@@ -385,10 +385,10 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
                     float arz = ((crz * srx * sry - cry * srz) * ox + (-cry * crz - srx * sry * srz) * oy) * kx
                               + (crx * crz * ox - crx * srz * oy) * ky
                               + ((sry * srz + cry * crz * srx) * ox + (crz * sry - cry * srx * srz) * oy) * kz;
-                    double* row = s_rows[warp][lane];
-                    row[0] = (double)arz; row[1] = (double)arx; row[2] = (double)ary;
-                    row[3] = (double)kz;  row[4] = (double)kx;  row[5] = (double)ky;
-                    row[6] = (double)(-coeff.w);
+                    float* row = s_rows[warp][lane];
+                    row[0] = arz; row[1] = arx; row[2] = ary;
+                    row[3] = kz;  row[4] = kx;  row[5] = ky;
+                    row[6] = -coeff.w;
                 }
             }
             // fold the warp's staged rows into the lane-owned entries (rows in point order, f64)
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             else if (lane < 27) {
                 while (m) {
                     const int rr = __ffs(m) - 1; m &= m - 1;
-                    acc += s_rows[warp][rr][ei] * s_rows[warp][rr][ej];
+                    acc += (double)s_rows[warp][rr][ei] * (double)s_rows[warp][rr][ej];
                 }
             }
             __syncwarp();
@@ -498,7 +498,7 @@ __global__ void transform_update_kernel(FrameMeta* meta, int first, int count, f
 
 }  // namespace
 
-static size_t lm_dyn_smem(int tpb) { return (size_t)(tpb / 32) * 32 * 7 * sizeof(double); }    // s_rows
+static size_t lm_dyn_smem(int tpb) { return (size_t)(tpb / 32) * 32 * 7 * sizeof(float); }    // s_rows
 
 // one-time function attributes of both variants (cluster sizes above 8, dynamic shared memory above the default limit)
 static int lm_configure() {
@@ -506,6 +506,9 @@ static int lm_configure() {
     if (configured) return 0;
     cudaError_t e = cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(NonPortableClusterSizeAllowed)", __FILE__, __LINE__);
+    // 4 CTAs x ~22 KB of shared memory: ask for the smallest carve-out that holds them and leave the rest to L1, which the
+    // neighbour searches live on (LM ms per 128 frames at carve-out 25 / 35 / 40 / 55 / 70 / 100 %: 7.52 / 5.17 / 5.15 / 5.23 / 5.40 / 6.76)
+    cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
     e = cudaFuncSetAttribute(lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dyn_smem(LM_TPB_GRID));
     if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", __FILE__, __LINE__);
     configured = 1;
