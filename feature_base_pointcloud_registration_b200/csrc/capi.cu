@@ -68,7 +68,7 @@ struct fbpr_handle {
     int *picked = nullptr, *label = nullptr, *ringCorner = nullptr, *cornerStage = nullptr, *ringSurf = nullptr, *ringSurfDS = nullptr, *cornerIndex = nullptr;
     float4 *mapCorner = nullptr, *mapSurf = nullptr;
     float* poseTrace = nullptr;
-    float4* qanchor = nullptr; int* qcache = nullptr; double* partials = nullptr; double* partialsGrid = nullptr; int lmGridBlocks = 0; bool lmWholeGpu = true;
+    float4* qanchor = nullptr; int* qcache = nullptr; double* partials = nullptr; double* partialsGrid = nullptr; double* chunkPart = nullptr; int chunkCap = 0; int lmGridBlocks = 0; bool lmWholeGpu = true;
     // descriptors
     VoxSeg* d_scanSegs = nullptr;      // [2F]  downsampleCurrentScan
     GridSeg* d_gridSegs = nullptr;     // [2F]  map index
@@ -194,6 +194,8 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     ALLOC(h->qcache, (size_t)F * (h->cornerCap + P) * FBPR_KNN_CACHE_SLOTS);
     ALLOC(h->partials, (size_t)F * 2 * 16 * 28);
     ALLOC(h->partialsGrid, (size_t)2 * 1024 * 28);
+    h->chunkCap = (h->cornerCap + P) / 32 + 260;
+    ALLOC(h->chunkPart, (size_t)F * h->chunkCap * 28);
     h->lmGridBlocks = fbpr_lm_grid_blocks(device);
     if (h->lmGridBlocks > 1024) h->lmGridBlocks = 1024;
     h->lmWholeGpu = params->lm_single_frame_mode == 0;
@@ -556,7 +558,7 @@ static LmArgs lm_args(fbpr_handle* h, int first) {
     a.meta = h->meta; a.cornerDS = h->cornerDS; a.cornerCap = h->cornerCap; a.surfDS = h->surfDS; a.surfCap = h->P;
     a.gsegs = h->d_gridSegs; a.first = first;
     a.qanchor = h->qanchor; a.qcache = h->qcache; a.qCap = h->cornerCap + h->P; a.firstRadius = h->p.knn_first_radius > 0 ? h->p.knn_first_radius : 0.3f;
-    a.partials = h->partials; a.teamMax = 16; a.partialsGrid = h->partialsGrid; a.gridMax = 1024;
+    a.partials = h->partials; a.teamMax = 16; a.partialsGrid = h->partialsGrid; a.gridMax = 1024; a.chunkPart = h->chunkPart; a.chunkCap = h->chunkCap;
     a.edgeMin = h->p.edgeFeatureMinValidNum; a.surfMin = h->p.surfFeatureMinValidNum;
     a.z_tol = h->p.z_tollerance; a.rot_tol = h->p.rotation_tollerance;
     a.debug_iter = (h->debugIter >= 0 && first + 0 < h->dbgSlots) ? h->debugIter : -1;

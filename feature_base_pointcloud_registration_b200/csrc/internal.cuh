@@ -131,6 +131,7 @@ struct LmArgs {
     float firstRadius;            // metres the first iteration's search cube must cover
     double* partials; int teamMax;     // [slot][2][teamMax][28] per-CTA partial sums, double-buffered by iteration parity
     double* partialsGrid; int gridMax; // [2][gridMax][28] same for the whole-GPU single-frame variant
+    double* chunkPart; int chunkCap;   // [slot][chunkCap][28] per-chunk partial sums of the batched variant (chunk = 32 feature points)
     int first;
     int edgeMin, surfMin;
     float z_tol, rot_tol;

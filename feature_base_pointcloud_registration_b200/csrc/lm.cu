@@ -32,6 +32,9 @@ namespace {
 // Single-frame calls: one 768-thread CTA per SM over the whole GPU.
 constexpr int LM_TPB_CLUSTER = 256, LM_CTAS_CLUSTER = 4;
 constexpr int LM_TPB_GRID = 768, LM_CTAS_GRID = 1;
+#ifndef LM_CARVEOUT
+#define LM_CARVEOUT 16
+#endif
 constexpr int LM_PART_SLOTS = 64;      // chunks of one CTA whose partial sums have their own shared-memory slot
 constexpr int NACC = 28;          // 21 (upper triangle of A^T A) + 6 (A^T b) + 1 (row count)
 
@@ -231,7 +234,9 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
     float (*s_rows)[32][7] = reinterpret_cast<float (*)[32][7]>(s_dyn);      // staged as f32 (what they are); widened exactly when folded
     // one 28-double partial per CHUNK (dynamic dispatch, summed in chunk order: the result does not depend on which warp
     // took which chunk) or, when this CTA has more chunks than slots, one per WARP (static dispatch)
-    constexpr int SLOTS = LM_PART_SLOTS > WPB ? LM_PART_SLOTS : WPB;
+    // Batched (cluster) shape: the per-chunk partials live in global memory (L2) instead, so that a CTA needs only ~8 KB of
+    // shared memory and the rest of the SM's 228 KB serves as L1 for the neighbour searches.
+    constexpr int SLOTS = GRID ? (LM_PART_SLOTS > WPB ? LM_PART_SLOTS : WPB) : 1;
     __shared__ double s_part[SLOTS][NACC];
     __shared__ int s_next;
     __shared__ double sh_tot[NACC];
@@ -267,7 +272,8 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
     while (CS > 1 && nQ <= (CS / 2) * C * WPB) CS >>= 1;
     const int nChunks = (nQ + CS - 1) / CS;
     const int myChunks = rank < nChunks ? (nChunks - rank + C - 1) / C : 0;      // chunks k * C + rank of this CTA
-    const bool dynamic = myChunks <= LM_PART_SLOTS;
+    const bool dynamic = !GRID || myChunks <= LM_PART_SLOTS;
+    double* cpart = GRID ? nullptr : a.chunkPart + (size_t)slot * a.chunkCap * NACC;        // [chunk][28], chunk = k * C + rank
     unsigned flags = 0; int isDegenerate = 0; int iters = 0;
     for (int iter = 0; iter < FBPR_MAX_ITERS; iter++) {
         // --- pose -> rigid transform + the six sines/cosines LMOptimization needs (:1259-1264)
@@ -403,7 +409,7 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             }
             __syncwarp();
             if (dynamic) {
-                if (lane < NACC) s_part[k][lane] = acc;
+                if (lane < NACC) { if (GRID) s_part[k][lane] = acc; else cpart[(size_t)chunk * NACC + lane] = acc; }
                 acc = 0.0;
                 if (lane == 0) k = atomicAdd(&s_next, 1);
                 k = __shfl_sync(0xffffffffu, k, 0);
@@ -412,14 +418,25 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             }
         }
         // --- CTA reduce (shared memory, fixed order) -> one partial per CTA in global memory
-        if (!dynamic && lane < NACC) s_part[warp][lane] = acc;
+        if (GRID && !dynamic && lane < NACC) s_part[warp][lane] = acc;
         __syncthreads();
         const int buf = iter & 1;
         double* mypart = part + ((size_t)buf * teamStride + rank) * NACC;
         if (tid < NACC) {
             double v = 0.0;
-            const int nslots = dynamic ? myChunks : WPB;
-            for (int w = 0; w < nslots; w++) v += s_part[w][tid];
+            if (GRID) {
+                const int nslots = dynamic ? myChunks : WPB;
+                for (int w = 0; w < nslots; w++) v += s_part[w][tid];
+            } else {
+                // chunk order, four loads in flight (L2: the lines were written by other warps of this CTA before the barrier)
+                int w = 0;
+                for (; w + 4 <= myChunks; w += 4) {
+                    const double p0 = __ldcg(cpart + (size_t)((w + 0) * C + rank) * NACC + tid), p1 = __ldcg(cpart + (size_t)((w + 1) * C + rank) * NACC + tid);
+                    const double p2 = __ldcg(cpart + (size_t)((w + 2) * C + rank) * NACC + tid), p3 = __ldcg(cpart + (size_t)((w + 3) * C + rank) * NACC + tid);
+                    v += p0; v += p1; v += p2; v += p3;
+                }
+                for (; w < myChunks; w++) v += __ldcg(cpart + (size_t)(w * C + rank) * NACC + tid);
+            }
             mypart[tid] = v;
             __threadfence();
         }
@@ -506,9 +523,11 @@ static int lm_configure() {
     if (configured) return 0;
     cudaError_t e = cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(NonPortableClusterSizeAllowed)", __FILE__, __LINE__);
-    // 4 CTAs x ~22 KB of shared memory: ask for the smallest carve-out that holds them and leave the rest to L1, which the
-    // neighbour searches live on (LM ms per 128 frames at carve-out 25 / 35 / 40 / 55 / 70 / 100 %: 7.52 / 5.17 / 5.15 / 5.23 / 5.40 / 6.76)
-    cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 40);
+    // The batched shape keeps its per-chunk partial sums in global memory, so a CTA needs ~8 KB of shared memory; ask for the
+    // smallest carve-out that holds 4 CTAs and leave the rest of the SM's 228 KB to L1, which the neighbour searches live on.
+    // LM ms per 128 frames: partials in shared memory (22 KB per CTA) at carve-out 25 / 40 / 55 / 100 %: 7.52 / 5.15 / 5.23 / 6.76;
+    // partials in global memory at 8 / 14 / 16 / 20 / 28 / 40 %: 5.08 / 4.81 / 4.50 / 4.52 / 4.58 / 4.54.
+    cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, LM_CARVEOUT);
     e = cudaFuncSetAttribute(lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dyn_smem(LM_TPB_GRID));
     if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", __FILE__, __LINE__);
     configured = 1;
