@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             const int li = isCorner ? q : q - nC;
             float4 pOri = make_float4(0, 0, 0, 0);
             float x0 = 0.f, y0 = 0.f, z0 = 0.f;
-            if (inRange) { pOri = isCorner ? cpts[li] : spts[li]; transform_point(sh_T, pOri, x0, y0, z0); }
+            if (inRange) { pOri = __ldcs(isCorner ? cpts + li : spts + li); transform_point(sh_T, pOri, x0, y0, z0); }
             const int kind = isCorner ? 0 : 1;
             const bool active = inRange && sh_gd[kind].n >= 5;
             float4* anchor = a.qanchor + (size_t)slot * a.qCap + q;
@@ -326,16 +326,16 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             if (active) {
                 if (iter == 0) rad0 = max(1, (int)ceilf(a.firstRadius / (sh_gd[kind].h * 0.9995f)));
                 else {
-                    const float4 an = *anchor;
+                    const float4 an = __ldcs(anchor);
                     if (an.w > 0.f) {
                         const int4* c4 = reinterpret_cast<const int4*>(cache);
                         #pragma unroll
                         for (int half = 0; half < FBPR_KNN_CACHE / 8; half++) {     // 8 independent gathers in flight
-                            const int4 va = c4[2 * half], vb = c4[2 * half + 1];
+                            const int4 va = __ldcs(c4 + 2 * half), vb = __ldcs(c4 + 2 * half + 1);
                             const int ci[8] = { va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w };
                             float4 cm[8];
                             #pragma unroll
-                            for (int k = 0; k < 8; k++) if (ci[k] >= 0) cm[k] = __ldg(mo + ci[k]);
+                            for (int k = 0; k < 8; k++) if (ci[k] >= 0) cm[k] = __ldcg(mo + ci[k]);
                             #pragma unroll
                             for (int k = 0; k < 8; k++) if (ci[k] >= 0) knn_offer_idx(r, cm[k].x, cm[k].y, cm[k].z, ci[k], x0, y0, z0);
                         }
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
                     // the five neighbours' coordinates, by original map index (mapOptmization.h:1028-1036, :1157-1163)
                     float4 nb[5];
                     #pragma unroll
-                    for (int k = 0; k < 5; k++) nb[k] = __ldg(mo + knn_index(r, k));
+                    for (int k = 0; k < 5; k++) nb[k] = __ldcg(mo + knn_index(r, k));
                     ok = isCorner ? corner_fit(nb, x0, y0, z0, coeff) : surf_fit(nb, x0, y0, z0, coeff);
                 }
                 if (cap) {
