@@ -248,6 +248,8 @@ __device__ __forceinline__ unsigned bit_window(const unsigned* words, int w, int
 
 enum : unsigned char { ST_NONE = 0, ST_UNDECIDED = 1, ST_PICKED = 2, ST_DEAD = 3 };
 
+__host__ __device__ inline bool feat_sort_free(const FeatArgs& a) { return a.segPad <= RING_TPB && a.segPad >= 32; }
+
 __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
     extern __shared__ unsigned char smem_raw[];
     const int slot = a.first + blockIdx.y, ring = blockIdx.x;
@@ -295,7 +297,8 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
         for (int t = tid; t < W; t += RING_TPB) {
             int g = w0 + t;
             s_curv[t] = g_curv[g]; s_col[t] = g_col[g];
-            s_picked[t] = (unsigned char)(g_picked[g] != 0); s_label[t] = 0; s_state0[t] = ST_NONE; s_state1[t] = ST_NONE;
+            s_picked[t] = (unsigned char)(g_picked[g] != 0); s_label[t] = 0;
+            if (!feat_sort_free(a)) { s_state0[t] = ST_NONE; s_state1[t] = ST_NONE; }     // only the full-sort path has state arrays
         }
         __syncthreads();
         // static suppression reach of every index (featureExtraction.h:226-240)
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
         // array walked from the top), so only those few are listed and sorted; and the flat loop's outcome depends only on the
         // ORDER BETWEEN NEIGHBOURS within the +-5 suppression reach, which is a direct comparison of their
         // (curvature, index) keys -- slot `ep` is never sorted (:203 sorts [sp, ep)), so it ranks after everything else.
-        const bool sortFree = a.segPad <= RING_TPB && a.segPad >= 32;   // one thread per segment element is possible
+        const bool sortFree = feat_sort_free(a);                       // one thread per segment element is possible
         if (sortFree) {
             const int warp = tid >> 5, lane = tid & 31;
             if (tid < FBPR_SEGS) s_ccnt[tid] = 0;
@@ -768,7 +771,8 @@ __global__ void __launch_bounds__(256) feat_gather(FeatArgs a) {
 
 size_t fbpr_feat_ring_smem(const FeatArgs& a) {
     size_t keyCount = (size_t)(FBPR_SEGS * a.segPad > a.voxPad ? FBPR_SEGS * a.segPad : a.voxPad);
-    return keyCount * 8 + (size_t)a.wcap * (4 + 4 + 4 + 4 + 1 + 1 + 1 + 1) + 64;
+    // the two flat-loop state arrays exist only on the full-sort path; without them three CTAs fit the 196 KB carve-out and L1 doubles
+    return keyCount * 8 + (size_t)a.wcap * (4 + 4 + 4 + 4 + 1 + 1 + (feat_sort_free(a) ? 0 : 2)) + 64;
 }
 
 int fbpr_launch_features(const FeatArgs& a, int count, cudaStream_t st, long long* launches) {
