@@ -133,6 +133,31 @@ def cpu_model():
     return "unknown"
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off (sysfs), so that first-touch / cudaHostAlloc place the
+    pinned input buffers in that node's memory: with 8 ranks on one box, uploads out of a single node's DRAM halve the
+    aggregate PCIe rate.  Returns a short description for the JSON line; silently does nothing where sysfs has no answer."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return "gpu %s -> numa node %d, cpus %s" % (bdf, node, cpulist)
+        return "gpu %s: numa node %d (no binding)" % (bdf, node)
+    except Exception as e:      # no sysfs entry, no permission, old torch: run unbound
+        return "unbound (%s)" % type(e).__name__
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank):
     if rank != 0:
@@ -172,6 +197,7 @@ def run_b200(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)      # before any pinned allocation: host buffers land next to this GPU's PCIe root
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -429,7 +455,8 @@ def run_b200(args, rank, world, local_rank):
                    "sync_call": {"value": world * F * args.steps / (e2e_ms["sync"] * 1e-3), "ms_per_step": e2e_ms["sync"] / args.steps,
                                  "api": "fbpr_register_frames (one blocking call per step)"},
                    "h2d_only_ms_per_step": h2d_only_ms,
-                   "host_buffers": "two pinned arenas (sweeps, maps), frames back to back; dense groups cross PCIe as one copy per chunk"},
+                   "host_buffers": "two pinned arenas (sweeps, maps), frames back to back; dense groups cross PCIe as one copy per chunk",
+                   "numa": numa},
            "gpu_launches": int(launches),
            "clocks": clocks,
            "roofline": roofline,
