@@ -168,6 +168,13 @@ def test_imu_deskew_info_host_equals_oracle(case):
     n = want["imuPointerCur"] + 1
     for a, k in ((t, "imuTime"), (rx, "imuRotX"), (ry, "imuRotY"), (rz, "imuRotZ")):
         assert np.array_equal(a[:n], want[k][:n])
+    if case in ("normal", "unnormalised"):
+        # independent check of the tf quaternion -> roll/pitch/yaw convention (fixed axes x, y, z) against scipy
+        from scipy.spatial.transform import Rotation
+        kept = q[popped:]
+        last_before = kept[kept[:, 0] <= cur][-1]
+        rpy = Rotation.from_quat(last_before[4:8] / np.linalg.norm(last_before[4:8])).as_euler("xyz")
+        assert np.allclose([want["imuRollInit"], want["imuPitchInit"], want["imuYawInit"]], rpy, rtol=0, atol=2e-6)
     if case == "normal":
         assert want["imuAvailable"] == 1 and popped == 45        # stamps < 99.99 are dropped
         # the integrated ramp is the running sum of gyro * dt from the first kept sample
