@@ -637,3 +637,55 @@ def test_pcl_xyzi32_wire_roundtrip(fb):
     assert np.max(np.abs(pose[3:] - pose_w[3:])) <= POSE_TOL_T and np.max(np.abs(pose[:3] - pose_w[:3])) <= POSE_TOL_R
     assert np.array_equal(r.get_buffer_xyzi32(0, "SURF_DS")[:, [0, 1, 2, 4]], mo.get_cloud(1))
     r.close()
+
+
+# ------------------------------------------------------------------ full-size properties that need no oracle (BASELINE configs[3] sizes)
+def test_full_size_properties_config4(fb):
+    """A 64 x 2048 sweep against its 200 k-point map, checked through properties that hold at any size: VoxelGrid keys strictly
+    ascending and covering every input key with counts that add up, centroids inside their voxel; 5-NN distances ascending, equal
+    to the f32 distance recomputed from the coordinates, never beaten by a brute-force scan on a sample; idempotent re-registration
+    from the converged pose; the final pose within centimetres of the synthetic ground truth."""
+    fr = synth.make_frame(4, 7)
+    P = fr["params"]
+    r = _reg(fb, P, max_map_corner=len(fr["map_corner"]) + 64, max_map_surf=len(fr["map_surf"]) + 64)
+    # VoxelGrid of the 160 k surface map at the mapping leaf size
+    m = fr["map_surf"]
+    leaf = float(P["mappingSurfLeafSize"])
+    vg = r.voxel_grid(m, leaf)
+    ok_, pk = vg["out_keys"], vg["point_keys"]
+    assert np.all(np.diff(ok_) > 0)                                           # ascending, one output per voxel
+    uniq, cnt = np.unique(pk, return_counts=True)
+    assert np.array_equal(uniq, ok_) and cnt.sum() == len(m)
+    inv = np.float32(1.0) / np.float32(leaf)
+    cell_of_centroid = np.floor(vg["points"][:, :3] * inv)
+    order = np.argsort(pk, kind="stable")
+    starts = np.searchsorted(pk[order], ok_, side="left")
+    member_cell = np.floor(m[order[starts], :3] * inv)
+    assert np.max(np.abs(cell_of_centroid - member_cell)) <= 1.0              # a centroid may round onto the voxel face, never farther
+    # exact 5-NN of 4000 perturbed map points
+    rng = np.random.default_rng(11)
+    q = (m[rng.choice(len(m), 4000), :3] + rng.normal(0, 0.05, (4000, 3))).astype(np.float32)
+    idx, d2 = r.knn5(m, q, cell=0.33, first_radius=1)
+    acc = idx[:, 0] >= 0
+    assert acc.mean() > 0.95
+    assert np.all(np.diff(d2[acc], axis=1) >= 0)
+    nb = m[idx[acc]][:, :, :3]
+    dx = q[acc][:, None, 0] - nb[:, :, 0]; dy = q[acc][:, None, 1] - nb[:, :, 1]; dz = q[acc][:, None, 2] - nb[:, :, 2]
+    rec = (dx * dx + dy * dy) + dz * dz                                       # the oracle's f32 expression order
+    assert np.array_equal(rec.astype(np.float32), d2[acc])
+    for i in np.flatnonzero(acc)[:200]:                                       # brute force on a sample: nothing closer was missed
+        d = ((q[i, 0] - m[:, 0]) ** 2 + (q[i, 1] - m[:, 1]) ** 2) + (q[i, 2] - m[:, 2]) ** 2
+        best = np.lexsort((np.arange(len(m)), d))[:5]
+        assert np.array_equal(best, idx[i]), i
+    # whole path, then a second registration started from the converged pose changes nothing measurable
+    r.set_raw_scan(0, fb.api.pack_raw(fr["scan"]), imu=fr["imu"], imu_available=fr["imu_available"])
+    r.set_local_map(0, fr["map_corner"], fr["map_surf"])
+    r.set_pose(0, fr["guess"])
+    r.run_frames(0, 1)
+    pose, iters, flags = r.get_pose(0)
+    assert flags & 8 and iters <= 12                                          # FBPR_FLAG_CONVERGED
+    assert np.max(np.abs(pose[3:] - fr["gt"][3:])) < 0.05 and np.max(np.abs(pose[:3] - fr["gt"][:3])) < 0.01
+    r.scan2MapOptimization(0, 1)
+    pose2, iters2, flags2 = r.get_pose(0)
+    assert flags2 & 8 and iters2 <= 2 and np.max(np.abs(pose2 - pose)) < 2e-3
+    r.close()
