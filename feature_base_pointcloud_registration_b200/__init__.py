@@ -7,6 +7,6 @@ importing :mod:`.api` without the built library, or creating a handle without a 
 """
 from .api import (  # noqa: F401
     FbprError, Params, Registration, load_library, library_path, RAW_POINT_DTYPE, RESULT_DTYPE,
-    FLAG_NOT_ENOUGH_FEATURES, FLAG_TOO_FEW_CORRESPONDENCES, FLAG_DEGENERATE, FLAG_CONVERGED, BUF,
+    FLAG_NOT_ENOUGH_FEATURES, FLAG_TOO_FEW_CORRESPONDENCES, FLAG_DEGENERATE, FLAG_CONVERGED, FLAG_MAP_TRUNCATED, BUF,
 )
 from .params import load_params_yaml  # noqa: F401

@@ -13,6 +13,7 @@ FLAG_NOT_ENOUGH_FEATURES = 1
 FLAG_TOO_FEW_CORRESPONDENCES = 2
 FLAG_DEGENERATE = 4
 FLAG_CONVERGED = 8
+FLAG_MAP_TRUNCATED = 16
 MEM_HOST, MEM_DEVICE = 0, 1
 
 RAW_POINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("intensity", "<f4"), ("ring", "<i4"), ("time", "<f4")])
@@ -362,6 +363,16 @@ class Registration:
         nb = self._ck(self.lib.fbpr_get_buffer(self.h, slot, BUF[name], _vp(buf), cap))
         out = buf[:nb].view(dt).copy()
         return out.reshape(-1, w) if w > 1 else out
+
+    def selftest_smallmat(self, which, rows):
+        """fbpr_selftest_smallmat: the device small-matrix routines on `rows` ([n, in_width] f32); which = name below."""
+        names = ["JACOBI3", "JACOBI6", "QR6", "LU6", "PLANE5X3", "NOT_DEGENERATE"]
+        out_w = [12, 42, 6, 36, 3, 1]
+        k = names.index(which)
+        a = _f32(rows).reshape(len(rows), -1)
+        out = np.zeros((len(a), out_w[k]), np.float32)
+        self._ck(self.lib.fbpr_selftest_smallmat(self.h, k, _vp(a), len(a), _vp(out)))
+        return out
 
     # ---- stand-alone primitives
     def voxel_grid(self, xyzi, leaf):

@@ -12,30 +12,7 @@
 
 #include "internal.cuh"
 
-int fbpr_knn_cache_slots();
 #define FBPR_KNN_CACHE_SLOTS fbpr_knn_cache_slots()
-
-// ---- kernel-side argument blocks and launchers (defined in the other translation units) ----
-void fbpr_launch_projection(const ProjArgs& a, int count, cudaStream_t st, long long* launches);
-int fbpr_launch_features(const FeatArgs& a, int count, cudaStream_t st, long long* launches);
-size_t fbpr_feat_ring_smem(const FeatArgs& a);
-void fbpr_launch_voxel(const VoxSeg* d_segs, int nsegs, int max_n, int tiles_cap, cudaStream_t st, long long* launches);
-int fbpr_voxel_tile();
-void fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cells_cap, cudaStream_t st, long long* launches);
-void fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, int rad0, cudaStream_t st, long long* launches);
-int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blocks, cudaStream_t st, long long* launches);
-int fbpr_lm_grid_blocks(int device);
-void fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float rot_tol, float z_tol, cudaStream_t st, long long* launches);
-void fbpr_launch_keyframe_transform(const float* d_poses6, int K, const float4* d_in, const int* d_off, float4* d_out, int* d_n_out,
-                                    const float* d_last_xyz, float radius, const float* d_check_xyz, int max_pts, int* d_outoff, float* d_T,
-                                    cudaStream_t st, long long* launches);
-void fbpr_launch_crop_box(const float4* d_in, int n, const float* d_pose12, float4* d_out, int cap, int* d_n_out, int* d_tile,
-                          cudaStream_t st, long long* launches);
-void fbpr_launch_pose_decompose(const float* d_pose12, FrameMeta* meta, int slot, cudaStream_t st, long long* launches);
-void fbpr_launch_pose_compose(const FrameMeta* meta, int slot, float* d_pose12, cudaStream_t st, long long* launches);
-void fbpr_launch_pc2_to_raw(const unsigned char* d_src, int n, const fbpr_pc2_layout& L, fbpr_raw_point* d_dst, cudaStream_t st, long long* launches);
-void fbpr_launch_xyzi_repack(const float4* d_in, int n, float4* d_out, int to32, cudaStream_t st, long long* launches);
-void fbpr_launch_stage_scatter(const ScatterTable& t, cudaStream_t st, long long* launches);
 
 // ---- error reporting -------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -46,6 +23,10 @@ int fbpr_fail(cudaError_t e, const char* what, const char* file, int line) {
     return -2;
 }
 int fbpr_fail_msg(const char* msg) { g_err = msg; return -1; }
+int fbpr_launch_ok(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fbpr_fail(e, what, "kernel launch", 0);
+}
 
 // ---- handle ------------------------------------------------------------------------------------
 struct fbpr_handle {
@@ -96,6 +77,7 @@ struct fbpr_handle {
                     unsigned char* stage = nullptr; size_t stageBytes = 0, stageUsed = 0; };   // stage: landing area of merged uploads
     Ticket tickets[FBPR_MAX_TICKETS];                                       // batches between _begin and _end
     bool timing = false;
+    bool streamTouched = true;    // an operator other than the pipelined batch calls has queued work on `stream` since the upload streams last waited for it
     struct TimedSpan { int stage; cudaEvent_t a, b; };
     std::vector<TimedSpan> spans; size_t spansUsed = 0;
     float stageMs[FBPR_STAGE_COUNT] = { 0, 0, 0, 0, 0 }; int stageCalls[FBPR_STAGE_COUNT] = { 0, 0, 0, 0, 0 };
@@ -124,6 +106,7 @@ static cudaMemcpyKind kind_in(int mem) { return mem == FBPR_MEM_DEVICE ? cudaMem
 static int check_range(fbpr_handle* h, int first, int count) {
     if (!h) return fbpr_fail_msg("null handle");
     if (first < 0 || count < 0 || first + count > h->F) return fbpr_fail_msg("slot range out of bounds");
+    h->streamTouched = true;      // every slot operator passes here; fbpr_register_frames_begin clears it again for its own call
     return 0;
 }
 
@@ -208,10 +191,10 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
         for (int f = 0; f < F; f++) {
             VoxSeg c = {}; c.in = h->corner + (size_t)f * h->cornerCap; c.n_in = &h->meta[f].n_corner;
             c.out = h->cornerDS + (size_t)f * h->cornerCap; c.n_out = &h->meta[f].n_corner_ds;
-            c.leaf = params->mappingCornerLeafSize; c.cap = h->cornerCap;
+            c.leaf = params->mappingCornerLeafSize; c.cap = h->cornerCap; c.out_cap = h->cornerCap;
             VoxSeg s = {}; s.in = h->surf + (size_t)f * P; s.n_in = &h->meta[f].n_surf;
             s.out = h->surfDS + (size_t)f * P; s.n_out = &h->meta[f].n_surf_ds;
-            s.leaf = params->mappingSurfLeafSize; s.cap = P;
+            s.leaf = params->mappingSurfLeafSize; s.cap = P; s.out_cap = P;
             segs[2 * f] = c; segs[2 * f + 1] = s;
         }
         int rc = build_vox_segs(h, segs, &h->d_scanSegs); if (rc) return rc;
@@ -242,10 +225,10 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
         for (int f = 0; f < F; f++) {
             VoxSeg c = {}; c.in = h->kfCorner + (size_t)f * h->kfCap; c.n_in = h->kfCount + 2 * f;
             c.out = h->mapCorner + (size_t)f * h->mapCornerCap; c.n_out = &h->meta[f].n_map_corner;
-            c.leaf = params->mappingCornerLeafSize; c.cap = h->kfCap;
+            c.leaf = params->mappingCornerLeafSize; c.cap = h->kfCap; c.out_cap = h->mapCornerCap; c.truncated = &h->meta[f].mapTruncated;
             VoxSeg s = {}; s.in = h->kfSurf + (size_t)f * h->kfCap; s.n_in = h->kfCount + 2 * f + 1;
             s.out = h->mapSurf + (size_t)f * h->mapSurfCap; s.n_out = &h->meta[f].n_map_surf;
-            s.leaf = params->mappingSurfLeafSize; s.cap = h->kfCap;
+            s.leaf = params->mappingSurfLeafSize; s.cap = h->kfCap; s.out_cap = h->mapSurfCap; s.truncated = &h->meta[f].mapTruncated;
             segs[2 * f] = c; segs[2 * f + 1] = s;
         }
         int rc = build_vox_segs(h, segs, &h->d_kfSegs); if (rc) return rc;
@@ -352,7 +335,7 @@ int fbpr_set_raw_scan_pc2(fbpr_handle* h, int slot, const void* data, int n, con
     rc = fbpr_set_raw_scan(h, slot, nullptr, 0, FBPR_MEM_DEVICE, imuAvailable, deskewFlag, timeScanCur, imuTime, imuRotX, imuRotY, imuRotZ,
                            imuPointerCur, imuRollInit, imuPitchInit);
     if (rc) return rc;
-    fbpr_launch_pc2_to_raw(d_src, n, *L, h->raw + (size_t)slot * h->rawCap, h->stream, &h->launches);
+    rc = fbpr_launch_pc2_to_raw(d_src, n, *L, h->raw + (size_t)slot * h->rawCap, h->stream, &h->launches); if (rc) return rc;
     FBPR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->meta + slot) + offsetof(FrameMeta, n_raw), &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));            // `n` lives on the caller's stack
     return 0;
@@ -369,11 +352,11 @@ int fbpr_set_clouds_xyzi32(fbpr_handle* h, int slot, int kind, const void* corne
     float4* dS = kind == 0 ? h->surf + (size_t)slot * h->P : h->mapSurf + (size_t)slot * h->mapSurfCap;
     if (nC) FBPR_CUDA_OK(cudaMemcpyAsync(h->wireStage, corner32, (size_t)nC * 32, cudaMemcpyHostToDevice, h->stream));
     if (nS) FBPR_CUDA_OK(cudaMemcpyAsync(h->wireStage + (size_t)nC * 32, surf32, (size_t)nS * 32, cudaMemcpyHostToDevice, h->stream));
-    fbpr_launch_xyzi_repack(reinterpret_cast<const float4*>(h->wireStage), nC, dC, 0, h->stream, &h->launches);
-    fbpr_launch_xyzi_repack(reinterpret_cast<const float4*>(h->wireStage + (size_t)nC * 32), nS, dS, 0, h->stream, &h->launches);
-    int v[2] = { nC, nS };
+    rc = fbpr_launch_xyzi_repack(reinterpret_cast<const float4*>(h->wireStage), nC, dC, 0, h->stream, &h->launches); if (rc) return rc;
+    rc = fbpr_launch_xyzi_repack(reinterpret_cast<const float4*>(h->wireStage + (size_t)nC * 32), nS, dS, 0, h->stream, &h->launches); if (rc) return rc;
+    int v[3] = { nC, nS, 0 };                                  // a new local map also clears mapTruncated, which sits behind the two counts
     const size_t off = kind == 0 ? offsetof(FrameMeta, n_corner) : offsetof(FrameMeta, n_map_corner);
-    FBPR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->meta + slot) + off, v, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    FBPR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->meta + slot) + off, v, (kind == 0 ? 2 : 3) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -417,8 +400,9 @@ int fbpr_set_local_map(fbpr_handle* h, int slot, const float* corner, int nC, co
     cudaSetDevice(h->device);
     if (nC) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapCorner + (size_t)slot * h->mapCornerCap, corner, (size_t)nC * sizeof(float4), kind_in(mem), h->stream));
     if (nS) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapSurf + (size_t)slot * h->mapSurfCap, surf, (size_t)nS * sizeof(float4), kind_in(mem), h->stream));
-    int v[2] = { nC, nS };
-    FBPR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->meta + slot) + offsetof(FrameMeta, n_map_corner), v, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    static_assert(offsetof(FrameMeta, mapTruncated) == offsetof(FrameMeta, n_map_corner) + 8, "mapTruncated must follow the map counts");
+    int v[3] = { nC, nS, 0 };
+    FBPR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(h->meta + slot) + offsetof(FrameMeta, n_map_corner), v, 3 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     return 0;
 }
 
@@ -561,7 +545,7 @@ static LmArgs lm_args(fbpr_handle* h, int first) {
     a.partials = h->partials; a.teamMax = 16; a.partialsGrid = h->partialsGrid; a.gridMax = 1024; a.chunkPart = h->chunkPart; a.chunkCap = h->chunkCap;
     a.edgeMin = h->p.edgeFeatureMinValidNum; a.surfMin = h->p.surfFeatureMinValidNum;
     a.z_tol = h->p.z_tollerance; a.rot_tol = h->p.rotation_tollerance;
-    a.debug_iter = (h->debugIter >= 0 && first + 0 < h->dbgSlots) ? h->debugIter : -1;
+    a.debug_iter = h->debugIter; a.dbgSlots = h->dbgSlots;      // captured for the slots of the launch that are < dbgSlots
     a.knnC = h->knnC; a.d2C = h->d2C; a.coeffC = h->coeffC; a.flagC = h->flagC;
     a.knnS = h->knnS; a.d2S = h->d2S; a.coeffS = h->coeffS; a.flagS = h->flagS;
     a.dbgAtA = h->dbgAtA; a.dbgAtB = h->dbgAtB; a.dbgX = h->dbgX; a.poseTrace = h->poseTrace;
@@ -586,7 +570,7 @@ struct StageTimer {                      // records an event pair around one sta
 
 static int enqueue_project(fbpr_handle* h, int first, int count) {
     StageTimer t(h, FBPR_STAGE_PROJECT);
-    fbpr_launch_projection(proj_args(h, first), count, h->stream, &h->launches); return 0;
+    return fbpr_launch_projection(proj_args(h, first), count, h->stream, &h->launches);
 }
 static int enqueue_features(fbpr_handle* h, int first, int count) {
     StageTimer t(h, FBPR_STAGE_FEATURES);
@@ -594,18 +578,16 @@ static int enqueue_features(fbpr_handle* h, int first, int count) {
 }
 static int enqueue_downsample(fbpr_handle* h, int first, int count) {
     StageTimer t(h, FBPR_STAGE_DOWNSAMPLE);
-    fbpr_launch_voxel(h->d_scanSegs + 2 * (size_t)first, 2 * count, h->P, h->tilesCap, h->stream, &h->launches); return 0;
+    return fbpr_launch_voxel(h->d_scanSegs + 2 * (size_t)first, 2 * count, h->P, h->tilesCap, h->stream, &h->launches);
 }
 static int enqueue_map_index(fbpr_handle* h, int first, int count) {
     int maxMap = h->mapCornerCap > h->mapSurfCap ? h->mapCornerCap : h->mapSurfCap;
     int maxCells = h->cellsCorner > h->cellsSurf ? h->cellsCorner : h->cellsSurf;
     StageTimer t(h, FBPR_STAGE_MAP_INDEX);
-    fbpr_launch_grid_build(h->d_gridSegs + 2 * (size_t)first, 2 * count, maxMap, maxCells, h->stream, &h->launches);
-    return 0;
+    return fbpr_launch_grid_build(h->d_gridSegs + 2 * (size_t)first, 2 * count, maxMap, maxCells, h->stream, &h->launches);
 }
 static int enqueue_lm(fbpr_handle* h, int first, int count) {
     LmArgs a = lm_args(h, first);
-    if (a.debug_iter >= 0 && first + count > h->dbgSlots) return fbpr_fail_msg("debug capture only covers the first slots");
     StageTimer t(h, FBPR_STAGE_LM);
     return fbpr_launch_lm(a, count, h->cluster, h->lmWholeGpu ? h->lmGridBlocks : 0, h->stream, &h->launches);
 }
@@ -636,8 +618,7 @@ int fbpr_scan2map_optimization(fbpr_handle* h, int first, int count) {
 int fbpr_transform_update(fbpr_handle* h, int first, int count) {
     int rc = check_range(h, first, count); if (rc) return rc;
     cudaSetDevice(h->device);
-    fbpr_launch_transform_update(h->meta, first, count, h->p.rotation_tollerance, h->p.z_tollerance, h->stream, &h->launches);
-    return 0;
+    return fbpr_launch_transform_update(h->meta, first, count, h->p.rotation_tollerance, h->p.z_tollerance, h->stream, &h->launches);
 }
 int fbpr_run_frames(fbpr_handle* h, int first, int count, int with_projection, int with_features) {
     int rc = check_range(h, first, count); if (rc) return rc;
@@ -709,54 +690,36 @@ static int upload_group(fbpr_handle* h, fbpr_handle::Ticket& tk, const std::vect
     for (size_t i = 0; i < pcs.size(); i++) t.p[i] = ScatterPiece{ (unsigned long long)((uintptr_t)pcs[i].src - lo), pcs[i].dst, (unsigned long long)pcs[i].bytes };
     FBPR_CUDA_OK(cudaEventRecord(tmp, st));
     FBPR_CUDA_OK(cudaStreamWaitEvent(scatterSt, tmp, 0));
-    fbpr_launch_stage_scatter(t, scatterSt, &h->launches);
+    { int rc = fbpr_launch_stage_scatter(t, scatterSt, &h->launches); if (rc) return rc; }
     FBPR_CUDA_OK(cudaEventRecord(ready, scatterSt));
     tk.stageUsed = landing + (lo & 15) + span;
     return 0;
 }
 
-int fbpr_register_frames_begin(fbpr_handle* h, int first, int count, const fbpr_frame_input* fr, int chunk_frames) {
-    int rc = check_range(h, first, count); if (rc) return rc;
-    if (!fr && count > 0) return fbpr_fail_msg("null frames");
-    if (count > 0 && fbpr_feat_ring_smem(feat_args(h, first)) > 200 * 1024) return fbpr_fail_msg("Horizon_SCAN too large for the per-ring shared-memory kernel");
-    cudaSetDevice(h->device);
-    int ticket = -1;
-    for (int t = 0; t < FBPR_MAX_TICKETS; t++) if (!h->tickets[t].busy) { ticket = t; break; }
-    if (ticket < 0) return fbpr_fail_msg("too many fbpr_register_frames_begin calls in flight (call fbpr_register_frames_end first)");
-    for (int t = 0; t < FBPR_MAX_TICKETS; t++) {
-        const auto& o = h->tickets[t];
-        if (o.busy && first < o.first + o.count && o.first < first + count) return fbpr_fail_msg("slot range overlaps a batch that is still in flight");
-    }
+// everything of _begin that enqueues work; a failure midway leaves copies / kernels queued, which the caller below drains
+static int register_frames_enqueue(fbpr_handle* h, int ticket, int first, int count, const fbpr_frame_input* fr, int chunk_frames) {
+    int rc = 0;
     fbpr_handle::Ticket& tk = h->tickets[ticket];
-    if (!tk.done) FBPR_CUDA_OK(cudaEventCreateWithFlags(&tk.done, cudaEventDisableTiming));
-    if (tk.cap < count) {
-        if (tk.h_res) cudaFreeHost(tk.h_res);
-        tk.h_res = nullptr; tk.cap = 0;
-        FBPR_CUDA_OK(cudaHostAlloc((void**)&tk.h_res, sizeof(fbpr_result) * (size_t)(count > 0 ? count : 1), cudaHostAllocDefault));
-        tk.cap = count;
-    }
-    tk.first = first; tk.count = count;
     int inflight = 0;
     for (int t = 0; t < FBPR_MAX_TICKETS; t++) inflight += h->tickets[t].busy ? 1 : 0;
-    if (count == 0) { tk.busy = true; FBPR_CUDA_OK(cudaEventRecord(tk.done, h->stream)); return ticket; }
+    if (count == 0) { FBPR_CUDA_OK(cudaEventRecord(tk.done, h->stream)); return 0; }
     std::vector<int> bounds; chunk_schedule(count, chunk_frames, bounds);
     const int nchunks = (int)bounds.size() - 1;
-    if (!h->copyStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
-    if (!h->lmStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->lmStream, cudaStreamNonBlocking));
-    if (!h->scatterStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->scatterStream, cudaStreamNonBlocking));
     while ((int)h->pipeEvents.size() < 5 * nchunks + 3) {
         cudaEvent_t e; FBPR_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->pipeEvents.push_back(e);
     }
     bool anyImu = false;
     rc = stage_frames(h, count, fr, &anyImu); if (rc) return rc;
     cudaEvent_t evStart = h->pipeEvents[3 * nchunks], evMeta = h->pipeEvents[3 * nchunks + 1];
-    if (inflight == 0) {
-        // nothing pipelined is pending: the upload stream starts after everything already queued on the compute stream
-        // (earlier operators may still read these slots).  With another batch in flight (on DISJOINT slots, whose previous
-        // occupants were drained by fbpr_register_frames_end) the copies may start at once, under that batch's kernels.
+    if (inflight == 0 || h->streamTouched) {
+        // the upload and registration streams start after everything already queued on the handle's stream: earlier operators
+        // (fbpr_run_frames, fbpr_registration, setters, asynchronous getters) may still read or write these slots.  Only when
+        // nothing but pipelined batches has used the handle since the last such wait (their slot ranges are disjoint and their
+        // previous occupants were drained by fbpr_register_frames_end) may the copies start at once, under that batch's kernels.
         FBPR_CUDA_OK(cudaEventRecord(evStart, h->stream));
         FBPR_CUDA_OK(cudaStreamWaitEvent(h->copyStream, evStart, 0));
         FBPR_CUDA_OK(cudaStreamWaitEvent(h->lmStream, evStart, 0));
+        h->streamTouched = false;
     }
     rc = upload_staged(h, first, count, anyImu, h->copyStream); if (rc) return rc;
     FBPR_CUDA_OK(cudaEventRecord(evMeta, h->copyStream));
@@ -816,9 +779,50 @@ int fbpr_register_frames_begin(fbpr_handle* h, int first, int count, const fbpr_
     FBPR_CUDA_OK(cudaMemcpy2DAsync(tk.h_res, sizeof(fbpr_result), reinterpret_cast<char*>(h->meta + first) + offsetof(FrameMeta, pose), sizeof(FrameMeta),
                                    sizeof(fbpr_result), count, cudaMemcpyDeviceToHost, h->lmStream));
     FBPR_CUDA_OK(cudaEventRecord(tk.done, h->lmStream));
-    tk.busy = true;
+    return 0;
+}
+
+int fbpr_register_frames_begin(fbpr_handle* h, int first, int count, const fbpr_frame_input* fr, int chunk_frames) {
+    const bool touched = h ? h->streamTouched : true;
+    int rc = check_range(h, first, count); if (rc) return rc;
+    h->streamTouched = touched;
+    if (!fr && count > 0) return fbpr_fail_msg("null frames");
+    if (count > 0 && fbpr_feat_ring_smem(feat_args(h, first)) > 200 * 1024) return fbpr_fail_msg("Horizon_SCAN too large for the per-ring shared-memory kernel");
+    cudaSetDevice(h->device);
+    int ticket = -1;
+    for (int t = 0; t < FBPR_MAX_TICKETS; t++) if (!h->tickets[t].busy) { ticket = t; break; }
+    if (ticket < 0) return fbpr_fail_msg("too many fbpr_register_frames_begin calls in flight (call fbpr_register_frames_end first)");
+    for (int t = 0; t < FBPR_MAX_TICKETS; t++) {
+        const auto& o = h->tickets[t];
+        if (o.busy && first < o.first + o.count && o.first < first + count) return fbpr_fail_msg("slot range overlaps a batch that is still in flight");
+    }
+    fbpr_handle::Ticket& tk = h->tickets[ticket];
+    if (!tk.done) FBPR_CUDA_OK(cudaEventCreateWithFlags(&tk.done, cudaEventDisableTiming));
+    if (tk.cap < count) {
+        if (tk.h_res) cudaFreeHost(tk.h_res);
+        tk.h_res = nullptr; tk.cap = 0;
+        FBPR_CUDA_OK(cudaHostAlloc((void**)&tk.h_res, sizeof(fbpr_result) * (size_t)(count > 0 ? count : 1), cudaHostAllocDefault));
+        tk.cap = count;
+    }
+    tk.first = first; tk.count = count;
+    if (!h->copyStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+    if (!h->lmStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->lmStream, cudaStreamNonBlocking));
+    if (!h->scatterStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->scatterStream, cudaStreamNonBlocking));
+    tk.busy = true;                                              // from here on work may be queued for these slots
+    rc = register_frames_enqueue(h, ticket, first, count, fr, chunk_frames);
+    if (rc) {
+        // a failure midway (a launch or copy was refused) leaves earlier copies / kernels of this batch queued: wait for them so
+        // that the caller's host buffers and the slots are free again, then give the ticket back.  The error text is kept.
+        const std::string why = g_err;
+        cudaStreamSynchronize(h->copyStream); cudaStreamSynchronize(h->scatterStream); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->lmStream);
+        cudaGetLastError();
+        tk.busy = false;
+        g_err = why;
+        return rc;
+    }
     return ticket;
 }
+
 
 int fbpr_register_frames_end(fbpr_handle* h, int ticket, fbpr_result* out) {
     if (!h) return fbpr_fail_msg("null handle");
@@ -887,16 +891,17 @@ int fbpr_extract_cloud(fbpr_handle* h, int slot, int K, const float* key_poses6,
         if (ns) FBPR_CUDA_OK(cudaMemcpyAsync(d_sin, surf_xyzi, sizeof(float4) * ns, cudaMemcpyHostToDevice, h->stream));
     }
     FBPR_CUDA_OK(cudaMemcpyAsync(d_last, last_key_xyz, sizeof(float) * 3, cudaMemcpyHostToDevice, h->stream));
-    fbpr_launch_keyframe_transform(d_poses, K, d_cin, d_coff, h->kfCorner + (size_t)slot * h->kfCap, h->kfCount + 2 * slot,
-                                   d_last, h->p.surroundingKeyframeSearchRadius, d_check, nc, d_outoff, d_T, h->stream, &h->launches);
-    fbpr_launch_keyframe_transform(d_poses, K, d_sin, d_soff, h->kfSurf + (size_t)slot * h->kfCap, h->kfCount + 2 * slot + 1,
-                                   d_last, h->p.surroundingKeyframeSearchRadius, d_check, ns, d_outoff, d_T, h->stream, &h->launches);
-    fbpr_launch_voxel(h->d_kfSegs + 2 * (size_t)slot, 2, h->kfCap, h->tilesCap, h->stream, &h->launches);
+    FBPR_CUDA_OK(cudaMemsetAsync(&h->meta[slot].mapTruncated, 0, sizeof(int), h->stream));
+    rc = fbpr_launch_keyframe_transform(d_poses, K, d_cin, d_coff, h->kfCorner + (size_t)slot * h->kfCap, h->kfCount + 2 * slot,
+                                        d_last, h->p.surroundingKeyframeSearchRadius, d_check, nc, d_outoff, d_T, h->stream, &h->launches);
+    if (!rc) rc = fbpr_launch_keyframe_transform(d_poses, K, d_sin, d_soff, h->kfSurf + (size_t)slot * h->kfCap, h->kfCount + 2 * slot + 1,
+                                                 d_last, h->p.surroundingKeyframeSearchRadius, d_check, ns, d_outoff, d_T, h->stream, &h->launches);
+    if (!rc) rc = fbpr_launch_voxel(h->d_kfSegs + 2 * (size_t)slot, 2, h->kfCap, h->tilesCap, h->stream, &h->launches);
     cudaFreeAsync(d_poses, h->stream); cudaFreeAsync(d_coff, h->stream); cudaFreeAsync(d_soff, h->stream);
     cudaFreeAsync(d_cin, h->stream); cudaFreeAsync(d_sin, h->stream); cudaFreeAsync(d_last, h->stream);
     cudaFreeAsync(d_outoff, h->stream); cudaFreeAsync(d_T, h->stream);
     if (d_check) cudaFreeAsync(d_check, h->stream);
-    return 0;
+    return rc;
 }
 
 static int upload_global(fbpr_handle* h, const float* corner_global, int nCg, const float* surf_global, int nSg, int mem) {
@@ -939,12 +944,16 @@ int fbpr_registration(fbpr_handle* h, int slot, const float* corner_global, int 
     if (need / 2048 + 2 > (1 << 16)) return fbpr_fail_msg("global map too large for the CropBox scratch");
     FBPR_CUDA_OK(cudaMemcpyAsync(h->regPose, pose12, sizeof(float) * 12, cudaMemcpyHostToDevice, h->stream));
     // CropBox +-30/+-30/+-10 m around the guess (mapOptmization.h:284-304), order preserving
-    fbpr_launch_crop_box(d_c, nCg, h->regPose, h->mapCorner + (size_t)slot * h->mapCornerCap, h->mapCornerCap, &h->meta[slot].n_map_corner, h->regTile, h->stream, &h->launches);
-    fbpr_launch_crop_box(d_s, nSg, h->regPose, h->mapSurf + (size_t)slot * h->mapSurfCap, h->mapSurfCap, &h->meta[slot].n_map_surf, h->regTile, h->stream, &h->launches);
-    fbpr_launch_pose_decompose(h->regPose, h->meta, slot, h->stream, &h->launches);            // :309-310
+    // a cropped map larger than max_map_corner / max_map_surf is cut (the reference keeps every point): FBPR_FLAG_MAP_TRUNCATED
+    FBPR_CUDA_OK(cudaMemsetAsync(&h->meta[slot].mapTruncated, 0, sizeof(int), h->stream));
+    rc = fbpr_launch_crop_box(d_c, nCg, h->regPose, h->mapCorner + (size_t)slot * h->mapCornerCap, h->mapCornerCap, &h->meta[slot].n_map_corner,
+                              &h->meta[slot].mapTruncated, h->regTile, h->stream, &h->launches); if (rc) return rc;
+    rc = fbpr_launch_crop_box(d_s, nSg, h->regPose, h->mapSurf + (size_t)slot * h->mapSurfCap, h->mapSurfCap, &h->meta[slot].n_map_surf,
+                              &h->meta[slot].mapTruncated, h->regTile, h->stream, &h->launches); if (rc) return rc;
+    rc = fbpr_launch_pose_decompose(h->regPose, h->meta, slot, h->stream, &h->launches); if (rc) return rc;            // :309-310
     rc = enqueue_downsample(h, slot, 1); if (rc) return rc;                                    // :313
     rc = enqueue_scan2map(h, slot, 1); if (rc) return rc;                                      // :317
-    fbpr_launch_pose_compose(h->meta, slot, h->regPose, h->stream, &h->launches);              // :326
+    rc = fbpr_launch_pose_compose(h->meta, slot, h->regPose, h->stream, &h->launches); if (rc) return rc;              // :326
     FBPR_CUDA_OK(cudaMemcpyAsync(pose12, h->regPose, sizeof(float) * 12, cudaMemcpyDeviceToHost, h->stream));
     FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
     FBPR_CUDA_OK(cudaGetLastError());
@@ -1080,7 +1089,7 @@ int64_t fbpr_get_buffer_xyzi32(fbpr_handle* h, int slot, int which, void* dst, i
     if ((int64_t)bytes > cap_bytes) return fbpr_fail_msg("destination too small");
     if (n == 0) return 0;
     rc = wire_stage(h, bytes); if (rc) return rc;
-    fbpr_launch_xyzi_repack(src, n, reinterpret_cast<float4*>(h->wireStage), 1, h->stream, &h->launches);
+    rc = fbpr_launch_xyzi_repack(src, n, reinterpret_cast<float4*>(h->wireStage), 1, h->stream, &h->launches); if (rc) return rc;
     FBPR_CUDA_OK(cudaMemcpyAsync(dst, h->wireStage, bytes, cudaMemcpyDeviceToHost, h->stream));
     FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
     return (int64_t)bytes;
@@ -1106,7 +1115,7 @@ int fbpr_voxel_grid(fbpr_handle* h, const float* xyzi, int n, float leaf, float*
         FBPR_CUDA_OK(A((void**)&s.tile_hist, 4 * (size_t)256 * tiles)); FBPR_CUDA_OK(A((void**)&s.bbox, 32));
         FBPR_CUDA_OK(A((void**)&s.run_tile, 4 * (size_t)(tiles + 1))); FBPR_CUDA_OK(A((void**)&s.desc, sizeof(VoxDesc)));
         FBPR_CUDA_OK(A((void**)&h->d_soloVox, sizeof(VoxSeg)));
-        s.in = h->soloIn; s.n_in = h->soloN; s.out = h->soloOut; s.n_out = h->soloNout; s.cap = cap;
+        s.in = h->soloIn; s.n_in = h->soloN; s.out = h->soloOut; s.n_out = h->soloNout; s.cap = cap; s.out_cap = cap;
         s.point_keys = h->soloPK; s.out_keys = h->soloOK; s.leaf = leaf;
         FBPR_CUDA_OK(cudaMemcpy(h->d_soloVox, &s, sizeof(s), cudaMemcpyHostToDevice));
         h->soloVoxCap = cap;
@@ -1116,7 +1125,7 @@ int fbpr_voxel_grid(fbpr_handle* h, const float* xyzi, int n, float leaf, float*
     FBPR_CUDA_OK(cudaMemcpyAsync(h->soloN, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (n) FBPR_CUDA_OK(cudaMemcpyAsync(h->soloIn, xyzi, sizeof(float4) * (size_t)n, kind_in(mem), h->stream));
     int tiles_cap = (h->soloVoxCap + fbpr_voxel_tile() - 1) / fbpr_voxel_tile() + 1;
-    fbpr_launch_voxel(h->d_soloVox, 1, n > 0 ? n : 1, tiles_cap, h->stream, &h->launches);
+    { int rc = fbpr_launch_voxel(h->d_soloVox, 1, n > 0 ? n : 1, tiles_cap, h->stream, &h->launches); if (rc) return rc; }
     int m = 0;
     FBPR_CUDA_OK(cudaMemcpyAsync(&m, h->soloNout, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -1159,13 +1168,13 @@ int fbpr_knn5(fbpr_handle* h, const float* map_xyzi, int n_map, float cell, cons
     }
     FBPR_CUDA_OK(cudaMemcpyAsync(h->soloMapN, &n_map, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (n_map) FBPR_CUDA_OK(cudaMemcpyAsync(h->soloMap, map_xyzi, sizeof(float4) * (size_t)n_map, cudaMemcpyHostToDevice, h->stream));
-    fbpr_launch_grid_build(h->d_soloGrid, 1, n_map > 0 ? n_map : 1, cells, h->stream, &h->launches);
+    { int rc = fbpr_launch_grid_build(h->d_soloGrid, 1, n_map > 0 ? n_map : 1, cells, h->stream, &h->launches); if (rc) return rc; }
     float* d_q = nullptr; int* d_idx = nullptr; float* d_d2 = nullptr;
     FBPR_CUDA_OK(cudaMallocAsync(&d_q, sizeof(float) * 3 * (size_t)(nq + 1), h->stream));
     FBPR_CUDA_OK(cudaMallocAsync(&d_idx, sizeof(int) * 5 * (size_t)(nq + 1), h->stream));
     FBPR_CUDA_OK(cudaMallocAsync(&d_d2, sizeof(float) * 5 * (size_t)(nq + 1), h->stream));
     if (nq) FBPR_CUDA_OK(cudaMemcpyAsync(d_q, q_xyz, sizeof(float) * 3 * (size_t)nq, cudaMemcpyHostToDevice, h->stream));
-    fbpr_launch_knn5(h->d_soloGrid, d_q, nq, d_idx, d_d2, h->knnRad0, h->stream, &h->launches);
+    { int rc = fbpr_launch_knn5(h->d_soloGrid, d_q, nq, d_idx, d_d2, h->knnRad0, h->stream, &h->launches); if (rc) return rc; }
     if (nq) {
         FBPR_CUDA_OK(cudaMemcpyAsync(idx, d_idx, sizeof(int) * 5 * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));
         FBPR_CUDA_OK(cudaMemcpyAsync(d2, d_d2, sizeof(float) * 5 * (size_t)nq, cudaMemcpyDeviceToHost, h->stream));

@@ -789,5 +789,5 @@ int fbpr_launch_features(const FeatArgs& a, int count, cudaStream_t st, long lon
     feat_ring<<<dim3(a.N_SCAN, count), RING_TPB, smem, st>>>(a);
     feat_gather<<<dim3(a.N_SCAN, count), 256, 0, st>>>(a);
     if (launches) *launches += 3;
-    return 0;
+    return fbpr_launch_ok("features (feat_smooth / feat_ring / feat_gather)");
 }

@@ -21,8 +21,9 @@
 
 struct FrameMeta {
     int n_raw, n_valid, n_corner, n_surf, n_corner_ds, n_surf_ds, n_map_corner, n_map_surf;
+    int mapTruncated;             // the slot's local map lost points to max_map_corner / max_map_surf (CropBox, extractCloud); sits behind the map counts so one copy resets all three
     int first_valid_raw;          // min raw index that passed the projection gates (defines transStartInverse)
-    int deskewFlag, imuPointerCur, pad0;
+    int deskewFlag, imuPointerCur;
     long long imuAvailable;
     double timeScanCur;
     float imuRollInit, imuPitchInit;
@@ -62,7 +63,9 @@ struct VoxSeg {                   // host-built descriptor of one VoxelGrid segm
     float4* out;
     int* n_out;
     float leaf;
-    int cap;                      // capacity of in / out / scratch
+    int cap;                      // capacity of in / scratch
+    int out_cap;                  // capacity of out (voxels beyond it are dropped and *truncated is raised)
+    int* truncated;               // optional flag word (FrameMeta::mapTruncated of the slot that owns `out`)
     unsigned* key[2];             // ping-pong keys
     unsigned* val[2];             // ping-pong point indices
     unsigned* tile_hist;          // [256][tiles_cap]
@@ -136,7 +139,7 @@ struct LmArgs {
     int edgeMin, surfMin;
     float z_tol, rot_tol;
     // debug capture (slots < dbgSlots only)
-    int debug_iter;
+    int debug_iter, dbgSlots;
     int* knnC; float* d2C; float4* coeffC; unsigned char* flagC;
     int* knnS; float* d2S; float4* coeffS; unsigned char* flagS;
     float* dbgAtA; float* dbgAtB; float* dbgX;      // [slot][36], [slot][6], [slot][6]
@@ -179,6 +182,30 @@ __device__ inline void get_transformation(float x, float y, float z, float roll,
     T[8] = -D;    T[9] = C * F;          T[10] = C * E;          T[11] = z;
 }
 
+// ---- launchers (one per operator; each returns 0 or the launch error, named) ------------------
+int fbpr_launch_projection(const ProjArgs& a, int count, cudaStream_t st, long long* launches);
+int fbpr_launch_features(const FeatArgs& a, int count, cudaStream_t st, long long* launches);
+size_t fbpr_feat_ring_smem(const FeatArgs& a);
+int fbpr_launch_voxel(const VoxSeg* d_segs, int nsegs, int max_n, int tiles_cap, cudaStream_t st, long long* launches);
+int fbpr_voxel_tile();
+int fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cells_cap, cudaStream_t st, long long* launches);
+int fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, int rad0, cudaStream_t st, long long* launches);
+int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blocks, cudaStream_t st, long long* launches);
+int fbpr_lm_grid_blocks(int device);
+int fbpr_knn_cache_slots();
+int fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float rot_tol, float z_tol, cudaStream_t st, long long* launches);
+int fbpr_launch_keyframe_transform(const float* d_poses6, int K, const float4* d_in, const int* d_off, float4* d_out, int* d_n_out,
+                                   const float* d_last_xyz, float radius, const float* d_check_xyz, int max_pts, int* d_outoff, float* d_T,
+                                   cudaStream_t st, long long* launches);
+int fbpr_launch_crop_box(const float4* d_in, int n, const float* d_pose12, float4* d_out, int cap, int* d_n_out, int* d_truncated, int* d_tile,
+                         cudaStream_t st, long long* launches);
+int fbpr_launch_pose_decompose(const float* d_pose12, FrameMeta* meta, int slot, cudaStream_t st, long long* launches);
+int fbpr_launch_pose_compose(const FrameMeta* meta, int slot, float* d_pose12, cudaStream_t st, long long* launches);
+int fbpr_launch_pc2_to_raw(const unsigned char* d_src, int n, const fbpr_pc2_layout& L, fbpr_raw_point* d_dst, cudaStream_t st, long long* launches);
+int fbpr_launch_xyzi_repack(const float4* d_in, int n, float4* d_out, int to32, cudaStream_t st, long long* launches);
+int fbpr_launch_stage_scatter(const ScatterTable& t, cudaStream_t st, long long* launches);
+
 #define FBPR_CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fbpr_fail(e_, #expr, __FILE__, __LINE__); } while (0)
 int fbpr_fail(cudaError_t e, const char* what, const char* file, int line);
 int fbpr_fail_msg(const char* msg);
+int fbpr_launch_ok(const char* what);        // cudaGetLastError() after a group of launches: 0, or the error with the operator's name

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
 
     const int nC = M.n_corner_ds, nS = M.n_surf_ds;
     if (!(nC > a.edgeMin && nS > a.surfMin)) {     // mapOptmization.h:1410 / :1439-1441
-        if (rank == 0 && tid == 0) { M.flags = FBPR_FLAG_NOT_ENOUGH_FEATURES; M.iters = 0; M.nSel = 0; M.isDegenerate = 0; }
+        if (rank == 0 && tid == 0) { M.flags = FBPR_FLAG_NOT_ENOUGH_FEATURES | (M.mapTruncated ? FBPR_FLAG_MAP_TRUNCATED : 0u); M.iters = 0; M.nSel = 0; M.isDegenerate = 0; }
         return;
     }
     const int nQ = nC + nS;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             sh_T[8] = -D;     sh_T[9] = Cc * F;         sh_T[10] = Cc * E;         sh_T[11] = sh_pose[5];
         }
         __syncthreads();
-        const bool cap = iter == a.debug_iter;
+        const bool cap = iter == a.debug_iter && slot < a.dbgSlots;
 
         // --- association: one thread per feature point
         double acc = 0.0;
@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
         float pose[6];
         for (int k = 0; k < 6; k++) pose[k] = sh_pose[k];
         if (isDegenerate) flags |= FBPR_FLAG_DEGENERATE;
+        if (M.mapTruncated) flags |= FBPR_FLAG_MAP_TRUNCATED;
         transform_update(pose, M.imuAvailable, M.imuRollInit, M.imuPitchInit, a.rot_tol, a.z_tol);
         for (int k = 0; k < 6; k++) M.pose[k] = pose[k];
         M.iters = iters; M.flags = flags; M.nSel = sh_nsel; M.isDegenerate = isDegenerate;
@@ -610,8 +611,9 @@ int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blo
     return 0;
 }
 
-void fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float rot_tol, float z_tol, cudaStream_t st, long long* launches) {
-    if (count <= 0) return;
+int fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float rot_tol, float z_tol, cudaStream_t st, long long* launches) {
+    if (count <= 0) return 0;
     transform_update_kernel<<<(count + 63) / 64, 64, 0, st>>>(meta, first, count, rot_tol, z_tol);
     if (launches) *launches += 1;
+    return fbpr_launch_ok("transform_update_kernel");
 }

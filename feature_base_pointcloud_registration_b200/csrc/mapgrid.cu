@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(TPB) grid_minmax(const GridSeg* segs) {
         int i = base + k * TPB + threadIdx.x;
         if (i < n) {
             float4 p = s.pts[i];
+            if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;  // KdTreeFLANN::setInputCloud indexes finite points only (Appendix B-2); such a point lands in a clamped cell and never ranks
             unsigned ex = f2ord(p.x), ey = f2ord(p.y), ez = f2ord(p.z);
             mn[0] = min(mn[0], ex); mn[1] = min(mn[1], ey); mn[2] = min(mn[2], ez);
             mx[0] = max(mx[0], ex); mx[1] = max(mx[1], ey); mx[2] = max(mx[2], ez);
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(TPB) grid_setup_zero(const GridSeg* segs) {
         GridDesc g;
         g.n = n;
         float mn[3] = { 0, 0, 0 }, mx[3] = { 0, 0, 0 };
-        if (n > 0) for (int c = 0; c < 3; c++) { mn[c] = ord2f(s.bbox[c]); mx[c] = ord2f(s.bbox[3 + c]); }
+        if (n > 0 && s.bbox[0] <= s.bbox[3]) for (int c = 0; c < 3; c++) { mn[c] = ord2f(s.bbox[c]); mx[c] = ord2f(s.bbox[3 + c]); }   // (no finite point: a one-cell grid at the origin)
         float h = s.h0;
         while (true) {
             float inv = 1.0f / h;
@@ -221,8 +222,8 @@ __global__ void __launch_bounds__(128) knn5_query(const GridSeg* segs, const flo
 
 }  // namespace
 
-void fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cells_cap, cudaStream_t st, long long* launches) {
-    if (nsegs <= 0) return;
+int fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cells_cap, cudaStream_t st, long long* launches) {
+    if (nsegs <= 0) return 0;
     int tiles = (max_n + TILE - 1) / TILE; if (tiles < 1) tiles = 1;
     int stiles = (cells_cap + 1 + SCAN_TILE - 1) / SCAN_TILE;
     // grid-stride zeroing / scanning with about two waves of CTAs over all segments (every zeroing CTA repeats the serial choice of
@@ -240,10 +241,12 @@ void fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cel
     grid_scan_apply<<<gs, 1024, 0, st>>>(d_segs);
     grid_scatter<<<g, TPB, 0, st>>>(d_segs);
     if (launches) *launches += 7;
+    return fbpr_launch_ok("map index (grid_*)");
 }
 
-void fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, int rad0, cudaStream_t st, long long* launches) {
-    if (nq <= 0) return;
+int fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, int rad0, cudaStream_t st, long long* launches) {
+    if (nq <= 0) return 0;
     knn5_query<<<(nq + 127) / 128, 128, 0, st>>>(d_seg, d_q, nq, rad0, d_idx, d_d2);
     if (launches) *launches += 1;
+    return fbpr_launch_ok("knn5_query");
 }

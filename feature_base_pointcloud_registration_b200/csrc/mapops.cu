@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(TPB) crop_count(const float4* in, int n, const
     if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < TPB / 32; k++) t += ws[k]; tile[blockIdx.x] = t; }
 }
 
-__global__ void __launch_bounds__(1024) crop_scan(int* tile, int ntiles, int* n_out, int cap) {
+__global__ void __launch_bounds__(1024) crop_scan(int* tile, int ntiles, int* n_out, int cap, int* truncated) {
     __shared__ int ws[32];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(1024) crop_scan(int* tile, int ntiles, int* n_
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *n_out = min(carry, cap);      // points beyond the slot's map capacity are dropped
+    if (threadIdx.x == 0) {                              // points beyond the slot's map capacity are dropped -- and reported:
+        *n_out = min(carry, cap);                        // the reference keeps every cropped point, so the frame's flags say so
+        if (carry > cap && truncated) atomicOr(truncated, 1);
+    }
 }
 
 __global__ void __launch_bounds__(TPB) crop_emit(const float4* in, int n, const float* pose12, const int* tile, float4* out, int cap) {
@@ -187,46 +190,53 @@ __global__ void __launch_bounds__(TPB) stage_scatter(const __grid_constant__ Sca
 
 }  // namespace
 
-void fbpr_launch_stage_scatter(const ScatterTable& t, cudaStream_t st, long long* launches) {
-    if (t.n <= 0) return;
+int fbpr_launch_stage_scatter(const ScatterTable& t, cudaStream_t st, long long* launches) {
+    if (t.n <= 0) return 0;
     stage_scatter<<<dim3(24, t.n), TPB, 0, st>>>(t);
     if (launches) *launches += 1;
+    return fbpr_launch_ok("stage_scatter");
 }
 
-void fbpr_launch_pc2_to_raw(const unsigned char* d_src, int n, const fbpr_pc2_layout& L, fbpr_raw_point* d_dst, cudaStream_t st, long long* launches) {
-    if (n <= 0) return;
+int fbpr_launch_pc2_to_raw(const unsigned char* d_src, int n, const fbpr_pc2_layout& L, fbpr_raw_point* d_dst, cudaStream_t st, long long* launches) {
+    if (n <= 0) return 0;
     pc2_to_raw<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(d_src, n, L, d_dst);
     if (launches) *launches += 1;
+    return fbpr_launch_ok("pc2_to_raw");
 }
-void fbpr_launch_xyzi_repack(const float4* d_in, int n, float4* d_out, int to32, cudaStream_t st, long long* launches) {
-    if (n <= 0) return;
+int fbpr_launch_xyzi_repack(const float4* d_in, int n, float4* d_out, int to32, cudaStream_t st, long long* launches) {
+    if (n <= 0) return 0;
     if (to32) xyzi16_to_32<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(d_in, n, d_out);
     else xyzi32_to_16<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(d_in, n, d_out);
     if (launches) *launches += 1;
+    return fbpr_launch_ok("xyzi repack");
 }
 
-void fbpr_launch_keyframe_transform(const float* d_poses6, int K, const float4* d_in, const int* d_off, float4* d_out, int* d_n_out,
+int fbpr_launch_keyframe_transform(const float* d_poses6, int K, const float4* d_in, const int* d_off, float4* d_out, int* d_n_out,
                                     const float* d_last_xyz, float radius, const float* d_check_xyz, int max_pts, int* d_outoff, float* d_T,
                                     cudaStream_t st, long long* launches) {
     kf_prepare<<<1, 256, 0, st>>>(d_poses6, K, d_off, d_last_xyz, radius, d_check_xyz, d_outoff, d_T, d_n_out);
     if (max_pts > 0 && K > 0) kf_transform<<<(max_pts + TPB - 1) / TPB, TPB, 0, st>>>(K, d_in, d_off, d_outoff, d_T, d_out, max_pts);
     if (launches) *launches += (max_pts > 0 && K > 0) ? 2 : 1;
+    return fbpr_launch_ok("kf_prepare / kf_transform");
 }
 
-void fbpr_launch_crop_box(const float4* d_in, int n, const float* d_pose12, float4* d_out, int cap, int* d_n_out, int* d_tile,
-                          cudaStream_t st, long long* launches) {
+int fbpr_launch_crop_box(const float4* d_in, int n, const float* d_pose12, float4* d_out, int cap, int* d_n_out, int* d_truncated, int* d_tile,
+                         cudaStream_t st, long long* launches) {
     int tiles = (n + TILE - 1) / TILE;
     if (tiles > 0) crop_count<<<tiles, TPB, 0, st>>>(d_in, n, d_pose12, d_tile);
-    crop_scan<<<1, 1024, 0, st>>>(d_tile, tiles, d_n_out, cap);
+    crop_scan<<<1, 1024, 0, st>>>(d_tile, tiles, d_n_out, cap, d_truncated);
     if (tiles > 0) crop_emit<<<tiles, TPB, 0, st>>>(d_in, n, d_pose12, d_tile, d_out, cap);
     if (launches) *launches += tiles > 0 ? 3 : 1;
+    return fbpr_launch_ok("CropBox (crop_count / crop_scan / crop_emit)");
 }
 
-void fbpr_launch_pose_decompose(const float* d_pose12, FrameMeta* meta, int slot, cudaStream_t st, long long* launches) {
+int fbpr_launch_pose_decompose(const float* d_pose12, FrameMeta* meta, int slot, cudaStream_t st, long long* launches) {
     pose_decompose<<<1, 32, 0, st>>>(d_pose12, meta, slot);
     if (launches) *launches += 1;
+    return fbpr_launch_ok("pose_decompose");
 }
-void fbpr_launch_pose_compose(const FrameMeta* meta, int slot, float* d_pose12, cudaStream_t st, long long* launches) {
+int fbpr_launch_pose_compose(const FrameMeta* meta, int slot, float* d_pose12, cudaStream_t st, long long* launches) {
     pose_compose<<<1, 32, 0, st>>>(meta, slot, d_pose12);
     if (launches) *launches += 1;
+    return fbpr_launch_ok("pose_compose");
 }

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(TPB) proj_scatter(ProjArgs a) {
         if (col < 0 || col >= a.H) continue;
         float rg = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
         if ((double)rg < 1.0) continue;
+        if (!isfinite(rg)) continue;            // the reference refuses non-dense clouds (imageProjection.cpp:250-254); here their NaN / Inf points are dropped
         atomicMin(&pix[p.ring * a.H + col], i);
         firstv = min(firstv, i);
     }
@@ -202,8 +203,8 @@ __global__ void __launch_bounds__(TPB) proj_compact(ProjArgs a) {
 
 }  // namespace
 
-void fbpr_launch_projection(const ProjArgs& a, int count, cudaStream_t st, long long* launches) {
-    if (count <= 0) return;
+int fbpr_launch_projection(const ProjArgs& a, int count, cudaStream_t st, long long* launches) {
+    if (count <= 0) return 0;
     int pb = (a.P + TPB * 4 - 1) / (TPB * 4);
     proj_clear<<<dim3(pb, count), TPB, 0, st>>>(a);
     int rb = (a.rawCap + TPB * 4 - 1) / (TPB * 4);
@@ -211,4 +212,5 @@ void fbpr_launch_projection(const ProjArgs& a, int count, cudaStream_t st, long 
     proj_ring_count<<<dim3(a.N_SCAN, count), TPB, 0, st>>>(a);
     proj_compact<<<dim3(a.N_SCAN, count), TPB, 0, st>>>(a);
     if (launches) *launches += 4;
+    return fbpr_launch_ok("projection (proj_clear / proj_scatter / proj_ring_count / proj_compact)");
 }

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(TPB) vox_minmax(const VoxSeg* segs) {
     unsigned mn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, mx[3] = { 0u, 0u, 0u };
     for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
         float4 p = s.in[i];
+        if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;      // PCL's getMinMax3D skips non-finite points of a non-dense cloud
         unsigned ex = f2ord(p.x), ey = f2ord(p.y), ez = f2ord(p.z);
         mn[0] = min(mn[0], ex); mn[1] = min(mn[1], ey); mn[2] = min(mn[2], ez);
         mx[0] = max(mx[0], ex); mx[1] = max(mx[1], ey); mx[2] = max(mx[2], ez);
@@ -63,6 +64,7 @@ __global__ void vox_setup(const VoxSeg* segs) {
     d.inv_leaf = inv;
     float mn[3], mx[3];
     for (int c = 0; c < 3; c++) { mn[c] = ord2f(s.bbox[c]); mx[c] = ord2f(s.bbox[3 + c]); }
+    if (s.bbox[0] > s.bbox[3]) for (int c = 0; c < 3; c++) mn[c] = mx[c] = 0.f;      // no finite point at all
     long long ex = (long long)((mx[0] - mn[0]) * inv) + 1;
     long long ey = (long long)((mx[1] - mn[1]) * inv) + 1;
     long long ez = (long long)((mx[2] - mn[2]) * inv) + 1;
@@ -241,7 +243,10 @@ __global__ void __launch_bounds__(TPB) vox_runs_count(const VoxSeg* segs) {
 __global__ void __launch_bounds__(1024) vox_runs_scan(const VoxSeg* segs) {
     const VoxSeg& s = segs[blockIdx.x];
     VoxDesc& d = *s.desc;
-    if (d.overflow) { if (threadIdx.x == 0) { d.n_out = d.n; *s.n_out = d.n; } return; }
+    if (d.overflow) {
+        if (threadIdx.x == 0) { d.n_out = d.n; *s.n_out = min(d.n, s.out_cap); if (d.n > s.out_cap && s.truncated) atomicOr(s.truncated, 1); }
+        return;
+    }
     if (d.n <= 0) { if (threadIdx.x == 0) { d.n_out = 0; *s.n_out = 0; } return; }
     const int ntiles = (d.n + TILE - 1) / TILE;
     __shared__ int wsum[32];
@@ -257,7 +262,10 @@ __global__ void __launch_bounds__(1024) vox_runs_scan(const VoxSeg* segs) {
         int v = wsum[l], iv = v;
         for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, iv, o); if (l >= o) iv += u; }
         wsum[l] = iv - v;
-        if (l == 31) { d.n_out = iv; *s.n_out = iv; }
+        if (l == 31) {                                     // d.n_out keeps the true voxel count; the cloud is cut at the output capacity
+            d.n_out = iv; *s.n_out = min(iv, s.out_cap);
+            if (iv > s.out_cap && s.truncated) atomicOr(s.truncated, 1);
+        }
     }
     __syncthreads();
     int run = wsum[w] + incl - sum;
@@ -273,7 +281,7 @@ __global__ void __launch_bounds__(TPB) vox_emit(const VoxSeg* segs) {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int base = tile * TILE;
     if (d.overflow) {             // PCL's "leaf size too small" path: output = input
-        for (int k = 0; k < IPT; k++) { int i = base + k * TPB + threadIdx.x; if (i < d.n) s.out[i] = s.in[i]; }
+        for (int k = 0; k < IPT; k++) { int i = base + k * TPB + threadIdx.x; if (i < d.n && i < s.out_cap) s.out[i] = s.in[i]; }
         continue;
     }
     const unsigned* key = s.key[d.npass & 1]; const unsigned* val = s.val[d.npass & 1];
@@ -300,8 +308,10 @@ __global__ void __launch_bounds__(TPB) vox_emit(const VoxSeg* segs) {
             sx += p.x; sy += p.y; sz += p.z; si += p.w; c++;
         }
         float fc = (float)c;
-        s.out[slot] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
-        if (s.out_keys) s.out_keys[slot] = (int)kk;
+        if (slot < s.out_cap) {
+            s.out[slot] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
+            if (s.out_keys) s.out_keys[slot] = (int)kk;
+        }
         slot++;
     }
     __syncthreads();                                      // ws is reused by the next tile
@@ -311,8 +321,8 @@ __global__ void __launch_bounds__(TPB) vox_emit(const VoxSeg* segs) {
 }  // namespace
 
 // Enqueue the VoxelGrid of `nsegs` segments (device descriptor array) whose sizes are all <= max_n.
-void fbpr_launch_voxel(const VoxSeg* d_segs, int nsegs, int max_n, int tiles_cap, cudaStream_t st, long long* launches) {
-    if (nsegs <= 0) return;
+int fbpr_launch_voxel(const VoxSeg* d_segs, int nsegs, int max_n, int tiles_cap, cudaStream_t st, long long* launches) {
+    if (nsegs <= 0) return 0;
     int tiles = (max_n + TILE - 1) / TILE; if (tiles < 1) tiles = 1;
     // the capacity is a worst case (every pixel a surface point): a few CTAs per segment walk the tiles that exist instead of a
     // launch that is mostly CTAs with nothing to do; small batches get more CTAs per segment
@@ -331,6 +341,7 @@ void fbpr_launch_voxel(const VoxSeg* d_segs, int nsegs, int max_n, int tiles_cap
     vox_runs_scan<<<nsegs, 1024, 0, st>>>(d_segs);
     vox_emit<<<g, TPB, 0, st>>>(d_segs);
     if (launches) *launches += 19;
+    return fbpr_launch_ok("VoxelGrid (vox_* / rs_*)");
 }
 
 int fbpr_voxel_tile() { return TILE; }

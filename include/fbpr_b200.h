@@ -20,6 +20,8 @@
  *   - a handle is not thread-safe (mirrors the reference's std::mutex mtx, mapOptmization.h:133);
  *     distinct handles may be used concurrently on distinct GPUs;
  *   - there is NO CPU fallback: every entry point fails if the CUDA device is unusable.
+ *   - clouds must be dense (finite coordinates): the reference refuses non-dense sweeps (imageProjection.cpp:250-254);
+ *     here a NaN / Inf raw point is dropped by the projection and a non-finite map point is never a neighbour;
  * Points are XYZI float4 (x, y, z, intensity), 16 bytes, the GPU layout of pcl::PointXYZI
  * (utility.h:55).  Poses are float[6] = (roll, pitch, yaw, x, y, z) = transformTobeMapped
  * (mapOptmization.h:131) unless stated otherwise.
@@ -44,7 +46,9 @@ enum {
     FBPR_FLAG_NOT_ENOUGH_FEATURES      = 1u,  /* :1410 gate failed; pose unchanged; transformUpdate skipped (:1439-1441) */
     FBPR_FLAG_TOO_FEW_CORRESPONDENCES  = 2u,  /* an iteration had < 50 rows (:1267-1270)                               */
     FBPR_FLAG_DEGENERATE               = 4u,  /* isDegenerate set at iteration 0 (:1346-1371)                          */
-    FBPR_FLAG_CONVERGED                = 8u   /* LMOptimization returned true before iteration 30 (:1397-1399)         */
+    FBPR_FLAG_CONVERGED                = 8u,  /* LMOptimization returned true before iteration 30 (:1397-1399)         */
+    FBPR_FLAG_MAP_TRUNCATED            = 16u  /* no reference counterpart: the slot's local map (CropBox :284-304 or extractCloud :948-954) had more points than
+                                                 max_map_corner / max_map_surf and was cut there -- the reference keeps them all, so the pose may differ  */
 };
 
 /* The knobs the path reads: include/utility.h:164-198, values of config/params.yaml:19-67. */
@@ -276,6 +280,13 @@ FBPR_API int fbpr_knn5(fbpr_handle* h, const float* map_xyzi, int n_map, float c
 /* first search-cube radius (grid cells) fbpr_knn5 starts from (default 1).  Results do not depend on it; the LM
    kernel derives the radius per point from the previous iteration, and the knob lets tests pin several starts. */
 FBPR_API int fbpr_knn5_first_radius(fbpr_handle* h, int cells);
+
+/* test hook: runs the DEVICE small-matrix routines of the LM kernel on n caller-supplied problems (host buffers), one thread each,
+   so that the tests can compare them directly with OpenCV's own results (cv::eigen mapOptmization.h:1060 / :1353,
+   cv::solve(DECOMP_QR) :1343, cv::Mat::inv :1370) and with Eigen's colPivHouseholderQr (:1169).  Row widths (floats) in / out:
+   JACOBI3 9 / 12 (W, V rows), JACOBI6 36 / 42, QR6 42 (A then b) / 6, LU6 36 / 36, PLANE5X3 15 / 3, NOT_DEGENERATE 36 / 1. */
+enum { FBPR_SELFTEST_JACOBI3 = 0, FBPR_SELFTEST_JACOBI6, FBPR_SELFTEST_QR6, FBPR_SELFTEST_LU6, FBPR_SELFTEST_PLANE5X3, FBPR_SELFTEST_NOT_DEGENERATE };
+FBPR_API int fbpr_selftest_smallmat(fbpr_handle* h, int which, const float* in, int n, float* out);
 
 #ifdef __cplusplus
 }

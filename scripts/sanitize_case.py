@@ -1,0 +1,59 @@
+"""Small end-to-end case for compute-sanitizer (one tool per gpurun call, B200_PROFILING.md):
+   compute-sanitizer --tool memcheck|racecheck|synccheck|initcheck python scripts/sanitize_case.py
+Runs every kernel of the path on shrunken BASELINE config-1/3 frames: projection (+deskew), features, VoxelGrid, map index,
+the LM loop in its three launch shapes (cooperative grid, cluster per frame at two cluster sizes), CropBox registration,
+extractCloud, the pipelined batch call, the stand-alone VoxelGrid / k-NN and the wire-format repacks."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import feature_base_pointcloud_registration_b200 as fb  # noqa: E402
+import synth  # noqa: E402
+
+small = (16, 450, 1500, 9000)
+frames = [synth.make_frame(3, 40 + i, small=small) for i in range(3)]
+P = frames[0]["params"]
+raws = [fb.api.pack_raw(fr["scan"]) for fr in frames]
+
+
+def inputs(reg):
+    return reg.make_frame_inputs([dict(raw_ptr=raw.ctypes.data, n_raw=len(raw), imu=fr["imu"], imu_available=fr["imu_available"],
+                                       map_corner_ptr=fr["map_corner"].ctypes.data, n_map_corner=len(fr["map_corner"]),
+                                       map_surf_ptr=fr["map_surf"].ctypes.data, n_map_surf=len(fr["map_surf"]), pose=fr["guess"])
+                                  for fr, raw in zip(frames, raws)])
+
+
+out = []
+for cluster, mode in ((0, 0), (2, 1), (4, 0)):
+    r = fb.Registration(P, max_frames=3, max_map_corner=2048, max_map_surf=16384, max_keyframe_points=8192,
+                        lm_cluster_size=cluster, lm_single_frame_mode=mode)
+    fin = inputs(r)
+    r.set_frames(0, fin)
+    r.set_debug_iteration(1)
+    r.run_frames(0, 3)                       # batched: one cluster per frame
+    res = r.get_results(0, 3)
+    r.set_debug_iteration(-1)
+    r.set_poses(0, np.stack([fr["guess"] for fr in frames]))
+    r.run_frames(0, 1)                       # single frame: cooperative grid (mode 0) or one cluster (mode 1)
+    one = r.get_results(0, 1)
+    assert np.array_equal(one["pose"][0], res["pose"][0]), (one, res[0])
+    got = r.register_frames(0, fin, 2)       # pipelined uploads, chunks of 2 + 1
+    assert np.array_equal(got["iters"], res["iters"])
+    out.append(res)
+    if cluster == 0:
+        fr = frames[0]
+        T0 = np.eye(4, dtype=np.float32)[:3].copy(); T0[:, 3] = fr["guess"][3:]
+        r.registration(0, fr["map_corner"], fr["map_surf"], T0)
+        poses = np.zeros((2, 6), np.float32)
+        r.extractSurroundingKeyFrames(1, poses, [fr["map_corner"][:700], fr["map_corner"][700:1400]], [fr["map_surf"][:3000], fr["map_surf"][3000:7000]], poses[0, 3:])
+        r.voxel_grid(fr["map_surf"], 0.4)
+        r.knn5(fr["map_surf"], fr["map_surf"][:500, :3] + 0.05, cell=0.33, first_radius=1)
+        wide = lambda a: np.concatenate([a[:, :3], np.ones((len(a), 1), np.float32), a[:, 3:4], np.zeros((len(a), 3), np.float32)], 1).astype(np.float32)
+        r.set_clouds_xyzi32(0, 1, wide(fr["map_corner"]), wide(fr["map_surf"]))
+        r.get_buffer_xyzi32(0, "MAP_SURF")
+        r.selftest_smallmat("JACOBI6", np.eye(6, dtype=np.float32).reshape(1, 36) * 200)
+    r.close()
+assert np.array_equal(out[0]["iters"], out[1]["iters"]) and np.array_equal(out[0]["iters"], out[2]["iters"])
+print("sanitize_case ok:", out[0]["iters"], out[0]["flags"])
