@@ -1,18 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- scan-to-map registration throughput / latency on B200 (BASELINE.json metric).
 
-A "step" = one pass of the whole hot path (projection+deskew -> smoothness/features -> VoxelGrid ->
-map index -> all LM iterations -> transformUpdate) over one batch of F independent synthetic
-64-beam frames per GPU, each against its own 200 k-point local map (BASELINE configs[3], i.e.
-config 3's frame geometry; F = 128 per GPU so that 8 GPUs process config 4's 1024 frames).
+A "step" = one pass of the whole hot path (projection+deskew -> smoothness/features -> VoxelGrid -> map index -> all LM
+iterations -> transformUpdate) over BASELINE configs[3]: 1024 independent synthetic 64-beam frames (config 3's frame
+geometry, 64 x 2048), each against its OWN 200 k-point local map, partitioned over the ranks in contiguous blocks
+(sharding.frame_range) and processed in batches of 128 frames per launch -- STRONG scaling: the 1024 frames of a step
+are fixed, N GPUs take 1024 / N each.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames-per-gpu F]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames-total 1024] [--batch 128]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
   python bench.py --impl reference ...      # the reference's CPU path (oracle restatement) on the host cores
 
-Prints ONE JSON line (rank 0).  `value` = frames/s over all ranks with inputs resident in HBM;
-`e2e` = the same through the C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region;
-`latency_ms_per_frame` = one frame at a time on one GPU (the north-star "< 1 ms / frame").
+Prints ONE JSON line (rank 0).  `value` = frames/s over all ranks with inputs resident in HBM (CUDA events, max over
+ranks); `e2e` = the same through the C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region;
+`latency_ms_per_frame` = one frame at a time on one GPU (the north-star "< 1 ms / frame"); `configs` = ms/frame of the
+other BASELINE configs; `cpu_baseline` = the CPU restatement of the reference on this box's host cores.
 """
 import argparse
 import json
@@ -29,6 +31,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ms/frame scan-to-map (64-beam synthetic); frames/sec/box at 1/2/4/8 GPUs"   # BASELINE.json; `value` is the frames/sec/box half
 CONFIG = 4   # synth config id: HDL-64E-like 64x2048 scan, own 200k map per frame
+WORKLOAD = ("configs[3]: 1024 independent synthetic HDL-64E-like 64x2048 frames (configs[2] geometry), each vs its own 200k-pt corner/surf "
+            "local map, sharded over the GPUs; projection+deskew, features, VoxelGrid, map index, <=30 LM iterations, transformUpdate")
 
 
 def parse():
@@ -37,13 +41,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-gpu", type=int, default=128)
+    ap.add_argument("--frames-total", type=int, default=1024, help="frames of one step over ALL ranks (BASELINE configs[3])")
+    ap.add_argument("--batch", type=int, default=128, help="frames per launch batch on one GPU")
     ap.add_argument("--ref-frames", type=int, default=6, help="frames per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cluster", type=int, default=0, help="lm_cluster_size override")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config ms/frame section")
+    ap.add_argument("--cpu-frames", type=int, default=100, help="frames timed per thread count by the cpu_baseline leg")
     ap.add_argument("--latency-frames", type=int, default=64)
     ap.add_argument("--e2e-chunk", type=int, default=0, help="frames per upload chunk of the pipelined e2e call (0 = 32)")
     return ap.parse_args()
+
+
+def config_dict(args):
+    """identical in both arms, so the driver compares like with like"""
+    return {"workload": WORKLOAD, "frames_total": args.frames_total, "batch": args.batch,
+            "l2": "inputs larger than L2: 6.4 MB of scan + map per frame, 814 MB per 128-frame batch, every step streams them from HBM"}
 
 
 # ------------------------------------------------------------------------------------------ helpers
@@ -112,7 +125,8 @@ def algorithmic_bytes(counts, iters):
 
 
 def oracle_frame(oracle, fr, threads):
-    """The reference's CPU path for one frame (projection -> features -> downsample -> scan2map)."""
+    """The reference's CPU path for one frame (projection -> features -> downsample -> scan2map).  Returns the result and the
+    seconds of the span the reference's own TicToc wraps (mapOptmization.h:315-318: kd-tree builds + LM loop + transformUpdate)."""
     P = dict(fr["params"]); P["numberOfCores"] = threads
     ci = oracle.project(P, fr["scan"], fr["imu"], fr["imu_available"])
     fe = oracle.extract_features(P, ci)
@@ -120,7 +134,7 @@ def oracle_frame(oracle, fr, threads):
     mo.set_imu(fr["imu_available"], 0.0, 0.0)
     mo.set_scan(fe["corner"], fe["surface"]); mo.set_map(fr["map_corner"], fr["map_surf"]); mo.downsample()
     pose, iters, flags, secs = mo.scan2map(fr["guess"])
-    return pose, iters, flags
+    return pose, iters, flags, float(secs[0] + secs[1])
 
 
 def cpu_model():
@@ -131,6 +145,22 @@ def cpu_model():
     except Exception:
         pass
     return "unknown"
+
+
+def _make_frame(idx):
+    import synth
+    return synth.make_frame(CONFIG, idx)
+
+
+def make_frames(lo, hi):
+    """frames [lo, hi) of the synthetic workload; generated by a few worker processes (0.05 s per frame each)"""
+    idx = list(range(lo, hi))
+    workers = min(8, os.cpu_count() or 1, max(1, len(idx) // 16))
+    if workers <= 1:
+        return [_make_frame(i) for i in idx]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(_make_frame, idx, chunksize=8)
 
 
 def bind_to_gpu_numa_node(torch, local_rank):
@@ -160,6 +190,9 @@ def bind_to_gpu_numa_node(torch, local_rank):
 
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank):
+    """The reference's CPU implementation of the path (the C++ restatement in oracle/: the reference itself needs ROS / PCL /
+    OpenCV / GTSAM and cannot be built here) with ALL host threads (OpenMP numberOfCores = nproc; the reference's own
+    params.yaml says 4 -- cpu_baseline of the B200 arm reports both), each step a bounded sample of the workload."""
     if rank != 0:
         return
     import oracle          # bench.py's reference / cpu_baseline legs are the only product-side users of oracle/
@@ -176,16 +209,168 @@ def run_reference(args, rank):
     nfr = args.steps * len(frames)
     val = nfr / dt
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "configs[3]/[2]: synthetic HDL-64E-like 64x2048 frames, each vs its own 200k-pt corner/surf local map, "
-                                  "projection+deskew, features, VoxelGrid, <=30 LM iterations", "frames_per_step": len(frames)},
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args),
            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port",
-                            "sample": f"{len(frames)} frames/step x {args.steps} steps, C++ restatement of the reference (oracle/), "
-                                      f"OpenMP numberOfCores={threads}, {cpu_model()}"},
+                            "sample": f"{len(frames)} of the workload's frames per step x {args.steps} steps, whole path, C++ restatement of the "
+                                      f"reference (oracle/), OpenMP numberOfCores={threads} (all host threads), {cpu_model()}"},
            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "ms_per_frame": 1e3 / val, "gpu_launches": 0}
     print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm: side measurements
+def measure_latency(torch, reg, stream, frames, nlat):
+    """single-frame latency (one frame at a time, CUDA-graph replay; distinct (scan, map) pairs rotate, so every map starts L2-cold)"""
+    reg.use_graphs(True)
+    times, times_s2m = [], []
+    for rep in range(3):
+        for s in range(nlat):
+            reg.set_pose(s, frames[s]["guess"])
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            reg.sync()
+            a.record(stream)
+            reg.run_frames(s, 1)
+            b.record(stream)
+            reg.sync()
+            if rep > 0:
+                times.append(a.elapsed_time(b))
+    # the span the reference's own TicToc wraps (mapOptmization.h:315-318): scan2MapOptimization alone
+    for rep in range(2):
+        for s in range(nlat):
+            reg.set_pose(s, frames[s]["guess"])
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            reg.sync()
+            a.record(stream)
+            reg.scan2MapOptimization(s, 1)
+            b.record(stream)
+            reg.sync()
+            times_s2m.append(a.elapsed_time(b))
+    reg.use_graphs(False)
+    return dict(median=float(np.median(times)), p95=float(np.percentile(times, 95)), frames=nlat, samples=len(times),
+                scan2map_only=dict(median=float(np.median(times_s2m)), p95=float(np.percentile(times_s2m, 95)), samples=len(times_s2m)),
+                note="one frame at a time, CUDA-graph replay, device-resident inputs, distinct (scan,map) pairs rotate so each map starts L2-cold; "
+                     "whole path = projection -> features -> VoxelGrid -> map index -> LM; scan2map_only = map index + LM + transformUpdate "
+                     "(the span of the reference's TicToc, mapOptmization.h:315-318)")
+
+
+def measure_host_latency(fb, frames, local_rank, n=24):
+    """host-to-host latency of ONE frame the way cloudHandler drives the reference (imageProjection.cpp:182-226): raw sweep in
+    host memory -> featureExtra -> registration() against a RESIDENT global map (CropBox on the device) -> pose on the host.
+    Wall clock around the blocking calls; the frame's own 200 k map stands in for the global map."""
+    import oracle
+    fr0 = frames[0]
+    reg = fb.Registration(fr0["params"], device=local_rank, max_frames=1, max_map_corner=len(fr0["map_corner"]) + 64, max_map_surf=len(fr0["map_surf"]) + 64)
+    reg.set_global_map(fr0["map_corner"], fr0["map_surf"])
+    gt0 = fr0["gt"]
+    times, res = [], []
+    raws = [fb.api.pack_raw(fr0["scan"])]
+    g = fr0["guess"].astype(np.float32)
+    cr, sr, cp, sp, cy, sy = (np.float32(f(g[k])) for k in range(3) for f in (np.cos, np.sin))
+    T0 = np.array([[cy * cp, cy * sp * sr - sy * cr, sy * sr + cy * sp * cr, g[3]],
+                   [sy * cp, cy * cr + sy * sp * sr, sy * sp * cr - cy * sr, g[4]],
+                   [-sp, cp * sr, cp * cr, g[5]]], np.float32)                      # pcl::getTransformation (SURVEY Appendix B-4)
+    for i in range(n + 4):
+        raw = raws[0]
+        t0 = time.perf_counter()
+        reg.set_raw_scan(0, raw, imu=fr0["imu"], imu_available=fr0["imu_available"])
+        reg.project(0, 1); reg.featureExtra(0, 1)
+        T = reg.registration(0, None, None, T0)
+        dt = (time.perf_counter() - t0) * 1e3
+        if i >= 4:
+            times.append(dt)
+        res.append(T)
+    pose, iters, flags = reg.get_pose(0)
+    reg.close()
+    # the CPU restatement of the same call sequence (cloudHandler -> featureExtra -> registration), all host threads
+    P = dict(fr0["params"]); P["numberOfCores"] = os.cpu_count() or 1
+    cpu = []
+    for i in range(4):
+        t0 = time.perf_counter()
+        ci = oracle.project(P, fr0["scan"], fr0["imu"], fr0["imu_available"])
+        fe = oracle.extract_features(P, ci)
+        mo = oracle.MapOptimization(P); mo.set_imu(fr0["imu_available"], 0.0, 0.0)
+        mo.set_scan(fe["corner"], fe["surface"])
+        Tw, iw, fw = mo.registration(fr0["map_corner"], fr0["map_surf"], T0)
+        if i >= 1:
+            cpu.append((time.perf_counter() - t0) * 1e3)
+    ok = bool(iw == iters and np.abs(np.asarray(Tw) - res[-1]).max() <= 1e-4)
+    return dict(median=float(np.median(times)), p95=float(np.percentile(times, 95)), samples=len(times),
+                cpu_oracle_ms=float(np.median(cpu)), cpu_threads=P["numberOfCores"], parity_ok=ok, iters=int(iters),
+                pose_err_vs_gt_m=float(np.abs(pose[3:] - gt0[3:]).max()),
+                api="fbpr_set_raw_scan (pageable host memory) + fbpr_project + fbpr_feature_extract + fbpr_registration with a resident global map; "
+                    "host wall clock, H2D of the 3.1 MB sweep and D2H of the pose included")
+
+
+def measure_configs(torch, fb, local_rank):
+    """ms/frame of the other BASELINE configs (single frame, device-resident inputs, CUDA-graph replay, 4 distinct frames)."""
+    import synth
+    out = {}
+    for cfg_id, label in ((1, "configs[0] VLP-16 16x1800 vs 50k map"), (2, "configs[1] HDL-32E 32x1800 vs 200k map"),
+                          (3, "configs[2] HDL-64E-like 64x2048 vs 200k map, deskewed projection"), (5, "configs[4] OS1-128-like 128x2048 vs 2M map, 0.2 m leaf")):
+        nfr = 2 if cfg_id == 5 else 4
+        frames = [synth.make_frame(cfg_id, 50 + i) for i in range(nfr)]
+        c = synth.CONFIGS[cfg_id]
+        reg = fb.Registration(frames[0]["params"], device=local_rank, max_frames=nfr, max_map_corner=c["map_corner"] + 64, max_map_surf=c["map_surf"] + 64)
+        stream = torch.cuda.ExternalStream(reg.stream(), device=torch.device("cuda", local_rank))
+        for s, fr in enumerate(frames):
+            reg.set_raw_scan(s, fb.api.pack_raw(fr["scan"]), imu=fr["imu"], imu_available=fr["imu_available"])
+            reg.set_local_map(s, fr["map_corner"], fr["map_surf"])
+        reg.use_graphs(True)
+        whole, s2m = [], []
+        for rep in range(6):
+            for s, fr in enumerate(frames):
+                for span, sink in (("whole", whole), ("s2m", s2m)):
+                    reg.set_pose(s, fr["guess"])
+                    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                    reg.sync()
+                    a.record(stream)
+                    if span == "whole":
+                        reg.run_frames(s, 1)
+                    else:
+                        reg.scan2MapOptimization(s, 1)
+                    b.record(stream)
+                    reg.sync()
+                    if rep > 0:
+                        sink.append(a.elapsed_time(b))
+        res = reg.get_results(0, nfr)
+        cnt = reg.get_counts(0)
+        out[str(cfg_id)] = dict(label=label, ms_per_frame=float(np.median(whole)), p95=float(np.percentile(whole, 95)),
+                                scan2map_only_ms=float(np.median(s2m)), iters=[int(v) for v in res["iters"]], converged=int(np.sum((res["flags"] & 8) != 0)),
+                                n_corner_ds=cnt["n_corner_ds"], n_surf_ds=cnt["n_surf_ds"], samples=len(whole))
+        reg.close()
+    return out
+
+
+def measure_cpu_baseline(args, frames, res):
+    """BASELINE.md section 2 protocol: the CPU restatement on this box's host cores, >= 10 warm-ups, median and p95 over
+    args.cpu_frames frame timings, both spans, at numberOfCores = 4 (the reference's params.yaml) and at nproc."""
+    import oracle      # cpu_baseline leg: the oracle is only the thing timed here, never part of the GPU path
+    nproc = os.cpu_count() or 1
+    n = min(len(frames), args.cpu_frames)
+    by = {}
+    ok = 0
+    for th in sorted({4, nproc}):
+        for i in range(10):
+            oracle_frame(oracle, frames[i % len(frames)], th)
+        whole, s2m = [], []
+        t_all = time.perf_counter()
+        for i in range(n):
+            t0 = time.perf_counter()
+            pw, iw, fw, span = oracle_frame(oracle, frames[i], th)
+            whole.append((time.perf_counter() - t0) * 1e3); s2m.append(span * 1e3)
+            if th == nproc and iw == int(res[i]["iters"]) and np.max(np.abs(pw - res[i]["pose"])) <= 1e-4:
+                ok += 1
+        dt = time.perf_counter() - t_all
+        by[str(th)] = dict(frames_per_s=n / dt, whole_path_ms=dict(median=float(np.median(whole)), p95=float(np.percentile(whole, 95))),
+                           scan2map_ms=dict(median=float(np.median(s2m)), p95=float(np.percentile(s2m, 95))), frames=n, warmups=10)
+    best = max(by, key=lambda k: by[k]["frames_per_s"])
+    return dict(value=by[best]["frames_per_s"], unit="frames/s", cores=int(best), kind="port",
+                sample=f"{n} of the benchmarked frames after 10 warm-ups, whole path per frame, C++ restatement of the reference (oracle/), "
+                       f"OpenMP numberOfCores = 4 (reference params.yaml:60) and {nproc} (all host threads; the --impl reference arm uses this one), {cpu_model()}",
+                by_threads=by, parity_frames_ok=f"{ok}/{n}",
+                note="scan2map_ms = kd-tree builds + LM loop + transformUpdate, the span the reference's TicToc wraps (mapOptmization.h:315-318); "
+                     "a restatement without PCL/FLANN/OpenCV/Eigen: indicative of, not identical to, the real reference")
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
@@ -193,27 +378,32 @@ def run_b200(args, rank, world, local_rank):
     import torch
     import synth
     import feature_base_pointcloud_registration_b200 as fb
+    from feature_base_pointcloud_registration_b200 import sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU path)")
+    lo, hi = sharding.frame_range(rank, world, args.frames_total)      # this rank's contiguous block of the step's frames
+    frames = make_frames(lo, hi)                         # worker processes: before CUDA / NCCL are initialised in this one
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_numa_node(torch, local_rank)      # before any pinned allocation: host buffers land next to this GPU's PCIe root
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    F = args.frames_per_gpu
+    F = hi - lo
+    B = min(args.batch, F)
+    nb = (F + B - 1) // B
+    batches = [(b * B, min(F, (b + 1) * B)) for b in range(nb)]
     cfg = synth.CONFIGS[CONFIG]
     params = synth.params_for(CONFIG)
-    frames = [synth.make_frame(CONFIG, rank * F + i) for i in range(F)]
-    extra = dict(max_frames=2 * F, max_map_corner=cfg["map_corner"] + 64, max_map_surf=cfg["map_surf"] + 64)   # 2F slots: e2e double-buffers
+    extra = dict(max_frames=max(F, 2 * B), max_map_corner=cfg["map_corner"] + 64, max_map_surf=cfg["map_surf"] + 64)   # >= 2B slots: e2e double-buffers
     if args.cluster:
         extra["lm_cluster_size"] = args.cluster
     reg = fb.Registration(params, device=local_rank, **extra)
     stream = torch.cuda.ExternalStream(reg.stream(), device=torch.device("cuda", local_rank))
 
-    # ---- host inputs in pinned memory (what a caller would hand to the C ABI): one pinned arena for the sweeps and one for the
-    # local maps, frames back to back (an ingest ring buffer) -- the library uploads a densely packed group of buffers as one copy
+    # ---- host inputs in pinned memory (what a caller would hand to the C ABI): per batch one pinned arena for the sweeps and one
+    # for the local maps, frames back to back (an ingest ring buffer) -- the library uploads a densely packed group as one copy
     raws = [fb.api.pack_raw(fr["scan"]) for fr in frames]
     pin = []
 
@@ -228,18 +418,20 @@ def run_b200(args, rank, world, local_rank):
             t[off:off + a_.nbytes] = torch.from_numpy(np.ascontiguousarray(a_).view(np.uint8).reshape(-1))
         return [t.data_ptr() + off for off in offs]
 
-    raw_ptrs = arena(raws)
-    map_ptrs = arena([m for fr in frames for m in (fr["map_corner"], fr["map_surf"])])
-    finputs = []
-    h2d = 0
-    for i, (fr, raw) in enumerate(zip(frames, raws)):
-        finputs.append(dict(raw_ptr=raw_ptrs[i], n_raw=len(raw), imu=fr["imu"], imu_available=fr["imu_available"],
-                            map_corner_ptr=map_ptrs[2 * i], n_map_corner=len(fr["map_corner"]),
-                            map_surf_ptr=map_ptrs[2 * i + 1], n_map_surf=len(fr["map_surf"]), pose=fr["guess"]))
-        h2d += raw.nbytes + fr["map_corner"].nbytes + fr["map_surf"].nbytes
-    h2d += F * 128 + (4 * 8 * 512 * F if frames[0]["imu_available"] else 0)     # packed scalars + IMU ramps
+    fins, h2d = [], 0
+    for (b0, b1) in batches:
+        raw_ptrs = arena(raws[b0:b1])
+        map_ptrs = arena([m for fr in frames[b0:b1] for m in (fr["map_corner"], fr["map_surf"])])
+        finputs = []
+        for i in range(b1 - b0):
+            fr, raw = frames[b0 + i], raws[b0 + i]
+            finputs.append(dict(raw_ptr=raw_ptrs[i], n_raw=len(raw), imu=fr["imu"], imu_available=fr["imu_available"],
+                                map_corner_ptr=map_ptrs[2 * i], n_map_corner=len(fr["map_corner"]),
+                                map_surf_ptr=map_ptrs[2 * i + 1], n_map_surf=len(fr["map_surf"]), pose=fr["guess"]))
+            h2d += raw.nbytes + fr["map_corner"].nbytes + fr["map_surf"].nbytes
+        fins.append(reg.make_frame_inputs(finputs))
+    h2d += F * 112 + (4 * 8 * 512 * F if frames[0]["imu_available"] else 0)     # packed scalars + IMU ramps
     d2h = F * 32
-    fin = reg.make_frame_inputs(finputs)
     guesses = torch.from_numpy(np.stack([fr["guess"] for fr in frames])).cuda()
 
     def barrier():
@@ -254,21 +446,21 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- upload once: inputs are resident in HBM for the `value` measurement
-    reg.set_frames(0, fin)
+    # ---- upload once: inputs are resident in HBM for the `value` measurement (frame i of this rank lives in slot i)
+    for (b0, b1), fin in zip(batches, fins):
+        reg.set_frames(b0, fin)
     reg.sync()
 
     def step_resident():
         reg.set_poses_device(0, F, guesses.data_ptr())      # the pose is in/out: restore the guesses (D2D, 24 B/frame)
-        reg.run_frames(0, F)
+        for (b0, b1) in batches:
+            reg.run_frames(b0, b1 - b0)
 
     for _ in range(args.warmup):
         step_resident()
     reg.sync()
     res = reg.get_results(0, F)
     counts = [list(reg.get_counts(s).values()) for s in range(F)]
-    reg.enable_stage_timing(True)
-    reg.get_stage_ms(reset=True)
     launches0 = reg.kernel_launches()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -283,32 +475,41 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = reg.kernel_launches() - launches0
+    value = args.frames_total * args.steps / (ms_total * 1e-3)
+
+    # ---- per-stage device times in a SEPARATE pass (event pairs around every stage serialise the launches a little)
+    reg.enable_stage_timing(True)
+    reg.get_stage_ms(reset=True)
+    for _ in range(max(3, args.steps // 2)):
+        step_resident()
     stage = reg.get_stage_ms(reset=True)
     reg.enable_stage_timing(False)
-    value = world * F * args.steps / (ms_total * 1e-3)
+    stage_steps = max(3, args.steps // 2)
 
     # ---- e2e: host buffers in, host results out, every step
-    # (a) streaming form: fbpr_register_frames_begin / _end, two batches in flight on disjoint slot ranges, so the uploads of
-    #     step k+1 run under the last kernels of step k (every step still uploads all its inputs and downloads its results);
-    # (b) one synchronous fbpr_register_frames call per step, for comparison.
+    # (a) streaming form: fbpr_register_frames_begin / _end per batch, two batches in flight on disjoint slot ranges, so the uploads
+    #     of batch k+1 run under the last kernels of batch k (every step still uploads all its inputs and downloads its results);
+    # (b) one synchronous fbpr_register_frames call per batch, for comparison.
     def run_e2e_stream(nsteps):
-        last = None
-        t = reg.register_frames_begin(0, fin, args.e2e_chunk)
-        for s_ in range(nsteps):
-            tn = reg.register_frames_begin(F * ((s_ + 1) % 2), fin, args.e2e_chunk) if s_ + 1 < nsteps else None
-            last = reg.register_frames_end(t)
+        out = [None] * nb
+        seq = [(s_, b) for s_ in range(nsteps) for b in range(nb)]
+        t = reg.register_frames_begin(0, fins[seq[0][1]], args.e2e_chunk)
+        for k, (s_, b) in enumerate(seq):
+            tn = reg.register_frames_begin(B * ((k + 1) % 2), fins[seq[k + 1][1]], args.e2e_chunk) if k + 1 < len(seq) else None
+            out[b] = reg.register_frames_end(t)
             t = tn
-        return last
+        return np.concatenate(out)
 
     def run_e2e_sync(nsteps):
-        last = None
+        out = [None] * nb
         for _ in range(nsteps):
-            last = reg.register_frames(0, fin, args.e2e_chunk)   # H2D + whole path + D2H + sync
-        return last
+            for b in range(nb):
+                out[b] = reg.register_frames(0, fins[b], args.e2e_chunk)   # H2D + whole path + D2H + sync
+        return np.concatenate(out)
 
     e2e_ms = {}
     for name, fn in (("sync", run_e2e_sync), ("stream", run_e2e_stream)):
-        fn(max(2, args.warmup // 2))
+        fn(1 if nb > 1 else max(2, args.warmup // 2))
         barrier()
         t_host0 = time.perf_counter()
         res_e2e = fn(args.steps)
@@ -316,75 +517,71 @@ def run_b200(args, rank, world, local_rank):
         t_host = (time.perf_counter() - t_host0) * 1e3         # host wall clock around the calls (they block until results are on the host)
         barrier()
         e2e_ms[name] = max_over_ranks(t_host)
-        assert np.array_equal(res_e2e["iters"], res["iters"])
+        assert np.array_equal(res_e2e["iters"], res["iters"]) and np.abs(res_e2e["pose"] - res["pose"]).max() <= 1e-5
     ms_e2e = e2e_ms["stream"]
-    e2e_value = world * F * args.steps / (ms_e2e * 1e-3)
+    e2e_value = args.frames_total * args.steps / (ms_e2e * 1e-3)
 
     # PCIe floor: the same host buffers copied with no compute at all -- all ranks at the same time (they share the host side of
-    # PCIe), several sets back to back, max over ranks
-    dev_scratch = [torch.empty(t_.numel(), dtype=torch.uint8, device="cuda") for t_ in pin]
-    h2d_reps = 5
+    # PCIe), max over ranks
+    dev_scratch = [torch.empty(max(t_.numel() for t_ in pin[k::2]), dtype=torch.uint8, device="cuda") for k in range(2)]
+    h2d_reps = 3
     with torch.cuda.stream(stream):
         for rep in range(2):
             barrier()
             a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
             a.record(stream)
             for _ in range(h2d_reps):
-                for src, dst in zip(pin, dev_scratch):
-                    dst.copy_(src, non_blocking=True)
+                for k, src in enumerate(pin):
+                    dev_scratch[k % 2][: src.numel()].copy_(src, non_blocking=True)
             b.record(stream)
             reg.sync()
             h2d_only_ms = max_over_ranks(a.elapsed_time(b) / h2d_reps)
     del dev_scratch
+    for (b0, b1), fin in list(zip(batches, fins))[:2]:      # the e2e passes left other batches' frames in the first 2B slots
+        reg.set_frames(b0, fin)
+    reg.sync()
 
-    # ---- single-frame latency (rank 0 reports; one frame at a time, CUDA-graph replay)
-    lat = None
-    if rank == 0:
-        nlat = min(F, args.latency_frames)
-        reg.use_graphs(True)
-        times = []
-        for rep in range(3):
-            for s in range(nlat):
-                reg.set_pose(s, frames[s]["guess"])
-                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-                reg.sync()
-                a.record(stream)
-                reg.run_frames(s, 1)
-                b.record(stream)
-                reg.sync()
-                if rep > 0:
-                    times.append(a.elapsed_time(b))
-        # (ii) the span the reference's own TicToc wraps (mapOptmization.h:315-318): scan2MapOptimization alone (map index + all LM
-        #      iterations + transformUpdate); features and downsampled clouds of the slot are already in place from the pass above
-        times_s2m = []
-        for rep in range(2):
-            for s in range(nlat):
-                reg.set_pose(s, frames[s]["guess"])
-                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-                reg.sync()
-                a.record(stream)
-                reg.scan2MapOptimization(s, 1)
-                b.record(stream)
-                reg.sync()
-                times_s2m.append(a.elapsed_time(b))
-        reg.use_graphs(False)
-        lat = dict(median=float(np.median(times)), p95=float(np.percentile(times, 95)), frames=nlat, samples=len(times),
-                   scan2map_only=dict(median=float(np.median(times_s2m)), p95=float(np.percentile(times_s2m, 95)), samples=len(times_s2m)),
-                   note="one frame at a time, CUDA-graph replay, distinct (scan,map) pairs rotate so each map starts L2-cold; "
-                        "whole path = projection -> features -> VoxelGrid -> map index -> LM; scan2map_only = map index + LM + transformUpdate")
-
-    # ---- gather result poses over NCCL (32 B / frame), the only collective of the job
+    # ---- gather the result records of all ranks over NCCL (32 B / frame), the only collective of the job; rank 0 checks them
+    gathered = None
     if dist is not None:
         mine = torch.empty(F * 8, dtype=torch.float32, device="cuda")
         reg.get_results_device(0, F, mine.data_ptr())
         reg.sync()
-        allres = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        dist.gather(mine, allres, dst=0)
+        allres = sharding.gather_results(mine.view(F, 8), dist)
+        if rank == 0:
+            ok = len(allres) == args.frames_total and np.array_equal(allres[:F]["pose"], res["pose"])
+            # frames of the OTHER ranks: rank 0 registers the first frame of every block itself and compares
+            checked = 0
+            for r_ in range(1, world):
+                flo, _ = sharding.frame_range(r_, world, args.frames_total)
+                fr = synth.make_frame(CONFIG, flo)
+                reg.set_raw_scan(0, fb.api.pack_raw(fr["scan"]), imu=fr["imu"], imu_available=fr["imu_available"])
+                reg.set_local_map(0, fr["map_corner"], fr["map_surf"]); reg.set_pose(0, fr["guess"])
+                reg.run_frames(0, 1)
+                p_, i_, f_ = reg.get_pose(0)
+                ok = ok and i_ == int(allres[flo]["iters"]) and f_ == int(allres[flo]["flags"]) and float(np.abs(p_ - allres[flo]["pose"]).max()) <= 1e-4
+                checked += 1
+            gathered = dict(records=int(len(allres)), ok=bool(ok), cross_checked_blocks=checked,
+                            converged=int(np.sum((allres["flags"] & 8) != 0)), mean_iters=float(np.mean(allres["iters"])))
+            reg.set_frames(0, fins[0]); reg.sync()      # slot 0 again holds this rank's first frame
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+
+    # ---- single-frame latency, other configs (rank 0 only)
+    lat = measure_latency(torch, reg, stream, frames, min(F, args.latency_frames))
+    try:
+        lat["e2e_host"] = measure_host_latency(fb, frames, local_rank)
+    except Exception as e:      # a side measurement must not take the headline line down
+        lat["e2e_host"] = {"error": repr(e)}
+    configs = None
+    if not args.no_configs:
+        try:
+            configs = measure_configs(torch, fb, local_rank)
+        except Exception as e:
+            configs = {"error": repr(e)}
 
     # ---- roofline of the dominant kernel (algorithmic bytes / live CUDA-event time)
     peak, peak_src = measured_peak()
@@ -395,71 +592,47 @@ def run_b200(args, rank, world, local_rank):
     stages = {}
     for k in fb.api.STAGES:
         ms, calls = stage[k]
-        per = ms / max(calls, 1)
-        stages[k] = dict(ms_per_step=per, alg_bytes_per_step=alg[k], alg_GBps=(alg[k] / (per * 1e-3) / 1e9) if per > 0 else None)
+        per_launch = ms / max(calls, 1)
+        launches_per_step = calls / stage_steps
+        alg_launch = alg[k] / max(launches_per_step, 1)
+        stages[k] = dict(ms_per_launch=per_launch, launches_per_step=launches_per_step, ms_per_step=ms / stage_steps,
+                         alg_bytes_per_launch=alg_launch, alg_GBps=(alg_launch / (per_launch * 1e-3) / 1e9) if per_launch > 0 else None)
     dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
     kernel_names = dict(project="proj_scatter+proj_compact", features="feat_ring", downsample="rs_scatter (radix-sort VoxelGrid)",
                         map_index="grid_count+grid_scatter", lm="lm_kernel")
     ach = stages[dom]["alg_GBps"] or 0.0
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r01_traffic.json), scaled per frame
     traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    try:       # DRAM traffic of the dominant kernel from the committed ncu --set full capture, per launch of args.batch frames
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if tj.get("kernel") == kernel_names[dom]:
-            traffic = float(tj["dram_bytes_per_frame"]) * F
+            traffic = float(tj["dram_bytes_per_frame"]) * B
     except Exception:
         pass
     roofline = dict(bound="hbm", kernel=kernel_names[dom], stage=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
                     traffic=traffic, peak_source=peak_src,
-                    note="achieved = SURVEY 8(d) algorithmic bytes of this stage for the F frames of one step / its CUDA-event time; "
-                         "the LM loop is latency/L2-gather bound by design (<=30 dependent iterations), see DESIGN.md; "
-                         "traffic = dram read+write bytes of one launch from profiles/ (ncu --set full at the same batch size)")
+                    note="achieved = SURVEY 8(d) algorithmic bytes of this stage for the frames of ONE launch (one batch) / its CUDA-event time "
+                         "(separate timing pass); traffic = dram read+write bytes of one launch from profiles/ (ncu --set full at the same batch "
+                         "size); the path is instruction-issue / latency bound by design (K=3 and 6x6 contractions, <=30 dependent iterations)")
     whole = sum(alg.values())
-    frame_GBps = whole / (ms_total / args.steps * 1e-3) / 1e9
+    frame_GBps = whole / (ms_total / args.steps * 1e-3) / 1e9 * (args.frames_total / F)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        import oracle      # cpu_baseline leg: the oracle is only the thing timed here, never part of the GPU path
-        nb = min(F, 6)
-        oracle_frame(oracle, frames[0], 4)
-        best = None
-        by_threads = {}
-        for th in sorted({4, os.cpu_count() or 1}):
-            t0 = time.perf_counter()
-            for fr in frames[:nb]:
-                pw, iw, fw = oracle_frame(oracle, fr, th)
-            dt = time.perf_counter() - t0
-            v = nb / dt
-            by_threads[str(th)] = v
-            if best is None or v > best[0]:
-                best = (v, th)
-        # parity spot-check of the benchmarked frames against the CPU path
-        ok = 0
-        for s in range(nb):
-            pw, iw, fw = oracle_frame(oracle, frames[s], os.cpu_count() or 1)
-            if iw == int(res[s]["iters"]) and np.max(np.abs(pw - res[s]["pose"])) <= 1e-4:
-                ok += 1
-        cpu = dict(value=best[0], unit="frames/s", cores=best[1], kind="port",
-                   sample=f"{nb} of the benchmarked frames, whole path, C++ restatement of the reference (oracle/), OpenMP on {best[1]} threads "
-                          f"(numberOfCores=4 also tried), {cpu_model()}",
-                   frames_per_s_by_threads=by_threads, parity_frames_ok=f"{ok}/{nb}")
+        cpu = measure_cpu_baseline(args, frames, res)
 
     out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "configs[3]/[2]: synthetic HDL-64E-like 64x2048 frames, each vs its own 200k-pt corner/surf local map, "
-                                  "projection+deskew, features, VoxelGrid, <=30 LM iterations",
-                      "frames_per_gpu": F, "frames_per_step": world * F, "lm_cluster_size": reg.params.lm_cluster_size or "auto",
-                      "l2": "inputs larger than L2: %.0f MB of scans+maps per GPU per step" % (h2d / 1e6)},
-           "ms_per_frame": ms_total / args.steps / F,
+           "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": config_dict(args),
+           "frames_per_gpu": F, "batches_per_gpu": nb, "lm_cluster_size": reg.params.lm_cluster_size or "auto",
+           "ms_per_frame": ms_total / args.steps / args.frames_total,
            "latency_ms_per_frame": lat,
-           "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": ms_e2e / args.steps, "api": "fbpr_register_frames_begin/_end, 2 batches in flight (double-buffered slots)",
+           "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+                   "ms_per_step": ms_e2e / args.steps, "api": "fbpr_register_frames_begin/_end per batch, 2 batches in flight (double-buffered slots)",
                    "chunk_frames": args.e2e_chunk or 32, "timer": "host wall clock around the blocking calls, max over ranks",
-                   "sync_call": {"value": world * F * args.steps / (e2e_ms["sync"] * 1e-3), "ms_per_step": e2e_ms["sync"] / args.steps,
-                                 "api": "fbpr_register_frames (one blocking call per step)"},
-                   "h2d_only_ms_per_step": h2d_only_ms,
-                   "host_buffers": "two pinned arenas (sweeps, maps), frames back to back; dense groups cross PCIe as one copy per chunk",
+                   "sync_call": {"value": args.frames_total * args.steps / (e2e_ms["sync"] * 1e-3), "ms_per_step": e2e_ms["sync"] / args.steps,
+                                 "api": "fbpr_register_frames (one blocking call per batch)"},
+                   "h2d_only_ms_per_step": h2d_only_ms, "h2d_bytes_per_gpu_per_step": int(h2d),
+                   "host_buffers": "per batch two pinned arenas (sweeps, maps), frames back to back; dense groups cross PCIe as one copy per chunk",
                    "numa": numa},
            "gpu_launches": int(launches),
            "clocks": clocks,
@@ -467,6 +640,8 @@ def run_b200(args, rank, world, local_rank):
            "stages": stages,
            "whole_path_alg_GBps": frame_GBps,
            "iters": {"mean": float(np.mean(res["iters"])), "max": int(np.max(res["iters"])), "converged": int(np.sum((res["flags"] & 8) != 0))},
+           "gathered": gathered,
+           "configs": configs,
            "cpu_baseline": cpu}
     print(json.dumps(out), flush=True)
     if dist is not None:

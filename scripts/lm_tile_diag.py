@@ -1,0 +1,43 @@
+"""F config-4 frames through the whole path: per-stage CUDA-event times and the LM kernel's tile statistics
+(fbpr_lm_tile_stats).   python scripts/lm_tile_diag.py [F] [reps] [cluster]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import feature_base_pointcloud_registration_b200 as fb  # noqa: E402
+import synth  # noqa: E402
+
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+cluster = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+frames = [synth.make_frame(4, i) for i in range(F)]
+cfg = synth.CONFIGS[4]
+r = fb.Registration(frames[0]["params"], max_frames=F, max_map_corner=cfg["map_corner"] + 64, max_map_surf=cfg["map_surf"] + 64, lm_cluster_size=cluster)
+raws = [fb.api.pack_raw(fr["scan"]) for fr in frames]
+fin = r.make_frame_inputs([dict(raw_ptr=raw.ctypes.data, n_raw=len(raw), imu=fr["imu"], imu_available=fr["imu_available"],
+                                map_corner_ptr=fr["map_corner"].ctypes.data, n_map_corner=len(fr["map_corner"]),
+                                map_surf_ptr=fr["map_surf"].ctypes.data, n_map_surf=len(fr["map_surf"]), pose=fr["guess"]) for fr, raw in zip(frames, raws)])
+guesses = np.stack([fr["guess"] for fr in frames])
+r.set_frames(0, fin)
+r.run_frames(0, F); r.sync()
+res = r.get_results(0, F)
+print("iters", res["iters"].tolist()[:16], "flags", sorted(set(res["flags"].tolist())))
+r.lm_tile_stats(True)
+r.set_poses(0, guesses); r.run_frames(0, F); r.sync()
+st = r.lm_tile_stats(False)
+c = r.get_counts(0)
+nq = sum(r.get_counts(s)["n_corner_ds"] + r.get_counts(s)["n_surf_ds"] for s in range(F))
+pit = float(sum((r.get_counts(s)["n_corner_ds"] + r.get_counts(s)["n_surf_ds"]) * int(res[s]["iters"]) for s in range(F)))
+print("counts slot0", c)
+print("tile stats", st)
+print("per point-iteration: staged points %.1f, fallback searches %.4f; per tile: points %.0f rows %.0f cell entries %.0f; retries/tile %.2f" % (
+    st["points"] / pit, st["fallback_searches"] / pit, st["points"] / max(st["tiles"], 1), st["rows"] / max(st["tiles"], 1),
+    st["cell_entries"] / max(st["tiles"], 1), st["retries"] / max(st["tiles"], 1)))
+r.enable_stage_timing(True); r.get_stage_ms(reset=True)
+for _ in range(reps):
+    r.set_poses(0, guesses); r.run_frames(0, F)
+r.sync()
+ms = r.get_stage_ms(reset=True)
+print("stage ms per %d frames:" % F, {k: round(v[0] / max(v[1], 1), 3) for k, v in ms.items()})
