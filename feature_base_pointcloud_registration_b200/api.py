@@ -364,11 +364,6 @@ class Registration:
         out = buf[:nb].view(dt).copy()
         return out.reshape(-1, w) if w > 1 else out
 
-    def lm_tile_stats(self, enable=True):
-        out = np.zeros(8, np.uint64)
-        self._ck(self.lib.fbpr_lm_tile_stats(self.h, int(enable), _vp(out)))
-        return dict(zip(["tiles", "points", "retries", "fallback_searches", "rows", "cell_entries", "no_tile", "_"], map(int, out)))
-
     def selftest_smallmat(self, which, rows):
         """fbpr_selftest_smallmat: the device small-matrix routines on `rows` ([n, in_width] f32); which = name below."""
         names = ["JACOBI3", "JACOBI6", "QR6", "LU6", "PLANE5X3", "NOT_DEGENERATE"]

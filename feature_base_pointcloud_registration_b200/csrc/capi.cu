@@ -3,6 +3,7 @@
 // handle's stream and returns; nothing here computes on the CPU and nothing falls back.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <utility>
@@ -48,7 +49,7 @@ struct fbpr_handle {
     int *picked = nullptr, *label = nullptr, *ringCorner = nullptr, *cornerStage = nullptr, *ringSurf = nullptr, *ringSurfDS = nullptr, *cornerIndex = nullptr;
     float4 *mapCorner = nullptr, *mapSurf = nullptr;
     float* poseTrace = nullptr;
-    float4* qpts = nullptr; int posBits = 11; unsigned long long* lmStats = nullptr; bool lmStatsOn = false; double* partials = nullptr; double* partialsGrid = nullptr; int lmGridBlocks = 0; bool lmWholeGpu = true;
+    float4* qanchor = nullptr; int* qcache = nullptr; double* partials = nullptr; double* partialsGrid = nullptr; double* chunkPart = nullptr; int chunkCap = 0; int lmGridBlocks = 0; bool lmWholeGpu = true;
     // descriptors
     VoxSeg* d_scanSegs = nullptr;      // [2F]  downsampleCurrentScan
     GridSeg* d_gridSegs = nullptr;     // [2F]  map index
@@ -172,16 +173,11 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     ALLOC(h->corner, (size_t)F * h->cornerCap); ALLOC(h->cornerDS, (size_t)F * h->cornerCap); ALLOC(h->cornerIndex, (size_t)F * h->cornerCap);
     ALLOC(h->mapCorner, (size_t)F * h->mapCornerCap); ALLOC(h->mapSurf, (size_t)F * h->mapSurfCap);
     ALLOC(h->poseTrace, (size_t)F * FBPR_MAX_ITERS * 6);
-    ALLOC(h->qpts, (size_t)F * (h->cornerCap + P));
-    {   // neighbour keys carry (map index << posBits | tile position) in their low word: the larger the map, the smaller the tile
-        const int maxMap = h->mapCornerCap > h->mapSurfCap ? h->mapCornerCap : h->mapSurfCap;
-        int idxBits = 1; while (idxBits < 31 && (1LL << idxBits) < (long long)maxMap) idxBits++;
-        int tileBits = 0; while ((1 << (tileBits + 1)) <= fbpr_lm_tile_points()) tileBits++;
-        h->posBits = 32 - idxBits < tileBits ? 32 - idxBits : tileBits;
-        if (h->posBits < 6) return fbpr_fail_msg("max_map_corner / max_map_surf above 64 M points are not supported");
-    }
+    ALLOC(h->qanchor, (size_t)F * (h->cornerCap + P));
+    ALLOC(h->qcache, (size_t)F * (h->cornerCap + P) * fbpr_knn_cache_slots());
+    h->chunkCap = (h->cornerCap + P) / 32 + 260;
+    ALLOC(h->chunkPart, (size_t)F * h->chunkCap * 28);
     ALLOC(h->partials, (size_t)F * 2 * 16 * 28);
-    ALLOC(h->lmStats, 8);
     h->lmGridBlocks = fbpr_lm_grid_blocks(device);
     if (h->lmGridBlocks > 1024) h->lmGridBlocks = 1024;
     ALLOC(h->partialsGrid, (size_t)F * 2 * (h->lmGridBlocks > 0 ? h->lmGridBlocks : 1) * 28);
@@ -545,15 +541,15 @@ static LmArgs lm_args(fbpr_handle* h, int first) {
     LmArgs a = {};
     a.meta = h->meta; a.cornerDS = h->cornerDS; a.cornerCap = h->cornerCap; a.surfDS = h->surfDS; a.surfCap = h->P;
     a.gsegs = h->d_gridSegs; a.first = first;
-    a.qpts = h->qpts; a.qCap = h->cornerCap + h->P; a.posBits = h->posBits; a.firstRadius = h->p.knn_first_radius > 0 ? h->p.knn_first_radius : 0.3f;
-    a.partials = h->partials; a.teamMax = 16; a.partialsGrid = h->partialsGrid; a.gridMax = h->lmGridBlocks > 0 ? h->lmGridBlocks : 1;
+    a.qanchor = h->qanchor; a.qcache = h->qcache; a.qCap = h->cornerCap + h->P; a.firstRadius = h->p.knn_first_radius > 0 ? h->p.knn_first_radius : 0.3f;
+    a.partials = h->partials; a.teamMax = 16; a.partialsGrid = h->partialsGrid; a.gridMax = h->lmGridBlocks > 0 ? h->lmGridBlocks : 1; a.chunkPart = h->chunkPart; a.chunkCap = h->chunkCap;
     a.edgeMin = h->p.edgeFeatureMinValidNum; a.surfMin = h->p.surfFeatureMinValidNum;
     a.z_tol = h->p.z_tollerance; a.rot_tol = h->p.rotation_tollerance;
     a.debug_iter = h->debugIter; a.dbgSlots = h->dbgSlots;      // captured for the slots of the launch that are < dbgSlots
     a.knnC = h->knnC; a.d2C = h->d2C; a.coeffC = h->coeffC; a.flagC = h->flagC;
     a.knnS = h->knnS; a.d2S = h->d2S; a.coeffS = h->coeffS; a.flagS = h->flagS;
     a.dbgAtA = h->dbgAtA; a.dbgAtB = h->dbgAtB; a.dbgX = h->dbgX; a.poseTrace = h->poseTrace;
-    a.stats = h->lmStatsOn ? h->lmStats : nullptr;
+
     return a;
 }
 
@@ -1005,18 +1001,6 @@ int fbpr_get_stage_ms(fbpr_handle* h, float ms[FBPR_STAGE_COUNT], int32_t calls[
     h->spansUsed = 0;
     for (int s = 0; s < FBPR_STAGE_COUNT; s++) { if (ms) ms[s] = h->stageMs[s]; if (calls) calls[s] = h->stageCalls[s]; }
     if (reset) for (int s = 0; s < FBPR_STAGE_COUNT; s++) { h->stageMs[s] = 0.f; h->stageCalls[s] = 0; }
-    return 0;
-}
-
-int fbpr_lm_tile_stats(fbpr_handle* h, int enable, uint64_t out[8]) {
-    if (!h) return fbpr_fail_msg("null handle");
-    cudaSetDevice(h->device);
-    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
-    if (out) FBPR_CUDA_OK(cudaMemcpy(out, h->lmStats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    FBPR_CUDA_OK(cudaMemset(h->lmStats, 0, 8 * sizeof(uint64_t)));
-    h->lmStatsOn = enable != 0;
-    for (auto& g : h->graphs) cudaGraphExecDestroy(g.second);      // captured launches carry the old argument block
-    h->graphs.clear(); h->graphLaunches.clear();
     return 0;
 }
 

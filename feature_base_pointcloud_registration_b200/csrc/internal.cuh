@@ -130,11 +130,11 @@ struct LmArgs {
     const float4* cornerDS; int cornerCap;
     const float4* surfDS; int surfCap;
     const GridSeg* gsegs;         // [2*slot + kind]
-    float4* qpts; int qCap;       // [slot][qCap] the down-sampled feature points in Morton order (corners, then surface points), w = index in its cloud
-    int posBits;                  // low bits of a neighbour key that hold the tile position; map indices must fit the remaining 32 - posBits
+    float4* qanchor; int* qcache; int qCap;   // [slot][qCap] per feature point: position + bound of its last full search, [..][16] cached map indices
     float firstRadius;            // metres the first iteration's search cube must cover
     double* partials; int teamMax;     // [slot][2][teamMax][28] per-CTA partial sums, double-buffered by iteration parity
     double* partialsGrid; int gridMax; // [slot][2][gridMax][28] same for the whole-GPU single-frame variant
+    double* chunkPart; int chunkCap;   // [slot][chunkCap][28] per-chunk partial sums of the batched variant (chunk = 32 feature points)
     int first;
     int edgeMin, surfMin;
     float z_tol, rot_tol;
@@ -144,7 +144,6 @@ struct LmArgs {
     int* knnS; float* d2S; float4* coeffS; unsigned char* flagS;
     float* dbgAtA; float* dbgAtB; float* dbgX;      // [slot][36], [slot][6], [slot][6]
     float* poseTrace;                               // [slot][30][6]
-    unsigned long long* stats;                      // optional [8] tile statistics: sub-passes, staged points, retries, fallback searches, rows, cell entries, sub-passes without a tile
 };
 
 // ordered-uint encoding of floats for atomicMin/atomicMax
@@ -193,7 +192,7 @@ int fbpr_launch_grid_build(const GridSeg* d_segs, int nsegs, int max_n, int cell
 int fbpr_launch_knn5(const GridSeg* d_seg, const float* d_q, int nq, int* d_idx, float* d_d2, int rad0, cudaStream_t st, long long* launches);
 int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blocks, cudaStream_t st, long long* launches);
 int fbpr_lm_grid_blocks(int device);
-int fbpr_lm_tile_points();
+int fbpr_knn_cache_slots();
 int fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float rot_tol, float z_tol, cudaStream_t st, long long* launches);
 int fbpr_launch_keyframe_transform(const float* d_poses6, int K, const float4* d_in, const int* d_off, float4* d_out, int* d_n_out,
                                    const float* d_last_xyz, float radius, const float* d_check_xyz, int max_pts, int* d_outoff, float* d_T,

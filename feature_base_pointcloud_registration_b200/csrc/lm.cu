@@ -4,28 +4,17 @@
 // cornerOptimization (:1002-1124), surfOptimization (:1126-1215), combineOptimizationCoeffs
 // (:1218-1243), LMOptimization (:1246-1401) and transformUpdate (:1444-1479).
 //
-// B200 mapping.  The team of one frame is a thread-block CLUSTER (batched calls: many frames per
-// launch, one hardware cluster barrier per iteration) or the whole cooperative GRID (one frame on
-// the whole GPU).  Inside an iteration a CTA walks MACRO-CHUNKS of spatially sorted feature
-// points (lm_order below sorts the down-sampled scan along a Morton curve once per frame):
-//   1. every thread transforms its point and finds its map cell; a block reduce gives the box of
-//      cells the chunk's search cubes cover;
-//   2. the cell_start entries of that box are copied to shared memory (they are the row bounds),
-//      a block scan turns the row lengths into tile offsets, and every cell ROW of the box -- one
-//      contiguous run of the cell-sorted map -- is fetched with ONE cp.async.bulk (1-D TMA) that
-//      completes on an mbarrier: the chunk's candidate points now sit in a shared-memory TILE;
-//   3. ONE THREAD PER POINT (G = 1; the single-frame shape uses G = 8 lanes per point) scans the
-//      cells of its own cube out of the tile -- exact 5-NN by (d^2, index) keys in registers, no
-//      dependent global loads, no cross-lane traffic -- and certifies the result against the
-//      cube's inscribed ball exactly like the warp-cooperative search (mapgrid.cuh), which
-//      remains the fallback for the few points whose cube must grow beyond the tile;
-//   4. the five neighbours are read back from the tile, line / plane fit, coefficient, Jacobian
-//      row; rows are folded warp-wise into the 21 + 6 unique entries of J^T J / J^T r in f64.
-// After the team barrier every CTA sums the per-CTA partials in the same order and redundantly
-// solves the 6x6 system, so a frame needs one barrier per iteration and no host round trip.
+// B200 mapping: one thread-block CLUSTER per frame.  Warps own chunks of 32 feature points
+// (transform -> exact 5-NN in the grid index, warp-cooperative -> line / plane fit, coefficient and
+// Jacobian row, one thread per point); rows are staged in shared memory and folded warp-wise into the 21+6 unique entries of J^T J / J^T r
+// in f64; a shared-memory block reduce produces one partial per CTA; after ONE hardware cluster
+// barrier every CTA reads all partials in rank order and redundantly solves the 6x6 system (QR,
+// degeneracy projection at iteration 0, pose update, convergence test), so a frame needs one
+// cluster.sync() per iteration and no grid-wide or host synchronisation at all.
+// Independent frames are independent clusters (blockIdx.x / cluster size); a single frame can
+// instead take the whole GPU as one cooperative grid (grid.sync() per iteration).
 //
-// Bound: instruction issue + shared-memory bandwidth of the tile scans and L2 -> shared-memory
-// bulk copies (about 20 staged map points per feature point and iteration); never tensor cores
+// Bound: latency (<= 30 dependent iterations) and L1/L2 gathers of map cells; never tensor cores
 // (contractions are K=3 and 6x6).  Compulsory traffic per iteration: 16 B per feature point +
 // 5 x 16 B neighbours (B_iter = 96 * (n_c + n_s)).
 #include <cooperative_groups.h>
@@ -39,39 +28,15 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-// Launch shapes.  Batched calls: one cluster per frame, 256-thread CTAs, one thread per feature point (4 CTAs resident per
-// SM at 64 registers and ~53 KB of shared memory each).  Single-frame calls: one 512-thread CTA per SM over the whole GPU,
-// 8 lanes per feature point (a frame has only ~50 points per SM; the lanes split the rows of the point's search cube).
-constexpr int LM_TPB_CLUSTER = 256, LM_CTAS_CLUSTER = 4, LM_G_CLUSTER = 1;
-constexpr int LM_TPB_GRID = 512, LM_CTAS_GRID = 1, LM_G_GRID = 8;
+// Launch shapes.  Batched calls: one cluster per frame, 256-thread CTAs (4 resident per SM at 64 registers).
+// Single-frame calls: one 768-thread CTA per SM over the whole GPU.
+constexpr int LM_TPB_CLUSTER = 256, LM_CTAS_CLUSTER = 4;
+constexpr int LM_TPB_GRID = 768, LM_CTAS_GRID = 1;
+#ifndef LM_CARVEOUT
+#define LM_CARVEOUT 16
+#endif
+constexpr int LM_PART_SLOTS = 64;      // chunks of one CTA whose partial sums have their own shared-memory slot
 constexpr int NACC = 28;          // 21 (upper triangle of A^T A) + 6 (A^T b) + 1 (row count)
-// shared-memory tile of one macro-chunk
-constexpr int LM_TILE_PTS = 2048; // staged map points (the usable count is 2^posBits - 1 <= 2047: the top position marks "not in the tile")
-constexpr int LM_CS_CAP = 4096;   // staged cell_start entries = rows * (cells per row + 1)
-constexpr int LM_ROW_CAP = 768;   // cell rows of the box (3 per thread of the batched shape)
-constexpr size_t LM_DYN_SMEM = (size_t)LM_TILE_PTS * 16 + (size_t)LM_CS_CAP * 4 + (size_t)(LM_ROW_CAP + 8) * 4;
-
-// ---- 1-D bulk async copy (TMA) + mbarrier, sm_90+ PTX ------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");      // make the initialised barrier visible to the async proxy
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned done;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-// global -> this CTA's shared memory, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 __device__ __forceinline__ void transform_point(const float* T, float4 p, float& x, float& y, float& z) {
     x = T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3];
@@ -243,185 +208,18 @@ __device__ __noinline__ int lm_solve_step(const float* AtA, const float* AtB, in
     return ((double)deltaR < 0.05 && (double)deltaT < 0.05) ? 1 : 0;
 }
 
-// ---- lm_order: spatial order of the down-sampled feature points, once per frame ---------------------------------------
-// The association works on macro-chunks of consecutive feature points and stages the map cells around a chunk in shared
-// memory, so consecutive points must be close in space.  laserCloud{Corner,Surf}LastDS come out of the VoxelGrid in voxel-key
-// order (x fastest: long thin strips).  One CTA per window of LM_ORDER_WIN points sorts them along a Morton curve of their
-// position in the map frame (initial guess) with a shared-memory bitonic sort of (morton18 << 13 | index) keys and writes the
-// permuted points with their original index in w.  The ORDER affects only the speed of the association and the association
-// order of the f64 normal-equation sums, never a per-point result.
-constexpr int LM_ORDER_WIN = 8192, LM_ORDER_TPB = 1024;
-
-__device__ __forceinline__ unsigned morton_spread6(unsigned v) {     // abcdef -> a00b00c00d00e00f
-    v &= 63u;
-    v = (v | (v << 8)) & 0x300Fu;
-    v = (v | (v << 4)) & 0x30C3u;
-    v = (v | (v << 2)) & 0x9249u;
-    return v;
-}
-
-__global__ void __launch_bounds__(LM_ORDER_TPB) lm_order(LmArgs a) {
-    const int slot = a.first + blockIdx.z, kind = blockIdx.y, win = blockIdx.x;
-    const FrameMeta& M = a.meta[slot];
-    const int nC = min(M.n_corner_ds, a.cornerCap), nS = min(M.n_surf_ds, a.surfCap);
-    const int n = kind == 0 ? nC : nS;
-    const int base = win * LM_ORDER_WIN;
-    if (base >= n) return;
-    const int cnt = min(LM_ORDER_WIN, n - base);
-    const float4* src = (kind == 0 ? a.cornerDS + (size_t)slot * a.cornerCap : a.surfDS + (size_t)slot * a.surfCap) + base;
-    float4* dst = a.qpts + (size_t)slot * a.qCap + (kind == 0 ? 0 : nC) + base;
-    __shared__ unsigned s_key[LM_ORDER_WIN];
-    __shared__ float s_T[12];
-    __shared__ unsigned s_bb[6];
-    const int tid = threadIdx.x;
-    if (tid == 0) get_transformation(M.pose[3], M.pose[4], M.pose[5], M.pose[0], M.pose[1], M.pose[2], s_T);
-    if (tid < 3) s_bb[tid] = 0xffffffffu; else if (tid < 6) s_bb[tid] = 0u;
-    __syncthreads();
-    constexpr int IPT = LM_ORDER_WIN / LM_ORDER_TPB;
-    float px[IPT], py[IPT], pz[IPT];
-    unsigned mn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, mx[3] = { 0u, 0u, 0u };
-    #pragma unroll
-    for (int k = 0; k < IPT; k++) {
-        const int i = k * LM_ORDER_TPB + tid;
-        px[k] = py[k] = pz[k] = 0.f;
-        if (i < cnt) {
-            const float4 p = src[i];
-            px[k] = s_T[0] * p.x + s_T[1] * p.y + s_T[2] * p.z + s_T[3];
-            py[k] = s_T[4] * p.x + s_T[5] * p.y + s_T[6] * p.z + s_T[7];
-            pz[k] = s_T[8] * p.x + s_T[9] * p.y + s_T[10] * p.z + s_T[11];
-            if (isfinite(px[k]) && isfinite(py[k]) && isfinite(pz[k])) {
-                const unsigned ex = f2ord(px[k]), ey = f2ord(py[k]), ez = f2ord(pz[k]);
-                mn[0] = min(mn[0], ex); mn[1] = min(mn[1], ey); mn[2] = min(mn[2], ez);
-                mx[0] = max(mx[0], ex); mx[1] = max(mx[1], ey); mx[2] = max(mx[2], ez);
-            }
-        }
-    }
-    #pragma unroll
-    for (int c = 0; c < 3; c++) { mn[c] = __reduce_min_sync(0xffffffffu, mn[c]); mx[c] = __reduce_max_sync(0xffffffffu, mx[c]); }
-    if ((tid & 31) == 0) for (int c = 0; c < 3; c++) { atomicMin(&s_bb[c], mn[c]); atomicMax(&s_bb[3 + c], mx[c]); }
-    __syncthreads();
-    int npad = 32; while (npad < cnt) npad <<= 1;
-    {
-        float lo[3] = { 0.f, 0.f, 0.f }, sc[3] = { 0.f, 0.f, 0.f };
-        if (s_bb[0] <= s_bb[3]) {
-            #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                lo[c] = ord2f(s_bb[c]);
-                const float ext = ord2f(s_bb[3 + c]) - lo[c];
-                sc[c] = ext > 0.f ? 63.999f / ext : 0.f;
-            }
-            // one scale for all axes (cubic Morton cells): the largest extent decides
-            const float smin = fminf(sc[0] > 0.f ? sc[0] : 3.0e38f, fminf(sc[1] > 0.f ? sc[1] : 3.0e38f, sc[2] > 0.f ? sc[2] : 3.0e38f));
-            sc[0] = sc[1] = sc[2] = smin < 3.0e38f ? smin : 0.f;
-        }
-        #pragma unroll
-        for (int k = 0; k < IPT; k++) {
-            const int i = k * LM_ORDER_TPB + tid;
-            if (i < npad) {
-                unsigned key = 0xffffffffu;
-                if (i < cnt) {
-                    const float fx = (px[k] - lo[0]) * sc[0], fy = (py[k] - lo[1]) * sc[1], fz = (pz[k] - lo[2]) * sc[2];
-                    const unsigned qx = (unsigned)min(max((int)fx, 0), 63), qy = (unsigned)min(max((int)fy, 0), 63), qz = (unsigned)min(max((int)fz, 0), 63);
-                    const unsigned mort = morton_spread6(qx) | (morton_spread6(qy) << 1) | (morton_spread6(qz) << 2);      // 18 bits
-                    key = (mort << 13) | (unsigned)i;
-                }
-                s_key[i] = key;
-            }
-        }
-    }
-    __syncthreads();
-    for (int k = 2; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (npad >> 1); t += LM_ORDER_TPB) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
-                const unsigned x = s_key[i], y = s_key[p];
-                const bool up = (i & k) == 0;
-                if ((x > y) == up) { s_key[i] = y; s_key[p] = x; }
-            }
-            __syncthreads();
-        }
-    }
-    for (int r = tid; r < cnt; r += LM_ORDER_TPB) {
-        const int i = (int)(s_key[r] & (LM_ORDER_WIN - 1));
-        const float4 p = src[i];
-        dst[r] = make_float4(p.x, p.y, p.z, __int_as_float(base + i));          // w = index inside its cloud (corner or surface)
-    }
-}
-
-// ---- exact 5-NN of one point out of the shared-memory tile ---------------------------------------------------------------
-// Keys are (d^2 bits << 32) | (original map index << posBits) | position in the tile: the (d^2, index) total order of the
-// oracle (a map point occupies one tile position, so the low bits never decide), and the position lets the fit read the
-// neighbour's coordinates back from shared memory.  Position 2^posBits - 1 means "not in the tile" (fallback search).
-__device__ __forceinline__ void tile_offer(ThreadKnn5& r, const float4 m, int pos, int posBits, float qx, float qy, float qz) {
-    const float ddx = qx - m.x, ddy = qy - m.y, ddz = qz - m.z;
-    float dd = ddx * ddx; dd += ddy * ddy; dd += ddz * ddz;
-    if (__float_as_uint(dd) > (unsigned)(r.key[4] >> 32)) return;          // cannot enter the top-5 (the common case)
-    const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | (((unsigned)__float_as_int(m.w) << posBits) | (unsigned)pos);
-    if (key >= r.key[4]) return;
-    r.key[4] = key;
-    knn_cswap(r.key[3], r.key[4]); knn_cswap(r.key[2], r.key[3]); knn_cswap(r.key[1], r.key[2]); knn_cswap(r.key[0], r.key[1]);
-}
-
-struct TileBox { int x0, y0, z0, nx1, ny; };     // first cell of the staged box, entries per staged cell_start row (cells + 1), rows per z layer
-
-// scan the cells of the cube of radius `rad` around cell (cx, cy, cz); lane `sub` of the point's G lanes takes every G-th row
-template <int G>
-__device__ __forceinline__ void tile_scan(ThreadKnn5& p, const float4* __restrict__ s_tile, const int* __restrict__ s_cs, const int* __restrict__ s_rowOff,
-                                          const TileBox& B, const GridDesc& g, int cx, int cy, int cz, int rad, int sub, int posBits,
-                                          float qx, float qy, float qz) {
-    const int xa = max(cx - rad, 0), xb = min(cx + rad, g.dx - 1);
-    const int ya = max(cy - rad, 0), yb = min(cy + rad, g.dy - 1);
-    const int za = max(cz - rad, 0), zb = min(cz + rad, g.dz - 1);
-    if (xa > xb || ya > yb || za > zb) return;
-    const int wy = yb - ya + 1, nrow = wy * (zb - za + 1);
-    for (int i = sub; i < nrow; i += G) {
-        const int zi = i / wy, yi = i - zi * wy;
-        const int row = (za + zi - B.z0) * B.ny + (ya + yi - B.y0);
-        const int* cs = s_cs + row * B.nx1;
-        const int off = s_rowOff[row] - cs[0];
-        int j = off + cs[xa - B.x0];
-        const int hi = off + cs[xb + 1 - B.x0];
-        for (; j + 4 <= hi; j += 4) {                       // four shared-memory loads in flight
-            const float4 m0 = s_tile[j], m1 = s_tile[j + 1], m2 = s_tile[j + 2], m3 = s_tile[j + 3];
-            tile_offer(p, m0, j, posBits, qx, qy, qz); tile_offer(p, m1, j + 1, posBits, qx, qy, qz);
-            tile_offer(p, m2, j + 2, posBits, qx, qy, qz); tile_offer(p, m3, j + 3, posBits, qx, qy, qz);
-        }
-        for (; j < hi; j++) tile_offer(p, s_tile[j], j, posBits, qx, qy, qz);
-    }
-}
-
-// merge the private lists of the G lanes of one point (G consecutive lanes of a warp); every lane ends with the merged top-5
-template <int G>
-__device__ __forceinline__ void tile_merge(ThreadKnn5& p) {
-    if (G == 1) return;
-    // only the G lanes of this point are known to be here together (other points of the warp may have no search to do)
-    const unsigned gmask = (G >= 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) & ~(G - 1));
-    ThreadKnn5 m;
-    #pragma unroll
-    for (int k = 0; k < 5; k++) {
-        unsigned long long best = p.key[0];
-        #pragma unroll
-        for (int o = G >> 1; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(gmask, best, o); best = other < best ? other : best; }
-        m.key[k] = best;
-        if (p.key[0] == best && best != ~0ull) { p.key[0] = p.key[1]; p.key[1] = p.key[2]; p.key[2] = p.key[3]; p.key[3] = p.key[4]; p.key[4] = ~0ull; }
-    }
-    #pragma unroll
-    for (int k = 0; k < 5; k++) p.key[k] = m.key[k];
-}
-
-// One LM iteration = association over the CTA's macro-chunks (see the file header) -> every warp folds the Jacobian rows of
-// its points into the 27 unique entries of J^T J / J^T r (+ the row count), one entry per lane, f64 -> CTA reduce in fixed warp
-// order -> one partial per CTA -> team barrier -> every CTA sums all partials in the same fixed order and solves redundantly.
-// The TEAM of one frame is a thread-block cluster (GRID = false, many frames per launch) or the whole cooperative grid
-// (GRID = true, one frame).  Macro-chunk k * C + rank belongs to CTA `rank` of the team in every iteration (static, so
-// the summation order is fixed); corner chunks come first, chunks never mix the two maps.
+// One LM iteration = association (a warp takes 32 consecutive feature points: transform, then the exact 5-NN
+// of each point on the grid index by the WHOLE WARP, one point after the other (mapgrid.cuh), then ONE
+// THREAD per point: line / plane fit -> coefficient -> Jacobian row, staged as f64 in shared memory) -> every
+// warp folds its 32 staged rows into the 27 unique entries of J^T J / J^T r (+ the row count), one
+// entry per lane, f64 -> CTA reduce in fixed warp order -> one partial per CTA -> team barrier ->
+// every CTA sums all partials in the same fixed order and solves redundantly.
+// The TEAM of one frame is a thread-block cluster (GRID = false, many frames per launch) or the whole
+// cooperative grid (GRID = true, one frame).  A warp takes 32 CONSECUTIVE points of the scan (voxel order),
+// so successive queries touch neighbouring map cells and find their candidates in L1.
 template <bool GRID>
 __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM_CTAS_GRID : LM_CTAS_CLUSTER) lm_kernel(LmArgs a) {
     constexpr int LM_TPB = GRID ? LM_TPB_GRID : LM_TPB_CLUSTER;
-    constexpr int G = GRID ? LM_G_GRID : LM_G_CLUSTER;       // lanes per feature point
-    constexpr int MC = LM_TPB / G;                           // feature points per macro-chunk
-    constexpr int WPB = LM_TPB / 32;
-    constexpr int QPW = 32 / G;                              // feature points per warp
     cg::cluster_group cluster = cg::this_cluster();
     cg::grid_group grid = cg::this_grid();
     const int C = GRID ? (int)gridDim.x : (int)cluster.num_blocks();        // CTAs in the team
@@ -429,33 +227,38 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
     const int slot = GRID ? a.first : a.first + (int)(blockIdx.x / C);
     FrameMeta& M = a.meta[slot];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int qi = tid / G, sub = tid % G;                   // point of the macro-chunk this thread works for, lane among that point's G
+    constexpr int WPB = LM_TPB / 32;
 
-    extern __shared__ __align__(128) unsigned char s_dyn[];
-    float4* s_tile = reinterpret_cast<float4*>(s_dyn);                                           // [LM_TILE_PTS]
-    int* s_cs = reinterpret_cast<int*>(s_dyn + (size_t)LM_TILE_PTS * 16);                        // [LM_CS_CAP]
-    int* s_rowOff = s_cs + LM_CS_CAP;                                                            // [LM_ROW_CAP + 1]
-    float (*s_rows)[QPW][7] = reinterpret_cast<float (*)[QPW][7]>(s_cs);                         // aliases s_cs once the scans are done
-    __shared__ double s_part[WPB][NACC];
+    // per-warp staging of the 32 Jacobian rows (6) and -residual (1) of the warp's current 32 points, as f32 -- widened exactly when folded (dynamic shared memory)
+    extern __shared__ float s_dyn[];
+    float (*s_rows)[32][7] = reinterpret_cast<float (*)[32][7]>(s_dyn);      // staged as f32 (what they are); widened exactly when folded
+    // one 28-double partial per CHUNK (dynamic dispatch, summed in chunk order: the result does not depend on which warp
+    // took which chunk) or, when this CTA has more chunks than slots, one per WARP (static dispatch)
+    // Batched (cluster) shape: the per-chunk partials live in global memory (L2) instead, so that a CTA needs only ~8 KB of
+    // shared memory and the rest of the SM's 228 KB serves as L1 for the neighbour searches.
+    constexpr int SLOTS = GRID ? (LM_PART_SLOTS > WPB ? LM_PART_SLOTS : WPB) : 1;
+    __shared__ double s_part[SLOTS][NACC];
+    __shared__ int s_next;
     __shared__ double sh_tot[NACC];
     __shared__ GridDesc sh_gd[2];
     __shared__ float sh_pose[6], sh_T[12], sh_trig[6], sh_AtA[36], sh_AtB[6];
-    __shared__ int sh_stop, sh_nsel, s_bbox[2][6], s_wsum[WPB + 1];
-    __shared__ unsigned long long s_mbar;
+    __shared__ int sh_stop, sh_nsel;
 
     const int nC = min(M.n_corner_ds, a.cornerCap), nS = min(M.n_surf_ds, a.surfCap);
     if (!(nC > a.edgeMin && nS > a.surfMin)) {     // mapOptmization.h:1410 / :1439-1441
         if (rank == 0 && tid == 0) { M.flags = FBPR_FLAG_NOT_ENOUGH_FEATURES | (M.mapTruncated ? FBPR_FLAG_MAP_TRUNCATED : 0u); M.iters = 0; M.nSel = 0; M.isDegenerate = 0; }
         return;
     }
+    const int nQ = nC + nS;
     const GridSeg gc = a.gsegs[2 * slot], gs = a.gsegs[2 * slot + 1];
-    const float4* qpts = a.qpts + (size_t)slot * a.qCap;     // corners [0, nC), surface points [nC, nC + nS), each Morton-ordered (lm_order)
+    const float4* cpts = a.cornerDS + (size_t)slot * a.cornerCap;
+    const float4* spts = a.surfDS + (size_t)slot * a.surfCap;
     double* part = GRID ? a.partialsGrid + (size_t)slot * 2 * a.gridMax * NACC : a.partials + (size_t)slot * 2 * a.teamMax * NACC;
     const int teamStride = GRID ? a.gridMax : a.teamMax;
     if (tid < 6) sh_pose[tid] = M.pose[tid];
     if (tid == 32) sh_gd[0] = *gc.desc;
     if (tid == 64) sh_gd[1] = *gs.desc;
-    if (tid == 0) mbar_init(&s_mbar, 1);
+    if (tid == 0) s_next = 0;
     // the accumulator entry this lane owns: 0..20 = upper triangle (ei <= ej), 21..26 = (ei, 6) = A^T b, 27 = row count
     int ei = 0, ej = 6;
     if (lane < 21) { int rr = 0, qx = lane; while (qx >= 6 - rr) { qx -= 6 - rr; rr++; } ei = rr; ej = rr + qx; }
@@ -463,20 +266,14 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
     __syncthreads();
 
     KnnMaps maps; maps.gd = sh_gd; maps.cell_start[0] = gc.cell_start; maps.cell_start[1] = gs.cell_start; maps.pts[0] = gc.sorted; maps.pts[1] = gs.sorted;
-    const int posBits = a.posBits;
-    const unsigned posMask = (1u << posBits) - 1u;           // also the "not in the tile" position
-    const int tileCap = min((int)posMask, LM_TILE_PTS);
-    // points per macro-chunk: the smallest multiple of a warp's points that needs no more rounds over the team than MC would
-    // (balances the CTAs: e.g. one frame on the whole GPU gets exactly one chunk per CTA)
-    int mcSize = MC;
-    {
-        const int rounds = max(1, ((nC + MC - 1) / MC + (nS + MC - 1) / MC + C - 1) / C);
-        for (int s = QPW; s < MC; s += QPW) if ((nC + s - 1) / s + (nS + s - 1) / s <= rounds * C) { mcSize = s; break; }
-    }
-    const int chunksC = (nC + mcSize - 1) / mcSize, chunksS = (nS + mcSize - 1) / mcSize;
-    const int nChunks = chunksC + chunksS;
-    unsigned mbarPhase = 0;
-    int bbSel = 0;
+    // points per warp chunk: 32 when the team has fewer warps than chunks (batched calls); when a whole GPU works
+    // on one frame there are more warps than that, so chunks shrink until every warp has a few points to search
+    int CS = 32;
+    while (CS > 1 && nQ <= (CS / 2) * C * WPB) CS >>= 1;
+    const int nChunks = (nQ + CS - 1) / CS;
+    const int myChunks = rank < nChunks ? (nChunks - rank + C - 1) / C : 0;      // chunks k * C + rank of this CTA
+    const bool dynamic = !GRID || myChunks <= LM_PART_SLOTS;
+    double* cpart = GRID ? nullptr : a.chunkPart + (size_t)slot * a.chunkCap * NACC;        // [chunk][28], chunk = k * C + rank
     unsigned flags = 0; int isDegenerate = 0; int iters = 0;
     for (int iter = 0; iter < FBPR_MAX_ITERS; iter++) {
         // --- pose -> rigid transform + the six sines/cosines LMOptimization needs (:1259-1264)
@@ -496,240 +293,154 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
         __syncthreads();
         const bool cap = iter == a.debug_iter && slot < a.dbgSlots;
 
+        // --- association: one thread per feature point
         double acc = 0.0;
-        for (int mc = rank; mc < nChunks; mc += C) {
-            // ---- the macro-chunk's points: corners occupy chunks [0, chunksC), surface points follow
-            const bool isCorner = mc < chunksC;
-            const int kind = isCorner ? 0 : 1;
-            const int li0 = (isCorner ? mc : mc - chunksC) * mcSize;                 // first point of the chunk inside its cloud
-            const int nk = isCorner ? nC : nS;
-            const int mcCount = min(mcSize, nk - li0);
-            const GridDesc& gd = sh_gd[kind];
-            const bool inRange = qi < mcCount;
-            float4 pOri = make_float4(0.f, 0.f, 0.f, 0.f);
+        // chunks of CS consecutive points are dealt round-robin over the team's CTAs (chunk = k * C + rank), so the (more
+        // expensive) corner chunks at the front of the index range spread evenly; inside the CTA the warps take the
+        // CTA's chunks from a shared counter, because a chunk costs anything between 0 and 32 full searches
+        int k = warp;
+        if (dynamic) { if (lane == 0) k = atomicAdd(&s_next, 1); k = __shfl_sync(0xffffffffu, k, 0); }
+        while (k < myChunks) {
+            const int chunk = k * C + rank;
+            const int q = chunk * CS + lane;
+            bool ok = false;
+            // corners occupy [0, nC), surface points follow; each lane searches the map of its own kind
+            const bool inRange = lane < CS && q < nQ;
+            const bool isCorner = q < nC;
+            const int li = isCorner ? q : q - nC;
+            float4 pOri = make_float4(0, 0, 0, 0);
             float x0 = 0.f, y0 = 0.f, z0 = 0.f;
-            if (inRange) { pOri = __ldg(qpts + (isCorner ? 0 : nC) + li0 + qi); transform_point(sh_T, pOri, x0, y0, z0); }
-            const int li = __float_as_int(pOri.w);                               // index in laserCloud{Corner,Surf}LastDS
-            const int cx = (int)floorf((x0 - gd.ox) * gd.inv_h), cy = (int)floorf((y0 - gd.oy) * gd.inv_h), cz = (int)floorf((z0 - gd.oz) * gd.inv_h);
-            // a point whose 1 m ball cannot reach the map's bounding box has no neighbour at all (the search would find nothing)
-            const bool reach = cx + gd.rmax >= 0 && cx - gd.rmax < gd.dx && cy + gd.rmax >= 0 && cy - gd.rmax < gd.dy && cz + gd.rmax >= 0 && cz - gd.rmax < gd.dz;
-            const bool active = inRange && gd.n >= 5 && reach;
-            const float4* mo = isCorner ? gc.pts : gs.pts;                       // the map in original order (only the fallback reads it)
-            const float4* sorted = isCorner ? gc.sorted : gs.sorted;
-            const int* cell_start = isCorner ? gc.cell_start : gs.cell_start;
-            // first cube radius: one cell (after the first iteration 99.9 % of the surface points are certified there); the very
-            // first iteration starts from knn_first_radius.  The tile is staged with a margin of up to two cells so that a point
-            // may grow its cube once without leaving it.
-            const int radStart = iter == 0 ? min(max(1, (int)ceilf(a.firstRadius / (gd.h * 0.9995f))), gd.rmax) : 1;
-            int margin = min((iter == 0 || isCorner) ? max(2, radStart) : 1, gd.rmax);
-
-            // ---- adaptive sub-passes over [pa, pa + plen) of the chunk's points: the whole chunk if its tile fits
-            int pa = 0, plen = MC;
-            while (pa < mcCount) {
-                const bool mine = active && qi >= pa && qi < pa + plen;
-                // (1) box of cells covered by the cubes of radius `margin` (two copies used in turn: a retry re-initialises the box
-                //     while slower threads may still be reading the previous one)
-                bbSel ^= 1;
-                int* s_bb = s_bbox[bbSel];
-                if (tid < 3) s_bb[tid] = 0x7fffffff; else if (tid < 6) s_bb[tid] = -0x7fffffff;
-                __syncthreads();                                                 // also: everyone is done with the previous tile / s_rows
-                {
-                    int lo0 = 0x7fffffff, lo1 = 0x7fffffff, lo2 = 0x7fffffff, hi0 = -0x7fffffff, hi1 = -0x7fffffff, hi2 = -0x7fffffff;
-                    if (mine) {
-                        const int xa = max(cx - margin, 0), xb = min(cx + margin, gd.dx - 1);
-                        const int ya = max(cy - margin, 0), yb = min(cy + margin, gd.dy - 1);
-                        const int za = max(cz - margin, 0), zb = min(cz + margin, gd.dz - 1);
-                        if (xa <= xb && ya <= yb && za <= zb) { lo0 = xa; hi0 = xb; lo1 = ya; hi1 = yb; lo2 = za; hi2 = zb; }
-                    }
-                    lo0 = __reduce_min_sync(0xffffffffu, lo0); lo1 = __reduce_min_sync(0xffffffffu, lo1); lo2 = __reduce_min_sync(0xffffffffu, lo2);
-                    hi0 = __reduce_max_sync(0xffffffffu, hi0); hi1 = __reduce_max_sync(0xffffffffu, hi1); hi2 = __reduce_max_sync(0xffffffffu, hi2);
-                    if (lane == 0 && lo0 <= hi0) {
-                        atomicMin(&s_bb[0], lo0); atomicMin(&s_bb[1], lo1); atomicMin(&s_bb[2], lo2);
-                        atomicMax(&s_bb[3], hi0); atomicMax(&s_bb[4], hi1); atomicMax(&s_bb[5], hi2);
-                    }
-                }
-                __syncthreads();
-                TileBox B; B.x0 = s_bb[0]; B.y0 = s_bb[1]; B.z0 = s_bb[2];
-                const bool anyBox = s_bb[0] <= s_bb[3];
-                const int nx1 = anyBox ? s_bb[3] - s_bb[0] + 2 : 0, ny = anyBox ? s_bb[4] - s_bb[1] + 1 : 0, nz = anyBox ? s_bb[5] - s_bb[2] + 1 : 0;
-                B.nx1 = nx1; B.ny = ny;
-                const int rows = ny * nz;
-                bool fits = rows <= LM_ROW_CAP && (long long)rows * nx1 <= LM_CS_CAP;
-                int total = 0;
-                if (fits && anyBox) {
-                    // (2) cell_start entries of the box, one warp per cell row (coalesced), then the rows' lengths -> tile offsets
-                    for (int r = warp; r < rows; r += WPB) {
-                        const int zi = r / ny, yi = r - zi * ny;
-                        const int* src = cell_start + ((size_t)(B.z0 + zi) * gd.dy + (B.y0 + yi)) * gd.dx + B.x0;
-                        for (int xi = lane; xi < nx1; xi += 32) s_cs[r * nx1 + xi] = __ldg(src + xi);
-                    }
-                    __syncthreads();
-                    constexpr int RPT = (LM_ROW_CAP + LM_TPB - 1) / LM_TPB;           // rows per thread in the block scan
-                    int len[RPT], sum = 0;
-                    #pragma unroll
-                    for (int k = 0; k < RPT; k++) {
-                        const int r = tid * RPT + k;
-                        len[k] = r < rows ? s_cs[r * nx1 + nx1 - 1] - s_cs[r * nx1] : 0;
-                        sum += len[k];
-                    }
-                    int incl = sum;
-                    #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                    if (lane == 31) s_wsum[warp] = incl;
-                    __syncthreads();
-                    if (tid == 0) { int run = 0; for (int w = 0; w < WPB; w++) { const int v = s_wsum[w]; s_wsum[w] = run; run += v; } s_wsum[WPB] = run; }
-                    __syncthreads();
-                    total = s_wsum[WPB];
-                    fits = total <= tileCap;
-                    if (fits) {
-                        int run = s_wsum[warp] + incl - sum;
+            if (inRange) { pOri = __ldcs(isCorner ? cpts + li : spts + li); transform_point(sh_T, pOri, x0, y0, z0); }
+            const int kind = isCorner ? 0 : 1;
+            const bool active = inRange && sh_gd[kind].n >= 5;
+            float4* anchor = a.qanchor + (size_t)slot * a.qCap + q;
+            int* cache = a.qcache + ((size_t)slot * a.qCap + q) * FBPR_KNN_CACHE;
+            const float4* mo = isCorner ? gc.pts : gs.pts;   // the map in original order (XYZI)
+            ThreadKnn5 r;
+            #pragma unroll
+            for (int k = 0; k < 5; k++) r.key[k] = ~0ull;
+            // (1) candidate cache of this point's last full search: re-rank the cached map points (one thread); the
+            //     result is the exact 5-NN when every uncached map point is provably farther (mapgrid.cuh)
+            bool need = active;
+            int rad0 = 1;
+            if (active) {
+                if (iter == 0) rad0 = max(1, (int)ceilf(a.firstRadius / (sh_gd[kind].h * 0.9995f)));
+                else {
+                    const float4 an = __ldcs(anchor);
+                    if (an.w > 0.f) {
+                        const int4* c4 = reinterpret_cast<const int4*>(cache);
                         #pragma unroll
-                        for (int k = 0; k < RPT; k++) { const int r = tid * RPT + k; if (r < rows) s_rowOff[r] = run; run += len[k]; }
-                        // (3) one bulk copy per non-empty cell row into the tile; thread 0 arms the barrier with the byte count
-                        if (tid == 0 && total > 0) mbar_arrive_expect_tx(&s_mbar, (unsigned)total * 16u);
-                        run = s_wsum[warp] + incl - sum;
-                        #pragma unroll
-                        for (int k = 0; k < RPT; k++) {
-                            const int r = tid * RPT + k;
-                            if (r < rows && len[k] > 0) bulk_g2s(s_tile + run, sorted + s_cs[r * nx1], (unsigned)len[k] * 16u, &s_mbar);
-                            run += len[k];
-                        }
-                    }
-                }
-                if (!fits) {                        // uniform decision: fewer points first (down to two warps' worth), then the margin, then fewer points again
-                    if (a.stats && tid == 0) atomicAdd(a.stats + 2, 1ull);
-                    if (plen > 2 * QPW) { plen >>= 1; continue; }
-                    if (margin > 1) { margin = 1; continue; }
-                    if (plen > QPW) { plen >>= 1; continue; }
-                }
-                const bool haveTile = fits && anyBox;
-                if (a.stats && tid == 0) {
-                    atomicAdd(a.stats + 0, 1ull); atomicAdd(a.stats + 1, (unsigned long long)total);
-                    atomicAdd(a.stats + 4, (unsigned long long)rows); atomicAdd(a.stats + 5, (unsigned long long)rows * nx1);
-                    if (!haveTile) atomicAdd(a.stats + 6, 1ull);
-                }
-                if (haveTile) {
-                    __syncthreads();                                             // s_rowOff complete
-                    if (total > 0) { mbar_wait(&s_mbar, mbarPhase); mbarPhase ^= 1u; }
-                }
-                // (4) exact 5-NN out of the tile: cube of radStart cells, grown cell by cell while the result is not certified and
-                //     the cube stays inside the staged margin
-                ThreadKnn5 r;
-                #pragma unroll
-                for (int k = 0; k < 5; k++) r.key[k] = ~0ull;
-                bool need = mine;                                                // still needs a (fallback) search
-                int radNext = 1;
-                if (mine && haveTile) {
-                    int rad = min(radStart, margin);
-                    while (true) {
-                        #pragma unroll
-                        for (int k = 0; k < 5; k++) r.key[k] = ~0ull;
-                        tile_scan<G>(r, s_tile, s_cs, s_rowOff, B, gd, cx, cy, cz, rad, sub, posBits, x0, y0, z0);
-                        tile_merge<G>(r);
-                        const float guard = (float)rad * gd.h * 0.9995f;
-                        if (knn_d5(r) < guard * guard || rad >= gd.rmax) { need = false; break; }
-                        if (rad >= margin) break;
-                        rad++;
-                    }
-                    radNext = min(rad * 2, gd.rmax);
-                }
-                __syncthreads();                                                 // every warp is done with s_cs: s_rows may overwrite it
-                // (5) fallback: warp-cooperative search on the global index for the points the tile could not certify
-                {
-                    const bool needW = need && sub == 0;
-                    if (a.stats) { const unsigned nb_ = __ballot_sync(0xffffffffu, needW); if (lane == 0 && nb_) atomicAdd(a.stats + 3, (unsigned long long)__popc(nb_)); }
-                    if (__any_sync(0xffffffffu, needW)) {
-                        ThreadKnn5 rf;
-                        #pragma unroll
-                        for (int k = 0; k < 5; k++) rf.key[k] = ~0ull;
-                        warp_knn5(maps, kind, x0, y0, z0, radNext, needW, rf, nullptr, nullptr);
-                        if (G > 1) {
+                        for (int half = 0; half < FBPR_KNN_CACHE / 8; half++) {     // 8 independent gathers in flight
+                            const int4 va = __ldcs(c4 + 2 * half), vb = __ldcs(c4 + 2 * half + 1);
+                            const int ci[8] = { va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w };
+                            float4 cm[8];
                             #pragma unroll
-                            for (int k = 0; k < 5; k++) rf.key[k] = __shfl_sync(0xffffffffu, rf.key[k], lane & ~(G - 1));
-                        }
-                        if (need) {
+                            for (int k = 0; k < 8; k++) if (ci[k] >= 0) cm[k] = __ldcg(mo + ci[k]);
                             #pragma unroll
-                            for (int k = 0; k < 5; k++)
-                                r.key[k] = rf.key[k] == ~0ull ? ~0ull : ((rf.key[k] & 0xffffffff00000000ull) | (((unsigned)rf.key[k] << posBits) | posMask));
+                            for (int k = 0; k < 8; k++) if (ci[k] >= 0) knn_offer_idx(r, cm[k].x, cm[k].y, cm[k].z, ci[k], x0, y0, z0);
                         }
+                        const float mx = x0 - an.x, my = y0 - an.y, mz = z0 - an.z;
+                        const float moved = sqrtf(mx * mx + my * my + mz * mz);
+                        const float lim = an.w * 0.9999f - moved * 1.0001f - 1.0e-5f;     // every uncached point is farther than this
+                        const float lim2 = lim > 0.f ? lim * lim * 0.9999f : 0.f;
+                        need = !(knn_d5(r) < lim2 || lim2 >= 1.0f);                       // 2nd case: the cache decides the whole 1 m ball
+                        rad0 = knn5_radius_from_bound(sh_gd[kind], knn_d5(r));
+                    } else {
+                        rad0 = sh_gd[kind].rmax;
                     }
                 }
-                // (6) fit, coefficient, Jacobian row: one lane per point
-                const bool worker = inRange && qi >= pa && qi < pa + plen && sub == 0;
-                bool ok = mine && knn_d5(r) < 1.0f;
-                if (worker) {
-                    if (cap) {
-                        const size_t o = isCorner ? (size_t)slot * a.cornerCap + li : (size_t)slot * a.surfCap + li;
-                        int* kd = isCorner ? a.knnC : a.knnS; float* dd = isCorner ? a.d2C : a.d2S;
-                        #pragma unroll
-                        for (int k = 0; k < 5; k++) {
-                            kd[5 * o + k] = ok ? (int)((unsigned)r.key[k] >> posBits) : -1;
-                            dd[5 * o + k] = (gd.n >= 5 && r.key[k] != ~0ull) ? __uint_as_float((unsigned)(r.key[k] >> 32)) : 3.0e38f;
-                        }
-                    }
-                    float4 coeff = make_float4(0, 0, 0, 0);
-                    if (ok) {
-                        // the five neighbours' coordinates (mapOptmization.h:1028-1036, :1157-1163): from the tile, or by original index
-                        float4 nb[5];
-                        #pragma unroll
-                        for (int k = 0; k < 5; k++) {
-                            const unsigned low = (unsigned)r.key[k], pos = low & posMask;
-                            nb[k] = pos != posMask ? s_tile[pos] : __ldcg(mo + (low >> posBits));
-                        }
-                        ok = isCorner ? corner_fit(nb, x0, y0, z0, coeff) : surf_fit(nb, x0, y0, z0, coeff);
-                    }
-                    if (cap) {
-                        if (isCorner) { size_t o = (size_t)slot * a.cornerCap + li; a.coeffC[o] = coeff; a.flagC[o] = ok ? 1 : 0; }
-                        else          { size_t o = (size_t)slot * a.surfCap + li;   a.coeffS[o] = coeff; a.flagS[o] = ok ? 1 : 0; }
-                    }
-                    if (ok) {
-                        // Jacobian row, lidar -> "camera" axis permutation (mapOptmization.h:1286-1332)
-                        const float srz = sh_trig[0], srx = sh_trig[1], sry = sh_trig[2], crz = sh_trig[3], crx = sh_trig[4], cry = sh_trig[5];
-                        const float ox = pOri.y, oy = pOri.z, oz = pOri.x;
-                        const float kx = coeff.y, ky = coeff.z, kz = coeff.x;
-                        float arx = (crx * sry * srz * ox + crx * crz * sry * oy - srx * sry * oz) * kx
-                                  + (-srx * srz * ox - crz * srx * oy - crx * oz) * ky
-                                  + (crx * cry * srz * ox + crx * cry * crz * oy - cry * srx * oz) * kz;
-                        float ary = ((cry * srx * srz - crz * sry) * ox
-                                  + (sry * srz + cry * crz * srx) * oy + crx * cry * oz) * kx
-                                  + ((-cry * crz - srx * sry * srz) * ox
-                                  + (cry * srz - crz * srx * sry) * oy - crx * sry * oz) * kz;
-                        float arz = ((crz * srx * sry - cry * srz) * ox + (-cry * crz - srx * sry * srz) * oy) * kx
-                                  + (crx * crz * ox - crx * srz * oy) * ky
-                                  + ((sry * srz + cry * crz * srx) * ox + (crz * sry - cry * srx * srz) * oy) * kz;
-                        float* row = s_rows[warp][lane / G];
-                        row[0] = arz; row[1] = arx; row[2] = ary;
-                        row[3] = kz;  row[4] = kx;  row[5] = ky;
-                        row[6] = -coeff.w;
-                    }
-                } else {
-                    ok = false;
-                }
-                // fold the warp's staged rows into the lane-owned entries (rows in point order, f64)
-                unsigned m = __ballot_sync(0xffffffffu, ok);
-                __syncwarp();
-                if (lane == 27) acc += (double)__popc(m);
-                else if (lane < 27) {
-                    while (m) {
-                        const int rr = (__ffs(m) - 1) / G; m &= m - 1;
-                        acc += (double)s_rows[warp][rr][ei] * (double)s_rows[warp][rr][ej];
-                    }
-                }
-                pa += plen;
             }
-            __syncthreads();                         // the next macro-chunk's box reduce reuses s_bb, its tile overwrites s_tile / s_rows
+            // (2) full search by the whole warp for the points that need one; it refreshes their cache
+            warp_knn5(maps, kind, x0, y0, z0, rad0, need, r, anchor, cache);
+            ok = active && knn_d5(r) < 1.0f;
+            if (inRange) {
+                const GridDesc& gd = sh_gd[isCorner ? 0 : 1];
+                if (cap) {
+                    const size_t o = isCorner ? (size_t)slot * a.cornerCap + li : (size_t)slot * a.surfCap + li;
+                    int* kd = isCorner ? a.knnC : a.knnS; float* dd = isCorner ? a.d2C : a.d2S;
+                    #pragma unroll
+                    for (int k = 0; k < 5; k++) {
+                        kd[5 * o + k] = ok ? (int)(unsigned)(r.key[k] & 0xffffffffu) : -1;
+                        dd[5 * o + k] = (gd.n >= 5 && r.key[k] != ~0ull) ? __uint_as_float((unsigned)(r.key[k] >> 32)) : 3.0e38f;
+                    }
+                }
+                float4 coeff = make_float4(0, 0, 0, 0);
+                if (ok) {
+                    // the five neighbours' coordinates, by original map index (mapOptmization.h:1028-1036, :1157-1163)
+                    float4 nb[5];
+                    #pragma unroll
+                    for (int k = 0; k < 5; k++) nb[k] = __ldcg(mo + knn_index(r, k));
+                    ok = isCorner ? corner_fit(nb, x0, y0, z0, coeff) : surf_fit(nb, x0, y0, z0, coeff);
+                }
+                if (cap) {
+                    if (isCorner) { size_t o = (size_t)slot * a.cornerCap + li; a.coeffC[o] = coeff; a.flagC[o] = ok ? 1 : 0; }
+                    else          { size_t o = (size_t)slot * a.surfCap + li;   a.coeffS[o] = coeff; a.flagS[o] = ok ? 1 : 0; }
+                }
+                if (ok) {
+                    // Jacobian row, lidar -> "camera" axis permutation (mapOptmization.h:1286-1332)
+                    const float srz = sh_trig[0], srx = sh_trig[1], sry = sh_trig[2], crz = sh_trig[3], crx = sh_trig[4], cry = sh_trig[5];
+                    const float ox = pOri.y, oy = pOri.z, oz = pOri.x;
+                    const float kx = coeff.y, ky = coeff.z, kz = coeff.x;
+                    float arx = (crx * sry * srz * ox + crx * crz * sry * oy - srx * sry * oz) * kx
+                              + (-srx * srz * ox - crz * srx * oy - crx * oz) * ky
+                              + (crx * cry * srz * ox + crx * cry * crz * oy - cry * srx * oz) * kz;
+                    float ary = ((cry * srx * srz - crz * sry) * ox
+                              + (sry * srz + cry * crz * srx) * oy + crx * cry * oz) * kx
+                              + ((-cry * crz - srx * sry * srz) * ox
+                              + (cry * srz - crz * srx * sry) * oy - crx * sry * oz) * kz;
+                    float arz = ((crz * srx * sry - cry * srz) * ox + (-cry * crz - srx * sry * srz) * oy) * kx
+                              + (crx * crz * ox - crx * srz * oy) * ky
+                              + ((sry * srz + cry * crz * srx) * ox + (crz * sry - cry * srx * srz) * oy) * kz;
+                    float* row = s_rows[warp][lane];
+                    row[0] = arz; row[1] = arx; row[2] = ary;
+                    row[3] = kz;  row[4] = kx;  row[5] = ky;
+                    row[6] = -coeff.w;
+                }
+            }
+            // fold the warp's staged rows into the lane-owned entries (rows in point order, f64)
+            unsigned m = __ballot_sync(0xffffffffu, ok);
+            __syncwarp();
+            if (lane == 27) acc += (double)__popc(m);
+            else if (lane < 27) {
+                while (m) {
+                    const int rr = __ffs(m) - 1; m &= m - 1;
+                    acc += (double)s_rows[warp][rr][ei] * (double)s_rows[warp][rr][ej];
+                }
+            }
+            __syncwarp();
+            if (dynamic) {
+                if (lane < NACC) { if (GRID) s_part[k][lane] = acc; else cpart[(size_t)chunk * NACC + lane] = acc; }
+                acc = 0.0;
+                if (lane == 0) k = atomicAdd(&s_next, 1);
+                k = __shfl_sync(0xffffffffu, k, 0);
+            } else {
+                k += WPB;
+            }
         }
-        // --- CTA reduce (shared memory, fixed warp order) -> one partial per CTA in global memory
-        if (lane < NACC) s_part[warp][lane] = acc;
+        // --- CTA reduce (shared memory, fixed order) -> one partial per CTA in global memory
+        if (GRID && !dynamic && lane < NACC) s_part[warp][lane] = acc;
         __syncthreads();
         const int buf = iter & 1;
         double* mypart = part + ((size_t)buf * teamStride + rank) * NACC;
         if (tid < NACC) {
             double v = 0.0;
-            for (int w = 0; w < WPB; w++) v += s_part[w][tid];
+            if (GRID) {
+                const int nslots = dynamic ? myChunks : WPB;
+                for (int w = 0; w < nslots; w++) v += s_part[w][tid];
+            } else {
+                // chunk order, four loads in flight (L2: the lines were written by other warps of this CTA before the barrier)
+                int w = 0;
+                for (; w + 4 <= myChunks; w += 4) {
+                    const double p0 = __ldcg(cpart + (size_t)((w + 0) * C + rank) * NACC + tid), p1 = __ldcg(cpart + (size_t)((w + 1) * C + rank) * NACC + tid);
+                    const double p2 = __ldcg(cpart + (size_t)((w + 2) * C + rank) * NACC + tid), p3 = __ldcg(cpart + (size_t)((w + 3) * C + rank) * NACC + tid);
+                    v += p0; v += p1; v += p2; v += p3;
+                }
+                for (; w < myChunks; w++) v += __ldcg(cpart + (size_t)(w * C + rank) * NACC + tid);
+            }
             mypart[tid] = v;
             __threadfence();
         }
+        if (tid == 0) s_next = 0;                    // next iteration's dispatch counter (ordered by the barriers below)
         if (GRID) grid.sync(); else cluster.sync();
         // --- every CTA sums all partials in the same fixed order (bitwise identical everywhere), then solves redundantly
         if (tid < NACC * 8) {                        // 224 threads <= LM_TPB in both shapes
@@ -793,7 +504,6 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
     }
 }
 
-
 __global__ void transform_update_kernel(FrameMeta* meta, int first, int count, float rot_tol, float z_tol) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -806,23 +516,26 @@ __global__ void transform_update_kernel(FrameMeta* meta, int first, int count, f
 
 }  // namespace
 
+static size_t lm_dyn_smem(int tpb) { return (size_t)(tpb / 32) * 32 * 7 * sizeof(float); }    // s_rows
+
 // one-time function attributes of both variants (cluster sizes above 8, dynamic shared memory above the default limit)
 static int lm_configure() {
     static int configured = 0;
     if (configured) return 0;
     cudaError_t e = cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(NonPortableClusterSizeAllowed)", __FILE__, __LINE__);
-    e = cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_DYN_SMEM);
-    if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize, batched)", __FILE__, __LINE__);
-    e = cudaFuncSetAttribute(lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_DYN_SMEM);
-    if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize, single frame)", __FILE__, __LINE__);
-    // four CTAs of ~53 KB per SM: ask for the whole shared-memory carve-out (the tiles replaced L1 as the neighbour cache)
-    cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // The batched shape keeps its per-chunk partial sums in global memory, so a CTA needs ~8 KB of shared memory; ask for the
+    // smallest carve-out that holds 4 CTAs and leave the rest of the SM's 228 KB to L1, which the neighbour searches live on.
+    // LM ms per 128 frames: partials in shared memory (22 KB per CTA) at carve-out 25 / 40 / 55 / 100 %: 7.52 / 5.15 / 5.23 / 6.76;
+    // partials in global memory at 8 / 14 / 16 / 20 / 28 / 40 %: 5.08 / 4.81 / 4.50 / 4.52 / 4.58 / 4.54.
+    cudaFuncSetAttribute(lm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, LM_CARVEOUT);
+    e = cudaFuncSetAttribute(lm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_dyn_smem(LM_TPB_GRID));
+    if (e != cudaSuccess) return fbpr_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", __FILE__, __LINE__);
     configured = 1;
     return 0;
 }
 
-int fbpr_lm_tile_points() { return LM_TILE_PTS; }
+int fbpr_knn_cache_slots() { return FBPR_KNN_CACHE; }
 
 int fbpr_lm_grid_blocks(int device) {
     // co-resident CTAs of the cooperative (one frame on the whole GPU) variant: one per SM
@@ -830,7 +543,7 @@ int fbpr_lm_grid_blocks(int device) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
     int per = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lm_kernel<true>, LM_TPB_GRID, LM_DYN_SMEM) != cudaSuccess || per < 1) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lm_kernel<true>, LM_TPB_GRID, lm_dyn_smem(LM_TPB_GRID)) != cudaSuccess || per < 1) return 0;
     return sms;
 }
 
@@ -840,7 +553,7 @@ static int lm_max_active_clusters(int c) {
     if (c < 1 || c > 16) return 0;
     if (!known[c]) {
         cudaLaunchConfig_t cfg = {};
-        cfg.blockDim = dim3(LM_TPB_CLUSTER); cfg.gridDim = dim3((unsigned)(c * 64)); cfg.dynamicSmemBytes = LM_DYN_SMEM;
+        cfg.blockDim = dim3(LM_TPB_CLUSTER); cfg.gridDim = dim3((unsigned)(c * 64)); cfg.dynamicSmemBytes = lm_dyn_smem(LM_TPB_CLUSTER);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -856,6 +569,8 @@ static int lm_max_active_clusters(int c) {
 // that minimises it (a small batch gets big clusters to fill the GPU, a big batch small ones for fewer waves);
 // ties go to the smaller cluster (cheaper barrier, fewer redundant solves)
 int fbpr_lm_auto_cluster(int count) {
+    // powers of two only: odd sizes are allowed when asked for (lm_cluster_size = 1..16) but measured no better
+    // (128 frames: 4 -> 5.78 ms, 8 -> 5.77, 9 -> 5.97, 10 -> 5.80, 16 -> 7.1)
     const int sizes[5] = { 1, 2, 4, 8, 16 };
     int best = 8; double bestScore = 1e30;
     for (int k = 0; k < 5; k++) {
@@ -870,20 +585,14 @@ int fbpr_lm_auto_cluster(int count) {
 int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blocks, cudaStream_t st, long long* launches) {
     if (count <= 0) return 0;
     { int rc = lm_configure(); if (rc) return rc; }
-    // spatial order of the down-sampled feature points (once per frame, from the initial guess)
-    {
-        const int maxPts = args.cornerCap > args.surfCap ? args.cornerCap : args.surfCap;
-        lm_order<<<dim3((unsigned)((maxPts + LM_ORDER_WIN - 1) / LM_ORDER_WIN), 2, (unsigned)count), LM_ORDER_TPB, 0, st>>>(args);
-        if (launches) *launches += 1;
-    }
     cudaLaunchConfig_t cfg = {};
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.dynamicSmemBytes = LM_DYN_SMEM;
     cudaError_t e;
     if (count == 1 && grid_blocks > 0) {           // one frame: the whole GPU cooperates, grid-wide barrier per iteration
         cfg.blockDim = dim3(LM_TPB_GRID);
+        cfg.dynamicSmemBytes = lm_dyn_smem(LM_TPB_GRID);
         cfg.gridDim = dim3((unsigned)grid_blocks);
         attr[0].id = cudaLaunchAttributeCooperative;
         attr[0].val.cooperative = 1;
@@ -891,6 +600,7 @@ int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blo
     } else {                                        // many frames: one cluster per frame, hardware cluster barrier per iteration
         if (cluster_size <= 0) cluster_size = fbpr_lm_auto_cluster(count);
         cfg.blockDim = dim3(LM_TPB_CLUSTER);
+        cfg.dynamicSmemBytes = lm_dyn_smem(LM_TPB_CLUSTER);
         cfg.gridDim = dim3((unsigned)(count * cluster_size));
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -898,7 +608,7 @@ int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blo
     }
     if (e != cudaSuccess) return fbpr_fail(e, "cudaLaunchKernelEx(lm_kernel)", __FILE__, __LINE__);
     if (launches) *launches += 1;
-    return fbpr_launch_ok("lm_order / lm_kernel");
+    return fbpr_launch_ok("lm_kernel");
 }
 
 int fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float rot_tol, float z_tol, cudaStream_t st, long long* launches) {

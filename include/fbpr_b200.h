@@ -267,11 +267,6 @@ FBPR_API int fbpr_set_clouds_xyzi32(fbpr_handle* h, int slot, int kind, const vo
 /* capture per-point kNN / coefficients / AtA / AtB / X of LM iteration `iter` on the next scan2map (-1 = off) */
 FBPR_API int fbpr_set_debug_iteration(fbpr_handle* h, int iter);
 
-/* counters of the LM kernel's shared-memory tile staging since the last call (then reset); enable != 0 keeps counting:
-   [0] staged tiles (sub-passes), [1] map points staged, [2] retries (tile over budget), [3] fallback warp-cooperative searches,
-   [4] cell rows staged, [5] cell_start entries staged, [6] sub-passes without a tile, [7] unused.  A tuning aid, not a result. */
-FBPR_API int fbpr_lm_tile_stats(fbpr_handle* h, int enable, uint64_t out[8]);
-
 /* stand-alone VoxelGrid (pcl::VoxelGrid<PointXYZI>::filter; call sites featureExtraction.h:289-290,
    mapOptmization.h:251-257,:948-953,:985-991).  out_xyzi capacity n; point_keys (n) and out_keys
    (n) may be NULL.  Returns the number of output points, < 0 on error. */

@@ -1,5 +1,5 @@
-"""F config-4 frames through the whole path: per-stage CUDA-event times and the LM kernel's tile statistics
-(fbpr_lm_tile_stats).   python scripts/lm_tile_diag.py [F] [reps] [cluster]"""
+"""F config-4 frames through the whole path: per-stage CUDA-event times.
+python scripts/lm_tile_diag.py [F] [reps] [cluster]      (FBPR_LM_NO_MORTON=1 switches the spatial ordering of the LM kernel off)"""
 import os
 import sys
 
@@ -24,17 +24,6 @@ r.set_frames(0, fin)
 r.run_frames(0, F); r.sync()
 res = r.get_results(0, F)
 print("iters", res["iters"].tolist()[:16], "flags", sorted(set(res["flags"].tolist())))
-r.lm_tile_stats(True)
-r.set_poses(0, guesses); r.run_frames(0, F); r.sync()
-st = r.lm_tile_stats(False)
-c = r.get_counts(0)
-nq = sum(r.get_counts(s)["n_corner_ds"] + r.get_counts(s)["n_surf_ds"] for s in range(F))
-pit = float(sum((r.get_counts(s)["n_corner_ds"] + r.get_counts(s)["n_surf_ds"]) * int(res[s]["iters"]) for s in range(F)))
-print("counts slot0", c)
-print("tile stats", st)
-print("per point-iteration: staged points %.1f, fallback searches %.4f; per tile: points %.0f rows %.0f cell entries %.0f; retries/tile %.2f" % (
-    st["points"] / pit, st["fallback_searches"] / pit, st["points"] / max(st["tiles"], 1), st["rows"] / max(st["tiles"], 1),
-    st["cell_entries"] / max(st["tiles"], 1), st["retries"] / max(st["tiles"], 1)))
 r.enable_stage_timing(True); r.get_stage_ms(reset=True)
 for _ in range(reps):
     r.set_poses(0, guesses); r.run_frames(0, F)
