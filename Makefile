@@ -5,7 +5,7 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 PKG := feature_base_pointcloud_registration_b200
 CSRC := $(PKG)/csrc
-CU := $(CSRC)/capi.cu $(CSRC)/voxel.cu $(CSRC)/mapgrid.cu $(CSRC)/lm.cu $(CSRC)/projection.cu $(CSRC)/features.cu $(CSRC)/mapops.cu $(CSRC)/selftest.cu
+CU := $(CSRC)/capi.cu $(CSRC)/voxel.cu $(CSRC)/mapgrid.cu $(CSRC)/lm.cu $(CSRC)/projection.cu $(CSRC)/features.cu $(CSRC)/mapops.cu $(CSRC)/keyframes.cu $(CSRC)/selftest.cu
 HDR := $(CSRC)/internal.cuh $(CSRC)/mapgrid.cuh $(CSRC)/smallmat.cuh include/fbpr_b200.h
 # -fmad=false / -prec-div / -prec-sqrt: the kernels mirror the reference's f32 arithmetic op for op
 NVFLAGS := $(EXTRA) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true \

@@ -316,6 +316,32 @@ class Registration:
         self._ck(self.lib.fbpr_extract_surrounding_keyframes(self.h, slot, K, _vp(kp), _vp(call), _vp(coff), _vp(sall), _vp(soff), _vp(lk), MEM_HOST))
         self.sync()
 
+    # ---- resident keyframe store (cloudKeyPoses3D/6D + corner/surfCloudKeyFrames, mapOptmization.h:84-88)
+    def keyframes_clear(self): self._ck(self.lib.fbpr_keyframes_clear(self.h))
+    def keyframes_count(self): return self._ck(self.lib.fbpr_keyframes_count(self.h))
+
+    def keyframe_push(self, pose6, time, corner, surf):
+        """saveKeyFramesAndFactor's push_backs (:1690-1726); returns the keyframe index"""
+        p = _f32(pose6).reshape(6); c = _f32(corner).reshape(-1, 4); s = _f32(surf).reshape(-1, 4)
+        self.lib.fbpr_keyframe_push.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        return self._ck(self.lib.fbpr_keyframe_push(self.h, _vp(p), float(time), _vp(c), len(c), _vp(s), len(s), MEM_HOST))
+
+    def keyframes_set_poses(self, first, poses6):
+        p = _f32(poses6).reshape(-1, 6)
+        self._ck(self.lib.fbpr_keyframes_set_poses(self.h, first, len(p), _vp(p)))
+
+    def extractSurroundingKeyFramesResident(self, slot, time_last, density=1.0, loop_closure=False, keyframe_size=50):
+        """mapOptimization::extractSurroundingKeyFrames (:964-978) end to end on the device over the resident store"""
+        self.lib.fbpr_extract_surrounding_keyframes_resident.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_int, C.c_int]
+        self._ck(self.lib.fbpr_extract_surrounding_keyframes_resident(self.h, slot, float(time_last), float(density), 1 if loop_closure else 0, int(keyframe_size)))
+
+    def keyframe_selection(self):
+        """cloudToExtract of the last resident extraction: (list [K,4], keyframe index per entry, -1 = dropped by the re-check)"""
+        n = max(self.keyframes_count(), 1)
+        lst = np.zeros((2 * n + 8, 4), np.float32); idx = np.zeros(2 * n + 8, np.int32)
+        K = self._ck(self.lib.fbpr_get_keyframe_selection(self.h, _vp(lst), _vp(idx), len(lst)))
+        return lst[:K].copy(), idx[:K].copy()
+
     def set_global_map(self, corner_global, surf_global):
         c = _f32(corner_global).reshape(-1, 4); s = _f32(surf_global).reshape(-1, 4)
         self._ck(self.lib.fbpr_set_global_map(self.h, _vp(c), len(c), _vp(s), len(s), MEM_HOST))

@@ -57,6 +57,12 @@ struct fbpr_handle {
     VoxSeg* d_kfSegs = nullptr;        // [2F]  extractCloud VoxelGrid (keyframe concat -> local map)
     float4 *kfCorner = nullptr, *kfSurf = nullptr;   // [F][kfCap] transformed keyframe concat
     int* kfCount = nullptr;            // [F][2]
+    // resident keyframe store + the scratch of one selection (keyframes.cu); grown on demand
+    struct KfStore {
+        float* pose6 = nullptr; double* time = nullptr; int* off[2] = { nullptr, nullptr }; float4* pool[2] = { nullptr, nullptr };
+        int n = 0, poseCap = 0; long long poolCap[2] = { 0, 0 }, poolUsed[2] = { 0, 0 };
+        KfSelect sel = {}; VoxSeg* d_poseSeg = nullptr; int poseTilesCap = 0; float leaf = 0.f; std::vector<void*> selAllocs;
+    } kfs;
     // stand-alone ops scratch (grown on demand)
     VoxSeg* d_soloVox = nullptr; int soloVoxCap = 0; std::vector<void*> soloVoxAllocs;
     float4 *soloIn = nullptr, *soloOut = nullptr; int *soloN = nullptr, *soloNout = nullptr, *soloPK = nullptr, *soloOK = nullptr;
@@ -256,6 +262,9 @@ void fbpr_destroy(fbpr_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     for (void* p : h->soloVoxAllocs) cudaFree(p);
     for (void* p : h->soloGridAllocs) cudaFree(p);
+    for (void* p : h->kfs.selAllocs) cudaFree(p);
+    cudaFree(h->kfs.pose6); cudaFree(h->kfs.time);
+    for (int k = 0; k < 2; k++) { cudaFree(h->kfs.off[k]); cudaFree(h->kfs.pool[k]); }
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -903,6 +912,133 @@ int fbpr_extract_cloud(fbpr_handle* h, int slot, int K, const float* key_poses6,
     cudaFreeAsync(d_outoff, h->stream); cudaFreeAsync(d_T, h->stream);
     if (d_check) cudaFreeAsync(d_check, h->stream);
     return rc;
+}
+
+// ---- resident keyframe store --------------------------------------------------------------------
+static int kfs_grow_bytes(fbpr_handle* h, void** p, size_t usedBytes, size_t newBytes) {
+    void* q = nullptr;
+    FBPR_CUDA_OK(cudaMalloc(&q, newBytes));
+    FBPR_CUDA_OK(cudaMemsetAsync(q, 0, newBytes, h->stream));
+    if (*p && usedBytes) FBPR_CUDA_OK(cudaMemcpyAsync(q, *p, usedBytes, cudaMemcpyDeviceToDevice, h->stream));
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (*p) cudaFree(*p);
+    *p = q;
+    return 0;
+}
+#define kfs_grow(h, pp, used, cnt) kfs_grow_bytes((h), reinterpret_cast<void**>(pp), (used) * sizeof(**(pp)), (cnt) * sizeof(**(pp)))
+
+// scratch of a selection over up to `cap` key poses
+static int kfs_build_select(fbpr_handle* h, int cap) {
+    auto& K = h->kfs;
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    for (void* p : K.selAllocs) cudaFree(p);
+    K.selAllocs.clear();
+    auto A = [&](void** p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes); if (e == cudaSuccess) { cudaMemset(*p, 0, bytes); K.selAllocs.push_back(*p); } return e; };
+    KfSelect q = {};
+    q.cap = cap;
+    FBPR_CUDA_OK(A((void**)&q.keys, sizeof(unsigned long long) * (size_t)next_pow2(cap)));
+    FBPR_CUDA_OK(A((void**)&q.counters, 4 * sizeof(int)));
+    FBPR_CUDA_OK(A((void**)&q.hitPts, sizeof(float4) * (size_t)cap));
+    FBPR_CUDA_OK(A((void**)&q.list, sizeof(float4) * 2 * (size_t)cap));
+    FBPR_CUDA_OK(A((void**)&q.selIdx, sizeof(int) * 2 * (size_t)cap));
+    for (int k = 0; k < 2; k++) FBPR_CUDA_OK(A((void**)&q.outoff[k], sizeof(int) * (2 * (size_t)cap + 1)));
+    FBPR_CUDA_OK(A((void**)&q.T, sizeof(float) * 12 * 2 * (size_t)cap));
+    // downSizeFilterSurroundingKeyPoses (mapOptmization.h:887-888): hit poses -> the head of cloudToExtract
+    VoxSeg s = {};
+    const int tiles = (cap + fbpr_voxel_tile() - 1) / fbpr_voxel_tile() + 1;
+    for (int b = 0; b < 2; b++) { FBPR_CUDA_OK(A((void**)&s.key[b], 4 * (size_t)cap)); FBPR_CUDA_OK(A((void**)&s.val[b], 4 * (size_t)cap)); }
+    FBPR_CUDA_OK(A((void**)&s.tile_hist, 4 * (size_t)256 * tiles)); FBPR_CUDA_OK(A((void**)&s.bbox, 32));
+    FBPR_CUDA_OK(A((void**)&s.run_tile, 4 * (size_t)(tiles + 1))); FBPR_CUDA_OK(A((void**)&s.desc, sizeof(VoxDesc)));
+    FBPR_CUDA_OK(A((void**)&K.d_poseSeg, sizeof(VoxSeg)));
+    s.in = q.hitPts; s.n_in = q.counters; s.out = q.list; s.n_out = q.counters + 1; s.cap = cap; s.out_cap = cap; s.leaf = K.leaf > 0.f ? K.leaf : 1.0f;
+    FBPR_CUDA_OK(cudaMemcpy(K.d_poseSeg, &s, sizeof(s), cudaMemcpyHostToDevice));
+    K.sel = q; K.poseTilesCap = tiles; K.leaf = s.leaf;
+    return 0;
+}
+
+int fbpr_keyframes_clear(fbpr_handle* h) {
+    if (!h) return fbpr_fail_msg("null handle");
+    h->kfs.n = 0; h->kfs.poolUsed[0] = h->kfs.poolUsed[1] = 0;      // capacity is kept; offsets restart at 0 (off[k][0] is always 0)
+    return 0;
+}
+int fbpr_keyframes_count(fbpr_handle* h) { return h ? h->kfs.n : fbpr_fail_msg("null handle"); }
+
+int fbpr_keyframe_push(fbpr_handle* h, const float pose6[6], double time, const float* corner_xyzi, int n_corner,
+                       const float* surf_xyzi, int n_surf, int mem) {
+    if (!h) return fbpr_fail_msg("null handle");
+    if (!pose6 || n_corner < 0 || n_surf < 0 || (n_corner && !corner_xyzi) || (n_surf && !surf_xyzi)) return fbpr_fail_msg("bad keyframe");
+    cudaSetDevice(h->device);
+    auto& K = h->kfs;
+    if (K.n + 1 > K.poseCap) {
+        const int cap = K.poseCap ? 2 * K.poseCap : 1024;
+        int rc = kfs_grow(h, &K.pose6, 6 * (size_t)K.n, 6 * (size_t)cap); if (rc) return rc;
+        rc = kfs_grow(h, &K.time, (size_t)K.n, (size_t)cap); if (rc) return rc;
+        for (int k = 0; k < 2; k++) { rc = kfs_grow(h, &K.off[k], (size_t)K.n + 1, (size_t)cap + 1); if (rc) return rc; }
+        rc = kfs_build_select(h, cap); if (rc) return rc;
+        K.poseCap = cap;
+    }
+    const float* src[2] = { corner_xyzi, surf_xyzi }; const int len[2] = { n_corner, n_surf };
+    for (int k = 0; k < 2; k++) {
+        if (K.poolUsed[k] + len[k] > 0x7fffffffLL) return fbpr_fail_msg("keyframe store: more than 2^31 points of one kind");
+        if (K.poolUsed[k] + len[k] > K.poolCap[k]) {
+            long long cap = K.poolCap[k] ? 2 * K.poolCap[k] : (1LL << 20);
+            while (cap < K.poolUsed[k] + len[k]) cap *= 2;
+            int rc = kfs_grow(h, &K.pool[k], (size_t)K.poolUsed[k], (size_t)cap); if (rc) return rc;
+            K.poolCap[k] = cap;
+        }
+        if (len[k]) FBPR_CUDA_OK(cudaMemcpyAsync(K.pool[k] + K.poolUsed[k], src[k], sizeof(float4) * (size_t)len[k], kind_in(mem), h->stream));
+        K.poolUsed[k] += len[k];
+        const int end = (int)K.poolUsed[k];
+        FBPR_CUDA_OK(cudaMemcpyAsync(K.off[k] + K.n + 1, &end, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    FBPR_CUDA_OK(cudaMemcpyAsync(K.pose6 + 6 * (size_t)K.n, pose6, 6 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    FBPR_CUDA_OK(cudaMemcpyAsync(K.time + K.n, &time, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return K.n++;
+}
+
+int fbpr_keyframes_set_poses(fbpr_handle* h, int first, int count, const float* pose6) {
+    if (!h) return fbpr_fail_msg("null handle");
+    if (first < 0 || count < 0 || first + count > h->kfs.n || (count && !pose6)) return fbpr_fail_msg("keyframe range out of bounds");
+    cudaSetDevice(h->device);
+    if (count) FBPR_CUDA_OK(cudaMemcpyAsync(h->kfs.pose6 + 6 * (size_t)first, pose6, 6 * sizeof(float) * (size_t)count, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int fbpr_extract_surrounding_keyframes_resident(fbpr_handle* h, int slot, double timeLaserCloudInfoLast, float surroundingKeyframeDensity,
+                                                int loopClosureEnableFlag, int surroundingKeyframeSize) {
+    int rc = check_range(h, slot, 1); if (rc) return rc;
+    if (h->kfCap <= 0) return fbpr_fail_msg("handle created with max_keyframe_points = 0");
+    auto& K = h->kfs;
+    if (K.n == 0) return 0;                                       // mapOptmization.h:966-967: nothing to extract, the local map is left alone
+    if (!loopClosureEnableFlag && !(surroundingKeyframeDensity > 0.f)) return fbpr_fail_msg("surroundingKeyframeDensity must be positive");
+    cudaSetDevice(h->device);
+    if (!loopClosureEnableFlag && surroundingKeyframeDensity != K.leaf) {
+        FBPR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(K.d_poseSeg) + offsetof(VoxSeg, leaf), &surroundingKeyframeDensity, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        K.leaf = surroundingKeyframeDensity;
+    }
+    KfStoreView v = {};
+    v.pose6 = K.pose6; v.time = K.time; v.n = K.n;
+    for (int k = 0; k < 2; k++) { v.off[k] = K.off[k]; v.pool[k] = K.pool[k]; }
+    FBPR_CUDA_OK(cudaMemsetAsync(&h->meta[slot].mapTruncated, 0, sizeof(int), h->stream));
+    rc = fbpr_launch_keyframe_select(v, K.sel, K.d_poseSeg, K.poseTilesCap, timeLaserCloudInfoLast, h->p.surroundingKeyframeSearchRadius,
+                                     surroundingKeyframeDensity, loopClosureEnableFlag != 0, surroundingKeyframeSize,
+                                     h->kfCorner + (size_t)slot * h->kfCap, h->kfSurf + (size_t)slot * h->kfCap, h->kfCap,
+                                     h->kfCount + 2 * slot, &h->meta[slot].mapTruncated, h->stream, &h->launches);
+    if (!rc) rc = fbpr_launch_voxel(h->d_kfSegs + 2 * (size_t)slot, 2, h->kfCap, h->tilesCap, h->stream, &h->launches);
+    return rc;
+}
+
+int fbpr_get_keyframe_selection(fbpr_handle* h, float* list_xyzi, int32_t* key_index, int cap) {
+    if (!h) return fbpr_fail_msg("null handle");
+    if (!h->kfs.sel.counters) return 0;
+    cudaSetDevice(h->device);
+    int c[4] = { 0, 0, 0, 0 };
+    FBPR_CUDA_OK(cudaMemcpyAsync(c, h->kfs.sel.counters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    FBPR_CUDA_OK(cudaStreamSynchronize(h->stream));
+    const int Kn = c[2], m = Kn < cap ? Kn : cap;
+    if (m > 0 && list_xyzi) FBPR_CUDA_OK(cudaMemcpy(list_xyzi, h->kfs.sel.list, sizeof(float4) * (size_t)m, cudaMemcpyDeviceToHost));
+    if (m > 0 && key_index) FBPR_CUDA_OK(cudaMemcpy(key_index, h->kfs.sel.selIdx, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost));
+    return Kn;
 }
 
 static int upload_global(fbpr_handle* h, const float* corner_global, int nCg, const float* surf_global, int nSg, int mem) {

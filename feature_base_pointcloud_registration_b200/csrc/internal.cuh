@@ -90,6 +90,27 @@ struct GridSeg {                  // host-built descriptor of one map-index segm
 };
 
 
+// resident keyframe store: cloudKeyPoses3D / cloudKeyPoses6D + cornerCloudKeyFrames / surfCloudKeyFrames (mapOptmization.h:84-88),
+// appended to by fbpr_keyframe_push (saveKeyFramesAndFactor, :1690-1726); key pose i has intensity = i (:1689)
+struct KfStoreView {
+    const float* pose6;           // [n][6] roll, pitch, yaw, x, y, z
+    const double* time;           // [n] cloudKeyPoses6D[i].time
+    const int* off[2];            // [n+1] CSR offsets into the pools: 0 corner, 1 surf
+    const float4* pool[2];        // keyframe clouds, lidar frame
+    int n;
+};
+// scratch of one keyframe selection (extractNearby :872-907 / extractForLoopClosure :857-870), sized for the store's pose capacity
+struct KfSelect {
+    unsigned long long* keys;     // [pow2 >= cap] radius hits as (d^2 bits << 32 | index)
+    int* counters;                // [0] radius hits, [1] surroundingKeyPosesDS size (VoxelGrid output), [2] K = entries of cloudToExtract
+    float4* hitPts;               // [cap] surroundingKeyPoses: the hits in ascending (d^2, index) order
+    float4* list;                 // [2 cap] cloudToExtract: surroundingKeyPosesDS followed by the key poses of the last 10 s
+    int* selIdx;                  // [2 cap] keyframe named by entry k ((int)intensity, :927), -1 = dropped by the distance re-check (:924)
+    int* outoff[2];               // [2 cap + 1] output offsets of the entries' clouds in the concatenation
+    float* T;                     // [2 cap][12] pcl::getTransformation of the named keyframes' poses
+    int cap;
+};
+
 // pieces of one dense host span that was uploaded with a single copy and is now scattered to its slots (capi.cu, mapops.cu)
 #define FBPR_SCATTER_MAX 112
 struct ScatterPiece { unsigned long long src_off; void* dst; unsigned long long bytes; };     // offsets / sizes are multiples of 4
@@ -197,6 +218,9 @@ int fbpr_launch_transform_update(FrameMeta* meta, int first, int count, float ro
 int fbpr_launch_keyframe_transform(const float* d_poses6, int K, const float4* d_in, const int* d_off, float4* d_out, int* d_n_out,
                                    const float* d_last_xyz, float radius, const float* d_check_xyz, int max_pts, int* d_outoff, float* d_T,
                                    cudaStream_t st, long long* launches);
+int fbpr_launch_keyframe_select(const KfStoreView& store, const KfSelect& sel, const VoxSeg* d_poseSeg, int poseTilesCap,
+                                double timeLast, float radius, float density, int loopClosure, int keyframeSize,
+                                float4* d_outCorner, float4* d_outSurf, int kfCap, int* d_kfCount, int* d_truncated, cudaStream_t st, long long* launches);
 int fbpr_launch_crop_box(const float4* d_in, int n, const float* d_pose12, float4* d_out, int cap, int* d_n_out, int* d_truncated, int* d_tile,
                          cudaStream_t st, long long* launches);
 int fbpr_launch_pose_decompose(const float* d_pose12, FrameMeta* meta, int slot, cudaStream_t st, long long* launches);

@@ -43,6 +43,7 @@ bool ParamServer::loadYaml(const std::string& path) {
         else if (key == "numberOfCores") is >> numberOfCores; else if (key == "mappingProcessInterval") is >> mappingProcessInterval;
         else if (key == "surroundingKeyframeSearchRadius") is >> surroundingKeyframeSearchRadius;
         else if (key == "surroundingKeyframeDensity") is >> surroundingKeyframeDensity;
+        else if (key == "surroundingKeyframeSize") is >> surroundingKeyframeSize;
         else if (key == "loopClosureEnableFlag") loopClosureEnableFlag = (val == "true" || val == "True" || val == "1");
     }
     return true;
@@ -257,70 +258,76 @@ void mapOptimization::registration(const cloud_info& cloud_info_, Affine3f& pose
     }
 }
 
-std::vector<int> mapOptimization::extractNearby() {                                            // :872-907
-    std::vector<int> out;
+// mirror cloudKeyPoses6D / cornerCloudKeyFrames / surfCloudKeyFrames into the device-resident store: append the keyframes that
+// are new since the last call, start over when the history shrank, refresh the poses when correctPoses (:1735-1766) moved them
+void mapOptimization::syncKeyframeStore() {
     const int n = (int)cloudKeyPoses6D.size();
-    if (n == 0) return out;
-    const PointTypePose& last = cloudKeyPoses6D.back();
-    // radiusSearch(cloudKeyPoses3D->back(), radius): FLANN L2_Simple d^2 < (float)(r*r), sorted ascending (ties by index)
-    std::vector<std::pair<float, int>> hit;
-    const float r2 = (float)((double)surroundingKeyframeSearchRadius * (double)surroundingKeyframeSearchRadius);
+    int have = fbpr_keyframes_count(ctx_->h);
+    check(have, "fbpr_keyframes_count");
+    if (have > n || devicePoses_.size() != 6 * (size_t)have) {
+        check(fbpr_keyframes_clear(ctx_->h), "fbpr_keyframes_clear");
+        have = 0; devicePoses_.clear();
+    }
+    std::vector<float> cur(6 * (size_t)n);
     for (int i = 0; i < n; i++) {
         const PointTypePose& p = cloudKeyPoses6D[i];
-        const float dx = last.x - p.x, dy = last.y - p.y, dz = last.z - p.z;
-        float d = dx * dx; d += dy * dy; d += dz * dz;
-        if (d < r2) hit.push_back({ d, i });                    // flann::RadiusResultSet::addPoint: strictly inside
+        const float v[6] = { p.roll, p.pitch, p.yaw, p.x, p.y, p.z };
+        std::memcpy(&cur[6 * (size_t)i], v, sizeof(v));
     }
-    std::sort(hit.begin(), hit.end());
-    // VoxelGrid(surroundingKeyframeDensity) of the XYZI key poses (intensity = keyframe index, cloudKeyPoses3D): on the device
-    std::vector<float> in(hit.size() * 4), ds(hit.size() * 4);
-    for (size_t k = 0; k < hit.size(); k++) {
-        const PointTypePose& p = cloudKeyPoses6D[hit[k].second];
-        in[4 * k] = p.x; in[4 * k + 1] = p.y; in[4 * k + 2] = p.z; in[4 * k + 3] = p.intensity;
-    }
-    int m = 0;
-    if (!hit.empty()) {
-        m = fbpr_voxel_grid(ctx_->h, in.data(), (int)hit.size(), surroundingKeyframeDensity, ds.data(), nullptr, nullptr, FBPR_MEM_HOST);
-        check(m, "fbpr_voxel_grid(key poses)");
-    }
+    if (have > 0 && std::memcmp(cur.data(), devicePoses_.data(), 6 * sizeof(float) * (size_t)have) != 0)
+        check(fbpr_keyframes_set_poses(ctx_->h, 0, have, cur.data()), "fbpr_keyframes_set_poses");
+    for (int i = have; i < n; i++)
+        check(fbpr_keyframe_push(ctx_->h, &cur[6 * (size_t)i], cloudKeyPoses6D[i].time,
+                                 reinterpret_cast<const float*>(cornerCloudKeyFrames[i].data()), (int)cornerCloudKeyFrames[i].size(),
+                                 reinterpret_cast<const float*>(surfCloudKeyFrames[i].data()), (int)surfCloudKeyFrames[i].size(), FBPR_MEM_HOST),
+              "fbpr_keyframe_push");
+    devicePoses_.swap(cur);
+}
+
+void mapOptimization::extractResident(bool loopClosure) {
+    syncKeyframeStore();
+    check(fbpr_extract_surrounding_keyframes_resident(ctx_->h, 0, timeLaserCloudInfoLast, surroundingKeyframeDensity, loopClosure ? 1 : 0,
+                                                      surroundingKeyframeSize), "fbpr_extract_surrounding_keyframes_resident");
+}
+void mapOptimization::extractNearby() { extractResident(false); }                              // :872-907
+void mapOptimization::extractForLoopClosure() { extractResident(true); }                       // :857-870
+
+std::vector<int> mapOptimization::downloadSelection() {
+    const int cap = 2 * (int)cloudKeyPoses6D.size() + 8;
+    std::vector<float> lst(4 * (size_t)cap); std::vector<int32_t> idx((size_t)cap);
+    const int K = fbpr_get_keyframe_selection(ctx_->h, lst.data(), idx.data(), cap);
+    check(K, "fbpr_get_keyframe_selection");
     surroundingKeyPosesDS.clear();
-    for (int k = 0; k < m; k++) surroundingKeyPosesDS.push_back(PointType{ ds[4 * k], ds[4 * k + 1], ds[4 * k + 2], ds[4 * k + 3] });
-    // key poses of the last 10 s, newest first (:897-904)
-    for (int i = n - 1; i >= 0; --i) {
-        if (timeLaserCloudInfoLast - cloudKeyPoses6D[i].time < 10.0) {
-            const PointTypePose& p = cloudKeyPoses6D[i];
-            surroundingKeyPosesDS.push_back(PointType{ p.x, p.y, p.z, p.intensity });
-        } else break;
+    std::vector<int> out;
+    for (int k = 0; k < K && k < cap; k++) {
+        surroundingKeyPosesDS.push_back(PointType{ lst[4 * k], lst[4 * k + 1], lst[4 * k + 2], lst[4 * k + 3] });
+        out.push_back(idx[k]);
     }
-    for (const PointType& p : surroundingKeyPosesDS) out.push_back((int)p.intensity);           // thisKeyInd = (int)intensity (:927)
     return out;
 }
 
 void mapOptimization::extractSurroundingKeyFrames() {                                          // :964-978
     if (cloudKeyPoses6D.empty()) return;
-    const PointTypePose& last = cloudKeyPoses6D.back();
-    std::vector<int> sel = surroundingKeyframeIndices;
-    std::vector<PointType> selPoses;                          // positions the distance re-check of extractCloud (:924) looks at
-    if (sel.empty()) {
-        sel = extractNearby();
-        selPoses = surroundingKeyPosesDS;
+    if (surroundingKeyframeIndices.empty()) {
+        if (loopClosureEnableFlag) extractForLoopClosure(); else extractNearby();              // :970-977, all on the device
+    } else {
+        // caller-side selection: extractCloud (:909-955) over the named keyframes
+        const PointTypePose& last = cloudKeyPoses6D.back();
+        std::vector<float> poses; std::vector<int32_t> coff(1, 0), soff(1, 0); PointCloud call, sall;
+        for (int i : surroundingKeyframeIndices) {
+            const PointTypePose& p = cloudKeyPoses6D[i];
+            const float v[6] = { p.roll, p.pitch, p.yaw, p.x, p.y, p.z };
+            poses.insert(poses.end(), v, v + 6);
+            call.insert(call.end(), cornerCloudKeyFrames[i].begin(), cornerCloudKeyFrames[i].end());
+            sall.insert(sall.end(), surfCloudKeyFrames[i].begin(), surfCloudKeyFrames[i].end());
+            coff.push_back((int32_t)call.size()); soff.push_back((int32_t)sall.size());
+        }
+        const float lk[3] = { last.x, last.y, last.z };
+        check(fbpr_extract_cloud(ctx_->h, 0, (int)surroundingKeyframeIndices.size(), poses.data(), nullptr,
+                                 reinterpret_cast<const float*>(call.data()), coff.data(),
+                                 reinterpret_cast<const float*>(sall.data()), soff.data(), lk, FBPR_MEM_HOST),
+              "fbpr_extract_cloud");
     }
-    std::vector<float> poses; std::vector<int32_t> coff(1, 0), soff(1, 0); PointCloud call, sall;
-    for (int i : sel) {
-        const PointTypePose& p = cloudKeyPoses6D[i];
-        const float v[6] = { p.roll, p.pitch, p.yaw, p.x, p.y, p.z };
-        poses.insert(poses.end(), v, v + 6);
-        call.insert(call.end(), cornerCloudKeyFrames[i].begin(), cornerCloudKeyFrames[i].end());
-        sall.insert(sall.end(), surfCloudKeyFrames[i].begin(), surfCloudKeyFrames[i].end());
-        coff.push_back((int32_t)call.size()); soff.push_back((int32_t)sall.size());
-    }
-    const float lk[3] = { last.x, last.y, last.z };
-    std::vector<float> chk;
-    for (const PointType& p : selPoses) { chk.push_back(p.x); chk.push_back(p.y); chk.push_back(p.z); }
-    check(fbpr_extract_cloud(ctx_->h, 0, (int)sel.size(), poses.data(), chk.empty() ? nullptr : chk.data(),
-                             reinterpret_cast<const float*>(call.data()), coff.data(),
-                             reinterpret_cast<const float*>(sall.data()), soff.data(), lk, FBPR_MEM_HOST),
-          "fbpr_extract_cloud");
     check(fbpr_sync(ctx_->h), "fbpr_sync");
     int32_t c[8]; check(fbpr_get_counts(ctx_->h, 0, c), "fbpr_get_counts");
     laserCloudCornerFromMapDSNum = c[6]; laserCloudSurfFromMapDSNum = c[7];
@@ -399,7 +406,8 @@ int fm_cloud_handler(const char* params_yaml, int N_SCAN, int Horizon_SCAN,
 extern "C" __attribute__((visibility("default")))
 int fm_extract_surrounding(const char* params_yaml, int N_SCAN, int Horizon_SCAN, const float* keyPoses6, const double* keyTime, int nKeys,
                            double timeLaserCloudInfoLast, const float* corner_all, const int32_t* corner_off, const float* surf_all, const int32_t* surf_off,
-                           float* ds_out, int ds_cap, int* n_ds, float* map_corner, int capC, float* map_surf, int capS, int* counts2, char* err, int errlen) {
+                           float* ds_out, int ds_cap, int* n_ds, float* map_corner, int capC, float* map_surf, int capS, int* counts2, char* err, int errlen,
+                           int loopClosureEnableFlag, int surroundingKeyframeSize) {
     try {
         ParamServer ps;
         if (params_yaml && params_yaml[0] && !ps.loadYaml(params_yaml)) throw std::runtime_error("cannot read params yaml");
@@ -415,8 +423,11 @@ int fm_extract_surrounding(const char* params_yaml, int N_SCAN, int Horizon_SCAN
             m.surfCloudKeyFrames.emplace_back(s + surf_off[i], s + surf_off[i + 1]);
         }
         m.timeLaserCloudInfoLast = timeLaserCloudInfoLast;
+        m.loopClosureEnableFlag = loopClosureEnableFlag != 0;
+        if (surroundingKeyframeSize >= 0) m.surroundingKeyframeSize = surroundingKeyframeSize;
         m.extractSurroundingKeyFrames();
         m.syncHostClouds();
+        m.downloadSelection();
         *n_ds = (int)m.surroundingKeyPosesDS.size();
         for (int i = 0; i < *n_ds && i < ds_cap; i++) std::memcpy(ds_out + 4 * i, &m.surroundingKeyPosesDS[i], 16);
         counts2[0] = (int)m.laserCloudCornerFromMapDS.size(); counts2[1] = (int)m.laserCloudSurfFromMapDS.size();

@@ -84,7 +84,8 @@ public:
     double mappingProcessInterval = 0.15;
     float surroundingKeyframeSearchRadius = 50.0f;
     float surroundingKeyframeDensity = 1.0f;                  // utility.h:197 (params.yaml: 2.0)
-    bool loopClosureEnableFlag = false;
+    bool loopClosureEnableFlag = false;                       // utility.h:199 -> extractForLoopClosure instead of extractNearby (:970-977)
+    int surroundingKeyframeSize = 50;                         // utility.h:201 (params.yaml:71: 25)
     ParamServer() {}
     explicit ParamServer(const std::string& params_yaml) { loadYaml(params_yaml); }
     bool loadYaml(const std::string& path);                   // flat `key: value` reader of config/params.yaml
@@ -110,13 +111,17 @@ public:
     PointCloud corner_GlobalMap, surf_GlobalMap;              // the fork's pre-built feature maps (mapOptmization.h:245-260)
     std::vector<PointTypePose> cloudKeyPoses6D;               // keyframe store for extractSurroundingKeyFrames
     std::vector<PointCloud> cornerCloudKeyFrames, surfCloudKeyFrames;
-    std::vector<int> surroundingKeyframeIndices;              // optional caller-side selection (overrides extractNearby)
-    PointCloud surroundingKeyPosesDS;                         // what extractNearby hands to extractCloud (positions + averaged index)
-    // mapOptimization::extractNearby (mapOptmization.h:872-907): key poses within surroundingKeyframeSearchRadius of the last one
-    // (ascending distance, ties by index), VoxelGrid(surroundingKeyframeDensity) of those poses INCLUDING the averaged intensity
-    // that the reference then truncates to a keyframe index (:927), plus the key poses of the last 10 s, newest first.
-    // Returns the keyframe index of every selected entry, in extractCloud's order.
-    std::vector<int> extractNearby();
+    std::vector<int> surroundingKeyframeIndices;              // optional caller-side selection (overrides the device-side selection)
+    PointCloud surroundingKeyPosesDS;                         // cloudToExtract of the last extraction (filled by downloadSelection)
+    // The keyframe containers above are mirrored into a store that is RESIDENT in HBM (appended to as they grow, poses refreshed
+    // when correctPoses (:1735-1766) moved them); selection AND extraction then run on the device with no host round trip:
+    // extractNearby (mapOptmization.h:872-907): key poses within surroundingKeyframeSearchRadius of the last one (ascending
+    // distance, ties by index), VoxelGrid(surroundingKeyframeDensity) of those poses INCLUDING the averaged intensity that the
+    // reference then truncates to a keyframe index (:927), plus the key poses of the last 10 s, newest first, then extractCloud;
+    // extractForLoopClosure (:857-870): the newest surroundingKeyframeSize + 1 key poses, then extractCloud.
+    void extractNearby();
+    void extractForLoopClosure();
+    std::vector<int> downloadSelection();                     // keyframe index of every entry of cloudToExtract (-1: dropped by the re-check, :924)
     float transformTobeMapped[6] = { 0, 0, 0, 0, 0, 0 };
     bool isDegenerate = false;
     int laserCloudCornerFromMapDSNum = 0, laserCloudSurfFromMapDSNum = 0, laserCloudCornerLastDSNum = 0, laserCloudSurfLastDSNum = 0;
@@ -137,6 +142,9 @@ private:
     std::shared_ptr<DeviceContext> ctx_;
     void pushPose();
     void pullPose();
+    void syncKeyframeStore();
+    void extractResident(bool loopClosure);
+    std::vector<float> devicePoses_;                          // poses as uploaded (6 per keyframe)
 };
 
 }  // namespace feature_matching_b200

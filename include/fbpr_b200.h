@@ -181,7 +181,8 @@ FBPR_API int fbpr_project(fbpr_handle* h, int first, int count);
 FBPR_API int fbpr_feature_extract(fbpr_handle* h, int first, int count);
 /* replaces: mapOptimization::extractSurroundingKeyFrames -> extractCloud (mapOptmization.h:909-978):
    transform K selected keyframes by their poses, concatenate in list order, VoxelGrid both kinds.
-   Keyframe SELECTION stays with the caller. Clouds are concatenated with
+   The caller names the keyframes here (fbpr_extract_surrounding_keyframes_resident below selects them on the device).
+   Clouds are concatenated with
    CSR offsets (K+1 entries). */
 FBPR_API int fbpr_extract_surrounding_keyframes(fbpr_handle* h, int slot, int K, const float* key_poses6,
                                                 const float* corner_xyzi, const int32_t* corner_off,
@@ -194,6 +195,27 @@ FBPR_API int fbpr_extract_cloud(fbpr_handle* h, int slot, int K, const float* ke
                                 const float* corner_xyzi, const int32_t* corner_off,
                                 const float* surf_xyzi, const int32_t* surf_off,
                                 const float last_key_xyz[3], int mem);
+/* replaces: the keyframe containers cloudKeyPoses3D / cloudKeyPoses6D / cornerCloudKeyFrames / surfCloudKeyFrames
+   (mapOptmization.h:84-88) by a store that is RESIDENT in HBM.  fbpr_keyframe_push = the push_backs of saveKeyFramesAndFactor
+   (:1690, :1700, :1725-1726): pose6 = (roll, pitch, yaw, x, y, z), time = cloudKeyPoses6D[i].time, the two clouds in the lidar
+   frame; returns the keyframe's index (= cloudKeyPoses3D[i].intensity, :1689).  fbpr_keyframes_set_poses = correctPoses (:1735-1766)
+   writing optimised poses back.  fbpr_keyframes_clear empties the store (capacity is kept). */
+FBPR_API int fbpr_keyframes_clear(fbpr_handle* h);
+FBPR_API int fbpr_keyframes_count(fbpr_handle* h);
+FBPR_API int fbpr_keyframe_push(fbpr_handle* h, const float pose6[6], double time, const float* corner_xyzi, int n_corner,
+                                const float* surf_xyzi, int n_surf, int mem);
+FBPR_API int fbpr_keyframes_set_poses(fbpr_handle* h, int first, int count, const float* pose6);
+/* replaces: mapOptimization::extractSurroundingKeyFrames (mapOptmization.h:964-978) END TO END on the device over the resident
+   store: extractNearby (:872-907: radius search around the newest key pose, VoxelGrid(surroundingKeyframeDensity) of the hits,
+   the key poses of the last 10 s) or, when loopClosureEnableFlag != 0, extractForLoopClosure (:857-870: the newest
+   surroundingKeyframeSize + 1 key poses), then extractCloud (:909-955) into the slot's local map.  No host round trip; an
+   empty store leaves the local map untouched (:966-967).  Needs max_keyframe_points > 0. */
+FBPR_API int fbpr_extract_surrounding_keyframes_resident(fbpr_handle* h, int slot, double timeLaserCloudInfoLast,
+                                                         float surroundingKeyframeDensity, int loopClosureEnableFlag,
+                                                         int surroundingKeyframeSize);
+/* parity getter: cloudToExtract of the last resident extraction (surroundingKeyPosesDS + the last-10-s poses, or the loop-closure
+   list) and, per entry, the keyframe it names (-1: dropped by the distance re-check, :924).  Returns the list length. */
+FBPR_API int fbpr_get_keyframe_selection(fbpr_handle* h, float* list_xyzi, int32_t* key_index, int cap);
 /* replaces: mapOptimization::downsampleCurrentScan (mapOptmization.h:981-993). */
 FBPR_API int fbpr_downsample_current_scan(fbpr_handle* h, int first, int count);
 /* replaces: mapOptimization::scan2MapOptimization (mapOptmization.h:1403-1442) including the two

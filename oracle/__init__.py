@@ -110,6 +110,12 @@ def get_translation_and_euler(T):
 
 
 # ------------------------------------------------------------------ cloud primitives
+def set_literal_sort(on):
+    """1: featureExtraction's std::sort compares the curvature only and VoxelGrid's the voxel index only, exactly as the reference
+    does (ties land where libstdc++'s introsort leaves them); 0 (default): ties broken by point index.  Returns the old value."""
+    return int(lib().orc_set_literal_sort(1 if on else 0))
+
+
 def voxel_grid(xyzi, leaf):
     xyzi = f32(xyzi).reshape(-1, 4); n = xyzi.shape[0]
     out = np.zeros((max(n, 1), 4), np.float32)
@@ -216,9 +222,11 @@ class MapOptimization:
         lib().orc_mo_extract_cloud(self.h, _f(kp), K, _f(call), _i(coff), _f(sall), _i(soff), _f(lk), _i(counts))
         return counts
 
-    def extract_surrounding(self, key_poses6_all, key_times, density, time_last, corner_frames, surf_frames):
-        """extractNearby + extractCloud over the whole keyframe store (mapOptmization.h:872-955).
-        Returns (surroundingKeyPosesDS [m,4], counts[4])."""
+    def extract_surrounding(self, key_poses6_all, key_times, density, time_last, corner_frames, surf_frames,
+                            loop_closure=False, keyframe_size=50):
+        """extractSurroundingKeyFrames over the whole keyframe store (mapOptmization.h:964-978): extractNearby (:872-907) or, with
+        loop_closure, extractForLoopClosure (:857-870), then extractCloud (:909-955).
+        Returns (cloudToExtract [m,4], counts[4])."""
         n = len(corner_frames)
         kp = f32(key_poses6_all).reshape(n, 6); kt = np.ascontiguousarray(key_times, np.float64)
         coff = np.zeros(n + 1, np.int32); soff = np.zeros(n + 1, np.int32)
@@ -228,9 +236,10 @@ class MapOptimization:
         fn = lib().orc_mo_extract_surrounding
         fn.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int, C.c_float, C.c_double,
                        C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int),
-                       C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
+                       C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]
         fn.restype = C.c_int
-        m = fn(self.h, _f(kp), _d(kt), n, float(density), float(time_last), _f(call), _i(coff), _f(sall), _i(soff), _f(ds), len(ds), _i(counts))
+        m = fn(self.h, _f(kp), _d(kt), n, float(density), float(time_last), _f(call), _i(coff), _f(sall), _i(soff), _f(ds), len(ds), _i(counts),
+               1 if loop_closure else 0, int(keyframe_size))
         return ds[:m].copy(), counts
 
     def downsample(self):

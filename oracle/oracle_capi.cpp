@@ -145,6 +145,8 @@ void orc_mo_set_map(orc_mo* h, const float* corner, int nC, const float* surf, i
 void orc_mo_set_imu(orc_mo* h, int64_t imuAvailable, float imuRollInit, float imuPitchInit) {
     h->mo.imuAvailable = imuAvailable; h->mo.imuRollInit = imuRollInit; h->mo.imuPitchInit = imuPitchInit;
 }
+// 1: the path's two std::sort calls compare only what the reference compares (see oracle_literal_sort); returns the old value
+int orc_set_literal_sort(int on) { int old = oracle_literal_sort(); oracle_literal_sort() = on ? 1 : 0; return old; }
 // keyframe clouds are given concatenated with CSR offsets (K+1 entries)
 void orc_mo_extract_cloud(orc_mo* h, const float* keyPoses6, int K, const float* corner_all, const int* corner_off,
                           const float* surf_all, const int* surf_off, const float* lastKeyXYZ, int* counts) {
@@ -159,13 +161,15 @@ void orc_mo_extract_cloud(orc_mo* h, const float* keyPoses6, int K, const float*
 }
 // extractSurroundingKeyFrames as the reference runs it: extractNearby (:872-907) + extractCloud (:909-955) over the whole
 // keyframe store (key pose i = row i of keyPoses6All, cloudKeyPoses3D[i].intensity = i).  ds_out = surroundingKeyPosesDS.
+// loopClosureEnableFlag != 0: extractForLoopClosure (:857-870) with surroundingKeyframeSize instead of extractNearby (:970-977).
 int orc_mo_extract_surrounding(orc_mo* h, const float* keyPoses6All, const double* keyTime, int nKeys, float density, double timeLast,
                                const float* corner_all, const int* corner_off, const float* surf_all, const int* surf_off,
-                               float* ds_out, int ds_cap, int* counts) {
+                               float* ds_out, int ds_cap, int* counts, int loopClosureEnableFlag, int surroundingKeyframeSize) {
     std::vector<P4> k3(nKeys);
     for (int i = 0; i < nKeys; i++) k3[i] = P4{ keyPoses6All[6 * i + 3], keyPoses6All[6 * i + 4], keyPoses6All[6 * i + 5], (float)i };
     std::vector<P4> ds;
-    MapOptimization::extractNearby(k3.data(), keyTime, nKeys, h->mo.P.surroundingKeyframeSearchRadius, density, timeLast, ds);
+    if (loopClosureEnableFlag) MapOptimization::extractForLoopClosure(k3.data(), nKeys, surroundingKeyframeSize, ds);
+    else MapOptimization::extractNearby(k3.data(), keyTime, nKeys, h->mo.P.surroundingKeyframeSearchRadius, density, timeLast, ds);
     std::vector<const P4*> cf(nKeys), sf(nKeys); std::vector<int> cn(nKeys), sn(nKeys);
     for (int i = 0; i < nKeys; i++) {
         cf[i] = reinterpret_cast<const P4*>(corner_all) + corner_off[i]; cn[i] = corner_off[i + 1] - corner_off[i];

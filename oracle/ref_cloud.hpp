@@ -21,6 +21,13 @@ namespace orc {
 
 struct P4 { float x, y, z, i; };
 
+// Oracle contract vs the literal reference: by default every unstable sort is made a total order by the
+// point index.  With this flag set the two std::sort calls of the path compare exactly what the reference compares
+// (featureExtraction.h:13-17 by_value on the curvature only; pcl::VoxelGrid on the voxel index only), so ties fall wherever
+// libstdc++'s introsort leaves them.  tests / scripts use it to COUNT how many frames the tie-break rule changes.
+inline int& oracle_literal_sort() { static int v = 0; return v; }
+
+
 // Returns the number of output points.  keys_out (optional): per INPUT point voxel key.
 // overflow (optional) is set when PCL's "leaf size too small" path copies input to output.
 static inline int voxel_grid(const P4* in, int n, float leaf, std::vector<P4>& out,
@@ -61,7 +68,10 @@ static inline int voxel_grid(const P4* in, int n, float leaf, std::vector<P4>& o
         ki[k] = { idx, k };
         if (keys_out) (*keys_out)[k] = idx;
     }
-    std::sort(ki.begin(), ki.end());   // (key, point index): total order
+    // (key, point index): total order.  Literal mode: pcl::VoxelGrid's own call, std::sort on the voxel index alone
+    // (cloud_point_index_idx::operator<, voxel_grid.h) -- libstdc++ introsort, members of a voxel in unspecified order
+    if (oracle_literal_sort()) std::sort(ki.begin(), ki.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+    else std::sort(ki.begin(), ki.end());
     int first = 0;
     while (first < n) {
         int last = first + 1;

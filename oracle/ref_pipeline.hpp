@@ -269,6 +269,9 @@ static inline void extract_features(const Params& P, const CloudInfo& ci, Featur
             int sp = (ci.startRingIndex[i] * (6 - j) + ci.endRingIndex[i] * j) / 6;
             int ep = (ci.startRingIndex[i] * (5 - j) + ci.endRingIndex[i] * (j + 1)) / 6 - 1;
             if (sp >= ep) continue;
+            if (oracle_literal_sort())                        // featureExtraction.h:203 with by_value (:13-17): value only
+                std::sort(cloudSmoothness.begin() + sp, cloudSmoothness.begin() + ep, [](const Smooth& l, const Smooth& r) { return l.value < r.value; });
+            else
             std::sort(cloudSmoothness.begin() + sp, cloudSmoothness.begin() + ep,
                       [](const Smooth& l, const Smooth& r) { return l.value < r.value || (l.value == r.value && l.ind < r.ind); });
             int largestPickedNum = 0;
@@ -381,6 +384,15 @@ public:
         voxel_grid(surroundingKeyPoses.data(), (int)surroundingKeyPoses.size(), density, surroundingKeyPosesDS);
         for (int i = n - 1; i >= 0; --i) {
             if (timeLaserCloudInfoLast - keyTime[i] < 10.0) surroundingKeyPosesDS.push_back(cloudKeyPoses3D[i]);
+            else break;
+        }
+    }
+    // extractForLoopClosure  mapOptmization.h:857-870: key poses from the newest backwards while the list holds
+    // <= surroundingKeyframeSize entries, i.e. surroundingKeyframeSize + 1 of them when the store is large enough
+    static void extractForLoopClosure(const P4* cloudKeyPoses3D, int n, int surroundingKeyframeSize, std::vector<P4>& cloudToExtract) {
+        cloudToExtract.clear();
+        for (int i = n - 1; i >= 0; --i) {
+            if ((int)cloudToExtract.size() <= surroundingKeyframeSize) cloudToExtract.push_back(cloudKeyPoses3D[i]);
             else break;
         }
     }

@@ -566,11 +566,72 @@ def test_cpp_host_extract_nearby_matches_oracle(fb, tmp_path):
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     kt = np.ascontiguousarray(times, np.float64); kp = f32(poses)
     rc = lib.fm_extract_surrounding(str(y).encode(), int(P["N_SCAN"]), int(P["Horizon_SCAN"]), vp(kp), vp(kt), n, C.c_double(tlast),
-                                    vp(call), vp(coff), vp(sall), vp(soff), vp(ds), len(ds), C.byref(nds), vp(mc), capC, vp(ms), capS, counts, err, 512)
+                                    vp(call), vp(coff), vp(sall), vp(soff), vp(ds), len(ds), C.byref(nds), vp(mc), capC, vp(ms), capS, counts, err, 512, 0, -1)
     assert rc == 0, err.value.decode()
     assert nds.value == len(ds_w) and np.array_equal(ds[:nds.value], ds_w)
     assert (counts[0], counts[1]) == (int(counts_w[2]), int(counts_w[3]))
     assert np.array_equal(mc[:counts[0]], mo.get_cloud(2)) and np.array_equal(ms[:counts[1]], mo.get_cloud(3))
+    # loopClosureEnableFlag: extractForLoopClosure (mapOptmization.h:857-870) with surroundingKeyframeSize = 7
+    ds_w, counts_w = mo.extract_surrounding(poses, times, 2.0, tlast, cf, sf, loop_closure=True, keyframe_size=7)
+    assert len(ds_w) == 8
+    rc = lib.fm_extract_surrounding(str(y).encode(), int(P["N_SCAN"]), int(P["Horizon_SCAN"]), vp(kp), vp(kt), n, C.c_double(tlast),
+                                    vp(call), vp(coff), vp(sall), vp(soff), vp(ds), len(ds), C.byref(nds), vp(mc), capC, vp(ms), capS, counts, err, 512, 1, 7)
+    assert rc == 0, err.value.decode()
+    assert nds.value == len(ds_w) and np.array_equal(ds[:nds.value], ds_w)
+    assert np.array_equal(mc[:counts[0]], mo.get_cloud(2)) and np.array_equal(ms[:counts[1]], mo.get_cloud(3))
+
+
+@pytest.mark.parametrize("mode", ["nearby", "loop_closure", "nearby_all_recent"])
+def test_resident_keyframe_store_matches_oracle(fb, mode):
+    """fbpr_extract_surrounding_keyframes_resident: extractSurroundingKeyFrames (mapOptmization.h:964-978) end to end on the device
+    over >= 1000 resident key poses -- radius search sorted by (d^2, index), key-pose VoxelGrid with averaged indices, last-10-s
+    rule / extractForLoopClosure, distance re-check, transform + concat + VoxelGrid x2 -- against the oracle: selection list and
+    both local maps bit-exact.  The store grows past its first capacity and has its poses corrected in place (correctPoses)."""
+    rng = np.random.default_rng(21)
+    P = dict(synth.params_for(1)); P["surroundingKeyframeSearchRadius"] = 18.0
+    n = 1300
+    # a trajectory that winds back on itself, so the radius holds old and new key poses and voxels average far-apart indices
+    t = np.linspace(0, 6 * np.pi, n)
+    xyz = np.stack([30 * np.cos(t) + 3 * np.sin(7 * t), 30 * np.sin(t) + 2 * np.cos(5 * t), 0.3 * np.sin(3 * t)], 1)
+    poses = np.concatenate([rng.uniform(-0.2, 0.2, (n, 3)), xyz + rng.normal(0, 0.3, (n, 3))], 1).astype(np.float32)
+    cf = [np.concatenate([rng.uniform(-10, 10, (20 + k % 7, 3)), np.full((20 + k % 7, 1), k)], 1).astype(np.float32) for k in range(n)]
+    sf = [np.concatenate([rng.uniform(-10, 10, (60 + k % 11, 3)), np.full((60 + k % 11, 1), k)], 1).astype(np.float32) for k in range(n)]
+    times = np.arange(n) * (0.002 if mode == "nearby_all_recent" else 0.4)        # all_recent: every key pose is younger than 10 s
+    tlast = float(times[-1] + 0.05)
+    lc = mode == "loop_closure"
+    mo = oracle.MapOptimization(P)
+    r = _reg(fb, P, max_keyframe_points=1 << 18, max_map_corner=1 << 16, max_map_surf=1 << 17)
+    wrong = poses.copy(); wrong[:500, 3:] += 1.0
+    for k in range(n):                                           # pushed with stale poses for the first 500, corrected below
+        assert r.keyframe_push(wrong[k], times[k], cf[k], sf[k]) == k
+        if k == 399:                                             # an extraction in the middle of the sequence, before the store grows
+            ds_w, counts_w = mo.extract_surrounding(wrong[:400], times[:400], 2.0, float(times[399] + 0.05), cf[:400], sf[:400], loop_closure=lc, keyframe_size=25)
+            r.extractSurroundingKeyFramesResident(0, float(times[399] + 0.05), 2.0, loop_closure=lc, keyframe_size=25)
+            lst, idx = r.keyframe_selection()
+            assert np.array_equal(lst, ds_w)
+            assert np.array_equal(r.get_buffer(0, "MAP_SURF").reshape(-1, 4), mo.get_cloud(3))
+    assert r.keyframes_count() == n
+    r.keyframes_set_poses(0, poses[:500])
+    ds_w, counts_w = mo.extract_surrounding(poses, times, 2.0, tlast, cf, sf, loop_closure=lc, keyframe_size=25)
+    r.extractSurroundingKeyFramesResident(0, tlast, 2.0, loop_closure=lc, keyframe_size=25)
+    lst, idx = r.keyframe_selection()
+    assert len(lst) == len(ds_w) and np.array_equal(lst, ds_w)
+    if mode == "nearby":
+        assert np.any(lst[:, 3] != np.floor(lst[:, 3])) and len(lst) > 60          # averaged indices and a real radius result
+    if lc:
+        assert len(lst) == 26
+    keep = idx >= 0
+    assert np.array_equal(idx[keep], lst[keep, 3].astype(np.int32))
+    c = r.get_counts(0)
+    assert (c["n_map_corner"], c["n_map_surf"]) == (int(counts_w[2]), int(counts_w[3]))
+    assert np.array_equal(r.get_buffer(0, "MAP_CORNER").reshape(-1, 4), mo.get_cloud(2))
+    assert np.array_equal(r.get_buffer(0, "MAP_SURF").reshape(-1, 4), mo.get_cloud(3))
+    _, _, flags = r.get_pose(0)
+    # an empty store leaves the local map alone (:966-967)
+    r.keyframes_clear()
+    r.extractSurroundingKeyFramesResident(0, tlast, 2.0)
+    assert r.get_counts(0)["n_map_surf"] == int(counts_w[3])
+    r.close()
 
 
 @pytest.mark.parametrize("layout", ["velodyne22", "pcl32", "no_time_ring8"])
