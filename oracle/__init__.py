@@ -35,6 +35,9 @@ def make_params(d):
 
 
 def build(force=False):
+    if os.environ.get("ORACLE_SANITIZE"):          # scripts/oracle_sanitize.sh: the ASan + UBSan build (needs libasan preloaded)
+        subprocess.check_call(["make", "-C", _HERE, "liboracle_asan.so"], stdout=subprocess.DEVNULL)
+        return os.path.join(_HERE, "liboracle_asan.so")
     so = os.path.join(_HERE, "liboracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ref_pipeline.hpp", "ref_cloud.hpp", "ref_smallmat.hpp")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):

@@ -9,6 +9,9 @@
 
 using namespace orc;
 
+// memcpy that is a no-op for empty ranges (an empty std::vector's data() may be null, which memcpy must not be given)
+static inline void cpy(void* dst, const void* src, size_t bytes) { if (bytes) std::memcpy(dst, src, bytes); }
+
 extern "C" {
 
 struct orc_params {
@@ -35,15 +38,15 @@ static Params to_params(const orc_params* p) {
 
 // ---------------------------------------------------------------- small matrices
 void orc_eigen_sym(int n, const float* A, float* W, float* V) {
-    float Aw[36]; std::memcpy(Aw, A, sizeof(float) * n * n);
+    float Aw[36]; cpy(Aw, A, sizeof(float) * n * n);
     jacobi_eigen_sym(n, Aw, W, V);
 }
 int orc_qr_solve(int n, const float* A, const float* b, float* x) {
-    float Aw[36], bw[6]; std::memcpy(Aw, A, sizeof(float) * n * n); std::memcpy(bw, b, sizeof(float) * n);
+    float Aw[36], bw[6]; cpy(Aw, A, sizeof(float) * n * n); cpy(bw, b, sizeof(float) * n);
     return qr_solve(n, Aw, bw, x);
 }
 int orc_lu_invert(int n, const float* A, float* Ainv) {
-    float Aw[36]; std::memcpy(Aw, A, sizeof(float) * n * n);
+    float Aw[36]; cpy(Aw, A, sizeof(float) * n * n);
     return lu_invert(n, Aw, Ainv);
 }
 void orc_matmul_f64acc(int r, int k, int c, const float* A, const float* B, float* C) { matmul_f64acc(r, k, c, A, B, C); }
@@ -59,14 +62,14 @@ void orc_get_translation_and_euler(const float T[12], float pose6[6]) {
 int orc_voxel_grid(const float* xyzi, int n, float leaf, float* out_xyzi, int* point_keys, int* out_keys, int* overflow) {
     std::vector<P4> out; std::vector<int> pk, ok;
     int m = voxel_grid(reinterpret_cast<const P4*>(xyzi), n, leaf, out, point_keys ? &pk : nullptr, out_keys ? &ok : nullptr, overflow);
-    std::memcpy(out_xyzi, out.data(), sizeof(P4) * m);
-    if (point_keys && !pk.empty()) std::memcpy(point_keys, pk.data(), sizeof(int) * n);
-    if (out_keys && !ok.empty()) std::memcpy(out_keys, ok.data(), sizeof(int) * ok.size());
+    cpy(out_xyzi, out.data(), sizeof(P4) * m);
+    if (point_keys && !pk.empty()) cpy(point_keys, pk.data(), sizeof(int) * n);
+    if (out_keys && !ok.empty()) cpy(out_keys, ok.data(), sizeof(int) * ok.size());
     return m;
 }
 int orc_crop_box(const float* xyzi, int n, const float mn[3], const float mx[3], float* out_xyzi) {
     std::vector<P4> out; crop_box(reinterpret_cast<const P4*>(xyzi), n, mn, mx, out);
-    std::memcpy(out_xyzi, out.data(), sizeof(P4) * out.size());
+    cpy(out_xyzi, out.data(), sizeof(P4) * out.size());
     return (int)out.size();
 }
 void orc_kdtree_knn5(const float* map_xyzi, int M, const float* q_xyz, int nq, int* idx, float* d2, int threads) {
@@ -92,12 +95,12 @@ int orc_project(const orc_params* p, const float* x, const float* y, const float
     CloudInfo ci; std::vector<int> win;
     project(P, raw, imuAvailable, deskewFlag, imu, ci, winner_raw ? &win : nullptr);
     int nv = (int)ci.cloud_deskewed.size();
-    std::memcpy(startRingIndex, ci.startRingIndex.data(), sizeof(int) * P.N_SCAN);
-    std::memcpy(endRingIndex, ci.endRingIndex.data(), sizeof(int) * P.N_SCAN);
-    std::memcpy(pointColInd, ci.pointColInd.data(), sizeof(int) * nv);
-    std::memcpy(pointRange, ci.pointRange.data(), sizeof(float) * nv);
-    std::memcpy(cloud_xyzi, ci.cloud_deskewed.data(), sizeof(P4) * nv);
-    if (winner_raw) std::memcpy(winner_raw, win.data(), sizeof(int) * nv);
+    cpy(startRingIndex, ci.startRingIndex.data(), sizeof(int) * P.N_SCAN);
+    cpy(endRingIndex, ci.endRingIndex.data(), sizeof(int) * P.N_SCAN);
+    cpy(pointColInd, ci.pointColInd.data(), sizeof(int) * nv);
+    cpy(pointRange, ci.pointRange.data(), sizeof(float) * nv);
+    cpy(cloud_xyzi, ci.cloud_deskewed.data(), sizeof(P4) * nv);
+    if (winner_raw) cpy(winner_raw, win.data(), sizeof(int) * nv);
     return nv;
 }
 
@@ -117,15 +120,15 @@ void orc_extract_features(const orc_params* p, const int* startRingIndex, const 
     ci.cloud_deskewed.assign(reinterpret_cast<const P4*>(cloud_xyzi), reinterpret_cast<const P4*>(cloud_xyzi) + n_valid);
     FeatureOut fo; extract_features(P, ci, fo);
     counts[0] = (int)fo.cornerCloud.size(); counts[1] = (int)fo.surfaceCloud.size(); counts[2] = (int)fo.surfaceRawIndex.size();
-    if (corner_xyzi) std::memcpy(corner_xyzi, fo.cornerCloud.data(), sizeof(P4) * fo.cornerCloud.size());
-    if (corner_index) std::memcpy(corner_index, fo.cornerIndex.data(), sizeof(int) * fo.cornerIndex.size());
-    if (surface_xyzi) std::memcpy(surface_xyzi, fo.surfaceCloud.data(), sizeof(P4) * fo.surfaceCloud.size());
-    if (surface_raw_index) std::memcpy(surface_raw_index, fo.surfaceRawIndex.data(), sizeof(int) * fo.surfaceRawIndex.size());
-    if (ring_surf_count) std::memcpy(ring_surf_count, fo.surfaceRingCount.data(), sizeof(int) * P.N_SCAN);
-    if (ring_surf_count_ds) std::memcpy(ring_surf_count_ds, fo.surfaceRingCountDS.data(), sizeof(int) * P.N_SCAN);
-    if (curvature) std::memcpy(curvature, fo.cloudCurvature.data(), sizeof(float) * n_valid);
-    if (picked) std::memcpy(picked, fo.cloudNeighborPicked.data(), sizeof(int) * n_valid);
-    if (label) std::memcpy(label, fo.cloudLabel.data(), sizeof(int) * n_valid);
+    if (corner_xyzi) cpy(corner_xyzi, fo.cornerCloud.data(), sizeof(P4) * fo.cornerCloud.size());
+    if (corner_index) cpy(corner_index, fo.cornerIndex.data(), sizeof(int) * fo.cornerIndex.size());
+    if (surface_xyzi) cpy(surface_xyzi, fo.surfaceCloud.data(), sizeof(P4) * fo.surfaceCloud.size());
+    if (surface_raw_index) cpy(surface_raw_index, fo.surfaceRawIndex.data(), sizeof(int) * fo.surfaceRawIndex.size());
+    if (ring_surf_count) cpy(ring_surf_count, fo.surfaceRingCount.data(), sizeof(int) * P.N_SCAN);
+    if (ring_surf_count_ds) cpy(ring_surf_count_ds, fo.surfaceRingCountDS.data(), sizeof(int) * P.N_SCAN);
+    if (curvature) cpy(curvature, fo.cloudCurvature.data(), sizeof(float) * n_valid);
+    if (picked) cpy(picked, fo.cloudNeighborPicked.data(), sizeof(int) * n_valid);
+    if (label) cpy(label, fo.cloudLabel.data(), sizeof(int) * n_valid);
 }
 
 // ---------------------------------------------------------------- mapOptimization handle
@@ -179,7 +182,7 @@ int orc_mo_extract_surrounding(orc_mo* h, const float* keyPoses6All, const doubl
     counts[0] = (int)h->mo.laserCloudCornerFromMap.size(); counts[1] = (int)h->mo.laserCloudSurfFromMap.size();
     counts[2] = (int)h->mo.laserCloudCornerFromMapDS.size(); counts[3] = (int)h->mo.laserCloudSurfFromMapDS.size();
     const int m = (int)ds.size();
-    for (int i = 0; i < m && i < ds_cap; i++) std::memcpy(ds_out + 4 * i, &ds[i], 16);
+    for (int i = 0; i < m && i < ds_cap; i++) cpy(ds_out + 4 * i, &ds[i], 16);
     return m;
 }
 // ImageProjection::imuDeskewInfo (imageProjection.cpp:323-393); out5 = imuAvailable, imuPointerCur, roll, pitch, yaw
@@ -198,22 +201,22 @@ void orc_mo_downsample(orc_mo* h, int* counts) {
 int orc_mo_get_cloud(orc_mo* h, int which, float* out, int cap) {
     const std::vector<P4>* v = which == 0 ? &h->mo.laserCloudCornerLastDS : which == 1 ? &h->mo.laserCloudSurfLastDS
                              : which == 2 ? &h->mo.laserCloudCornerFromMapDS : &h->mo.laserCloudSurfFromMapDS;
-    int n = (int)v->size(); if (out && n <= cap) std::memcpy(out, v->data(), sizeof(P4) * n);
+    int n = (int)v->size(); if (out && n <= cap) cpy(out, v->data(), sizeof(P4) * n);
     return n;
 }
 void orc_mo_scan2map(orc_mo* h, float pose6[6], int debug_iter, int* iters, unsigned* flags, double* seconds /*[2] build, loop*/) {
-    std::memcpy(h->mo.transformTobeMapped, pose6, sizeof(float) * 6);
+    cpy(h->mo.transformTobeMapped, pose6, sizeof(float) * 6);
     h->mo.debug = debug_iter >= 0 ? &h->dbg : nullptr; h->mo.debugIter = debug_iter; h->dbg.iter = -1;
     h->mo.scan2MapOptimization();
-    std::memcpy(pose6, h->mo.transformTobeMapped, sizeof(float) * 6);
+    cpy(pose6, h->mo.transformTobeMapped, sizeof(float) * 6);
     if (iters) *iters = h->mo.itersDone;
     if (flags) *flags = h->mo.flags;
     if (seconds) { seconds[0] = h->mo.buildSeconds; seconds[1] = h->mo.loopSeconds; }
 }
 void orc_mo_transform_update(orc_mo* h, float pose6[6]) {
-    std::memcpy(h->mo.transformTobeMapped, pose6, sizeof(float) * 6);
+    cpy(h->mo.transformTobeMapped, pose6, sizeof(float) * 6);
     h->mo.transformUpdate();
-    std::memcpy(pose6, h->mo.transformTobeMapped, sizeof(float) * 6);
+    cpy(pose6, h->mo.transformTobeMapped, sizeof(float) * 6);
 }
 void orc_mo_registration(orc_mo* h, const float* corner_global, int nCg, const float* surf_global, int nSg, float pose12[12],
                          int* iters, unsigned* flags) {
@@ -224,7 +227,7 @@ void orc_mo_registration(orc_mo* h, const float* corner_global, int nCg, const f
 }
 int orc_mo_pose_trace(orc_mo* h, float* out, int cap_iters) {
     int n = (int)h->mo.poseTrace.size() / 6;
-    if (out) std::memcpy(out, h->mo.poseTrace.data(), sizeof(float) * 6 * (n < cap_iters ? n : cap_iters));
+    if (out) cpy(out, h->mo.poseTrace.data(), sizeof(float) * 6 * (n < cap_iters ? n : cap_iters));
     return n;
 }
 // debug capture of the iteration chosen in orc_mo_scan2map
@@ -232,17 +235,17 @@ int orc_mo_debug(orc_mo* h, int* cornerKnn, float* cornerD2, float* cornerCoeff,
                  int* surfKnn, float* surfD2, float* surfCoeff, uint8_t* surfFlag, float* AtA, float* AtB, float* X, int* nSel) {
     const IterDebug& d = h->dbg;
     if (d.iter < 0) return -1;
-    if (cornerKnn) std::memcpy(cornerKnn, d.cornerKnn.data(), sizeof(int) * d.cornerKnn.size());
-    if (cornerD2) std::memcpy(cornerD2, d.cornerD2.data(), sizeof(float) * d.cornerD2.size());
-    if (cornerCoeff) std::memcpy(cornerCoeff, d.cornerCoeff.data(), sizeof(P4) * d.cornerCoeff.size());
-    if (cornerFlag) std::memcpy(cornerFlag, d.cornerFlag.data(), d.cornerFlag.size());
-    if (surfKnn) std::memcpy(surfKnn, d.surfKnn.data(), sizeof(int) * d.surfKnn.size());
-    if (surfD2) std::memcpy(surfD2, d.surfD2.data(), sizeof(float) * d.surfD2.size());
-    if (surfCoeff) std::memcpy(surfCoeff, d.surfCoeff.data(), sizeof(P4) * d.surfCoeff.size());
-    if (surfFlag) std::memcpy(surfFlag, d.surfFlag.data(), d.surfFlag.size());
-    if (AtA) std::memcpy(AtA, d.AtA, sizeof(float) * 36);
-    if (AtB) std::memcpy(AtB, d.AtB, sizeof(float) * 6);
-    if (X) std::memcpy(X, d.X, sizeof(float) * 6);
+    if (cornerKnn) cpy(cornerKnn, d.cornerKnn.data(), sizeof(int) * d.cornerKnn.size());
+    if (cornerD2) cpy(cornerD2, d.cornerD2.data(), sizeof(float) * d.cornerD2.size());
+    if (cornerCoeff) cpy(cornerCoeff, d.cornerCoeff.data(), sizeof(P4) * d.cornerCoeff.size());
+    if (cornerFlag) cpy(cornerFlag, d.cornerFlag.data(), d.cornerFlag.size());
+    if (surfKnn) cpy(surfKnn, d.surfKnn.data(), sizeof(int) * d.surfKnn.size());
+    if (surfD2) cpy(surfD2, d.surfD2.data(), sizeof(float) * d.surfD2.size());
+    if (surfCoeff) cpy(surfCoeff, d.surfCoeff.data(), sizeof(P4) * d.surfCoeff.size());
+    if (surfFlag) cpy(surfFlag, d.surfFlag.data(), d.surfFlag.size());
+    if (AtA) cpy(AtA, d.AtA, sizeof(float) * 36);
+    if (AtB) cpy(AtB, d.AtB, sizeof(float) * 6);
+    if (X) cpy(X, d.X, sizeof(float) * 6);
     if (nSel) *nSel = d.nSel;
     return d.iter;
 }

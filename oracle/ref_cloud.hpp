@@ -47,7 +47,11 @@ static inline int voxel_grid(const P4* in, int n, float leaf, std::vector<P4>& o
     int64_t dx = (int64_t)((mx[0] - mn[0]) * inv) + 1;
     int64_t dy = (int64_t)((mx[1] - mn[1]) * inv) + 1;
     int64_t dz = (int64_t)((mx[2] - mn[2]) * inv) + 1;
-    if (dx * dy * dz > (int64_t)INT_MAX) {
+    // PCL tests dx*dy*dz in int64; the partial products are checked first so that the triple product itself cannot wrap
+    // (found by the UBSan build, scripts/oracle_sanitize.sh) -- the outcome is the same wherever PCL's own test is defined
+    const bool too_many = dx > (int64_t)INT_MAX || dy > (int64_t)INT_MAX || dz > (int64_t)INT_MAX || dx * dy > (int64_t)INT_MAX
+                          || dx * dy * dz > (int64_t)INT_MAX;
+    if (too_many) {
         out.assign(in, in + n);
         if (overflow) *overflow = 1;
         return n;

@@ -31,14 +31,15 @@ def one(args):
         out.append((fe, mo.get_cloud(0).copy(), mo.get_cloud(1).copy(), pose.copy(), iters, flags))
     oracle.set_literal_sort(0)
     a, b = out
-    curv = a[0]["curvature"]
+    curv = a[0]["curvature"]; nv = int(ci["n_valid"])
     return dict(
-        curvature_ties=int(len(curv) - len(np.unique(curv[5:-5]))) if len(curv) > 10 else 0,
+        curvature_ties=int((nv - 10) - len(np.unique(curv[5:nv - 5]))) if nv > 10 else 0,
         corner_index=not np.array_equal(a[0]["corner_index"], b[0]["corner_index"]),
         label=not np.array_equal(a[0]["label"], b[0]["label"]),
         surf_count=len(a[0]["surface"]) != len(b[0]["surface"]),
         surf_bits=not np.array_equal(a[0]["surface"], b[0]["surface"]),
-        surf_maxdiff=float(np.abs(a[0]["surface"] - b[0]["surface"]).max()) if len(a[0]["surface"]) == len(b[0]["surface"]) else float("nan"),
+        surf_maxdiff=float(np.abs(a[0]["surface"][:, :3] - b[0]["surface"][:, :3]).max()) if len(a[0]["surface"]) == len(b[0]["surface"]) else float("nan"),
+        surf_maxdiff_i=float(np.abs(a[0]["surface"][:, 3] - b[0]["surface"][:, 3]).max()) if len(a[0]["surface"]) == len(b[0]["surface"]) else float("nan"),
         ds_count=len(a[2]) != len(b[2]) or len(a[1]) != len(b[1]),
         ds_bits=not (np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])),
         iters=a[4] != b[4], flags=a[5] != b[5],
@@ -59,7 +60,7 @@ def main():
                      ("ds_bits", "downsampled scan clouds differ in any bit"), ("iters", "LM iteration count differs"), ("flags", "outcome flags differ"),
                      ("pose_bits", "final pose differs in any bit")):
         print(f"  {label:75s}: {cnt(k)} / {n}")
-    print(f"  max |centroid difference| over all frames                                  : {np.nanmax([r['surf_maxdiff'] for r in rows]):.3e} m")
+    print(f"  max |centroid difference| over all frames                                  : xyz {np.nanmax([r['surf_maxdiff'] for r in rows]):.3e} m, intensity {np.nanmax([r['surf_maxdiff_i'] for r in rows]):.3e}")
     print(f"  max |pose difference|: translation {max(r['pose_dt'] for r in rows):.3e} m, rotation {max(r['pose_dr'] for r in rows):.3e} rad (tolerance 1e-4 / 1e-4)")
 
 

@@ -48,6 +48,11 @@ for cluster, mode in ((0, 0), (2, 1), (4, 0)):
         r.registration(0, fr["map_corner"], fr["map_surf"], T0)
         poses = np.zeros((2, 6), np.float32)
         r.extractSurroundingKeyFrames(1, poses, [fr["map_corner"][:700], fr["map_corner"][700:1400]], [fr["map_surf"][:3000], fr["map_surf"][3000:7000]], poses[0, 3:])
+        for k in range(5):                   # resident keyframe store: selection + extraction on the device, both branches
+            r.keyframe_push(np.array([0.01 * k, 0, 0.02 * k, 0.8 * k, 0.1 * k, 0], np.float32), 0.5 * k, fr["map_corner"][200 * k:200 * k + 150], fr["map_surf"][900 * k:900 * k + 800])
+        r.extractSurroundingKeyFramesResident(1, 2.4, 2.0)
+        r.extractSurroundingKeyFramesResident(1, 2.4, 2.0, loop_closure=True, keyframe_size=2)
+        r.keyframe_selection()
         r.voxel_grid(fr["map_surf"], 0.4)
         r.knn5(fr["map_surf"], fr["map_surf"][:500, :3] + 0.05, cell=0.33, first_radius=1)
         wide = lambda a: np.concatenate([a[:, :3], np.ones((len(a), 1), np.float32), a[:, 3:4], np.zeros((len(a), 3), np.float32)], 1).astype(np.float32)

@@ -182,3 +182,36 @@ def test_extract_cloud_transforms_concats_and_filters():
     got = mo.get_cloud(2)
     assert counts[2] == len(got) and len(got) <= counts[0]
     assert np.min(np.linalg.norm(got[:, :3] - want, axis=1)) < 0.2  # its voxel centroid is nearby
+
+
+def test_literal_sort_mode_changes_no_selection():
+    """oracle.set_literal_sort(1) = the reference's own comparators (curvature only, featureExtraction.h:13-17; voxel index only in
+    pcl::VoxelGrid): selected corner indices, cloud sizes and iteration counts do not depend on the tie-break rule, centroids and
+    the pose move only in their last bits (profiles/r02_literal_sort_study.md has the 480-frame count)."""
+    import synth
+    moved = 0
+    for idx in range(6):
+        fr = synth.make_frame(1, 300 + idx, small=(16, 900, 4000, 20000))
+        P = fr["params"]
+        res = []
+        for mode in (0, 1):
+            old = oracle.set_literal_sort(mode)
+            assert old == 0
+            try:
+                ci = oracle.project(P, fr["scan"], fr["imu"], fr["imu_available"])
+                fe = oracle.extract_features(P, ci)
+                mo = oracle.MapOptimization(P)
+                mo.set_imu(fr["imu_available"], 0.0, 0.0)
+                mo.set_scan(fe["corner"], fe["surface"]); mo.set_map(fr["map_corner"], fr["map_surf"]); mo.downsample()
+                pose, iters, flags, _ = mo.scan2map(fr["guess"])
+            finally:
+                oracle.set_literal_sort(0)
+            res.append((fe, mo.get_cloud(1).copy(), pose.copy(), iters, flags))
+        a, b = res
+        assert np.array_equal(a[0]["corner_index"], b[0]["corner_index"])
+        assert a[0]["surface"].shape == b[0]["surface"].shape and a[1].shape == b[1].shape
+        assert np.abs(a[0]["surface"][:, :3] - b[0]["surface"][:, :3]).max() <= 2e-5
+        assert (a[3], a[4]) == (b[3], b[4])
+        assert np.abs(a[2] - b[2]).max() <= 1e-4
+        moved += int(not np.array_equal(a[0]["surface"], b[0]["surface"]))
+    assert moved > 0        # the mode really sorts differently
