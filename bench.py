@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config ms/frame section")
     ap.add_argument("--cpu-frames", type=int, default=100, help="frames timed per thread count by the cpu_baseline leg")
     ap.add_argument("--latency-frames", type=int, default=64)
+    ap.add_argument("--no-wire", dest="wire", action="store_false", help="host buffers as 24-byte packed records + 16-byte XYZI maps instead of the 22-byte / 12-byte wire formats")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="frames per upload chunk of the pipelined e2e call (0 = 32)")
     return ap.parse_args()
 
@@ -404,13 +405,23 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- host inputs in pinned memory (what a caller would hand to the C ABI): per batch one pinned arena for the sweeps and one
     # for the local maps, frames back to back (an ingest ring buffer) -- the library uploads a densely packed group as one copy
-    raws = [fb.api.pack_raw(fr["scan"]) for fr in frames]
+    # Wire formats (--wire, default): the sweeps as the Velodyne driver's 22-byte PointXYZIRT records (imageProjection.cpp:8-21)
+    # and the local maps as 12-byte XYZ (the registration never reads a map point's intensity); the device repacks them.
+    # --no-wire: 24-byte packed records and 16-byte XYZI maps as in round 1.
+    if args.wire:
+        raws = [fb.api.pack_wire22(fr["scan"]) for fr in frames]
+        maps = [(np.ascontiguousarray(fr["map_corner"][:, :3]), np.ascontiguousarray(fr["map_surf"][:, :3])) for fr in frames]
+        fmt = dict(raw_format=fb.api.RAW_VELODYNE22, map_format=fb.api.MAP_XYZ12)
+    else:
+        raws = [fb.api.pack_raw(fr["scan"]) for fr in frames]
+        maps = [(fr["map_corner"], fr["map_surf"]) for fr in frames]
+        fmt = {}
     pin = []
 
     def arena(arrays):
         offs, o = [], 0
         for a_ in arrays:
-            o = (o + 15) // 16 * 16
+            o = (o + 15) // 16 * 16 if not args.wire else (o + 3) // 4 * 4      # wire records are packed back to back
             offs.append(o); o += a_.nbytes
         t = torch.empty(o + 16, dtype=torch.uint8).pin_memory()
         pin.append(t)
@@ -421,14 +432,14 @@ def run_b200(args, rank, world, local_rank):
     fins, h2d = [], 0
     for (b0, b1) in batches:
         raw_ptrs = arena(raws[b0:b1])
-        map_ptrs = arena([m for fr in frames[b0:b1] for m in (fr["map_corner"], fr["map_surf"])])
+        map_ptrs = arena([m for mc_ms in maps[b0:b1] for m in mc_ms])
         finputs = []
         for i in range(b1 - b0):
             fr, raw = frames[b0 + i], raws[b0 + i]
             finputs.append(dict(raw_ptr=raw_ptrs[i], n_raw=len(raw), imu=fr["imu"], imu_available=fr["imu_available"],
                                 map_corner_ptr=map_ptrs[2 * i], n_map_corner=len(fr["map_corner"]),
-                                map_surf_ptr=map_ptrs[2 * i + 1], n_map_surf=len(fr["map_surf"]), pose=fr["guess"]))
-            h2d += raw.nbytes + fr["map_corner"].nbytes + fr["map_surf"].nbytes
+                                map_surf_ptr=map_ptrs[2 * i + 1], n_map_surf=len(fr["map_surf"]), pose=fr["guess"], **fmt))
+            h2d += raw.nbytes + maps[b0 + i][0].nbytes + maps[b0 + i][1].nbytes
         fins.append(reg.make_frame_inputs(finputs))
     h2d += F * 112 + (4 * 8 * 512 * F if frames[0]["imu_available"] else 0)     # packed scalars + IMU ramps
     d2h = F * 32
@@ -633,6 +644,8 @@ def run_b200(args, rank, world, local_rank):
                                  "api": "fbpr_register_frames (one blocking call per batch)"},
                    "h2d_only_ms_per_step": h2d_only_ms, "h2d_bytes_per_gpu_per_step": int(h2d),
                    "host_buffers": "per batch two pinned arenas (sweeps, maps), frames back to back; dense groups cross PCIe as one copy per chunk",
+                   "wire_formats": ("sweeps: 22-byte Velodyne PointXYZIRT records; maps: 12-byte XYZ (repacked on the device)" if args.wire
+                                    else "sweeps: 24-byte packed records; maps: 16-byte XYZI"),
                    "numa": numa},
            "gpu_launches": int(launches),
            "clocks": clocks,

@@ -81,7 +81,13 @@ class FrameInput(C.Structure):
                 ("timeScanCur", C.c_double), ("imuTime", C.c_void_p), ("imuRotX", C.c_void_p), ("imuRotY", C.c_void_p), ("imuRotZ", C.c_void_p),
                 ("imuPointerCur", C.c_int32), ("imuRollInit", C.c_float), ("imuPitchInit", C.c_float),
                 ("map_corner_xyzi", C.c_void_p), ("n_map_corner", C.c_int32), ("map_surf_xyzi", C.c_void_p), ("n_map_surf", C.c_int32),
-                ("pose", C.c_float * 6)]
+                ("pose", C.c_float * 6), ("raw_format", C.c_int32), ("map_format", C.c_int32)]
+
+
+RAW_PACKED24, RAW_VELODYNE22 = 0, 1
+MAP_XYZI16, MAP_XYZ12 = 0, 1
+VELODYNE22_DTYPE = np.dtype({"names": ["x", "y", "z", "intensity", "ring", "time"], "formats": ["<f4", "<f4", "<f4", "<f4", "<u2", "<f4"],
+                             "offsets": [0, 4, 8, 12, 16, 18], "itemsize": 22})
 
 
 STAGES = ["project", "features", "downsample", "map_index", "lm"]
@@ -130,6 +136,15 @@ def pack_raw(scan):
     for k in ("x", "y", "z", "intensity", "ring", "time"):
         raw[k] = scan[k][:n]
     return raw
+
+
+def pack_wire22(scan):
+    """synth scan dict (SoA) -> the Velodyne driver's 22-byte PointXYZIRT records (RAW_VELODYNE22)."""
+    n = int(scan["n"])
+    w = np.zeros(n, VELODYNE22_DTYPE)
+    for k in ("x", "y", "z", "intensity", "ring", "time"):
+        w[k] = scan[k][:n]
+    return w
 
 
 class Registration:
@@ -268,6 +283,7 @@ class Registration:
             a.map_surf_xyzi = f.get("map_surf_ptr"); a.n_map_surf = int(f.get("n_map_surf", 0))
             for q in range(6):
                 a.pose[q] = float(f["pose"][q])
+            a.raw_format = int(f.get("raw_format", RAW_PACKED24)); a.map_format = int(f.get("map_format", MAP_XYZI16))
         return arr
 
     def set_frames(self, first, frame_inputs, mem=MEM_HOST):
@@ -315,6 +331,10 @@ class Registration:
         lk = _f32(last_key_xyz)
         self._ck(self.lib.fbpr_extract_surrounding_keyframes(self.h, slot, K, _vp(kp), _vp(call), _vp(coff), _vp(sall), _vp(soff), _vp(lk), MEM_HOST))
         self.sync()
+
+    def check_guards(self):
+        """FBPR_GUARD=1 handles: number of overwritten guard zones (0 = no out-of-bounds write past any device array)"""
+        return self._ck(self.lib.fbpr_debug_check_guards(self.h))
 
     # ---- resident keyframe store (cloudKeyPoses3D/6D + corner/surfCloudKeyFrames, mapOptmization.h:84-88)
     def keyframes_clear(self): self._ck(self.lib.fbpr_keyframes_clear(self.h))

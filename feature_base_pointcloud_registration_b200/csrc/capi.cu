@@ -39,6 +39,7 @@ struct fbpr_handle {
     float cellCorner = 0.5f, cellSurf = 0.33f;
     std::vector<void*> allocs;
     size_t bytes = 0;
+    bool guard = false; std::vector<std::pair<unsigned char*, size_t>> guards;     // FBPR_GUARD=1: (allocation base, payload bytes)
     // per-slot arrays
     FrameMeta* meta = nullptr;
     fbpr_raw_point* raw = nullptr;
@@ -93,19 +94,36 @@ struct fbpr_handle {
     std::map<std::tuple<int, int, int, int>, long long> graphLaunches;
 };
 
+// Guarded allocations (FBPR_GUARD=1 in the environment at fbpr_create): compute-sanitizer is closed on the B200 pool this library
+// is developed on, so an out-of-bounds WRITE past either end of any per-handle array is caught by 256-byte guard zones filled with
+// a pattern in front of and behind every allocation, verified by fbpr_debug_check_guards (scripts/sanitize_case.py, tests).
+static const size_t GUARD_BYTES = 256;
+static const unsigned char GUARD_PATTERN = 0xA5;
 template <typename T>
 static int dev_alloc(fbpr_handle* h, T** p, size_t count, bool zero = true) {
     void* q = nullptr;
     size_t bytes = count * sizeof(T); if (bytes == 0) bytes = sizeof(T);
-    cudaError_t e = cudaMalloc(&q, bytes);
+    const size_t g = h->guard ? GUARD_BYTES : 0;
+    const size_t body = (bytes + 255) & ~(size_t)255;            // the rear guard begins right behind the payload and runs through the padding
+    cudaError_t e = cudaMalloc(&q, g ? body + 2 * g : bytes);
     if (e != cudaSuccess) return fbpr_fail(e, "cudaMalloc", __FILE__, __LINE__);
-    if (zero) { e = cudaMemsetAsync(q, 0, bytes, h->stream); if (e != cudaSuccess) return fbpr_fail(e, "cudaMemsetAsync", __FILE__, __LINE__); }
+    if (g) {
+        e = cudaMemsetAsync(q, GUARD_PATTERN, body + 2 * g, h->stream);
+        if (e != cudaSuccess) return fbpr_fail(e, "cudaMemsetAsync", __FILE__, __LINE__);
+        h->guards.push_back({ static_cast<unsigned char*>(q), bytes });
+    }
     h->allocs.push_back(q); h->bytes += bytes;
+    q = static_cast<unsigned char*>(q) + g;
+    if (zero || g) { e = cudaMemsetAsync(q, 0, bytes, h->stream); if (e != cudaSuccess) return fbpr_fail(e, "cudaMemsetAsync", __FILE__, __LINE__); }
     *p = reinterpret_cast<T*>(q);
     return 0;
 }
 #define ALLOC(ptr, count) do { int rc_ = dev_alloc(h, &(ptr), (size_t)(count)); if (rc_) return rc_; } while (0)
 
+static size_t raw_src_bytes(int fmt, int n) { return (size_t)n * (fmt == FBPR_RAW_VELODYNE22 ? 22 : sizeof(fbpr_raw_point)); }
+static size_t map_src_bytes(int fmt, int n) { return (size_t)n * (fmt == FBPR_MAP_XYZ12 ? 12 : sizeof(float4)); }
+static int raw_kind(int fmt) { return fmt == FBPR_RAW_VELODYNE22 ? FBPR_PIECE_WIRE22 : FBPR_PIECE_COPY; }
+static int map_kind(int fmt) { return fmt == FBPR_MAP_XYZ12 ? FBPR_PIECE_XYZ12 : FBPR_PIECE_COPY; }
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 static cudaMemcpyKind kind_in(int mem) { return mem == FBPR_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
 
@@ -147,6 +165,7 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     if (params->N_SCAN <= 0 || params->Horizon_SCAN <= 0 || params->max_frames <= 0) return fbpr_fail_msg("bad N_SCAN / Horizon_SCAN / max_frames");
     fbpr_handle* h = new fbpr_handle();
     h->p = *params; h->device = device;
+    { const char* g = getenv("FBPR_GUARD"); h->guard = g && g[0] == '1'; }
     FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const int F = h->F = params->max_frames;
     const int N = params->N_SCAN, H = params->Horizon_SCAN;
@@ -267,6 +286,29 @@ void fbpr_destroy(fbpr_handle* h) {
     for (int k = 0; k < 2; k++) { cudaFree(h->kfs.off[k]); cudaFree(h->kfs.pool[k]); }
     cudaStreamDestroy(h->stream);
     delete h;
+}
+
+int fbpr_debug_check_guards(fbpr_handle* h) {
+    if (!h) return fbpr_fail_msg("null handle");
+    if (!h->guard) return fbpr_fail_msg("handle was not created with FBPR_GUARD=1");
+    cudaSetDevice(h->device);
+    FBPR_CUDA_OK(cudaDeviceSynchronize());
+    int bad = 0;
+    std::vector<unsigned char> buf(3 * GUARD_BYTES);
+    for (size_t k = 0; k < h->guards.size(); k++) {
+        unsigned char* base = h->guards[k].first; const size_t bytes = h->guards[k].second;
+        const size_t body = (bytes + 255) & ~(size_t)255, rear = body - bytes + GUARD_BYTES;
+        FBPR_CUDA_OK(cudaMemcpy(buf.data(), base, GUARD_BYTES, cudaMemcpyDeviceToHost));
+        FBPR_CUDA_OK(cudaMemcpy(buf.data() + GUARD_BYTES, base + GUARD_BYTES + bytes, rear, cudaMemcpyDeviceToHost));
+        bool hit = false;
+        for (size_t b = 0; b < GUARD_BYTES + rear; b++) if (buf[b] != GUARD_PATTERN) { hit = true; break; }
+        if (hit) {
+            bad++;
+            char msg[160]; snprintf(msg, sizeof(msg), "guard zone of allocation #%zu (%zu bytes) was overwritten", k, bytes);
+            g_err = msg;
+        }
+    }
+    return bad;
 }
 
 int fbpr_sync(fbpr_handle* h) {
@@ -431,6 +473,9 @@ static int stage_frames(fbpr_handle* h, int count, const fbpr_frame_input* fr, b
         if (f.n_raw < 0 || f.n_raw > h->rawCap) return fbpr_fail_msg("raw scan larger than max_raw_points");
         if (f.n_map_corner < 0 || f.n_map_corner > h->mapCornerCap || f.n_map_surf < 0 || f.n_map_surf > h->mapSurfCap)
             return fbpr_fail_msg("local map exceeds max_map_corner / max_map_surf");
+        if (f.raw_format != FBPR_RAW_PACKED24 && f.raw_format != FBPR_RAW_VELODYNE22) return fbpr_fail_msg("unknown raw_format");
+        if (f.map_format != FBPR_MAP_XYZI16 && f.map_format != FBPR_MAP_XYZ12) return fbpr_fail_msg("unknown map_format");
+        if (f.map_format == FBPR_MAP_XYZ12 && ((((uintptr_t)f.map_corner_xyzi) | ((uintptr_t)f.map_surf_xyzi)) & 3)) return fbpr_fail_msg("XYZ12 maps must be 4-byte aligned");
         FrameMeta m = {};
         m.n_raw = f.raw ? f.n_raw : 0; m.n_map_corner = f.map_corner_xyzi ? f.n_map_corner : 0; m.n_map_surf = f.map_surf_xyzi ? f.n_map_surf : 0;
         m.deskewFlag = f.deskewFlag; m.imuAvailable = f.imuAvailable; m.timeScanCur = f.timeScanCur; m.imuPointerCur = f.imuPointerCur;
@@ -469,14 +514,39 @@ int fbpr_set_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input
     bool anyImu = false;
     rc = stage_frames(h, count, fr, &anyImu); if (rc) return rc;
     const cudaMemcpyKind k = kind_in(mem);
+    // wire-format pieces (22-byte sweeps, 12-byte maps) are repacked by stage_scatter: host buffers land in the handle's wire
+    // staging area first, device buffers are read where they are
+    size_t wire = 0;
+    for (int i = 0; i < count; i++) {
+        const fbpr_frame_input& f = fr[i]; const FrameMeta& m = h->h_metaStage[i];
+        if (f.raw_format != FBPR_RAW_PACKED24) wire += raw_src_bytes(f.raw_format, m.n_raw) + 512;
+        if (f.map_format != FBPR_MAP_XYZI16) wire += map_src_bytes(f.map_format, m.n_map_corner) + map_src_bytes(f.map_format, m.n_map_surf) + 1024;
+    }
+    if (wire && mem == FBPR_MEM_HOST) { rc = wire_stage(h, wire); if (rc) return rc; }
+    size_t used = 0;
+    ScatterTable t; t.stage = nullptr; t.n = 0; t.pad = 0;
+    auto flush = [&]() -> int { if (t.n == 0) return 0; int r = fbpr_launch_stage_scatter(t, h->stream, &h->launches); t.n = 0; return r; };
+    auto put = [&](const void* src, void* dst, size_t bytes, int kind) -> int {
+        if (!bytes) return 0;
+        if (kind == FBPR_PIECE_COPY) { FBPR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, k, h->stream)); return 0; }
+        const unsigned char* dsrc = static_cast<const unsigned char*>(src);
+        if (mem == FBPR_MEM_HOST) {
+            const size_t at = ((used + 255) & ~(size_t)255) + ((uintptr_t)src & 15);
+            FBPR_CUDA_OK(cudaMemcpyAsync(h->wireStage + at, src, bytes, cudaMemcpyHostToDevice, h->stream));
+            dsrc = h->wireStage + at; used = at + bytes;
+        }
+        t.p[t.n++] = ScatterPiece{ (unsigned long long)(uintptr_t)dsrc, dst, (unsigned long long)bytes | ((unsigned long long)kind << 60) };   // t.stage = 0: absolute addresses
+        return t.n == FBPR_SCATTER_MAX ? flush() : 0;
+    };
     for (int i = 0; i < count; i++) {
         const fbpr_frame_input& f = fr[i];
         const FrameMeta& m = h->h_metaStage[i];
         const int slot = first + i;
-        if (m.n_raw) FBPR_CUDA_OK(cudaMemcpyAsync(h->raw + (size_t)slot * h->rawCap, f.raw, (size_t)m.n_raw * sizeof(fbpr_raw_point), k, h->stream));
-        if (m.n_map_corner) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapCorner + (size_t)slot * h->mapCornerCap, f.map_corner_xyzi, (size_t)m.n_map_corner * sizeof(float4), k, h->stream));
-        if (m.n_map_surf) FBPR_CUDA_OK(cudaMemcpyAsync(h->mapSurf + (size_t)slot * h->mapSurfCap, f.map_surf_xyzi, (size_t)m.n_map_surf * sizeof(float4), k, h->stream));
+        rc = put(f.raw, h->raw + (size_t)slot * h->rawCap, raw_src_bytes(f.raw_format, m.n_raw), raw_kind(f.raw_format)); if (rc) return rc;
+        rc = put(f.map_corner_xyzi, h->mapCorner + (size_t)slot * h->mapCornerCap, map_src_bytes(f.map_format, m.n_map_corner), map_kind(f.map_format)); if (rc) return rc;
+        rc = put(f.map_surf_xyzi, h->mapSurf + (size_t)slot * h->mapSurfCap, map_src_bytes(f.map_format, m.n_map_surf), map_kind(f.map_format)); if (rc) return rc;
     }
+    rc = flush(); if (rc) return rc;
     rc = upload_staged(h, first, count, anyImu, h->stream); if (rc) return rc;
     FBPR_CUDA_OK(cudaEventRecord(h->stageDone, h->stream));
     h->stagePending = true;
@@ -656,7 +726,7 @@ static void chunk_schedule(int count, int chunk_frames, std::vector<int>& bounds
 // 50 GB/s, one copy of the same bytes 55.6 GB/s), so when the buffers of the group are packed densely in host memory (a caller
 // that fills one pinned arena) their whole span crosses PCIe as ONE copy into a landing area and a small kernel scatters the
 // pieces to their slots at HBM speed; otherwise one copy per buffer.
-struct UploadPiece { const void* src; void* dst; size_t bytes; };
+struct UploadPiece { const void* src; void* dst; size_t bytes; int kind; };      // bytes = SOURCE bytes; kind = FBPR_PIECE_*
 // true when [lo, hi) lies inside ONE pinned allocation known to the driver (cuMemGetAddressRange through the runtime's driver
 // entry point: no link-time dependency on libcuda).  Reading the gaps between separately allocated buffers would be a bug.
 static bool host_span_is_one_allocation(uintptr_t lo, uintptr_t hi) {
@@ -677,32 +747,65 @@ static bool host_span_is_one_allocation(uintptr_t lo, uintptr_t hi) {
 // does not wait for the scatter kernel
 static int upload_group(fbpr_handle* h, fbpr_handle::Ticket& tk, const std::vector<UploadPiece>& pcs, cudaStream_t st, cudaStream_t scatterSt, cudaEvent_t tmp, cudaEvent_t ready) {
     size_t sum = 0; uintptr_t lo = ~(uintptr_t)0, hi = 0;
+    bool repack = false;                                         // wire-format pieces must pass through the landing area
     for (const auto& p : pcs) {
         sum += p.bytes;
         const uintptr_t a = (uintptr_t)p.src;
         if (a < lo) lo = a;
         if (a + p.bytes > hi) hi = a + p.bytes;
+        repack = repack || p.kind != FBPR_PIECE_COPY;
     }
     const size_t span = pcs.empty() ? 0 : (size_t)(hi - lo);
     const size_t landing = (tk.stageUsed + 255) & ~(size_t)255;
-    bool merged = pcs.size() >= 2 && pcs.size() <= FBPR_SCATTER_MAX && span <= sum + sum / 16 + 4096 && (lo & 3) == 0 && tk.stage && landing + span + 16 <= tk.stageBytes;
-    if (merged) for (const auto& p : pcs) if ((p.bytes & 3) || (((uintptr_t)p.src - lo) & 3)) { merged = false; break; }
+    bool merged = pcs.size() >= 2 && pcs.size() <= FBPR_SCATTER_MAX && span <= sum + sum / 16 + 4096 && tk.stage && landing + span + 32 <= tk.stageBytes;
+    if (merged) for (const auto& p : pcs) if (p.kind == FBPR_PIECE_COPY && ((lo & 3) || (p.bytes & 3) || (((uintptr_t)p.src - lo) & 3))) { merged = false; break; }
     if (merged) merged = host_span_is_one_allocation(lo, hi);
-    if (!merged) {
+    if (!merged && !repack) {
         for (const auto& p : pcs) FBPR_CUDA_OK(cudaMemcpyAsync(p.dst, p.src, p.bytes, cudaMemcpyHostToDevice, st));
         FBPR_CUDA_OK(cudaEventRecord(ready, st));
         return 0;
     }
-    // keep the landing address congruent to the host address modulo 16 so that 16-byte-aligned pieces stay aligned
-    unsigned char* land = tk.stage + landing + (lo & 15);
-    FBPR_CUDA_OK(cudaMemcpyAsync(land, (const void*)lo, span, cudaMemcpyHostToDevice, st));
-    ScatterTable t; t.stage = land; t.n = (int)pcs.size(); t.pad = 0;
-    for (size_t i = 0; i < pcs.size(); i++) t.p[i] = ScatterPiece{ (unsigned long long)((uintptr_t)pcs[i].src - lo), pcs[i].dst, (unsigned long long)pcs[i].bytes };
-    FBPR_CUDA_OK(cudaEventRecord(tmp, st));
-    FBPR_CUDA_OK(cudaStreamWaitEvent(scatterSt, tmp, 0));
-    { int rc = fbpr_launch_stage_scatter(t, scatterSt, &h->launches); if (rc) return rc; }
-    FBPR_CUDA_OK(cudaEventRecord(ready, scatterSt));
-    tk.stageUsed = landing + (lo & 15) + span;
+    cudaEvent_t last = ready;
+    if (merged) {
+        // keep the landing address congruent to the host address modulo 16 so that 16-byte-aligned pieces stay aligned
+        unsigned char* land = tk.stage + landing + (lo & 15);
+        FBPR_CUDA_OK(cudaMemcpyAsync(land, (const void*)lo, span, cudaMemcpyHostToDevice, st));
+        ScatterTable t; t.stage = land; t.n = (int)pcs.size(); t.pad = 0;
+        for (size_t i = 0; i < pcs.size(); i++)
+            t.p[i] = ScatterPiece{ (unsigned long long)((uintptr_t)pcs[i].src - lo), pcs[i].dst, (unsigned long long)pcs[i].bytes | ((unsigned long long)pcs[i].kind << 60) };
+        FBPR_CUDA_OK(cudaEventRecord(tmp, st));
+        FBPR_CUDA_OK(cudaStreamWaitEvent(scatterSt, tmp, 0));
+        { int rc = fbpr_launch_stage_scatter(t, scatterSt, &h->launches); if (rc) return rc; }
+        tk.stageUsed = landing + (lo & 15) + span;
+    } else {
+        // scattered host buffers in a wire format: one copy per piece into the landing area (congruent modulo 16), repacked in
+        // groups of FBPR_SCATTER_MAX; plain pieces go straight to their slots
+        if (!tk.stage) return fbpr_fail_msg("no landing area for wire-format uploads (out of device memory)");
+        size_t used = tk.stageUsed;
+        ScatterTable t; t.stage = tk.stage; t.n = 0; t.pad = 0;
+        auto flush = [&]() -> int {
+            if (t.n == 0) return 0;
+            FBPR_CUDA_OK(cudaEventRecord(tmp, st));
+            FBPR_CUDA_OK(cudaStreamWaitEvent(scatterSt, tmp, 0));
+            int rc = fbpr_launch_stage_scatter(t, scatterSt, &h->launches);
+            t.n = 0;
+            return rc;
+        };
+        for (const auto& p : pcs) {
+            if (p.kind == FBPR_PIECE_COPY) { FBPR_CUDA_OK(cudaMemcpyAsync(p.dst, p.src, p.bytes, cudaMemcpyHostToDevice, st)); continue; }
+            const size_t at = ((used + 255) & ~(size_t)255) + ((uintptr_t)p.src & 15);
+            if (at + p.bytes + 32 > tk.stageBytes) return fbpr_fail_msg("landing area too small for the wire-format uploads");
+            FBPR_CUDA_OK(cudaMemcpyAsync(tk.stage + at, p.src, p.bytes, cudaMemcpyHostToDevice, st));
+            t.p[t.n++] = ScatterPiece{ (unsigned long long)at, p.dst, (unsigned long long)p.bytes | ((unsigned long long)p.kind << 60) };
+            used = at + p.bytes;
+            if (t.n == FBPR_SCATTER_MAX) { int rc = flush(); if (rc) return rc; }
+        }
+        { int rc = flush(); if (rc) return rc; }
+        tk.stageUsed = used;
+        FBPR_CUDA_OK(cudaEventRecord(tmp, st));                   // the plain pieces of the group
+        FBPR_CUDA_OK(cudaStreamWaitEvent(scatterSt, tmp, 0));
+    }
+    FBPR_CUDA_OK(cudaEventRecord(last, scatterSt));
     return 0;
 }
 
@@ -745,7 +848,7 @@ static int register_frames_enqueue(fbpr_handle* h, int ticket, int first, int co
             const FrameMeta& m = h->h_metaStage[i];
             need += (size_t)m.n_raw * sizeof(fbpr_raw_point) + ((size_t)m.n_map_corner + (size_t)m.n_map_surf) * sizeof(float4);
         }
-        need += need / 8 + (size_t)nchunks * 2 * 8192 + 65536;
+        need += need / 8 + (size_t)nchunks * 2 * 8192 + 65536 + (size_t)count * 3 * 512;      // upper bound for the wire formats too, with per-piece alignment slack
         if (tk.stageBytes < need) {
             if (tk.stage) { FBPR_CUDA_OK(cudaStreamSynchronize(h->copyStream)); cudaFree(tk.stage); tk.stage = nullptr; tk.stageBytes = 0; }
             if (cudaMalloc((void**)&tk.stage, need) == cudaSuccess) tk.stageBytes = need; else { cudaGetLastError(); tk.stage = nullptr; }   // no landing area: plain copies
@@ -758,14 +861,14 @@ static int register_frames_enqueue(fbpr_handle* h, int ticket, int first, int co
         pcs.clear();
         for (int i = lo; i < hi; i++) {
             const FrameMeta& m = h->h_metaStage[i];
-            if (m.n_raw) pcs.push_back(UploadPiece{ fr[i].raw, h->raw + (size_t)(first + i) * h->rawCap, (size_t)m.n_raw * sizeof(fbpr_raw_point) });
+            if (m.n_raw) pcs.push_back(UploadPiece{ fr[i].raw, h->raw + (size_t)(first + i) * h->rawCap, raw_src_bytes(fr[i].raw_format, m.n_raw), raw_kind(fr[i].raw_format) });
         }
         rc = upload_group(h, tk, pcs, h->copyStream, h->scatterStream, h->pipeEvents[3 * nchunks + 3 + 2 * c], h->pipeEvents[3 * c]); if (rc) return rc;
         pcs.clear();
         for (int i = lo; i < hi; i++) {
             const FrameMeta& m = h->h_metaStage[i];
-            if (m.n_map_corner) pcs.push_back(UploadPiece{ fr[i].map_corner_xyzi, h->mapCorner + (size_t)(first + i) * h->mapCornerCap, (size_t)m.n_map_corner * sizeof(float4) });
-            if (m.n_map_surf) pcs.push_back(UploadPiece{ fr[i].map_surf_xyzi, h->mapSurf + (size_t)(first + i) * h->mapSurfCap, (size_t)m.n_map_surf * sizeof(float4) });
+            if (m.n_map_corner) pcs.push_back(UploadPiece{ fr[i].map_corner_xyzi, h->mapCorner + (size_t)(first + i) * h->mapCornerCap, map_src_bytes(fr[i].map_format, m.n_map_corner), map_kind(fr[i].map_format) });
+            if (m.n_map_surf) pcs.push_back(UploadPiece{ fr[i].map_surf_xyzi, h->mapSurf + (size_t)(first + i) * h->mapSurfCap, map_src_bytes(fr[i].map_format, m.n_map_surf), map_kind(fr[i].map_format) });
         }
         rc = upload_group(h, tk, pcs, h->copyStream, h->scatterStream, h->pipeEvents[3 * nchunks + 4 + 2 * c], h->pipeEvents[3 * c + 1]); if (rc) return rc;
     }

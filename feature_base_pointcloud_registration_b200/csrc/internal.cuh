@@ -113,7 +113,12 @@ struct KfSelect {
 
 // pieces of one dense host span that was uploaded with a single copy and is now scattered to its slots (capi.cu, mapops.cu)
 #define FBPR_SCATTER_MAX 112
-struct ScatterPiece { unsigned long long src_off; void* dst; unsigned long long bytes; };     // offsets / sizes are multiples of 4
+// kind (bits 60..63 of `bytes`): 0 = plain copy (offsets / sizes multiples of 4), 1 = 22-byte Velodyne wire records -> 24-byte
+// fbpr_raw_point, 2 = 12-byte XYZ -> float4 XYZI with intensity 0.  `bytes` counts SOURCE bytes.
+#define FBPR_PIECE_COPY 0
+#define FBPR_PIECE_WIRE22 1
+#define FBPR_PIECE_XYZ12 2
+struct ScatterPiece { unsigned long long src_off; void* dst; unsigned long long bytes; };
 struct ScatterTable { const unsigned char* stage; int n; int pad; ScatterPiece p[FBPR_SCATTER_MAX]; };
 
 // ---- kernel argument blocks (passed by value) ----------------------------------------------

@@ -169,20 +169,59 @@ __global__ void __launch_bounds__(TPB) xyzi32_to_16(const float4* __restrict__ i
     out[i] = make_float4(a.x, a.y, a.z, b.x);
 }
 
-// one CTA column per piece (blockIdx.y); 16-byte copies when source and destination allow, 4-byte otherwise
+// one CTA column per piece (blockIdx.y); 16-byte copies when source and destination allow, 4-byte otherwise.  Pieces of kind
+// WIRE22 / XYZ12 are repacked on the way: the bytes that crossed PCIe are the wire format's, the slot gets the kernels' layout.
 __global__ void __launch_bounds__(TPB) stage_scatter(const __grid_constant__ ScatterTable t) {
     const ScatterPiece pc = t.p[blockIdx.y];
+    const int kind = (int)(pc.bytes >> 60);
+    const unsigned long long bytes = pc.bytes & 0x0fffffffffffffffull;
     const unsigned char* src = t.stage + pc.src_off;
     unsigned char* dst = reinterpret_cast<unsigned char*>(pc.dst);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if (kind == FBPR_PIECE_WIRE22) {
+        // the Velodyne driver's PointXYZIRT record: x, y, z, intensity (f32), ring (u16), time (f32) = 22 bytes, any alignment.
+        // A tile of 256 records (5632 bytes) is staged in shared memory with aligned word loads, then one thread per record
+        constexpr int REC = 22, TILE_BYTES = TPB * REC;
+        __shared__ unsigned sw[TILE_BYTES / 4 + 2];
+        const unsigned char* sb = reinterpret_cast<const unsigned char*>(sw);
+        const long long n = (long long)(bytes / REC);
+        fbpr_raw_point* out = reinterpret_cast<fbpr_raw_point*>(dst);
+        for (long long base = (long long)blockIdx.x * TPB; base < n; base += (long long)gridDim.x * TPB) {
+            const unsigned char* g = src + base * REC;
+            const unsigned shift = (unsigned)((size_t)g & 3);
+            const unsigned* gw = reinterpret_cast<const unsigned*>(g - shift);
+            const long long left = (n - base) * REC;
+            const int nb = (int)(left < TILE_BYTES ? left : TILE_BYTES);
+            const int nw = (int)((shift + nb + 3) >> 2);
+            for (int w = threadIdx.x; w < nw; w += TPB) sw[w] = gw[w];
+            __syncthreads();
+            if ((long long)threadIdx.x < n - base) {
+                const unsigned char* r = sb + shift + threadIdx.x * REC;
+                fbpr_raw_point o;
+                o.x = __uint_as_float(load_u32_unaligned(r)); o.y = __uint_as_float(load_u32_unaligned(r + 4));
+                o.z = __uint_as_float(load_u32_unaligned(r + 8)); o.intensity = __uint_as_float(load_u32_unaligned(r + 12));
+                o.ring = (int)r[16] | ((int)r[17] << 8);
+                o.time = __uint_as_float(load_u32_unaligned(r + 18));
+                out[base + threadIdx.x] = o;
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    if (kind == FBPR_PIECE_XYZ12) {
+        const size_t n = (size_t)(bytes / 12);
+        const float* s3 = reinterpret_cast<const float*>(src); float4* d4 = reinterpret_cast<float4*>(dst);
+        for (size_t i = tid; i < n; i += nth) d4[i] = make_float4(s3[3 * i], s3[3 * i + 1], s3[3 * i + 2], 0.f);
+        return;
+    }
     if ((((size_t)src | (size_t)dst) & 15) == 0) {
-        const size_t n16 = pc.bytes >> 4;
+        const size_t n16 = bytes >> 4;
         const uint4* s4 = reinterpret_cast<const uint4*>(src); uint4* d4 = reinterpret_cast<uint4*>(dst);
         for (size_t i = tid; i < n16; i += nth) d4[i] = s4[i];
         const size_t done = n16 << 4;
-        for (size_t i = done + 4 * tid; i < pc.bytes; i += 4 * nth) *reinterpret_cast<unsigned*>(dst + i) = *reinterpret_cast<const unsigned*>(src + i);
+        for (size_t i = done + 4 * tid; i < bytes; i += 4 * nth) *reinterpret_cast<unsigned*>(dst + i) = *reinterpret_cast<const unsigned*>(src + i);
     } else {
-        const size_t n4 = pc.bytes >> 2;
+        const size_t n4 = bytes >> 2;
         const unsigned* s1 = reinterpret_cast<const unsigned*>(src); unsigned* d1 = reinterpret_cast<unsigned*>(dst);
         for (size_t i = tid; i < n4; i += nth) d1[i] = s1[i];
     }

@@ -167,7 +167,15 @@ typedef struct fbpr_frame_input {
     const float*   map_corner_xyzi; int32_t n_map_corner;
     const float*   map_surf_xyzi;   int32_t n_map_surf;
     float          pose[6];
+    int32_t        raw_format;               /* FBPR_RAW_*: layout of the records behind `raw`                              */
+    int32_t        map_format;               /* FBPR_MAP_*: layout of the points behind map_corner_xyzi / map_surf_xyzi     */
 } fbpr_frame_input;
+/* wire formats of the batched uploads: what crosses PCIe is the caller's layout, the repack runs on the device.
+   FBPR_RAW_VELODYNE22 = the Velodyne driver's PointCloud2 record of PointXYZIRT (imageProjection.cpp:8-21): x, y, z, intensity
+   float32, ring uint16, time float32, 22 bytes, no padding.  FBPR_MAP_XYZ12 = x, y, z float32, 12 bytes: the registration never
+   reads a map point's intensity (mapOptmization.h:1028-1036, :1157-1163), so pose-only callers need not ship it (it reads as 0). */
+enum { FBPR_RAW_PACKED24 = 0, FBPR_RAW_VELODYNE22 = 1 };
+enum { FBPR_MAP_XYZI16 = 0, FBPR_MAP_XYZ12 = 1 };
 /* batched form of fbpr_set_raw_scan + fbpr_set_local_map + fbpr_set_pose for `count` independent frames
    (BASELINE config 4: 1024 frames, each against its own local map): one async copy per cloud, one packed
    copy for all the scalars.  The slots' counters and results are reset. */
@@ -216,6 +224,10 @@ FBPR_API int fbpr_extract_surrounding_keyframes_resident(fbpr_handle* h, int slo
 /* parity getter: cloudToExtract of the last resident extraction (surroundingKeyPosesDS + the last-10-s poses, or the loop-closure
    list) and, per entry, the keyframe it names (-1: dropped by the distance re-check, :924).  Returns the list length. */
 FBPR_API int fbpr_get_keyframe_selection(fbpr_handle* h, float* list_xyzi, int32_t* key_index, int cap);
+/* debugging aid (no reference counterpart): when the handle was created with FBPR_GUARD=1 in the environment every device
+   array it owns sits between two 256-byte guard zones; returns how many of them were overwritten since (0 = no out-of-bounds
+   write past any array end), < 0 on error. */
+FBPR_API int fbpr_debug_check_guards(fbpr_handle* h);
 /* replaces: mapOptimization::downsampleCurrentScan (mapOptmization.h:981-993). */
 FBPR_API int fbpr_downsample_current_scan(fbpr_handle* h, int first, int count);
 /* replaces: mapOptimization::scan2MapOptimization (mapOptmization.h:1403-1442) including the two

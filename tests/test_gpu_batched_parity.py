@@ -399,3 +399,40 @@ def test_non_finite_points_are_ignored(fb):
     pose, iters, flags = r.get_pose(0)
     assert (iters, flags) == (iters_w, flags_w) and np.abs(pose - pose_w).max() <= POSE_TOL
     r.close()
+
+
+def test_guard_zones_and_run_to_run_determinism(fb, monkeypatch):
+    """Stand-in for compute-sanitizer (closed on this B200 pool): a handle created with FBPR_GUARD=1 keeps every device array
+    between two pattern-filled guard zones.  The whole path runs with the frames in the LAST slot (so a write past a slot's
+    capacity lands in a guard), every operator family is exercised, the guards must be intact -- and the same batch run three
+    times must give bit-identical buffers (atomic-rank map index, warp-local fixed points and staged rows included: a race
+    would show as a differing bit)."""
+    monkeypatch.setenv("FBPR_GUARD", "1")
+    frames = [synth.make_frame(3, 70 + i, small=(16, 450, 1500, 9000)) for i in range(2)]
+    P = frames[0]["params"]
+    F = 3
+    r = fb.Registration(P, max_frames=F, max_map_corner=2048, max_map_surf=9216, max_keyframe_points=8192)
+    snaps = []
+    for rep in range(3):
+        for k, fr in enumerate(frames):
+            s = F - 1 - k                                        # slots 2 and 1
+            r.set_raw_scan(s, fb.api.pack_raw(fr["scan"]), imu=fr["imu"], imu_available=fr["imu_available"])
+            r.set_local_map(s, fr["map_corner"], fr["map_surf"])
+            r.set_pose(s, fr["guess"])
+        r.run_frames(1, 2)
+        res = r.get_results(1, 2)
+        snaps.append((res["pose"].copy(), res["iters"].copy(), r.get_buffer(F - 1, "SURF_DS").copy(), r.get_buffer(F - 1, "CORNER_DS").copy(),
+                      r.get_buffer(F - 1, "CORNER_INDEX").copy(), r.get_buffer(F - 1, "LABEL").copy()))
+    for sn in snaps[1:]:
+        for a, b in zip(snaps[0], sn):
+            assert np.array_equal(a, b)
+    assert np.all(snaps[0][1] > 0)
+    fr = frames[0]
+    T0 = np.eye(4, dtype=np.float32)[:3].copy(); T0[:, 3] = fr["guess"][3:]
+    r.registration(F - 1, fr["map_corner"], fr["map_surf"], T0)                      # CropBox into the last slot
+    for k in range(4):
+        r.keyframe_push(np.array([0, 0, 0.01 * k, 0.5 * k, 0, 0], np.float32), 0.3 * k, fr["map_corner"][100 * k:100 * k + 90], fr["map_surf"][500 * k:500 * k + 450])
+    r.extractSurroundingKeyFramesResident(F - 1, 1.0, 2.0)
+    r.sync()
+    assert r.check_guards() == 0
+    r.close()

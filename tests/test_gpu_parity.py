@@ -750,3 +750,79 @@ def test_full_size_properties_config4(fb):
     pose2, iters2, flags2 = r.get_pose(0)
     assert flags2 & 8 and iters2 <= 2 and np.max(np.abs(pose2 - pose)) < 2e-3
     r.close()
+
+
+def test_wire_format_batched_uploads(fb):
+    """fbpr_set_frames / fbpr_register_frames with the 22-byte Velodyne wire records (imageProjection.cpp:8-21) and 12-byte XYZ
+    maps: what crosses PCIe is the wire layout, the device repacks it -- projection, features and poses are bit-identical to the
+    packed 24-byte / 16-byte upload (a map point's intensity is never read by the registration).  Pageable buffers (one copy per
+    piece into the landing area), one pinned arena (one merged copy per chunk) and device-resident sources."""
+    import torch
+    F = 5
+    frames = [synth.make_frame(3, 80 + i, small=(16, 900, 2000, 8000)) for i in range(F)]
+    P = frames[0]["params"]
+    r = fb.Registration(P, max_frames=F, max_map_corner=4096, max_map_surf=16384)
+    raws = [fb.api.pack_raw(fr["scan"]) for fr in frames]
+    base = [dict(imu=fr["imu"], imu_available=fr["imu_available"], pose=fr["guess"], n_raw=len(raw),
+                 n_map_corner=len(fr["map_corner"]), n_map_surf=len(fr["map_surf"])) for fr, raw in zip(frames, raws)]
+    fin = r.make_frame_inputs([dict(b, raw_ptr=raw.ctypes.data, map_corner_ptr=fr["map_corner"].ctypes.data, map_surf_ptr=fr["map_surf"].ctypes.data)
+                               for b, fr, raw in zip(base, frames, raws)])
+    r.set_frames(0, fin); r.run_frames(0, F)
+    want = r.get_results(0, F)
+    want_cloud = [r.get_buffer(s, "CLOUD").copy() for s in range(F)]
+    want_surf = [r.get_buffer(s, "SURF_DS").copy() for s in range(F)]
+    assert np.all(want["iters"] > 0)
+    # wire copies: odd record counts make the 22-byte pieces end off any 4-byte boundary
+    wires = []
+    for raw in raws:
+        w = np.zeros(len(raw), fb.api.VELODYNE22_DTYPE)
+        for k in ("x", "y", "z", "intensity", "time"):
+            w[k] = raw[k]
+        w["ring"] = raw["ring"]
+        wires.append(w)
+    xyzc = [np.ascontiguousarray(fr["map_corner"][:, :3]) for fr in frames]
+    xyzs = [np.ascontiguousarray(fr["map_surf"][:, :3]) for fr in frames]
+    fmt = dict(raw_format=fb.api.RAW_VELODYNE22, map_format=fb.api.MAP_XYZ12)
+
+    def check(got):
+        assert np.array_equal(got["pose"], want["pose"]) and np.array_equal(got["iters"], want["iters"]) and np.array_equal(got["flags"], want["flags"])
+        for s in range(F):
+            assert np.array_equal(r.get_buffer(s, "CLOUD"), want_cloud[s])
+            assert np.array_equal(r.get_buffer(s, "SURF_DS"), want_surf[s])
+            m = r.get_buffer(s, "MAP_SURF").reshape(-1, 4)
+            assert np.array_equal(m[:, :3], xyzs[s]) and not m[:, 3].any()
+
+    # (1) pageable host buffers
+    fin_w = r.make_frame_inputs([dict(b, raw_ptr=w.ctypes.data, map_corner_ptr=c.ctypes.data, map_surf_ptr=s_.ctypes.data, **fmt)
+                                 for b, w, c, s_ in zip(base, wires, xyzc, xyzs)])
+    r.set_frames(0, fin_w); r.run_frames(0, F)
+    check(r.get_results(0, F))
+    for chunk in (0, 2):
+        check(r.register_frames(0, fin_w, chunk))
+    # mixed formats inside one batch
+    fin_m = r.make_frame_inputs([dict(b, raw_ptr=(w if i % 2 else raw).ctypes.data, map_corner_ptr=c.ctypes.data, map_surf_ptr=s_.ctypes.data,
+                                      raw_format=fb.api.RAW_VELODYNE22 if i % 2 else fb.api.RAW_PACKED24, map_format=fb.api.MAP_XYZ12)
+                                 for i, (b, w, raw, c, s_) in enumerate(zip(base, wires, raws, xyzc, xyzs))])
+    check(r.register_frames(0, fin_m, 2))
+    # (2) one pinned arena, pieces 2-byte aligned back to back
+    arrays = list(wires) + [m for c, s_ in zip(xyzc, xyzs) for m in (c, s_)]
+    offs, o = [], 0
+    for a_ in arrays:
+        o = (o + 3) // 4 * 4 if a_.dtype == np.float32 else (o + 1) // 2 * 2
+        offs.append(o); o += a_.nbytes
+    arena = torch.empty(o + 16, dtype=torch.uint8).pin_memory()
+    for a_, off in zip(arrays, offs):
+        arena[off:off + a_.nbytes] = torch.from_numpy(np.ascontiguousarray(a_).view(np.uint8).reshape(-1))
+    ptrs = [arena.data_ptr() + off for off in offs]
+    fin_a = r.make_frame_inputs([dict(b, raw_ptr=ptrs[i], map_corner_ptr=ptrs[F + 2 * i], map_surf_ptr=ptrs[F + 2 * i + 1], **fmt) for i, b in enumerate(base)])
+    for chunk in (5, 2):
+        check(r.register_frames(0, fin_a, chunk))
+    # (3) device-resident sources
+    dev = torch.empty(o + 16, dtype=torch.uint8, device="cuda"); dev.copy_(arena); torch.cuda.synchronize()
+    dptrs = [dev.data_ptr() + off for off in offs]
+    fin_d = r.make_frame_inputs([dict(b, raw_ptr=dptrs[i], map_corner_ptr=dptrs[F + 2 * i], map_surf_ptr=dptrs[F + 2 * i + 1], **fmt) for i, b in enumerate(base)])
+    r.set_frames(0, fin_d, mem=fb.api.MEM_DEVICE); r.run_frames(0, F)
+    check(r.get_results(0, F))
+    with pytest.raises(fb.FbprError, match="raw_format"):
+        r.set_frames(0, r.make_frame_inputs([dict(base[0], raw_ptr=raws[0].ctypes.data, raw_format=7)]))
+    r.close()

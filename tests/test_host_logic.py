@@ -51,7 +51,7 @@ def test_struct_layouts_match_the_header():
     assert fb.RAW_POINT_DTYPE.itemsize == 24
     assert fb.RESULT_DTYPE.itemsize == 32
     assert ctypes.sizeof(fb.api.Params) == 25 * 4
-    assert ctypes.sizeof(fb.api.FrameInput) == 8 + 4 + 4 + 8 + 8 + 32 + 4 + 4 + 4 + 4 + 8 + 8 + 8 + 8 + 24
+    assert ctypes.sizeof(fb.api.FrameInput) == 8 + 4 + 4 + 8 + 8 + 32 + 4 + 4 + 4 + 4 + 8 + 8 + 8 + 8 + 24 + 4 + 4
     assert ctypes.sizeof(fb.api.Pc2Layout) == 8 * 4          # fbpr_pc2_layout: eight int32 fields
 
 
