@@ -85,7 +85,7 @@ class FrameInput(C.Structure):
 
 
 RAW_PACKED24, RAW_VELODYNE22 = 0, 1
-MAP_XYZI16, MAP_XYZ12 = 0, 1
+MAP_XYZI16, MAP_XYZ12, MAP_FROM_GLOBAL = 0, 1, 2
 VELODYNE22_DTYPE = np.dtype({"names": ["x", "y", "z", "intensity", "ring", "time"], "formats": ["<f4", "<f4", "<f4", "<f4", "<u2", "<f4"],
                              "offsets": [0, 4, 8, 12, 16, 18], "itemsize": 22})
 
@@ -365,6 +365,10 @@ class Registration:
     def set_global_map(self, corner_global, surf_global):
         c = _f32(corner_global).reshape(-1, 4); s = _f32(surf_global).reshape(-1, 4)
         self._ck(self.lib.fbpr_set_global_map(self.h, _vp(c), len(c), _vp(s), len(s), MEM_HOST))
+
+    def crop_local_maps(self, first=0, count=1):
+        """fbpr_crop_local_maps: CropBox of the resident global maps around every slot's pose (mapOptmization.h:284-304), batched"""
+        self._ck(self.lib.fbpr_crop_local_maps(self.h, first, count))
 
     def registration(self, slot, corner_global, surf_global, pose12):
         T = _f32(pose12).reshape(-1).copy()

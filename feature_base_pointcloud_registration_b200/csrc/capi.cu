@@ -75,6 +75,7 @@ struct fbpr_handle {
     unsigned char *flagC = nullptr, *flagS = nullptr; float *dbgAtA = nullptr, *dbgAtB = nullptr, *dbgX = nullptr;
     // registration() scratch
     float4 *regGlobal = nullptr; int regGlobalCap = 0; int* regTile = nullptr; float* regPose = nullptr;
+    int* cropTile = nullptr; size_t cropTileInts = 0;            // batched CropBox scratch: [frames][2][tiles]
     int globalCornerN = -1, globalSurfN = 0;   // resident global maps (fbpr_set_global_map)
     // batched input staging (pinned) + stage timing
     FrameMeta* h_metaStage = nullptr; double* h_imuStage = nullptr; cudaEvent_t stageDone = nullptr; bool stagePending = false;
@@ -133,6 +134,8 @@ static int check_range(fbpr_handle* h, int first, int count) {
     h->streamTouched = true;      // every slot operator passes here; fbpr_register_frames_begin clears it again for its own call
     return 0;
 }
+
+static int enqueue_crop_local_maps(fbpr_handle* h, int first, int count);
 
 static int build_vox_segs(fbpr_handle* h, std::vector<VoxSeg>& segs, VoxSeg** d_out) {
     for (auto& s : segs) {
@@ -273,6 +276,7 @@ void fbpr_destroy(fbpr_handle* h) {
     for (auto& e : h->pipeEvents) cudaEventDestroy(e);
     for (auto& t : h->tickets) { if (t.done) cudaEventDestroy(t.done); if (t.h_res) cudaFreeHost(t.h_res); if (t.stage) cudaFree(t.stage); }
     if (h->wireStage) cudaFree(h->wireStage);
+    if (h->cropTile) cudaFree(h->cropTile);
     if (h->copyStream) cudaStreamDestroy(h->copyStream);
     if (h->scatterStream) cudaStreamDestroy(h->scatterStream);
     if (h->lmStream) cudaStreamDestroy(h->lmStream);
@@ -474,10 +478,13 @@ static int stage_frames(fbpr_handle* h, int count, const fbpr_frame_input* fr, b
         if (f.n_map_corner < 0 || f.n_map_corner > h->mapCornerCap || f.n_map_surf < 0 || f.n_map_surf > h->mapSurfCap)
             return fbpr_fail_msg("local map exceeds max_map_corner / max_map_surf");
         if (f.raw_format != FBPR_RAW_PACKED24 && f.raw_format != FBPR_RAW_VELODYNE22) return fbpr_fail_msg("unknown raw_format");
-        if (f.map_format != FBPR_MAP_XYZI16 && f.map_format != FBPR_MAP_XYZ12) return fbpr_fail_msg("unknown map_format");
+        if (f.map_format != FBPR_MAP_XYZI16 && f.map_format != FBPR_MAP_XYZ12 && f.map_format != FBPR_MAP_FROM_GLOBAL) return fbpr_fail_msg("unknown map_format");
+        if (f.map_format == FBPR_MAP_FROM_GLOBAL && h->globalCornerN < 0) return fbpr_fail_msg("map_format FROM_GLOBAL needs fbpr_set_global_map");
+        if ((f.map_format == FBPR_MAP_FROM_GLOBAL) != (fr[0].map_format == FBPR_MAP_FROM_GLOBAL)) return fbpr_fail_msg("FROM_GLOBAL must be used by all frames of a batch or by none");
         if (f.map_format == FBPR_MAP_XYZ12 && ((((uintptr_t)f.map_corner_xyzi) | ((uintptr_t)f.map_surf_xyzi)) & 3)) return fbpr_fail_msg("XYZ12 maps must be 4-byte aligned");
         FrameMeta m = {};
-        m.n_raw = f.raw ? f.n_raw : 0; m.n_map_corner = f.map_corner_xyzi ? f.n_map_corner : 0; m.n_map_surf = f.map_surf_xyzi ? f.n_map_surf : 0;
+        const bool own = f.map_format != FBPR_MAP_FROM_GLOBAL;
+        m.n_raw = f.raw ? f.n_raw : 0; m.n_map_corner = own && f.map_corner_xyzi ? f.n_map_corner : 0; m.n_map_surf = own && f.map_surf_xyzi ? f.n_map_surf : 0;
         m.deskewFlag = f.deskewFlag; m.imuAvailable = f.imuAvailable; m.timeScanCur = f.timeScanCur; m.imuPointerCur = f.imuPointerCur;
         m.imuRollInit = f.imuRollInit; m.imuPitchInit = f.imuPitchInit;
         for (int q = 0; q < 6; q++) m.pose[q] = f.pose[q];
@@ -550,6 +557,7 @@ int fbpr_set_frames(fbpr_handle* h, int first, int count, const fbpr_frame_input
     rc = upload_staged(h, first, count, anyImu, h->stream); if (rc) return rc;
     FBPR_CUDA_OK(cudaEventRecord(h->stageDone, h->stream));
     h->stagePending = true;
+    if (fr[0].map_format == FBPR_MAP_FROM_GLOBAL) { rc = enqueue_crop_local_maps(h, first, count); if (rc) return rc; }
     return 0;
 }
 
@@ -670,6 +678,23 @@ static int enqueue_lm(fbpr_handle* h, int first, int count) {
     LmArgs a = lm_args(h, first);
     StageTimer t(h, FBPR_STAGE_LM);
     return fbpr_launch_lm(a, count, h->cluster, h->lmWholeGpu ? h->lmGridBlocks : 0, h->stream, &h->launches);
+}
+// batched CropBox of the resident global maps into the slots' local maps (on h->stream)
+static int enqueue_crop_local_maps(fbpr_handle* h, int first, int count) {
+    if (h->globalCornerN < 0) return fbpr_fail_msg("no global map: call fbpr_set_global_map first");
+    const int nC = h->globalCornerN, nS = h->globalSurfN, need = nC > nS ? nC : nS;
+    const int tilesPer = need / 2048 + 2;
+    const size_t ints = (size_t)h->F * 2 * tilesPer;
+    if (ints > h->cropTileInts) {
+        FBPR_CUDA_OK(cudaDeviceSynchronize());
+        if (h->cropTile) cudaFree(h->cropTile);
+        h->cropTile = nullptr; h->cropTileInts = 0;
+        FBPR_CUDA_OK(cudaMalloc((void**)&h->cropTile, ints * sizeof(int)));
+        h->cropTileInts = ints;
+    }
+    // the scratch is indexed by slot, so batches in flight on disjoint slot ranges do not share tiles
+    return fbpr_launch_crop_box_batched(h->regGlobal, nC, h->regGlobal + nC, nS, h->meta, first, count, h->mapCorner, h->mapCornerCap, h->mapSurf, h->mapSurfCap,
+                                        h->cropTile + (size_t)first * 2 * tilesPer, tilesPer, h->stream, &h->launches);
 }
 static int enqueue_scan2map(fbpr_handle* h, int first, int count) {
     int rc = enqueue_map_index(h, first, count);
@@ -884,7 +909,8 @@ static int register_frames_enqueue(fbpr_handle* h, int ticket, int first, int co
         FBPR_CUDA_OK(cudaStreamWaitEvent(h->lmStream, h->pipeEvents[3 * c + 2], 0));
         FBPR_CUDA_OK(cudaStreamWaitEvent(h->lmStream, h->pipeEvents[3 * c + 1], 0));
         std::swap(h->stream, h->lmStream);                       // enqueue_* launch on h->stream
-        rc = enqueue_scan2map(h, lo, n);
+        rc = fr[0].map_format == FBPR_MAP_FROM_GLOBAL ? enqueue_crop_local_maps(h, lo, n) : 0;      // local maps cut from the resident global maps
+        if (!rc) rc = enqueue_scan2map(h, lo, n);
         std::swap(h->stream, h->lmStream);
         if (rc) return rc;
     }
@@ -1162,6 +1188,12 @@ int fbpr_set_global_map(fbpr_handle* h, const float* corner, int nC, const float
     int rc = upload_global(h, corner, nC, surf, nS, mem); if (rc) return rc;
     h->globalCornerN = nC; h->globalSurfN = nS;
     return 0;
+}
+
+int fbpr_crop_local_maps(fbpr_handle* h, int first, int count) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    cudaSetDevice(h->device);
+    return enqueue_crop_local_maps(h, first, count);
 }
 
 int fbpr_registration(fbpr_handle* h, int slot, const float* corner_global, int nCg, const float* surf_global, int nSg, int mem, float pose12[12]) {

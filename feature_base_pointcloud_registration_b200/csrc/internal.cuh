@@ -228,6 +228,8 @@ int fbpr_launch_keyframe_select(const KfStoreView& store, const KfSelect& sel, c
                                 float4* d_outCorner, float4* d_outSurf, int kfCap, int* d_kfCount, int* d_truncated, cudaStream_t st, long long* launches);
 int fbpr_launch_crop_box(const float4* d_in, int n, const float* d_pose12, float4* d_out, int cap, int* d_n_out, int* d_truncated, int* d_tile,
                          cudaStream_t st, long long* launches);
+int fbpr_launch_crop_box_batched(const float4* d_gc, int nC, const float4* d_gs, int nS, FrameMeta* meta, int first, int count,
+                                 float4* d_mapCorner, int capC, float4* d_mapSurf, int capS, int* d_tile, int tilesPer, cudaStream_t st, long long* launches);
 int fbpr_launch_pose_decompose(const float* d_pose12, FrameMeta* meta, int slot, cudaStream_t st, long long* launches);
 int fbpr_launch_pose_compose(const FrameMeta* meta, int slot, float* d_pose12, cudaStream_t st, long long* launches);
 int fbpr_launch_pc2_to_raw(const unsigned char* d_src, int n, const fbpr_pc2_layout& L, fbpr_raw_point* d_dst, cudaStream_t st, long long* launches);

@@ -115,6 +115,82 @@ __global__ void __launch_bounds__(TPB) crop_emit(const float4* in, int n, const 
     for (int k = 0; k < IPT; k++) if (flags & (1 << k)) { if (slot < cap) out[slot] = p[k]; slot++; }
 }
 
+// ---- batched CropBox: every slot of a range crops the SAME resident global maps around its own pose (blockIdx.y = frame,
+// blockIdx.z = kind).  The fork's live registration() (mapOptmization.h:284-304) for many independent frames at once: only the
+// sweeps cross PCIe, the local maps are cut on the device.  Same inclusive box and order-preserving compaction as above.
+__device__ inline bool in_box_t(float4 p, float tx, float ty, float tz) {
+    const float mnx = -30.0f + tx, mxx = 30.0f + tx, mny = -30.0f + ty, mxy = 30.0f + ty, mnz = -10.0f + tz, mxz = 10.0f + tz;
+    return !(p.x < mnx || p.y < mny || p.z < mnz || p.x > mxx || p.y > mxy || p.z > mxz);
+}
+__global__ void __launch_bounds__(TPB) crop_count_b(const float4* gc, int nC, const float4* gs, int nS, const FrameMeta* meta, int first, int* tile, int tilesPer) {
+    const int kind = blockIdx.z, n = kind ? nS : nC;
+    const int base = blockIdx.x * TILE;
+    if (base >= n) return;
+    const float4* in = kind ? gs : gc;
+    const FrameMeta& M = meta[first + blockIdx.y];
+    const float tx = M.pose[3], ty = M.pose[4], tz = M.pose[5];
+    int cnt = 0;
+    for (int k = 0; k < IPT; k++) { int i = base + k * TPB + threadIdx.x; if (i < n && in_box_t(in[i], tx, ty, tz)) cnt++; }
+    __shared__ int ws[TPB / 32];
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < TPB / 32; k++) t += ws[k]; tile[((size_t)blockIdx.y * 2 + kind) * tilesPer + blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) crop_scan_b(int* tile, int tilesPer, int nC, int nS, FrameMeta* meta, int first, int capC, int capS) {
+    const int kind = blockIdx.y, n = kind ? nS : nC, ntiles = (n + TILE - 1) / TILE, cap = kind ? capS : capC;
+    int* t = tile + ((size_t)blockIdx.x * 2 + kind) * tilesPer;
+    FrameMeta& M = meta[first + blockIdx.x];
+    __shared__ int ws[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b = 0; b < ntiles; b += 1024) {
+        int e = b + threadIdx.x;
+        int v = e < ntiles ? t[e] : 0;
+        int incl = v, l = threadIdx.x & 31, w = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
+        if (l == 31) ws[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int a = ws[l], ia = a;
+            for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, ia, o); if (l >= o) ia += u; }
+            ws[l] = ia - a;
+        }
+        __syncthreads();
+        int excl = carry + ws[w] + incl - v;
+        if (e < ntiles) t[e] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (kind) M.n_map_surf = min(carry, cap); else M.n_map_corner = min(carry, cap);
+        if (carry > cap) atomicOr(&M.mapTruncated, 1);
+    }
+}
+__global__ void __launch_bounds__(TPB) crop_emit_b(const float4* gc, int nC, const float4* gs, int nS, const FrameMeta* meta, int first, const int* tile, int tilesPer,
+                                                   float4* outC, int capC, float4* outS, int capS) {
+    const int kind = blockIdx.z, n = kind ? nS : nC, cap = kind ? capS : capC;
+    if (blockIdx.x * TILE >= n) return;
+    const float4* in = kind ? gs : gc;
+    const int slot = first + blockIdx.y;
+    float4* out = kind ? outS + (size_t)slot * capS : outC + (size_t)slot * capC;
+    const FrameMeta& M = meta[slot];
+    const float tx = M.pose[3], ty = M.pose[4], tz = M.pose[5];
+    int start = blockIdx.x * TILE + threadIdx.x * IPT;
+    float4 p[IPT]; int flags = 0, cnt = 0;
+    for (int k = 0; k < IPT; k++) { int i = start + k; if (i < n) { p[k] = in[i]; if (in_box_t(p[k], tx, ty, tz)) { flags |= 1 << k; cnt++; } } }
+    __shared__ int ws[TPB / 32];
+    int incl = cnt, l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
+    if (l == 31) ws[w] = incl;
+    __syncthreads();
+    int woff = 0; for (int q = 0; q < w; q++) woff += ws[q];
+    int at = tile[((size_t)blockIdx.y * 2 + kind) * tilesPer + blockIdx.x] + woff + incl - cnt;
+    for (int k = 0; k < IPT; k++) if (flags & (1 << k)) { if (at < cap) out[at] = p[k]; at++; }
+}
+
 __global__ void pose_decompose(const float* T, FrameMeta* meta, int slot) {
     if (threadIdx.x != 0) return;
     FrameMeta& M = meta[slot];
@@ -267,6 +343,19 @@ int fbpr_launch_crop_box(const float4* d_in, int n, const float* d_pose12, float
     if (tiles > 0) crop_emit<<<tiles, TPB, 0, st>>>(d_in, n, d_pose12, d_tile, d_out, cap);
     if (launches) *launches += tiles > 0 ? 3 : 1;
     return fbpr_launch_ok("CropBox (crop_count / crop_scan / crop_emit)");
+}
+
+int fbpr_launch_crop_box_batched(const float4* d_gc, int nC, const float4* d_gs, int nS, FrameMeta* meta, int first, int count,
+                                 float4* d_mapCorner, int capC, float4* d_mapSurf, int capS, int* d_tile, int tilesPer, cudaStream_t st, long long* launches) {
+    if (count <= 0) return 0;
+    const int need = nC > nS ? nC : nS;
+    const int tiles = (need + TILE - 1) / TILE;
+    if (tiles > tilesPer) return fbpr_fail_msg("CropBox scratch too small");
+    if (tiles > 0) crop_count_b<<<dim3(tiles, count, 2), TPB, 0, st>>>(d_gc, nC, d_gs, nS, meta, first, d_tile, tilesPer);
+    crop_scan_b<<<dim3(count, 2), 1024, 0, st>>>(d_tile, tilesPer, nC, nS, meta, first, capC, capS);
+    if (tiles > 0) crop_emit_b<<<dim3(tiles, count, 2), TPB, 0, st>>>(d_gc, nC, d_gs, nS, meta, first, d_tile, tilesPer, d_mapCorner, capC, d_mapSurf, capS);
+    if (launches) *launches += tiles > 0 ? 3 : 1;
+    return fbpr_launch_ok("batched CropBox (crop_*_b)");
 }
 
 int fbpr_launch_pose_decompose(const float* d_pose12, FrameMeta* meta, int slot, cudaStream_t st, long long* launches) {

@@ -175,7 +175,9 @@ typedef struct fbpr_frame_input {
    float32, ring uint16, time float32, 22 bytes, no padding.  FBPR_MAP_XYZ12 = x, y, z float32, 12 bytes: the registration never
    reads a map point's intensity (mapOptmization.h:1028-1036, :1157-1163), so pose-only callers need not ship it (it reads as 0). */
 enum { FBPR_RAW_PACKED24 = 0, FBPR_RAW_VELODYNE22 = 1 };
-enum { FBPR_MAP_XYZI16 = 0, FBPR_MAP_XYZ12 = 1 };
+enum { FBPR_MAP_XYZI16 = 0, FBPR_MAP_XYZ12 = 1,
+       FBPR_MAP_FROM_GLOBAL = 2 };           /* no map is uploaded: the slot's local map is the CropBox (+-30/+-30/+-10 m around the frame's
+                                                pose guess, mapOptmization.h:284-304) of the maps made resident by fbpr_set_global_map */
 /* batched form of fbpr_set_raw_scan + fbpr_set_local_map + fbpr_set_pose for `count` independent frames
    (BASELINE config 4: 1024 frames, each against its own local map): one async copy per cloud, one packed
    copy for all the scalars.  The slots' counters and results are reset. */
@@ -245,6 +247,9 @@ FBPR_API int fbpr_transform_update(fbpr_handle* h, int first, int count);
    keeps corner_GlobalMap / surf_GlobalMap resident in HBM; fbpr_registration() then takes NULL maps. */
 FBPR_API int fbpr_set_global_map(fbpr_handle* h, const float* corner_xyzi, int n_corner,
                                  const float* surf_xyzi, int n_surf, int mem);
+/* replaces: the CropBox block of registration() (mapOptmization.h:284-304) for a RANGE of slots at once: every slot's local map
+   becomes the crop of the resident global maps (fbpr_set_global_map) around that slot's current pose translation. */
+FBPR_API int fbpr_crop_local_maps(fbpr_handle* h, int first, int count);
 FBPR_API int fbpr_registration(fbpr_handle* h, int slot, const float* corner_global_xyzi, int n_corner,
                                const float* surf_global_xyzi, int n_surf, int mem, float pose12[12]);
 /* the whole per-frame path in one call: project -> feature_extract -> downsample -> scan2map */

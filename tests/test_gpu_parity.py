@@ -826,3 +826,48 @@ def test_wire_format_batched_uploads(fb):
     with pytest.raises(fb.FbprError, match="raw_format"):
         r.set_frames(0, r.make_frame_inputs([dict(base[0], raw_ptr=raws[0].ctypes.data, raw_format=7)]))
     r.close()
+
+
+def test_batched_registration_against_resident_global_map(fb):
+    """map_format = FROM_GLOBAL: no local map crosses PCIe; every frame of a batch crops the resident global maps around its own
+    pose guess on the device (the fork's live registration(), mapOptmization.h:284-304, for many independent frames) and registers
+    against that crop.  Cropped maps bit-exact vs the oracle's CropBox, iterations / flags equal, poses within tolerance; the
+    pipelined call gives the same as set_frames + run_frames."""
+    F = 4
+    frames = [synth.make_frame(3, 90 + i, small=(16, 900, 3000, 12000)) for i in range(F)]
+    P = frames[0]["params"]
+    # the global maps: two frames' maps of the same scene, plus far-away points that every crop must drop
+    far = np.array([[500.0, 0, 0, 1], [0, -500.0, 0, 2], [20, 15, 40.0, 3]], np.float32)
+    gc = np.concatenate([frames[0]["map_corner"], far, frames[1]["map_corner"]]).astype(np.float32)
+    gs = np.concatenate([frames[0]["map_surf"], far, frames[1]["map_surf"]]).astype(np.float32)
+    r = fb.Registration(P, max_frames=2 * F, max_map_corner=len(gc) + 64, max_map_surf=len(gs) + 64)
+    r.set_global_map(gc, gs)
+    raws = [fb.api.pack_wire22(fr["scan"]) for fr in frames]
+    fin = r.make_frame_inputs([dict(raw_ptr=raw.ctypes.data, n_raw=len(raw), imu=fr["imu"], imu_available=fr["imu_available"], pose=fr["guess"],
+                                    raw_format=fb.api.RAW_VELODYNE22, map_format=fb.api.MAP_FROM_GLOBAL) for fr, raw in zip(frames, raws)])
+    r.set_frames(F, fin); r.run_frames(F, F)
+    got = r.get_results(F, F)
+    for i, fr in enumerate(frames):
+        g = fr["guess"]
+        keep_c = oracle.crop_box(gc, g[3:] - np.float32([30, 30, 10]), g[3:] + np.float32([30, 30, 10]))
+        keep_s = oracle.crop_box(gs, g[3:] - np.float32([30, 30, 10]), g[3:] + np.float32([30, 30, 10]))
+        assert len(keep_c) < len(gc) and len(keep_s) < len(gs)
+        assert np.array_equal(r.get_buffer(F + i, "MAP_CORNER").reshape(-1, 4), keep_c)
+        assert np.array_equal(r.get_buffer(F + i, "MAP_SURF").reshape(-1, 4), keep_s)
+        ci = oracle.project(P, fr["scan"], fr["imu"], fr["imu_available"])
+        fe = oracle.extract_features(P, ci)
+        mo = oracle.MapOptimization(P); mo.set_imu(fr["imu_available"], 0.0, 0.0)
+        mo.set_scan(fe["corner"], fe["surface"]); mo.set_map(keep_c, keep_s); mo.downsample()
+        pose_w, iters_w, flags_w, _ = mo.scan2map(g)
+        assert (int(got["iters"][i]), int(got["flags"][i])) == (iters_w, flags_w)
+        assert np.max(np.abs(got["pose"][i][3:] - pose_w[3:])) <= POSE_TOL_T and np.max(np.abs(got["pose"][i][:3] - pose_w[:3])) <= POSE_TOL_R
+    for chunk in (0, 3):
+        again = r.register_frames(0, fin, chunk)
+        assert np.array_equal(again["pose"], got["pose"]) and np.array_equal(again["iters"], got["iters"])
+    # a mixed batch is refused
+    mixed = r.make_frame_inputs([dict(raw_ptr=raws[0].ctypes.data, n_raw=len(raws[0]), pose=frames[0]["guess"], raw_format=fb.api.RAW_VELODYNE22, map_format=fb.api.MAP_FROM_GLOBAL),
+                                 dict(raw_ptr=raws[1].ctypes.data, n_raw=len(raws[1]), pose=frames[1]["guess"], raw_format=fb.api.RAW_VELODYNE22,
+                                      map_corner_ptr=gc.ctypes.data, n_map_corner=len(gc), map_surf_ptr=gs.ctypes.data, n_map_surf=len(gs))])
+    with pytest.raises(fb.FbprError, match="FROM_GLOBAL"):
+        r.set_frames(0, mixed)
+    r.close()
