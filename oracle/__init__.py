@@ -119,6 +119,11 @@ def set_literal_sort(on):
     return int(lib().orc_set_literal_sort(1 if on else 0))
 
 
+def set_kdtree_flann_split(on):
+    """1 (default): the kd-tree is built with FLANN's middleSplit_ rule (CPU-timing fidelity); 0: median split.  Same results."""
+    return int(lib().orc_set_kdtree_flann_split(1 if on else 0))
+
+
 def voxel_grid(xyzi, leaf):
     xyzi = f32(xyzi).reshape(-1, 4); n = xyzi.shape[0]
     out = np.zeros((max(n, 1), 4), np.float32)

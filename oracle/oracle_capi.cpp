@@ -150,6 +150,8 @@ void orc_mo_set_imu(orc_mo* h, int64_t imuAvailable, float imuRollInit, float im
 }
 // 1: the path's two std::sort calls compare only what the reference compares (see oracle_literal_sort); returns the old value
 int orc_set_literal_sort(int on) { int old = oracle_literal_sort(); oracle_literal_sort() = on ? 1 : 0; return old; }
+// kd-tree split rule: 1 = FLANN middleSplit_ (default), 0 = median; returns the old value
+int orc_set_kdtree_flann_split(int on) { int old = oracle_kdtree_flann_split(); oracle_kdtree_flann_split() = on ? 1 : 0; return old; }
 // keyframe clouds are given concatenated with CSR offsets (K+1 entries)
 void orc_mo_extract_cloud(orc_mo* h, const float* keyPoses6, int K, const float* corner_all, const int* corner_off,
                           const float* surf_all, const int* surf_off, const float* lastKeyXYZ, int* counts) {

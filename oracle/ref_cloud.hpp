@@ -124,6 +124,13 @@ static inline float l2_simple(const float* a, const float* b) {
     return r;
 }
 
+// Split rule of the kd-tree: 1 (default) = FLANN's KDTreeSingleIndex::middleSplit_ (cut the widest box side at its middle, clipped
+// to the points' extent; planeSplit partition, index = lim1 / lim2 / count/2) so that tree depth and leaf occupancy -- i.e. the CPU
+// time of build and search -- follow the library the reference calls; 0 = median split (balanced).  The search is exact with
+// either rule, so results are identical by construction (tests assert it).  Restated from memory of FLANN 1.8 / 1.9
+// (flann/algorithms/kdtree_single_index.h); not verifiable in this container.
+inline int& oracle_kdtree_flann_split() { static int v = 1; return v; }
+
 class KdTree5 {
 public:
     void build(const P4* pts, int n) {
@@ -137,7 +144,10 @@ public:
             const float p[3] = { pts[k].x, pts[k].y, pts[k].z };
             for (int c = 0; c < 3; c++) { lo_[c] = std::min(lo_[c], p[c]); hi_[c] = std::max(hi_[c], p[c]); }
         }
-        if (n > 0) { float lo[3] = { lo_[0], lo_[1], lo_[2] }, hi[3] = { hi_[0], hi_[1], hi_[2] }; divide(0, n, lo, hi); }
+        if (n > 0) {
+            float lo[3] = { lo_[0], lo_[1], lo_[2] }, hi[3] = { hi_[0], hi_[1], hi_[2] };
+            if (oracle_kdtree_flann_split()) divide_flann(0, n, lo, hi); else divide(0, n, lo, hi);
+        }
         for (int k = 0; k < n; k++) { const P4& p = pts[ids_[k]]; xyz_[3 * k] = p.x; xyz_[3 * k + 1] = p.y; xyz_[3 * k + 2] = p.z; }
         src_ = nullptr;
     }
@@ -182,6 +192,64 @@ private:
         int r = divide(mid, hi, bl, bh);
         nodes_[me].left = l; nodes_[me].right = r; nodes_[me].feat = feat;
         nodes_[me].divlow = divlow; nodes_[me].divhigh = divhigh;
+        return me;
+    }
+    inline float coord(int id, int c) const { const P4& p = src_[id]; return c == 0 ? p.x : (c == 1 ? p.y : p.z); }
+    // FLANN KDTreeSingleIndex::divideTree + middleSplit_ + planeSplit.  bl / bh = the node's bounding box: on entry the box
+    // handed down by the parent, on exit the tight box of the points below (as FLANN updates it).
+    int divide_flann(int lo, int hi, float* bl, float* bh) {
+        const int me = (int)nodes_.size();
+        nodes_.push_back(Node{ -1, -1, 0, 0.f, 0.f, lo, hi });
+        const int count = hi - lo;
+        int* ind = ids_.data() + lo;
+        if (count <= 15) {                                   // leaf: its box is the extent of its points
+            for (int c = 0; c < 3; c++) { bl[c] = bh[c] = coord(ind[0], c); }
+            for (int k = 1; k < count; k++) for (int c = 0; c < 3; c++) { const float v = coord(ind[k], c); if (v < bl[c]) bl[c] = v; if (v > bh[c]) bh[c] = v; }
+            return me;
+        }
+        const float EPS = 0.00001f;
+        float max_span = bh[0] - bl[0];
+        for (int c = 1; c < 3; c++) { const float span = bh[c] - bl[c]; if (span > max_span) max_span = span; }
+        float max_spread = -1.f; int cutfeat = 0;
+        for (int c = 0; c < 3; c++) {
+            const float span = bh[c] - bl[c];
+            if (span > (float)((1 - EPS) * max_span)) {
+                float mn = coord(ind[0], c), mx = mn;
+                for (int k = 1; k < count; k++) { const float v = coord(ind[k], c); if (v < mn) mn = v; if (v > mx) mx = v; }
+                const float spread = mx - mn;
+                if (spread > max_spread) { cutfeat = c; max_spread = spread; }
+            }
+        }
+        const float split_val = (bl[cutfeat] + bh[cutfeat]) / 2;
+        float mn = coord(ind[0], cutfeat), mx = mn;
+        for (int k = 1; k < count; k++) { const float v = coord(ind[k], cutfeat); if (v < mn) mn = v; if (v > mx) mx = v; }
+        const float cutval = split_val < mn ? mn : (split_val > mx ? mx : split_val);
+        // planeSplit: [0, lim1) < cutval, [lim1, lim2) == cutval, [lim2, count) > cutval
+        int left = 0, right = count - 1;
+        for (;;) {
+            while (left <= right && coord(ind[left], cutfeat) < cutval) ++left;
+            while (left <= right && coord(ind[right], cutfeat) >= cutval) --right;
+            if (left > right) break;
+            std::swap(ind[left], ind[right]); ++left; --right;
+        }
+        const int lim1 = left;
+        right = count - 1;
+        for (;;) {
+            while (left <= right && coord(ind[left], cutfeat) <= cutval) ++left;
+            while (left <= right && coord(ind[right], cutfeat) > cutval) --right;
+            if (left > right) break;
+            std::swap(ind[left], ind[right]); ++left; --right;
+        }
+        const int lim2 = left;
+        int index = lim1 > count / 2 ? lim1 : (lim2 < count / 2 ? lim2 : count / 2);
+        if (index <= 0 || index >= count) return me;         // every point identical in every wide dimension: keep one (large) leaf
+        float lbl[3] = { bl[0], bl[1], bl[2] }, lbh[3] = { bh[0], bh[1], bh[2] }, rbl[3] = { bl[0], bl[1], bl[2] }, rbh[3] = { bh[0], bh[1], bh[2] };
+        lbh[cutfeat] = cutval; rbl[cutfeat] = cutval;
+        const int l = divide_flann(lo, lo + index, lbl, lbh);
+        const int r = divide_flann(lo + index, hi, rbl, rbh);
+        nodes_[me].left = l; nodes_[me].right = r; nodes_[me].feat = cutfeat;
+        nodes_[me].divlow = lbh[cutfeat]; nodes_[me].divhigh = rbl[cutfeat];
+        for (int c = 0; c < 3; c++) { bl[c] = std::min(lbl[c], rbl[c]); bh[c] = std::max(lbh[c], rbh[c]); }
         return me;
     }
     void search(int ni, const float q[3], float mindistsq, float* dists, Knn5& rs) const {

@@ -83,3 +83,24 @@ def test_crop_box_inclusive_and_order_preserving():
     pts = np.array([[0, 0, 0, 1], [30, 0, 0, 2], [30.0001, 0, 0, 3], [-30, -30, -10, 4], [1, 1, 10.5, 5]], np.float32)
     out = oracle.crop_box(pts, [-30, -30, -10], [30, 30, 10])
     assert list(out[:, 3]) == [1, 2, 4]
+
+
+def test_kdtree_split_rules_give_identical_results():
+    """The oracle's kd-tree is built with FLANN's middleSplit_ rule by default (CPU-timing fidelity); the
+    median-split build and brute force must return the same index sets and squared distances (the search is exact)."""
+    rng = np.random.default_rng(3)
+    # clustered + duplicated points: planeSplit's == cutval band and degenerate boxes are exercised
+    pts = np.concatenate([rng.uniform(-20, 20, (6000, 3)), np.repeat(rng.uniform(-1, 1, (40, 3)), 25, axis=0),
+                          np.full((40, 3), 2.5), rng.normal(0, 0.05, (2000, 3)) + [5, 5, 0]]).astype(np.float32)
+    m = np.concatenate([pts, np.arange(len(pts), dtype=np.float32)[:, None]], 1)
+    q = np.concatenate([rng.uniform(-21, 21, (400, 3)), pts[::40] + np.float32(0.01)]).astype(np.float32)
+    assert oracle.set_kdtree_flann_split(1) == 1                  # the default
+    try:
+        i_f, d_f = oracle.knn5(m, q)
+        oracle.set_kdtree_flann_split(0)
+        i_m, d_m = oracle.knn5(m, q)
+    finally:
+        oracle.set_kdtree_flann_split(1)
+    i_b, d_b = oracle.knn5(m, q, brute=True)
+    assert np.array_equal(i_f, i_b) and np.array_equal(d_f, d_b)
+    assert np.array_equal(i_m, i_b) and np.array_equal(d_m, d_b)
