@@ -250,7 +250,10 @@ enum : unsigned char { ST_NONE = 0, ST_UNDECIDED = 1, ST_PICKED = 2, ST_DEAD = 3
 
 __host__ __device__ inline bool feat_sort_free(const FeatArgs& a) { return a.segPad <= RING_TPB && a.segPad >= 32; }
 
-__global__ void __launch_bounds__(RING_TPB, 3) feat_ring(FeatArgs a) {
+#ifndef FEAT_RING_CTAS
+#define FEAT_RING_CTAS 3
+#endif
+__global__ void __launch_bounds__(RING_TPB, FEAT_RING_CTAS) feat_ring(FeatArgs a) {
     extern __shared__ unsigned char smem_raw[];
     const int slot = a.first + blockIdx.y, ring = blockIdx.x;
     const int n = a.meta[slot].n_valid;
