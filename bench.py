@@ -577,7 +577,10 @@ def run_b200(args, rank, world, local_rank):
     del dev_scratch
     for (b0, b1), fin in list(zip(batches, fins))[:2]:      # the e2e passes left other batches' frames in the first 2B slots
         reg.set_frames(b0, fin)
+    step_resident()                                          # every slot holds its own frame's result again (gather, latency section)
     reg.sync()
+    res_again = reg.get_results(0, F)
+    assert np.array_equal(res_again["iters"], res["iters"]) and np.array_equal(res_again["pose"], res["pose"])     # run-to-run identical
 
     # ---- gather the result records of all ranks over NCCL (32 B / frame), the only collective of the job; rank 0 checks them
     gathered = None
