@@ -161,13 +161,13 @@ __device__ __noinline__ void transform_update(float* pose, long long imuAvailabl
     pose[5] = clampf(pose[5], z_tol);
 }
 
-// LMOptimization after the reduction (mapOptmization.h:1336-1400), one thread.
-// Returns 1 when converged.  matP is the reference's LOCAL zero-initialised matrix (:1278).
-__device__ __noinline__ int lm_solve_step(const float* AtA, const float* AtB, int iter, int& isDegenerate, float* pose, float* Xout) {
-    float Aw[36], bw[6], X[6];
-    for (int k = 0; k < 36; k++) Aw[k] = AtA[k];
-    for (int k = 0; k < 6; k++) bw[k] = AtB[k];
-    dev_qr_solve6(Aw, bw, X);
+// LMOptimization after the reduction (mapOptmization.h:1336-1400).  The 6x6 QR solve (cv::solve, :1343) is run by the whole
+// first warp (dev_qr_solve6_warp: one matrix column per lane, registers only) -- it is on the critical path of every iteration
+// of a frame, and one thread walking local-memory arrays needed ~10 us for it; the rest (degeneracy test at iteration 0, pose
+// update, convergence) is one thread.  Returns 1 when converged.  matP is the reference's LOCAL zero-initialised matrix (:1278).
+__device__ __noinline__ int lm_solve_step(const float* AtA, const float* Xqr, int iter, int& isDegenerate, float* pose, float* Xout) {
+    float Aw[36], X[6];
+    for (int k = 0; k < 6; k++) X[k] = Xqr[k];
     float matP[36];
     for (int k = 0; k < 36; k++) matP[k] = 0.f;
     if (iter == 0 && dev_surely_not_degenerate(AtA)) {
@@ -469,6 +469,8 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             }
         }
         __syncthreads();
+        float Xqr[6];
+        if (tid < 32 && sh_nsel >= 50) dev_qr_solve6_warp(sh_AtA, sh_AtB, Xqr);      // cv::solve(matAtA, matAtB, matX, DECOMP_QR), :1343
         if (tid == 0) {
             int stop = 0;
             iters = iter + 1;
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             } else {
                 float pose[6], X[6];
                 for (int k = 0; k < 6; k++) pose[k] = sh_pose[k];
-                int conv = lm_solve_step(sh_AtA, sh_AtB, iter, isDegenerate, pose, X);
+                int conv = lm_solve_step(sh_AtA, Xqr, iter, isDegenerate, pose, X);
                 for (int k = 0; k < 6; k++) sh_pose[k] = pose[k];
                 if (conv) { flags |= FBPR_FLAG_CONVERGED; stop = 1; }
                 if (rank == 0 && cap) {

@@ -8,6 +8,21 @@
 namespace {
 
 __global__ void selftest_smallmat(int which, const float* __restrict__ in, int n, float* __restrict__ out) {
+    if (which == FBPR_SELFTEST_QR6_WARP) {           // one WARP per problem (64 threads per CTA = 2 problems); in / out as QR6
+        __shared__ float sA[2][36], sb[2][6];
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int p = blockIdx.x * 2 + w; p < n + (n & 1); p += gridDim.x * 2) {       // both warps of a CTA run the same trip count
+            const bool live = p < n;
+            for (int k = lane; k < 36; k += 32) sA[w][k] = live ? in[42 * p + k] : (k % 7 == 0 ? 1.f : 0.f);
+            if (lane < 6) sb[w][lane] = live ? in[42 * p + 36 + lane] : 0.f;
+            __syncwarp();
+            float x[6];
+            dev_qr_solve6_warp(sA[w], sb[w], x);
+            if (live && lane == 0) for (int k = 0; k < 6; k++) out[6 * p + k] = x[k];
+            __syncwarp();
+        }
+        return;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (which == FBPR_SELFTEST_JACOBI3) {            // in: full 3x3 (row-major), out: W[3] then V[9] (rows = eigenvectors)
@@ -46,9 +61,9 @@ __global__ void selftest_smallmat(int which, const float* __restrict__ in, int n
 }  // namespace
 
 extern "C" int fbpr_selftest_smallmat(fbpr_handle* h, int which, const float* in, int n, float* out) {
-    static const int in_w[] = { 9, 36, 42, 36, 15, 36 }, out_w[] = { 12, 42, 6, 36, 3, 1 };
+    static const int in_w[] = { 9, 36, 42, 36, 15, 36, 42 }, out_w[] = { 12, 42, 6, 36, 3, 1, 6 };
     if (!h) return fbpr_fail_msg("null handle");
-    if (which < 0 || which > FBPR_SELFTEST_NOT_DEGENERATE || n < 0 || (n > 0 && (!in || !out))) return fbpr_fail_msg("bad selftest arguments");
+    if (which < 0 || which > FBPR_SELFTEST_QR6_WARP || n < 0 || (n > 0 && (!in || !out))) return fbpr_fail_msg("bad selftest arguments");
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)fbpr_stream(h);
     float *d_in = nullptr, *d_out = nullptr;

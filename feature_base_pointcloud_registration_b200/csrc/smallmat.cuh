@@ -132,6 +132,68 @@ __device__ inline int dev_qr_solve6(float* A, float* b, float* x) {
     return 1;
 }
 
+// The same solve by ONE WARP (all 32 lanes must call it), registers only: lane j < 6 owns column j of A, the Householder vector
+// of step l is rebuilt by every lane from a broadcast of column l, every lane updates its own column (the columns of a step are
+// independent; inside a column the operations keep hal::QR32f's order, so every element sees exactly the roundings of the
+// one-thread routine), b and the back substitution are carried redundantly by all lanes.  A, b: 6x6 row-major and 6 values
+// readable by every lane (shared memory).  Every lane returns the same x and the same status.
+__device__ __forceinline__ int dev_qr_solve6_warp(const float* A, const float* b_in, float* x) {
+    const unsigned FULL = 0xffffffffu;
+    const int n = 6;
+    const float eps = FLT_EPSILON * 10;
+    const int lane = threadIdx.x & 31;
+    const int col = lane < n ? lane : 0;                      // lanes >= 6 shadow column 0 (their results are never read)
+    float c[6], b[6], h[6], vl[6];
+    #pragma unroll
+    for (int i = 0; i < n; i++) { c[i] = A[i * n + col]; b[i] = b_in[i]; }
+    #pragma unroll
+    for (int l = 0; l < n; l++) {
+        float vlNorm = 0.f;
+        #pragma unroll
+        for (int i = 0; i < n - l; i++) { vl[i] = __shfl_sync(FULL, c[l + i], l); vlNorm += vl[i] * vl[i]; }
+        const float tmpV = vl[0];
+        vl[0] = vl[0] + ((vl[0] >= 0) ? 1.f : -1.f) * sqrtf(vlNorm);
+        vlNorm = sqrtf(vlNorm + vl[0] * vl[0] - tmpV * tmpV);
+        #pragma unroll
+        for (int i = 0; i < n - l; i++) vl[i] /= vlNorm;
+        if (lane >= l) {                                      // columns l .. 5 (and the shadows)
+            float v_lA = 0.f;
+            #pragma unroll
+            for (int i = l; i < n; i++) v_lA += vl[i - l] * c[i];
+            #pragma unroll
+            for (int i = l; i < n; i++) c[i] -= 2 * vl[i - l] * v_lA;
+        }
+        h[l] = vl[0] * vl[0];
+        if (lane == l) {
+            #pragma unroll
+            for (int i = 1; i < n - l; i++) c[l + i] = vl[i] / vl[0];
+        }
+    }
+    #pragma unroll
+    for (int l = 0; l < n; l++) {
+        vl[0] = 1.f;
+        #pragma unroll
+        for (int j = 1; j < n - l; j++) vl[j] = __shfl_sync(FULL, c[j + l], l);
+        float v_lB = 0.f;
+        #pragma unroll
+        for (int i = l; i < n; i++) v_lB += vl[i - l] * b[i];
+        #pragma unroll
+        for (int i = l; i < n; i++) b[i] -= 2 * vl[i - l] * v_lB * h[l];
+    }
+    int ok = 1;
+    #pragma unroll
+    for (int i = n - 1; i >= 0; i--) {
+        #pragma unroll
+        for (int j = n - 1; j > i; j--) b[i] -= b[j] * __shfl_sync(FULL, c[i], j);
+        const float d = __shfl_sync(FULL, c[i], i);
+        if (fabsf(d) < eps) ok = 0;                           // uniform: every lane sees the same d
+        b[i] /= d;
+    }
+    #pragma unroll
+    for (int i = 0; i < n; i++) x[i] = ok ? b[i] : 0.f;
+    return ok;
+}
+
 // A destroyed; B = inverse (all zeros if singular by OpenCV's test).
 __device__ inline int dev_lu_invert6(float* A, float* B) {
     const int n = 6;

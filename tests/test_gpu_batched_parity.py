@@ -220,6 +220,13 @@ def test_device_smallmat_against_committed_cv2_vectors(fb):
     assert np.array_equal(out[:, :6], g["W6"]) and np.array_equal(out[:, 6:].reshape(-1, 6, 6), g["V6"])       # cv::eigen 6x6
     out = r.selftest_smallmat("QR6", np.concatenate([g["A6"].reshape(-1, 36), g["B6"]], 1))
     assert np.array_equal(out, g["X6"])                                                                         # cv::solve(DECOMP_QR)
+    out = r.selftest_smallmat("QR6_WARP", np.concatenate([g["A6"].reshape(-1, 36), g["B6"]], 1))
+    assert np.array_equal(out, g["X6"])                               # the warp-parallel form the LM kernel runs: same bits
+    sing = np.concatenate([np.zeros((3, 36), np.float32), np.ones((3, 6), np.float32)], 1)
+    sing[1, :36:7] = 1.0; sing[1, 35] = 1e-9                          # |R[5][5]| below OpenCV's eps: reported singular, x = 0
+    sing[2, :36:7] = 1.0; sing[2, 35] = 0.0                           # an all-zero column: NaN out of hal::QR32f, the same NaN here
+    xs, xw = r.selftest_smallmat("QR6", sing), r.selftest_smallmat("QR6_WARP", sing)
+    assert np.array_equal(xs, xw, equal_nan=True) and not xs[1].any()
     out = r.selftest_smallmat("LU6", g["V6"].reshape(-1, 36))
     assert np.array_equal(out.reshape(-1, 6, 6), g["I6"])                                                       # cv::Mat::inv (LU)
     # Eigen's 5x3 column-pivoted Householder has no library here: device against the oracle's restatement, and against f64 lstsq
