@@ -104,14 +104,15 @@ __device__ inline int block_excl_scan(int v, int* total, int* ws) {
 
 // bitonic network over `count` keys made of aligned blocks of `blk` (pow2); every block ends ascending.
 // Generic shared-memory form (any sizes); the register forms below are used for the common shapes.
-__device__ inline void bitonic_blocks(unsigned long long* keys, int count, int blk) {
+template <typename K>
+__device__ inline void bitonic_blocks(K* keys, int count, int blk) {
     for (int k = 2; k <= blk; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = threadIdx.x; t < count; t += RING_TPB) {
                 int p = t ^ j;
                 if (p > t) {
                     bool asc = ((t & k) == 0) || (k == blk);
-                    unsigned long long x = keys[t], y = keys[p];
+                    K x = keys[t], y = keys[p];
                     if ((x > y) == asc) { keys[t] = y; keys[p] = x; }
                 }
             }
@@ -120,8 +121,9 @@ __device__ inline void bitonic_blocks(unsigned long long* keys, int count, int b
     }
 }
 
-__device__ __forceinline__ void key_cswap(unsigned long long& a, unsigned long long& b, bool asc) {
-    const unsigned long long x = a, y = b;
+template <typename K>
+__device__ __forceinline__ void key_cswap(K& a, K& b, bool asc) {
+    const K x = a, y = b;
     const bool sw = (x > y) == asc;
     a = sw ? y : x; b = sw ? x : y;
 }
@@ -159,11 +161,11 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&k)[IPT], 
 
 // The whole CTA (RING_TPB threads) sorts RING_TPB * IPT keys of shared memory ascending, IPT keys per thread in
 // registers (element e = tid * IPT + i); only the strides that cross warps go through shared memory.
-template <int IPT>
-__device__ __forceinline__ void cta_bitonic_sort(unsigned long long* keys) {
+template <int IPT, typename K>
+__device__ __forceinline__ void cta_bitonic_sort(K* keys) {
     const int tid = threadIdx.x, lane = tid & 31;
     constexpr int N = RING_TPB * IPT;
-    unsigned long long k[IPT];
+    K k[IPT];
     #pragma unroll
     for (int i = 0; i < IPT; i++) k[i] = keys[tid * IPT + i];
     #pragma unroll
@@ -180,7 +182,7 @@ __device__ __forceinline__ void cta_bitonic_sort(unsigned long long* keys) {
                 const bool keepMin = ((tid & tj) == 0) == up;
                 #pragma unroll
                 for (int i = 0; i < IPT; i++) {
-                    const unsigned long long o = keys[(tid ^ tj) * IPT + i];
+                    const K o = keys[(tid ^ tj) * IPT + i];
                     const bool less = o < k[i];
                     k[i] = (less == keepMin) ? o : k[i];
                 }
@@ -190,7 +192,7 @@ __device__ __forceinline__ void cta_bitonic_sort(unsigned long long* keys) {
                 const bool keepMin = ((lane & lj) == 0) == up;
                 #pragma unroll
                 for (int i = 0; i < IPT; i++) {
-                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[i], lj);
+                    const K o = __shfl_xor_sync(0xffffffffu, k[i], lj);
                     const bool less = o < k[i];
                     k[i] = (less == keepMin) ? o : k[i];
                 }
@@ -663,10 +665,23 @@ __global__ void __launch_bounds__(RING_TPB, FEAT_RING_CTAS) feat_ring(FeatArgs a
     // ---- per-ring VoxelGrid (featureExtraction.h:287-292)
     float4* stage = a.surfStage + (size_t)slot * a.P + (size_t)ring * a.H;
     int nout = 0;
+#ifdef FEAT_SKIP_VOXEL
+    nsurf = 0;
+#endif
+#ifdef FEAT_SKIP_SEGMENTS
+    if (false)
+#endif
     if (nsurf > 0) {
+        // the ring's surface points, staged once in the shared memory the segment phase no longer needs (s_keys + s_curv)
+        float4* s_pts = reinterpret_cast<float4*>(smem_raw);
+        const bool staged = (size_t)nsurf * 16 <= (size_t)keyCount * 8 + (size_t)a.wcap * 4;
+        if (staged) {
+            for (int t = tid; t < nsurf; t += RING_TPB) s_pts[t] = g_cloud[s_list[t]];
+            __syncthreads();
+        }
         unsigned mn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, mx[3] = { 0u, 0u, 0u };
         for (int t = tid; t < nsurf; t += RING_TPB) {
-            float4 p = g_cloud[s_list[t]];
+            float4 p = staged ? s_pts[t] : g_cloud[s_list[t]];
             unsigned ex = f2ord(p.x), ey = f2ord(p.y), ez = f2ord(p.z);
             mn[0] = min(mn[0], ex); mn[1] = min(mn[1], ey); mn[2] = min(mn[2], ez);
             mx[0] = max(mx[0], ex); mx[1] = max(mx[1], ey); mx[2] = max(mx[2], ez);
@@ -689,12 +704,104 @@ __global__ void __launch_bounds__(RING_TPB, FEAT_RING_CTAS) feat_ring(FeatArgs a
             s_vox[0] = over ? 1 : 0;
             int div[3];
             for (int c = 0; c < 3; c++) { s_vox[1 + c] = (int)floorf(fmn[c] * inv); div[c] = (int)floorf(fmx[c] * inv) - s_vox[1 + c] + 1; }
-            s_vox[4] = div[0]; s_vox[5] = div[0] * div[1];
+            s_vox[4] = div[0]; s_vox[5] = div[0] * div[1]; s_vox[6] = div[2];
         }
         __syncthreads();
+        // 32-bit (voxel << tbits | sequence) keys and the surface points staged ONCE in shared memory, when the ring's voxel range and
+        // the ring's size allow (they do for every real sweep: the bounding box of one ring at the odometry leaf has < 2^21 voxels);
+        // otherwise 64-bit keys and gathers from global memory.  Same order, same sums.
+        int tbits = 0; while ((1 << tbits) < a.voxPad) tbits++;
+        const long long nvox = (long long)s_vox[5] * (long long)s_vox[6];
+        const bool small = staged && !s_vox[0] && nvox < (1ll << (32 - tbits)) && a.voxPad <= 2 * a.wcap;
         if (s_vox[0]) {                                   // leaf too small: output = input
             for (int t = tid; t < nsurf; t += RING_TPB) stage[t] = g_cloud[s_list[t]];
             nout = nsurf;
+        } else if (small) {
+            unsigned* s_k32 = reinterpret_cast<unsigned*>(s_col);        // spans s_col + s_list (2 * wcap words >= voxPad)
+            int* s_run = reinterpret_cast<int*>(s_meta);
+            const float inv = s_inv;
+            const unsigned tmask = (1u << tbits) - 1u;
+            // voxel index of every staged point (s_list is dead from here on: its words are reused)
+            for (int t = tid; t < nsurf; t += RING_TPB) {
+                const float4 p = s_pts[t];
+                const int i0 = (int)(floorf(p.x * inv) - (float)s_vox[1]);
+                const int i1 = (int)(floorf(p.y * inv) - (float)s_vox[2]);
+                const int i2 = (int)(floorf(p.z * inv) - (float)s_vox[3]);
+                s_k32[t] = (unsigned)(i0 + i1 * s_vox[4] + i2 * s_vox[5]);
+            }
+            __syncthreads();
+            // Consecutive points of a ring mostly fall into the same voxel (3 cm between neighbours at 10 m against a 0.4 m leaf), so
+            // the ring is a few hundred RUNS of equal voxel index.  Sorting the runs by (voxel, ordinal) instead of the points by
+            // (voxel, sequence) gives the same order -- a voxel's points are visited run by run, each run in sequence order -- with a
+            // sort a quarter of the size.  Rings with more than 1024 runs take the per-point sort below.
+            int R = 0;
+            for (int base = 0; base < nsurf; base += RING_TPB) {
+                const int t = base + tid;
+                const int flag = (t < nsurf) && (t == 0 || s_k32[t] != s_k32[t - 1]);
+                int tot; const int off = block_excl_scan(flag, &tot, s_ws);
+                if (flag) s_run[R + off] = t;
+                R += tot;
+            }
+            __syncthreads();
+            const int A = (nsurf + 31) & ~31, RP = R <= RING_TPB ? RING_TPB : 2 * RING_TPB;
+            if (R <= 2 * RING_TPB && A + 2 * RP <= 2 * a.wcap) {
+                unsigned* s_rk = s_k32 + A;                               // run keys: voxel << tbits | run ordinal
+                int* s_out = reinterpret_cast<int*>(s_rk + RP);           // first run of every output voxel
+                for (int r = tid; r < RP; r += RING_TPB) s_rk[r] = r < R ? ((s_k32[s_run[r]] << tbits) | (unsigned)r) : 0xffffffffu;
+                __syncthreads();
+                if (RP == RING_TPB) cta_bitonic_sort<1>(s_rk); else cta_bitonic_sort<2>(s_rk);
+                int V = 0;
+                for (int base = 0; base < R; base += RING_TPB) {
+                    const int i = base + tid;
+                    const int flag = (i < R) && (i == 0 || (s_rk[i] >> tbits) != (s_rk[i - 1] >> tbits));
+                    int tot; const int off = block_excl_scan(flag, &tot, s_ws);
+                    if (flag) s_out[V + off] = i;
+                    V += tot;
+                }
+                __syncthreads();
+                for (int v = tid; v < V; v += RING_TPB) {                 // one thread per output voxel, sequential f32 sums in sequence order
+                    const int i0 = s_out[v], i1 = v + 1 < V ? s_out[v + 1] : R;
+                    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f; int cnt = 0;
+                    for (int i = i0; i < i1; i++) {
+                        const int r = (int)(s_rk[i] & tmask);
+                        const int t0 = s_run[r], t1 = r + 1 < R ? s_run[r + 1] : nsurf;
+                        for (int t = t0; t < t1; t++) { const float4 p = s_pts[t]; sx += p.x; sy += p.y; sz += p.z; si += p.w; }
+                        cnt += t1 - t0;
+                    }
+                    const float fc = (float)cnt;
+                    stage[v] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
+                }
+                nout = V;
+            } else {
+            __syncthreads();
+            for (int t = tid; t < a.voxPad; t += RING_TPB) s_k32[t] = t < nsurf ? ((s_k32[t] << tbits) | (unsigned)t) : 0xffffffffu;
+            __syncthreads();
+            if (a.voxPad == 4 * RING_TPB) cta_bitonic_sort<4>(s_k32);
+            else if (a.voxPad == 2 * RING_TPB) cta_bitonic_sort<2>(s_k32);
+            else if (a.voxPad == 8 * RING_TPB) cta_bitonic_sort<8>(s_k32);
+            else bitonic_blocks(s_k32, a.voxPad, a.voxPad);
+            int carry = 0;
+            for (int base = 0; base < nsurf; base += RING_TPB) {
+                int t = base + tid;
+                int flag = (t < nsurf) && (t == 0 || (s_k32[t] >> tbits) != (s_k32[t - 1] >> tbits));
+                int tot, off = block_excl_scan(flag, &tot, s_ws);
+                if (flag) s_run[carry + off] = t;
+                carry += tot;
+            }
+            __syncthreads();
+            const unsigned tmask = (1u << tbits) - 1u;
+            for (int r = tid; r < carry; r += RING_TPB) {
+                const int t = s_run[r], end = r + 1 < carry ? s_run[r + 1] : nsurf;
+                float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+                for (int q = t; q < end; q++) {
+                    const float4 p = s_pts[s_k32[q] & tmask];
+                    sx += p.x; sy += p.y; sz += p.z; si += p.w;
+                }
+                const float fc = (float)(end - t);
+                stage[r] = make_float4(sx / fc, sy / fc, sz / fc, si / fc);
+            }
+            nout = carry;
+            }
         } else {
             const float inv = s_inv;
             for (int t = tid; t < a.voxPad; t += RING_TPB) {

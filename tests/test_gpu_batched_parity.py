@@ -274,6 +274,26 @@ def test_feature_extraction_full_sort_fallback(fb, n_scan, horizon):
     r.close()
 
 
+@pytest.mark.parametrize("n_scan,horizon,leaf", [(16, 2048, 0.4), (16, 2048, 0.1), (16, 2048, 0.02), (8, 1024, 0.05), (16, 900, 0.004)])
+def test_per_ring_voxel_grid_paths(fb, n_scan, horizon, leaf):
+    """The per-ring VoxelGrid of feat_ring (featureExtraction.h:287-292) has three shapes: runs of equal voxel index sorted with
+    32-bit keys (the usual ring), points sorted with 32-bit keys (more than 1024 runs, or a ring too small to hold the run
+    tables), points sorted with 64-bit keys (voxel range >= 2^(32 - log2 H): tiny leaves) -- plus PCL's "leaf too small" copy.
+    All must give the oracle's surface cloud bit for bit."""
+    fr = synth.make_frame(1, 11, small=(n_scan, horizon, 2000, 8000))
+    P = dict(fr["params"]); P["odometrySurfLeafSize"] = leaf
+    ci = oracle.project(P, fr["scan"], fr["imu"], 0)
+    want = oracle.extract_features(P, ci)
+    r = fb.Registration(P, max_frames=1, max_map_corner=4096, max_map_surf=16384)
+    r.set_cloud_info(0, ci)
+    r.featureExtra(0, 1)
+    r.sync()
+    assert np.array_equal(r.get_buffer(0, "RING_SURF_COUNT_DS"), want["ring_surf_count_ds"])
+    assert np.array_equal(r.get_buffer(0, "SURF"), want["surface"])
+    assert np.array_equal(r.get_buffer(0, "CORNER_INDEX"), want["corner_index"])
+    r.close()
+
+
 def _fuzz_cloud_info(rng, n_scan, horizon):
     """A cloud_info record made to stress the selection loops: ragged column gaps (the 10-column break of the suppression
     reach), plateaus of exactly equal curvature, range steps (occlusion marks that leak across segment boundaries), rings
