@@ -38,18 +38,20 @@ WORKLOAD = ("configs[3]: 1024 independent synthetic HDL-64E-like 64x2048 frames 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)          # 40 x 54 ms: a timed region above 2 s
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-total", type=int, default=1024, help="frames of one step over ALL ranks (BASELINE configs[3])")
     ap.add_argument("--batch", type=int, default=128, help="frames per launch batch on one GPU")
     ap.add_argument("--ref-frames", type=int, default=6, help="frames per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cluster", type=int, default=0, help="lm_cluster_size override")
+    ap.add_argument("--sequential", action="store_true", help="resident steps as one fbpr_run_frames per batch on one stream (round-1 schedule) instead of fbpr_run_frames_pipelined")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config ms/frame section")
     ap.add_argument("--cpu-frames", type=int, default=100, help="frames timed per thread count by the cpu_baseline leg")
     ap.add_argument("--latency-frames", type=int, default=64)
     ap.add_argument("--no-wire", dest="wire", action="store_false", help="host buffers as 24-byte packed records + 16-byte XYZI maps instead of the 22-byte / 12-byte wire formats")
+    ap.add_argument("--global-chunk", type=int, default=0, help="frames per upload chunk of the resident-global-map line (0 = the batch)")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="frames per upload chunk of the pipelined e2e call (0 = 32)")
     return ap.parse_args()
 
@@ -467,10 +469,15 @@ def run_b200(args, rank, world, local_rank):
         reg.set_frames(b0, fin)
     reg.sync()
 
-    def step_resident():
+    def step_resident(pipelined=True):
         reg.set_poses_device(0, F, guesses.data_ptr())      # the pose is in/out: restore the guesses (D2D, 24 B/frame)
-        for (b0, b1) in batches:
-            reg.run_frames(b0, b1 - b0)
+        if pipelined and not args.sequential:
+            # fbpr_run_frames_pipelined: the same kernels batch by batch, the front-end of batch k+1 and the map index on their own
+            # streams under the LM loop of batch k (identical results, asserted below)
+            reg.run_frames_pipelined(0, F, B)
+        else:
+            for (b0, b1) in batches:
+                reg.run_frames(b0, b1 - b0)
 
     for _ in range(args.warmup):
         step_resident()
@@ -497,8 +504,10 @@ def run_b200(args, rank, world, local_rank):
     reg.enable_stage_timing(True)
     reg.get_stage_ms(reset=True)
     for _ in range(max(3, args.steps // 2)):
-        step_resident()
+        step_resident(pipelined=False)                       # one stream, stage after stage: the un-overlapped stage times
     stage = reg.get_stage_ms(reset=True)
+    res_seq = reg.get_results(0, F)
+    assert np.array_equal(res_seq["iters"], res["iters"]) and np.array_equal(res_seq["pose"], res["pose"])    # pipelined == sequential, bit for bit
     reg.enable_stage_timing(False)
     stage_steps = max(3, args.steps // 2)
 
@@ -506,12 +515,13 @@ def run_b200(args, rank, world, local_rank):
     # (a) streaming form: fbpr_register_frames_begin / _end per batch, two batches in flight on disjoint slot ranges, so the uploads
     #     of batch k+1 run under the last kernels of batch k (every step still uploads all its inputs and downloads its results);
     # (b) one synchronous fbpr_register_frames call per batch, for comparison.
-    def run_e2e_stream(nsteps, fins=fins):
+    def run_e2e_stream(nsteps, fins=fins, chunk=None):
+        chunk = args.e2e_chunk if chunk is None else chunk
         out = [None] * nb
         seq = [(s_, b) for s_ in range(nsteps) for b in range(nb)]
-        t = reg.register_frames_begin(0, fins[seq[0][1]], args.e2e_chunk)
+        t = reg.register_frames_begin(0, fins[seq[0][1]], chunk)
         for k, (s_, b) in enumerate(seq):
-            tn = reg.register_frames_begin(B * ((k + 1) % 2), fins[seq[k + 1][1]], args.e2e_chunk) if k + 1 < len(seq) else None
+            tn = reg.register_frames_begin(B * ((k + 1) % 2), fins[seq[k + 1][1]], chunk) if k + 1 < len(seq) else None
             out[b] = reg.register_frames_end(t)
             t = tn
         return np.concatenate(out)
@@ -543,10 +553,11 @@ def run_b200(args, rank, world, local_rank):
     e2e_global = None
     try:
         reg.set_global_map(frames[0]["map_corner"], frames[0]["map_surf"])
-        run_e2e_stream(1 if nb > 1 else 2, fins_g)
+        gchunk = args.global_chunk or B                      # sweeps only: upload chunks as large as the LM likes its batches
+        run_e2e_stream(1 if nb > 1 else 2, fins_g, gchunk)
         barrier()
         t_host0 = time.perf_counter()
-        res_g = run_e2e_stream(args.steps, fins_g)
+        res_g = run_e2e_stream(args.steps, fins_g, gchunk)
         reg.sync()
         t_g = max_over_ranks((time.perf_counter() - t_host0) * 1e3)
         barrier()
@@ -664,7 +675,7 @@ def run_b200(args, rank, world, local_rank):
     out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic", "config": config_dict(args),
-           "frames_per_gpu": F, "batches_per_gpu": nb, "lm_cluster_size": reg.params.lm_cluster_size or "auto",
+           "frames_per_gpu": F, "batches_per_gpu": nb, "resident_schedule": "sequential" if args.sequential else "fbpr_run_frames_pipelined (3 streams)", "lm_cluster_size": reg.params.lm_cluster_size or "auto",
            "ms_per_frame": ms_total / args.steps / args.frames_total,
            "latency_ms_per_frame": lat,
            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,

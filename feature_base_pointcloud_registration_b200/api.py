@@ -382,6 +382,10 @@ class Registration:
     def run_frames(self, first=0, count=1, with_projection=True, with_features=True):
         self._ck(self.lib.fbpr_run_frames(self.h, first, count, int(with_projection), int(with_features)))
 
+    def run_frames_pipelined(self, first, count, batch_frames=0):
+        """fbpr_run_frames_pipelined: whole path for resident frames, front-end of batch k+1 overlapping the LM loop of batch k"""
+        self._ck(self.lib.fbpr_run_frames_pipelined(self.h, first, count, int(batch_frames)))
+
     def use_graphs(self, on=True): self._ck(self.lib.fbpr_use_graphs(self.h, int(on)))
     def sync(self): self._ck(self.lib.fbpr_sync(self.h))
     def stream(self): return self.lib.fbpr_stream(self.h)

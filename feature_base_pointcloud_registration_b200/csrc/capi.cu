@@ -136,6 +136,15 @@ static int check_range(fbpr_handle* h, int first, int count) {
 }
 
 static int enqueue_crop_local_maps(fbpr_handle* h, int first, int count);
+// the registration stream carries the longest chain of a pipelined batch (the LM loop): it gets the highest priority, so that a
+// ready LM launch is scheduled ahead of the next batch's front-end kernels
+static cudaError_t create_lm_stream(fbpr_handle* h) {
+    int lo = 0, hi = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e != cudaSuccess) return e;
+    const char* p = getenv("FBPR_LM_STREAM_PRIORITY");          // "0" switches the priority off (A/B measurements)
+    return cudaStreamCreateWithPriority(&h->lmStream, cudaStreamNonBlocking, (p && p[0] == '0') ? lo : hi);
+}
 
 static int build_vox_segs(fbpr_handle* h, std::vector<VoxSeg>& segs, VoxSeg** d_out) {
     for (auto& s : segs) {
@@ -738,6 +747,55 @@ int fbpr_run_frames(fbpr_handle* h, int first, int count, int with_projection, i
     });
 }
 
+// The resident form of the pipelined schedule: the slots [first, first + count) already hold their inputs; batches of
+// `batch_frames` go through the front-end (projection, features, downsample) on the handle's stream and through the map index +
+// LM loop on the registration stream, so that the front-end of batch k+1 fills the SMs that the latency-bound LM kernel of
+// batch k leaves idle (its tail, where the frames with few iterations have already finished).  Same kernels, same results as
+// fbpr_run_frames batch by batch.
+int fbpr_run_frames_pipelined(fbpr_handle* h, int first, int count, int batch_frames) {
+    int rc = check_range(h, first, count); if (rc) return rc;
+    if (count == 0) return 0;
+    if (batch_frames <= 0) batch_frames = 128;
+    if (fbpr_feat_ring_smem(feat_args(h, first)) > 200 * 1024) return fbpr_fail_msg("Horizon_SCAN too large for the per-ring shared-memory kernel");
+    for (int t = 0; t < FBPR_MAX_TICKETS; t++) if (h->tickets[t].busy) return fbpr_fail_msg("a pipelined upload batch is in flight (call fbpr_register_frames_end first)");
+    cudaSetDevice(h->device);
+    if (!h->lmStream) FBPR_CUDA_OK(create_lm_stream(h));
+    if (!h->scatterStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->scatterStream, cudaStreamNonBlocking));
+    cudaStream_t mapStream = h->scatterStream;                   // third stream: the map index needs only the map, not the sweep
+    const int nb = (count + batch_frames - 1) / batch_frames;
+    while ((int)h->pipeEvents.size() < 2 * nb + 2) {
+        cudaEvent_t e; FBPR_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->pipeEvents.push_back(e);
+    }
+    const bool timing = h->timing; h->timing = false;           // stage event pairs would serialise the streams
+    cudaEvent_t evStart = h->pipeEvents[2 * nb], evDone = h->pipeEvents[2 * nb + 1];
+    FBPR_CUDA_OK(cudaEventRecord(evStart, h->stream));           // everything queued so far on the handle's stream
+    FBPR_CUDA_OK(cudaStreamWaitEvent(h->lmStream, evStart, 0));
+    FBPR_CUDA_OK(cudaStreamWaitEvent(mapStream, evStart, 0));
+    cudaStream_t front = h->stream;
+    for (int b = 0; b < nb && !rc; b++) {
+        const int lo = first + b * batch_frames, n = (b + 1) * batch_frames <= count ? batch_frames : count - b * batch_frames;
+        rc = enqueue_project(h, lo, n);
+        if (!rc) rc = enqueue_features(h, lo, n);
+        if (!rc) rc = enqueue_downsample(h, lo, n);
+        if (rc) break;
+        cudaError_t e = cudaEventRecord(h->pipeEvents[2 * b], front);
+        h->stream = mapStream;                                   // enqueue_* launch on h->stream
+        if (e == cudaSuccess) rc = enqueue_map_index(h, lo, n);
+        if (e == cudaSuccess && !rc) e = cudaEventRecord(h->pipeEvents[2 * b + 1], mapStream);
+        h->stream = h->lmStream;
+        if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(h->lmStream, h->pipeEvents[2 * b], 0);
+        if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(h->lmStream, h->pipeEvents[2 * b + 1], 0);
+        if (e == cudaSuccess && !rc) rc = enqueue_lm(h, lo, n);
+        h->stream = front;
+        if (e != cudaSuccess) { h->timing = timing; return fbpr_fail(e, "event record / wait", __FILE__, __LINE__); }
+    }
+    h->timing = timing;
+    if (rc) { cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->lmStream); cudaStreamSynchronize(mapStream); return rc; }
+    FBPR_CUDA_OK(cudaEventRecord(evDone, h->lmStream));          // later operators on the handle's stream see the finished slots
+    FBPR_CUDA_OK(cudaStreamWaitEvent(h->stream, evDone, 0));
+    return 0;
+}
+
 // chunk schedule of the pipelined call: uniform chunks of `chunk_frames` (0 = 32).  A tapered tail (.., 16, 8, 8) was measured
 // and is slower (20.6 vs 19.3 ms per 128 frames for a lone call: small LM batches cost more than the shorter tail saves) and
 // makes no difference once two batches are in flight (16.8 ms, 97 % of the PCIe floor).
@@ -945,7 +1003,7 @@ int fbpr_register_frames_begin(fbpr_handle* h, int first, int count, const fbpr_
     }
     tk.first = first; tk.count = count;
     if (!h->copyStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
-    if (!h->lmStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->lmStream, cudaStreamNonBlocking));
+    if (!h->lmStream) FBPR_CUDA_OK(create_lm_stream(h));
     if (!h->scatterStream) FBPR_CUDA_OK(cudaStreamCreateWithFlags(&h->scatterStream, cudaStreamNonBlocking));
     tk.busy = true;                                              // from here on work may be queued for these slots
     rc = register_frames_enqueue(h, ticket, first, count, fr, chunk_frames);

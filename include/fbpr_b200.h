@@ -254,6 +254,10 @@ FBPR_API int fbpr_registration(fbpr_handle* h, int slot, const float* corner_glo
                                const float* surf_global_xyzi, int n_surf, int mem, float pose12[12]);
 /* the whole per-frame path in one call: project -> feature_extract -> downsample -> scan2map */
 FBPR_API int fbpr_run_frames(fbpr_handle* h, int first, int count, int with_projection, int with_features);
+/* the same whole path for `count` resident frames in batches of `batch_frames` (0 = 128), with the front-end of batch k+1 on the
+   handle's stream overlapping the map index + LM loop of batch k on a second stream.  Results are identical to fbpr_run_frames
+   batch by batch; work queued on the handle's stream afterwards is ordered behind it. */
+FBPR_API int fbpr_run_frames_pipelined(fbpr_handle* h, int first, int count, int batch_frames);
 
 /* the batch form of the caller's per-frame loop (cloudHandler -> featureExtra -> registration, imageProjection.cpp:182-226)
    for `count` INDEPENDENT frames given in HOST memory (pinned for full PCIe speed): uploads are issued in chunks of

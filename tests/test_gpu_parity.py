@@ -871,3 +871,30 @@ def test_batched_registration_against_resident_global_map(fb):
     with pytest.raises(fb.FbprError, match="FROM_GLOBAL"):
         r.set_frames(0, mixed)
     r.close()
+
+
+def test_run_frames_pipelined_equals_run_frames(fb):
+    """fbpr_run_frames_pipelined (front-end, map index and LM loop of consecutive batches on three streams) must give exactly what
+    fbpr_run_frames gives batch by batch, and later work on the handle's stream must see the finished slots."""
+    F = 7
+    frames = [synth.make_frame(3, 120 + i, small=(16, 900, 2000, 8000)) for i in range(F)]
+    r = fb.Registration(frames[0]["params"], max_frames=F, max_map_corner=4096, max_map_surf=16384)
+    guesses = np.stack([fr["guess"] for fr in frames])
+    for s, fr in enumerate(frames):
+        r.set_raw_scan(s, fb.api.pack_raw(fr["scan"]), imu=fr["imu"], imu_available=fr["imu_available"])
+        r.set_local_map(s, fr["map_corner"], fr["map_surf"])
+    r.set_poses(0, guesses)
+    r.run_frames(0, F)
+    want = r.get_results(0, F)
+    want_ds = [r.get_buffer(s, "SURF_DS").copy() for s in range(F)]
+    assert np.all(want["iters"] > 0)
+    for batch in (3, 1, 0, 7):
+        r.set_poses(0, guesses)
+        r.run_frames_pipelined(0, F, batch)
+        got = r.get_results(0, F)                                # queued on the handle's stream right behind the pipelined call
+        assert np.array_equal(got["pose"], want["pose"]) and np.array_equal(got["iters"], want["iters"]) and np.array_equal(got["flags"], want["flags"])
+        for s in range(F):
+            assert np.array_equal(r.get_buffer(s, "SURF_DS"), want_ds[s])
+    r.set_poses(0, guesses); r.run_frames_pipelined(2, 4, 2)     # a sub-range
+    assert np.array_equal(r.get_results(2, 4)["pose"], want["pose"][2:6])
+    r.close()
