@@ -188,7 +188,7 @@ int fbpr_create(const fbpr_params* params, int device, fbpr_handle** out) {
     h->mapSurfCap = params->max_map_surf > 0 ? params->max_map_surf : 262144;
     h->kfCap = params->max_keyframe_points;
     h->cellCorner = params->knn_cell_corner > 0 ? params->knn_cell_corner : 0.5f;
-    h->cellSurf = params->knn_cell_surf > 0 ? params->knn_cell_surf : 0.33f;     // measured on config 3/4 (scripts/knn_param_sweep.py): 0.25 / 0.5 m -> 7.42 ms of map index + LM per 128 frames, 0.33 / 0.3 m -> 6.72
+    h->cellSurf = params->knn_cell_surf > 0 ? params->knn_cell_surf : 0.4f;      // measured on config 3/4 (scripts/knn_param_sweep.py, profiles/r02_ncu_summary.md): map index + LM per 128 frames 4.95 ms at 0.33 m, 4.76 at 0.4 m (first radius 0.35 m)
     h->cellsCorner = params->grid_cells_corner > 0 ? params->grid_cells_corner : 262144;
     h->cellsSurf = params->grid_cells_surf > 0 ? params->grid_cells_surf : 1048576;
     h->cluster = params->lm_cluster_size;              // 0 = chosen per call from the batch size
@@ -637,7 +637,7 @@ static LmArgs lm_args(fbpr_handle* h, int first) {
     LmArgs a = {};
     a.meta = h->meta; a.cornerDS = h->cornerDS; a.cornerCap = h->cornerCap; a.surfDS = h->surfDS; a.surfCap = h->P;
     a.gsegs = h->d_gridSegs; a.first = first;
-    a.qanchor = h->qanchor; a.qcache = h->qcache; a.qCap = h->cornerCap + h->P; a.firstRadius = h->p.knn_first_radius > 0 ? h->p.knn_first_radius : 0.3f;
+    a.qanchor = h->qanchor; a.qcache = h->qcache; a.qCap = h->cornerCap + h->P; a.firstRadius = h->p.knn_first_radius > 0 ? h->p.knn_first_radius : 0.35f;
     a.partials = h->partials; a.teamMax = 16; a.partialsGrid = h->partialsGrid; a.gridMax = h->lmGridBlocks > 0 ? h->lmGridBlocks : 1; a.chunkPart = h->chunkPart; a.chunkCap = h->chunkCap;
     a.edgeMin = h->p.edgeFeatureMinValidNum; a.surfMin = h->p.surfFeatureMinValidNum;
     a.z_tol = h->p.z_tollerance; a.rot_tol = h->p.rotation_tollerance;

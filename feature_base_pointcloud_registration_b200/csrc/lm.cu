@@ -322,10 +322,9 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             // (1) candidate cache of this point's last full search: re-rank the cached map points (one thread); the
             //     result is the exact 5-NN when every uncached map point is provably farther (mapgrid.cuh)
             bool need = active;
-            int rad0 = 1;
+            float ball0 = a.firstRadius;             // radius of the first search pass (metres)
             if (active) {
-                if (iter == 0) rad0 = max(1, (int)ceilf(a.firstRadius / (sh_gd[kind].h * 0.9995f)));
-                else {
+                if (iter > 0) {
                     const float4 an = __ldcs(anchor);
                     if (an.w > 0.f) {
                         const int4* c4 = reinterpret_cast<const int4*>(cache);
@@ -344,14 +343,14 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
                         const float lim = an.w * 0.9999f - moved * 1.0001f - 1.0e-5f;     // every uncached point is farther than this
                         const float lim2 = lim > 0.f ? lim * lim * 0.9999f : 0.f;
                         need = !(knn_d5(r) < lim2 || lim2 >= 1.0f);                       // 2nd case: the cache decides the whole 1 m ball
-                        rad0 = knn5_radius_from_bound(sh_gd[kind], knn_d5(r));
+                        ball0 = knn5_ball_from_bound(knn_d5(r), a.firstRadius);
                     } else {
-                        rad0 = sh_gd[kind].rmax;
+                        ball0 = 2.0f;
                     }
                 }
             }
             // (2) full search by the whole warp for the points that need one; it refreshes their cache
-            warp_knn5(maps, kind, x0, y0, z0, rad0, need, r, anchor, cache);
+            warp_knn5(maps, kind, x0, y0, z0, ball0, need, r, anchor, cache);
             ok = active && knn_d5(r) < 1.0f;
             if (inRange) {
                 const GridDesc& gd = sh_gd[isCorner ? 0 : 1];

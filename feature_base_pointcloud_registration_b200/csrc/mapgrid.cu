@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128) knn5_query(const GridSeg* segs, const flo
     ThreadKnn5 r;
     #pragma unroll
     for (int k = 0; k < 5; k++) r.key[k] = ~0ull;
-    warp_knn5(M, 0, qx, qy, qz, rad0, active, r, nullptr, nullptr);
+    warp_knn5(M, 0, qx, qy, qz, (float)rad0 * gd[0].h, active, r, nullptr, nullptr);     // rad0 cells -> metres
     const bool ok = active && knn_d5(r) < 1.0f;
     if (i >= nq) return;
     #pragma unroll

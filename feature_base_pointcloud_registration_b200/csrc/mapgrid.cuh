@@ -15,11 +15,13 @@
 //     float4 points (coalesced), every load of a trip is issued before any is consumed, each lane
 //     keeps a private sorted top-5 of packed keys in registers (compare-exchange chain, no local
 //     memory), and five redux.sync rounds merge the 32 private lists;
-//   - the search radius R (in cells) of a query is chosen by the caller.  The LM kernel derives it
+//   - the radius of a query's first pass (metres) is chosen by the caller.  The LM kernel derives it
 //     from the previous iteration: the old 5 neighbours lie within sqrt(d5_old) + |p_new - p_old| of
 //     the new position, so a cube covering that radius contains the new exact 5-NN and ONE pass is
 //     enough.  If the covered ball does not yet certify the result (first iteration, R too small)
-//     the cube is doubled and only the cells it ADDS are scanned.
+//     the radius is doubled and the (larger) ball is scanned again.
+//   - a pass with radius R certifies its result only inside the ball of radius R * h around the query,
+//     so each row is trimmed to the chord of that ball: about a sixth of the cube's points are read.
 //   - temporal coherence across LM iterations: a full search also leaves a CANDIDATE CACHE for the point -- up
 //     to FBPR_KNN_CACHE (16) map indices and a radius tau such that every map point NOT in the cache is at least tau away from
 //     the search position.  At the next iteration the point has moved by delta, so every uncached map point
@@ -97,6 +99,7 @@ __device__ __forceinline__ void knn5_scan_ranges(ThreadKnn5& p, const float4* __
         float4 m[2]; bool v[2];
         #pragma unroll
         for (int u = 0; u < 2; u++) {
+            if (u == 1 && t0 + 32 >= total) { v[1] = false; break; }   // (uniform) the trip's second half is empty: most searches scan < 32 candidates
             const int t = t0 + u * 32 + lane;
             int j = 0;                                  // the last lane whose exclusive offset is <= t owns candidate t
             #pragma unroll
@@ -124,51 +127,61 @@ __device__ __forceinline__ void knn5_scan_ranges(ThreadKnn5& p, const float4* __
 // cache (may be null) receives up to FBPR_KNN_CACHE original indices (-1 = unused slot); the return value is tau (metres):
 // every map point whose index is not in the cache is at distance >= tau from the query (0 = cache not usable).
 __device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* __restrict__ cell_start, const float4* __restrict__ pts,
-                                                 float qx, float qy, float qz, int rad0, ThreadKnn5& r, int* cache) {
+                                                 float qx, float qy, float qz, float ball0, ThreadKnn5& r, int* cache) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int cx = (int)floorf((qx - g.ox) * g.inv_h);
     const int cy = (int)floorf((qy - g.oy) * g.inv_h);
     const int cz = (int)floorf((qz - g.oz) * g.inv_h);
-    ThreadKnn5 p;                                            // private list, kept across widening passes
-    #pragma unroll
-    for (int i = 0; i < 5; i++) p.key[i] = ~0ull;
-    int prev = -1, rad = min(max(rad0, 1), g.rmax);          // prev = radius of the cube already scanned (-1: none)
+    ThreadKnn5 p;                                            // private list of this lane
+    // ball = radius (metres) of the pass: everything within it is scanned, the result is final when the 5th distance lies inside
+    // it.  The last ball covers the 1 m gate of the caller.
+    const float ballMax = 1.35f;                             // beyond the 1 m gate: a point with nothing within 1.35 m keeps a cache that says so while it moves < 0.3 m
+    float ball = fminf(fmaxf(ball0, 0.05f), ballMax);
     float guard;
+    const float slack = g.h * 1.0e-3f + 1.0e-5f;             // cell edges as the f32 cell_of_point sees them
     while (true) {
+        // A pass certifies its result only inside a ball around the query, and the candidate cache can never reach farther either,
+        // so only the part of every cell row that can intersect that ball is scanned -- about a sixth of the points of the cube of
+        // cells around it -- and the ball's radius need not be a multiple of the cell edge.
+        guard = ball * 0.9995f;
+        const float ballR = ball * 1.0001f + 1.0e-5f;
+        const int rad = (int)ceilf(ballR * g.inv_h * 1.0001f);       // cells beyond cx +- rad are farther than the ball (the query lies in cell cx)
+        #pragma unroll
+        for (int i = 0; i < 5; i++) p.key[i] = ~0ull;        // a widening pass rescans its whole (larger) ball
         const int x0 = max(cx - rad, 0), x1 = min(cx + rad, g.dx - 1);
         const int y0 = max(cy - rad, 0), y1 = min(cy + rad, g.dy - 1);
         const int z0 = max(cz - rad, 0), z1 = min(cz + rad, g.dz - 1);
-        const int px0 = max(cx - prev, 0), px1 = min(cx + prev, g.dx - 1);   // x extent of the cube already scanned
-        const bool havePrev = prev >= 0 && px0 <= px1;
         const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
         const int nrows = (x0 <= x1 && ny > 0 && nz > 0) ? ny * nz : 0;
         const float inv_ny = 1.0f / (float)max(ny, 1);
         for (int rbase = 0; rbase < nrows; rbase += 32) {
             const int i = rbase + lane;
-            int a0 = 0, l0 = 0, a1 = 0, l1 = 0;
-            bool anyRight = false;
+            int a0 = 0, l0 = 0;
             if (i < nrows) {
                 const int zi = (int)(((float)i + 0.5f) * inv_ny);            // i / ny for the small integers involved
                 const int zz = z0 + zi, yy = y0 + (i - zi * ny);
                 const int row = (zz * g.dy + yy) * g.dx;
-                const bool inner = havePrev && abs(zz - cz) <= prev && abs(yy - cy) <= prev;
-                // left part [x0, lx1] and right part [rx0, x1]; a row outside the old footprint is all "left"
-                const int lx1 = inner ? px0 - 1 : x1;
-                const int rx0 = inner ? px1 + 1 : x1 + 1;
-                if (x0 <= lx1) { a0 = __ldg(cell_start + row + x0); l0 = __ldg(cell_start + row + lx1 + 1) - a0; }
-                if (rx0 <= x1) { a1 = __ldg(cell_start + row + rx0); l1 = __ldg(cell_start + row + x1 + 1) - a1; anyRight = true; }
+                // distance from the query to the row's cell column in y and z, then the chord of the ball along x
+                const float ylo = g.oy + (float)yy * g.h, zlo = g.oz + (float)zz * g.h;
+                const float dy = fmaxf(0.f, fmaxf(ylo - qy, qy - (ylo + g.h)) - slack);
+                const float dz = fmaxf(0.f, fmaxf(zlo - qz, qz - (zlo + g.h)) - slack);
+                const float rem = ballR * ballR - dy * dy - dz * dz;
+                if (rem >= 0.f) {
+                    const float hc = sqrtf(rem) * 1.0001f + slack;
+                    const int xa = max(x0, (int)floorf((qx - hc - g.ox) * g.inv_h));
+                    const int xb = min(x1, (int)floorf((qx + hc - g.ox) * g.inv_h));
+                    if (xa <= xb) { a0 = __ldg(cell_start + row + xa); l0 = __ldg(cell_start + row + xb + 1) - a0; }
+                }
             }
             knn5_scan_ranges(p, pts, a0, l0, qx, qy, qz);
-            if (__any_sync(FULL, anyRight)) knn5_scan_ranges(p, pts, a1, l1, qx, qy, qz);
         }
-        ThreadKnn5 pm;                                       // the merge consumes a copy; the private lists live on
+        ThreadKnn5 pm;                                       // the merge consumes a copy; the private lists feed the cache below
         #pragma unroll
         for (int i = 0; i < 5; i++) pm.key[i] = p.key[i];
         knn5_merge_warp(pm, r);
-        guard = (float)rad * g.h * 0.9995f;
-        if (knn_d5(r) < guard * guard || rad >= g.rmax) break;
-        prev = rad; rad = min(rad * 2, g.rmax);
+        if (knn_d5(r) < guard * guard || ball >= ballMax) break;
+        ball = fminf(ball * 2.0f, ballMax);
     }
     if (!cache) return 0.f;
     // ---- candidate cache.  Points outside it are: never scanned (>= guard away), pushed out of a full private
@@ -204,9 +217,9 @@ __device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* _
 }
 
 // Full searches for the lanes of a warp that `need` one (one query per lane; `kind` = which of the two maps it
-// searches, `rad0` = its first cube radius in cells); must be called by all 32 lanes.  A lane that does not need a
+// searches, `ball0` = the radius of its first pass in metres); must be called by all 32 lanes.  A lane that does not need a
 // search keeps its r.  anchor / cache (per lane: this lane's record, may be null) receive the candidate cache.
-__device__ __forceinline__ void warp_knn5(const KnnMaps& M, int kind, float qx, float qy, float qz, int rad0, bool need, ThreadKnn5& r,
+__device__ __forceinline__ void warp_knn5(const KnnMaps& M, int kind, float qx, float qy, float qz, float ball0, bool need, ThreadKnn5& r,
                                           float4* anchor, int* cache) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -214,7 +227,7 @@ __device__ __forceinline__ void warp_knn5(const KnnMaps& M, int kind, float qx, 
     while (todo) {
         const int src = __ffs(todo) - 1; todo &= todo - 1;
         const float bx = __shfl_sync(FULL, qx, src), by = __shfl_sync(FULL, qy, src), bz = __shfl_sync(FULL, qz, src);
-        const int bk = __shfl_sync(FULL, kind, src), br = __shfl_sync(FULL, rad0, src);
+        const int bk = __shfl_sync(FULL, kind, src); const float br = __shfl_sync(FULL, ball0, src);
         int* bc = reinterpret_cast<int*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(cache), src));
         ThreadKnn5 m;
         const float tau = warp_query_knn5(M.gd[bk], bk ? M.cell_start[1] : M.cell_start[0], bk ? M.pts[1] : M.pts[0], bx, by, bz, br, m, bc);
@@ -226,11 +239,10 @@ __device__ __forceinline__ void warp_knn5(const KnnMaps& M, int kind, float qx, 
     }
 }
 
-// First cube radius (cells) that certainly contains the exact 5-NN when 5 map points are known to lie within
-// squared distance d5_known of the query (huge = unknown: cover the whole 1 m ball).
-__device__ __forceinline__ int knn5_radius_from_bound(const GridDesc& g, float d5_known) {
-    if (!(d5_known < 1.0e30f)) return g.rmax;
-    const float rho = sqrtf(d5_known) * 1.001f + 1.0e-5f;
-    const float cells = rho / (g.h * 0.9995f);
-    return cells >= (float)g.rmax ? g.rmax : max(1, (int)ceilf(cells));
+// First ball radius (metres) that certainly contains the exact 5-NN when 5 map points are known to lie within squared distance
+// d5_known of the query (huge = unknown: cover the whole 1 m gate), never below `floor_m` -- the scan of a ball also decides how
+// far the candidate cache reaches, and a cache that reaches less than the first iteration's ball only brings the searches back.
+__device__ __forceinline__ float knn5_ball_from_bound(float d5_known, float floor_m) {
+    if (!(d5_known < 1.0e30f)) return 2.0f;
+    return fmaxf(sqrtf(d5_known) * 1.001f + 1.0e-5f, floor_m);
 }

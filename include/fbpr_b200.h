@@ -72,13 +72,13 @@ typedef struct fbpr_params {
     int32_t max_map_corner;                  /* local-map capacity per frame (after VoxelGrid)          */
     int32_t max_map_surf;
     int32_t max_keyframe_points;             /* extractCloud concat capacity per frame and kind (0 = no keyframe operator) */
-    float   knn_cell_corner;                 /* uniform-grid cell edge for the corner / surf map index (0 = 0.5 / 0.33); results do not depend on it */
+    float   knn_cell_corner;                 /* uniform-grid cell edge for the corner / surf map index (0 = 0.5 / 0.4); results do not depend on it */
     float   knn_cell_surf;
     int32_t grid_cells_corner;               /* dense-grid cell budget per map index (0 = 262144 / 1048576); the cell */
     int32_t grid_cells_surf;                 /*   edge is doubled until the map's bounding box fits the budget        */
     int32_t lm_cluster_size;                 /* CTAs cooperating on one frame's LM loop in batched calls: 1..16 (0 = per call, from the batch size) */
     int32_t lm_single_frame_mode;            /* count == 1 calls: 0 = whole GPU cooperates (grid barrier), 1 = one cluster   */
-    float   knn_first_radius;                /* metres the FIRST LM iteration's neighbour search must cover around each point (0 = 0.3):
+    float   knn_first_radius;                /* radius (metres) of the FIRST LM iteration's neighbour search around each point (0 = 0.35):
                                                 about the expected error of the initial guess; later iterations derive it exactly */
 } fbpr_params;
 
