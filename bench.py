@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-total", type=int, default=1024, help="frames of one step over ALL ranks (BASELINE configs[3])")
-    ap.add_argument("--batch", type=int, default=128, help="frames per launch batch on one GPU")
+    ap.add_argument("--batch", type=int, default=256, help="frames per launch batch on one GPU (256: two frames per SM-wave of LM clusters; measured best of 128 .. 1024)")
     ap.add_argument("--ref-frames", type=int, default=6, help="frames per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cluster", type=int, default=0, help="lm_cluster_size override")
     ap.add_argument("--sequential", action="store_true", help="resident steps as one fbpr_run_frames per batch on one stream (round-1 schedule) instead of fbpr_run_frames_pipelined")
