@@ -4,8 +4,8 @@
 A "step" = one pass of the whole hot path (projection+deskew -> smoothness/features -> VoxelGrid -> map index -> all LM
 iterations -> transformUpdate) over BASELINE configs[3]: 1024 independent synthetic 64-beam frames (config 3's frame
 geometry, 64 x 2048), each against its OWN 200 k-point local map, partitioned over the ranks in contiguous blocks
-(sharding.frame_range) and processed in batches of 128 frames per launch -- STRONG scaling: the 1024 frames of a step
-are fixed, N GPUs take 1024 / N each.
+(sharding.frame_range) and processed in batches of 256 frames per launch (fbpr_run_frames_pipelined: front-end, map index and LM
+loop of consecutive batches on three streams) -- STRONG scaling: the 1024 frames of a step are fixed, N GPUs take 1024 / N each.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--frames-total 1024] [--batch 128]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
@@ -59,7 +59,7 @@ def parse():
 def config_dict(args):
     """identical in both arms, so the driver compares like with like"""
     return {"workload": WORKLOAD, "frames_total": args.frames_total, "batch": args.batch,
-            "l2": "inputs larger than L2: 6.4 MB of scan + map per frame, 814 MB per 128-frame batch, every step streams them from HBM"}
+            "l2": "inputs larger than L2: 6.4 MB of scan + map per frame resident in HBM, 1.6 GB per 256-frame batch, every step streams them from HBM"}
 
 
 # ------------------------------------------------------------------------------------------ helpers
