@@ -394,7 +394,7 @@ def run_b200(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     F = hi - lo
-    B = min(args.batch, F)
+    B = min(args.batch, F, max(128, F // 2))      # at least two batches per GPU when there are >= 256 frames, so that the pipelined schedule has something to overlap
     nb = (F + B - 1) // B
     batches = [(b * B, min(F, (b + 1) * B)) for b in range(nb)]
     cfg = synth.CONFIGS[CONFIG]
