@@ -64,18 +64,21 @@ def config_dict(args):
 
 # ------------------------------------------------------------------------------------------ helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The sampler starts before the
+    region and every row carries nvidia-smi's own timestamp, so that the rows that fall INSIDE [mark_begin, mark_end] can be told
+    from the ones around it: at 8 GPUs the timed region of a strong-scaling run is only ~150 ms long."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -84,27 +87,52 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        import datetime
+
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for f in rows:
+                try:
+                    sm.append(float(f[2])); mx.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[6:10]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        fields = []
+        for t_read, r in self.rows:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+            try:      # nvidia-smi's own stamp (local time, ms resolution); the pipe read time is the fallback
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
             except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+                ts = t_read
+            fields.append((ts, f))
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        inside = [f for ts, f in fields if t0 <= ts <= t1]
+        where = "inside the timed region"
+        if not inside:      # region shorter than nvidia-smi's sampling period: the samples right around it
+            inside = [f for ts, f in fields if t0 - 0.25 <= ts <= t1 + 0.25]
+            where = "within 250 ms of the timed region (it is shorter than the sampling period)"
+        sm, mx, reasons = parse(inside)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), sampled=where, region_ms=None if self.t1 is None else 1e3 * (self.t1 - self.t0))
 
 
 def measured_peak():
@@ -486,14 +514,18 @@ def run_b200(args, rank, world, local_rank):
     counts = [list(reg.get_counts(s).values()) for s in range(F)]
     launches0 = reg.kernel_launches()
     sampler = ClockSampler(local_rank)
+    sampler.start()                                          # nvidia-smi needs ~100 ms to deliver its first row: start it ahead of the region
+    step_resident(); reg.sync()                              # (one more untimed step while it comes up)
+    launches0 = reg.kernel_launches()
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
         step_resident()
     e1.record(stream)
     reg.sync()
+    sampler.mark_end()
     barrier()
     clocks = sampler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
