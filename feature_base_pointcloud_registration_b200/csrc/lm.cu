@@ -349,6 +349,12 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
                     }
                 }
             }
+#ifdef FBPR_KNN_STATS
+            {
+                const unsigned ba = __ballot_sync(0xffffffffu, active), bn = __ballot_sync(0xffffffffu, need), bi = __ballot_sync(0xffffffffu, active && iter > 0);
+                KNN_STAT(19, __popc(ba)); KNN_STAT(17, __popc(bi)); KNN_STAT(18, __popc(bi & ~bn)); KNN_STAT(20 + min(iter, 7), __popc(bn));
+            }
+#endif
             // (2) full search by the whole warp for the points that need one; it refreshes their cache
             warp_knn5(maps, kind, x0, y0, z0, ball0, need, r, anchor, cache);
             ok = active && knn_d5(r) < 1.0f;
@@ -537,6 +543,15 @@ static int lm_configure() {
 }
 
 int fbpr_knn_cache_slots() { return FBPR_KNN_CACHE; }
+
+#ifdef FBPR_KNN_STATS
+extern "C" __attribute__((visibility("default"))) int fbpr_debug_knn_stats(unsigned long long* out, int reset) {     // diagnostics build only
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, g_knn_stats, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = { 0 }; cudaMemcpyToSymbol(g_knn_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int fbpr_lm_grid_blocks(int device) {
     // co-resident CTAs of the cooperative (one frame on the whole GPU) variant: one per SM

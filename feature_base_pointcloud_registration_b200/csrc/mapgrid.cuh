@@ -35,6 +35,16 @@
 #pragma once
 #include "internal.cuh"
 
+#ifdef FBPR_KNN_STATS
+// diagnostics build only (make EXTRA=-DFBPR_KNN_STATS, scripts/knn_stats.py; never shipped): [0] searches [1] passes [3] candidates
+// [4] rows [5..12] passes by candidate count <=8, <=16, <=32, <=64, <=128, <=256, <=512, more  [13..16] passes by rows <=9, <=25, <=32,
+// more [17] cache re-ranks [18] re-ranks that certify [19] point-iterations [20..27] searches at iteration 0..7+
+static __device__ unsigned long long g_knn_stats[32];
+#define KNN_STAT(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_knn_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define KNN_STAT(i, v) do { } while (0)
+#endif
+
 // the (up to) two map indices a warp's queries may refer to: kind 0 = corner map, kind 1 = surface map
 struct KnnMaps {
     const GridDesc* gd;           // [2], usually in shared memory
@@ -87,7 +97,7 @@ __device__ __forceinline__ void knn5_merge_warp(ThreadKnn5& p, ThreadKnn5& m) {
 
 // Stream the concatenation of 32 ranges (lane i owns [a, a + len)) through the lanes' private top-5 lists:
 // 64 candidates per trip, consecutive lanes on consecutive points, both loads of a trip issued before use.
-__device__ __forceinline__ void knn5_scan_ranges(ThreadKnn5& p, const float4* __restrict__ pts, int a, int len, float qx, float qy, float qz) {
+__device__ __forceinline__ int knn5_scan_ranges(ThreadKnn5& p, const float4* __restrict__ pts, int a, int len, float qx, float qy, float qz) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     int incl = len;
@@ -114,6 +124,7 @@ __device__ __forceinline__ void knn5_scan_ranges(ThreadKnn5& p, const float4* __
         #pragma unroll
         for (int u = 0; u < 2; u++) if (v[u]) knn_offer(p, m[u], qx, qy, qz);
     }
+    return total;
 }
 
 #ifndef FBPR_KNN_CACHE
@@ -140,7 +151,9 @@ __device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* _
     float ball = fminf(fmaxf(ball0, 0.05f), ballMax);
     float guard;
     const float slack = g.h * 1.0e-3f + 1.0e-5f;             // cell edges as the f32 cell_of_point sees them
+    KNN_STAT(0, 1);
     while (true) {
+        int st_tot = 0;                                      // candidates of this pass (diagnostics build only)
         // A pass certifies its result only inside a ball around the query, and the candidate cache can never reach farther either,
         // so only the part of every cell row that can intersect that ball is scanned -- about a sixth of the points of the cube of
         // cells around it -- and the ball's radius need not be a multiple of the cell edge.
@@ -174,8 +187,14 @@ __device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* _
                     if (xa <= xb) { a0 = __ldg(cell_start + row + xa); l0 = __ldg(cell_start + row + xb + 1) - a0; }
                 }
             }
-            knn5_scan_ranges(p, pts, a0, l0, qx, qy, qz);
+            st_tot += knn5_scan_ranges(p, pts, a0, l0, qx, qy, qz);
         }
+#ifdef FBPR_KNN_STATS
+        KNN_STAT(1, 1); KNN_STAT(3, st_tot); KNN_STAT(4, nrows);
+        KNN_STAT(st_tot <= 8 ? 5 : st_tot <= 16 ? 6 : st_tot <= 32 ? 7 : st_tot <= 64 ? 8 : st_tot <= 128 ? 9 : st_tot <= 256 ? 10 : st_tot <= 512 ? 11 : 12, 1);
+        KNN_STAT(nrows <= 9 ? 13 : nrows <= 25 ? 14 : nrows <= 32 ? 15 : 16, 1);
+#endif
+        (void)st_tot;
         ThreadKnn5 pm;                                       // the merge consumes a copy; the private lists feed the cache below
         #pragma unroll
         for (int i = 0; i < 5; i++) pm.key[i] = p.key[i];

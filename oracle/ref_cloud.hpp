@@ -128,7 +128,10 @@ static inline float l2_simple(const float* a, const float* b) {
 // to the points' extent; planeSplit partition, index = lim1 / lim2 / count/2) so that tree depth and leaf occupancy -- i.e. the CPU
 // time of build and search -- follow the library the reference calls; 0 = median split (balanced).  The search is exact with
 // either rule, so results are identical by construction (tests assert it).  Restated from memory of FLANN 1.8 / 1.9
-// (flann/algorithms/kdtree_single_index.h); not verifiable in this container.
+// (flann/algorithms/kdtree_single_index.h).  The search RESULTS (index order, squared distances, the strict radius rule) are
+// pinned against a real FLANN KDTreeSingleIndex -- cv2.flann, OpenCV's vendored copy of the library: tests/golden/flann_cv2.npz,
+// tests/test_oracle_cloud.py -- bit for bit wherever distances are distinct; among exactly equal distances FLANN's order follows
+// its tree traversal and the oracle's (d^2, index) rule is the documented deviation.
 inline int& oracle_kdtree_flann_split() { static int v = 1; return v; }
 
 class KdTree5 {

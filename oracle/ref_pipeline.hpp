@@ -364,7 +364,7 @@ public:
         voxel_grid(laserCloudSurfFromMap.data(), (int)laserCloudSurfFromMap.size(), P.mappingSurfLeafSize, laserCloudSurfFromMapDS);
     }
     // extractNearby  mapOptmization.h:872-907.  cloudKeyPoses3D[i] = (x, y, z, intensity = i); radiusSearch is FLANN's
-    // RadiusResultSet: d^2 < (float)(r*r) (strict, from memory of flann/util/result_set.h), sorted by (d^2, index);
+    // RadiusResultSet: d^2 < (float)(r*r) (strict -- confirmed against cv2.flann's radiusSearch, tests/golden/flann_cv2.npz), sorted by (d^2, index);
     // VoxelGrid(surroundingKeyframeDensity) averages xyz AND the intensity; then the key poses of the last 10 s, newest first.
     static void extractNearby(const P4* cloudKeyPoses3D, const double* keyTime, int n, float searchRadius, float density,
                               double timeLaserCloudInfoLast, std::vector<P4>& surroundingKeyPosesDS) {

@@ -2,6 +2,9 @@
 
   smallmat_cv2.npz    inputs and the outputs of cv2 4.13 (OpenCV's own JacobiImpl_ / QR32f / LU32f): pins the
                       oracle's restated small-matrix routines to the library the reference calls.
+  flann_cv2.npz       inputs and the outputs of cv2.flann's KDTreeSingleIndex (OpenCV 4.13 vendors the FLANN library: the same
+                      kd-tree class, result sets and L2 functor PCL's KdTreeFLANN instantiates): pins the oracle's exact 5-NN
+                      (index order and squared distances, bit for bit) and the strict radius rule of extractNearby.
   pipeline_small.npz  a small seeded frame and the oracle's outputs for every stage: a regression pin of the
                       oracle itself and a fixed-input case for the GPU parity tests.
 
@@ -38,6 +41,40 @@ def smallmat():
                         W6=np.array(W6), V6=np.array(V6), B6=np.array(B6), X6=np.array(X6), I6=np.array(I6), cv2_version=cv2.__version__)
 
 
+def flann():
+    """pcl::KdTreeFLANN = flann::KDTreeSingleIndex, leaf_max_size 15, reorder, exact search (eps 0), sorted result set
+    (SURVEY Appendix B-2); nearestKSearch(k = 5) at mapOptmization.h:1020 / :1143, radiusSearch at :880."""
+    sp = dict(checks=-1, eps=0.0, sorted=True)
+    fr = synth.make_frame(1, 7, small=(16, 600, 3000, 12000))
+    rng = np.random.default_rng(20261019)
+    out = {}
+    for name in ("map_corner", "map_surf"):
+        m = fr[name]; xyz = np.ascontiguousarray(m[:, :3], dtype=np.float32)
+        q = xyz[rng.integers(0, len(xyz), 1500)] + rng.normal(scale=0.12, size=(1500, 3))
+        q[:100] += rng.uniform(-2, 2, (100, 3))                           # some far from the map: the 1 m gate rejects them later
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        index = cv2.flann_Index(xyz, dict(algorithm=4, leaf_max_size=15, reorder=True))       # 4 = FLANN_INDEX_KDTREE_SINGLE
+        idx, d2 = index.knnSearch(q, 5, params=sp)
+        out[name] = m.astype(np.float32); out[name + "_q"] = q; out[name + "_idx"] = idx.astype(np.int32); out[name + "_d2"] = d2.astype(np.float32)
+    # lattice + exact duplicates: many exactly equal distances.  FLANN's order among equal distances follows its tree
+    # traversal; the distances themselves are what the test pins there.
+    g = np.stack(np.meshgrid(np.arange(10), np.arange(10), np.arange(5), indexing="ij"), -1).reshape(-1, 3).astype(np.float32) * np.float32(0.25)
+    g = g[rng.permutation(len(g))]; g = np.ascontiguousarray(np.concatenate([g, g[:40]]))
+    q = np.ascontiguousarray(g[rng.integers(0, len(g), 400)] + np.float32(0.125) * rng.integers(0, 2, size=(400, 3)).astype(np.float32))
+    idx, d2 = cv2.flann_Index(g, dict(algorithm=4, leaf_max_size=15, reorder=True)).knnSearch(q, 5, params=sp)
+    out["lattice"] = g; out["lattice_q"] = q; out["lattice_idx"] = idx.astype(np.int32); out["lattice_d2"] = d2.astype(np.float32)
+    # radius search over key poses (a trajectory that winds back on itself), query = the newest pose, radius 50 m; PCL hands
+    # FLANN radius * radius.  Three poses sit exactly ON the sphere (3-4-5 triangles): FLANN's RadiusResultSet is strict.
+    t = np.linspace(0, 6 * np.pi, 900)
+    kp = np.stack([40 * np.cos(t) + 0.02 * t, 30 * np.sin(2 * t), 0.1 * t], 1).astype(np.float32)
+    last = kp[-1].copy()
+    kp[100] = last + np.array([30, 40, 0], np.float32); kp[200] = last + np.array([0, -30, 40], np.float32); kp[300] = last + np.array([48, 14, 0], np.float32)
+    r2 = np.float32(50.0 * 50.0)
+    n, ri, rd = cv2.flann_Index(np.ascontiguousarray(kp), dict(algorithm=4, leaf_max_size=15, reorder=True)).radiusSearch(last[None, :], float(r2), len(kp), params=sp)
+    out["keyposes"] = kp; out["radius"] = np.float32(50.0); out["radius_idx"] = ri[0, :n].astype(np.int32); out["radius_d2"] = rd[0, :n].astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "flann_cv2.npz"), cv2_version=cv2.__version__, **out)
+
+
 def pipeline():
     small = (16, 450, 1500, 9000)
     fr = synth.make_frame(3, 11, small=small)            # config 3 flavour: IMU ramp -> deskew on
@@ -65,6 +102,8 @@ def pipeline():
 
 if __name__ == "__main__":
     smallmat()
-    pipeline()
-    for f in ("smallmat_cv2.npz", "pipeline_small.npz"):
+    flann()
+    if "--flann-only" not in sys.argv:
+        pipeline()
+    for f in ("smallmat_cv2.npz", "flann_cv2.npz", "pipeline_small.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

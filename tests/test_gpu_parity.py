@@ -2,6 +2,8 @@
 seeded synthetic inputs.  Bars (BASELINE.json north_star): voxel keys, selected-feature indices
 and kNN index sets bit-exact; per-point residual coefficients within 1e-5 relative; final pose
 within 1e-4 m / 1e-4 rad; iteration counts equal."""
+import os
+
 import numpy as np
 import pytest
 
@@ -9,6 +11,7 @@ import oracle
 import synth
 
 pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 POSE_TOL_T = 1e-4      # metres
 POSE_TOL_R = 1e-4      # radians
@@ -82,6 +85,26 @@ def test_knn5_ties_and_tiny_maps(fb, first_radius):
     assert np.array_equal(idx, ridx) and np.array_equal(d2, rd2)
     idx, _ = r.knn5(m[:4], q[:10], cell=0.25, first_radius=first_radius)                     # fewer than 5 map points: reject
     assert np.all(idx == -1)
+
+
+@pytest.mark.parametrize("cell", [0.3, 0.5])
+def test_knn5_against_committed_flann_vectors(fb, cell):
+    """The DEVICE search against the outputs of a real FLANN KDTreeSingleIndex (tests/golden/flann_cv2.npz, made with cv2.flann by
+    tests/golden/make_golden.py) -- no oracle in between: index order and squared distances bit for bit inside the 1 m gate."""
+    g = np.load(os.path.join(GOLDEN, "flann_cv2.npz"))
+    r = _reg(fb, synth.params_for(1))
+    for name in ("map_corner", "map_surf"):
+        idx, d2 = r.knn5(g[name], g[name + "_q"], cell=cell, first_radius=1)
+        fi, fd = g[name + "_idx"], g[name + "_d2"]
+        accept = fd[:, 4] < 1.0
+        distinct = np.all(np.diff(fd, axis=1) > 0, axis=1)
+        assert accept.sum() > 1000
+        assert np.array_equal(d2[accept].view(np.uint32), fd[accept].view(np.uint32))
+        assert np.array_equal(idx[accept & distinct], fi[accept & distinct])
+        assert np.all(idx[~accept] == -1)
+    m = np.concatenate([g["lattice"], np.zeros((len(g["lattice"]), 1), np.float32)], 1)
+    idx, d2 = r.knn5(m, g["lattice_q"], cell=cell, first_radius=1)
+    assert np.array_equal(d2, g["lattice_d2"])                    # ties: FLANN's order follows its traversal, the distances are pinned
 
 
 # ------------------------------------------------------------------ projection
