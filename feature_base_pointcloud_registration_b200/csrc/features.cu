@@ -89,17 +89,22 @@ __global__ void __launch_bounds__(TPB1) feat_smooth(FeatArgs a) {
 }
 
 // ---- block helpers -----------------------------------------------------------------------
+// exclusive scan of a 0 / 1 flag over the CTA (every call site scans a flag): ballot + popc inside the warp, and the
+// RING_TPB / 32 warp counts are scanned by every warp for itself with shuffles
 __device__ inline int block_excl_scan(int v, int* total, int* ws) {
+    static_assert(RING_TPB / 32 <= 32, "one lane per warp count");
     const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int incl = v;
-    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
+    const unsigned b = __ballot_sync(0xffffffffu, v != 0);
+    __syncthreads();                                      // ws may still be read by the previous scan
+    if (l == 0) ws[w] = __popc(b);
     __syncthreads();
-    if (l == 31) ws[w] = incl;
-    __syncthreads();
-    int off = 0, tot = 0;
-    for (int q = 0; q < RING_TPB / 32; q++) { int c = ws[q]; if (q < w) off += c; tot += c; }
-    *total = tot;
-    return off + incl - v;
+    const int c = l < RING_TPB / 32 ? ws[l] : 0;
+    int incl = c;
+    #pragma unroll
+    for (int o = 1; o < RING_TPB / 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
+    *total = __shfl_sync(0xffffffffu, incl, RING_TPB / 32 - 1);
+    const int before = __shfl_sync(0xffffffffu, incl - c, w);
+    return before + __popc(b & ((1u << l) - 1u));
 }
 
 // bitonic network over `count` keys made of aligned blocks of `blk` (pow2); every block ends ascending.
@@ -241,8 +246,7 @@ __device__ __forceinline__ void warp_sort_list(unsigned long long* base, int lan
 
 // bits e-5 .. e+5 (bit 5 = e itself) of a bit vector stored one word per warp, for element e = 32 * w + l
 __device__ __forceinline__ unsigned bit_window3(unsigned lo, unsigned mid, unsigned hi, int l) {
-    return l >= 5 ? (unsigned)((((unsigned long long)hi << 32) | mid) >> (l - 5))
-                  : (unsigned)((((unsigned long long)mid << 32) | lo) >> (l + 27));
+    return l >= 5 ? __funnelshift_r(mid, hi, l - 5) : __funnelshift_r(lo, mid, l + 27);     // low word of (hi:mid) >> (l - 5) / (mid:lo) >> (l + 27)
 }
 __device__ __forceinline__ unsigned bit_window(const unsigned* words, int w, int l) {
     return bit_window3(w > 0 ? words[w - 1] : 0u, words[w], w + 1 < RING_TPB / 32 ? words[w + 1] : 0u, l);
@@ -342,8 +346,9 @@ __global__ void __launch_bounds__(RING_TPB, FEAT_RING_CTAS) feat_ring(FeatArgs a
                 }
             }
             __syncthreads();
+            const int segShift = 31 - __clz(a.segPad);                       // segPad is a power of two (fbpr_launch_features)
             for (int t = tid; t < FBPR_SEGS * a.segPad; t += RING_TPB) {      // pad every list to a power of two with +inf keys
-                const int j = t / a.segPad, q = t - j * a.segPad, c = s_ccnt[j];
+                const int j = t >> segShift, q = t - (j << segShift), c = s_ccnt[j];
                 int pad = 32; while (pad < c) pad <<= 1;
                 if (q >= c && q < pad) s_keys[t] = ~0ull;
             }

@@ -30,7 +30,10 @@ namespace {
 
 // Launch shapes.  Batched calls: one cluster per frame, 256-thread CTAs (4 resident per SM at 64 registers).
 // Single-frame calls: one 768-thread CTA per SM over the whole GPU.
-constexpr int LM_TPB_CLUSTER = 256, LM_CTAS_CLUSTER = 4;
+#ifndef LM_CTAS
+#define LM_CTAS 4                  // resident CTAs per SM the batched shape is compiled for (register budget = 65536 / (256 * LM_CTAS))
+#endif
+constexpr int LM_TPB_CLUSTER = 256, LM_CTAS_CLUSTER = LM_CTAS;
 constexpr int LM_TPB_GRID = 768, LM_CTAS_GRID = 1;
 #ifndef LM_CARVEOUT
 #define LM_CARVEOUT 16
@@ -523,7 +526,10 @@ __global__ void transform_update_kernel(FrameMeta* meta, int first, int count, f
 
 }  // namespace
 
-static size_t lm_dyn_smem(int tpb) { return (size_t)(tpb / 32) * 32 * 7 * sizeof(float); }    // s_rows
+#ifndef LM_EXTRA_SMEM
+#define LM_EXTRA_SMEM 0            // experiments only: unused dynamic shared memory per batched CTA (limits the CTAs resident per SM)
+#endif
+static size_t lm_dyn_smem(int tpb) { return (size_t)(tpb / 32) * 32 * 7 * sizeof(float) + (tpb == LM_TPB_CLUSTER ? LM_EXTRA_SMEM : 0); }    // s_rows
 
 // one-time function attributes of both variants (cluster sizes above 8, dynamic shared memory above the default limit)
 static int lm_configure() {

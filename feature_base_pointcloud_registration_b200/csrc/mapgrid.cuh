@@ -56,6 +56,26 @@ struct ThreadKnn5 {
     unsigned long long key[5];   // ascending; 0xffff... = empty.  Only ever indexed with compile-time constants (registers).
 };
 
+// Bounds that only decide WHICH cells are scanned (always with explicit margins, never a result) use the one-instruction
+// approximations (relative error <= 2^-22) instead of the IEEE sequences the library is otherwise compiled for (-prec-div / -prec-sqrt).
+#ifndef FBPR_KNN_APPROX
+#define FBPR_KNN_APPROX 1
+#endif
+__device__ __forceinline__ float knn_sqrt_bound(float x) {
+#if FBPR_KNN_APPROX
+    float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return sqrtf(x);
+#endif
+}
+__device__ __forceinline__ float knn_rcp_bound(float x) {
+#if FBPR_KNN_APPROX
+    return __fdividef(1.0f, x);
+#else
+    return 1.0f / x;
+#endif
+}
+
 __device__ __forceinline__ void knn_cswap(unsigned long long& lo, unsigned long long& hi) {   // order a pair
     const unsigned long long a = lo, b = hi;
     const bool sw = b < a;
@@ -167,7 +187,7 @@ __device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* _
         const int z0 = max(cz - rad, 0), z1 = min(cz + rad, g.dz - 1);
         const int ny = y1 - y0 + 1, nz = z1 - z0 + 1;
         const int nrows = (x0 <= x1 && ny > 0 && nz > 0) ? ny * nz : 0;
-        const float inv_ny = 1.0f / (float)max(ny, 1);
+        const float inv_ny = knn_rcp_bound((float)max(ny, 1));
         for (int rbase = 0; rbase < nrows; rbase += 32) {
             const int i = rbase + lane;
             int a0 = 0, l0 = 0;
@@ -181,7 +201,7 @@ __device__ __forceinline__ float warp_query_knn5(const GridDesc& g, const int* _
                 const float dz = fmaxf(0.f, fmaxf(zlo - qz, qz - (zlo + g.h)) - slack);
                 const float rem = ballR * ballR - dy * dy - dz * dz;
                 if (rem >= 0.f) {
-                    const float hc = sqrtf(rem) * 1.0001f + slack;
+                    const float hc = knn_sqrt_bound(rem) * 1.0001f + slack;
                     const int xa = max(x0, (int)floorf((qx - hc - g.ox) * g.inv_h));
                     const int xb = min(x1, (int)floorf((qx + hc - g.ox) * g.inv_h));
                     if (xa <= xb) { a0 = __ldg(cell_start + row + xa); l0 = __ldg(cell_start + row + xb + 1) - a0; }

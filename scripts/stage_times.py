@@ -13,6 +13,14 @@ F = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 cluster = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 frames = [synth.make_frame(4, i) for i in range(F)]
+if os.environ.get("FBPR_MAP_ORDER") == "voxel":
+    # the order pcl::VoxelGrid leaves a local map in (mapOptmization.h:948-954: ascending voxel index, x fastest) instead of the
+    # random order synth.c draws the map points in
+    for fr in frames:
+        for name, leaf in (("map_corner", 0.2), ("map_surf", 0.4)):
+            m = fr[name]; ijk = np.floor(m[:, :3] / np.float32(leaf)).astype(np.int64); ijk -= ijk.min(0)
+            d = ijk.max(0) + 1
+            fr[name] = np.ascontiguousarray(m[np.argsort(ijk[:, 0] + d[0] * (ijk[:, 1] + d[1] * ijk[:, 2]), kind="stable")])
 cfg = synth.CONFIGS[4]
 r = fb.Registration(frames[0]["params"], max_frames=F, max_map_corner=cfg["map_corner"] + 64, max_map_surf=cfg["map_surf"] + 64, lm_cluster_size=cluster)
 raws = [fb.api.pack_raw(fr["scan"]) for fr in frames]
