@@ -363,7 +363,11 @@ __global__ void __launch_bounds__(RING_TPB, FEAT_RING_CTAS) feat_ring(FeatArgs a
                 else warp_sort_list<16>(base, lane);
             }
             __syncthreads();
+#ifdef FEAT_SKIP_SEGLOOP                                                  // phase timing only (results are wrong)
+            for (int j = 0; j < 0; j++) {
+#else
             for (int j = 0; j < FBPR_SEGS; j++) {
+#endif
                 const int sp = s_sp[j], ep = s_ep[j];
                 if (sp >= ep) continue;                                   // uniform across the CTA
                 const unsigned long long* keys = s_keys + j * a.segPad;

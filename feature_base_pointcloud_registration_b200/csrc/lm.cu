@@ -28,12 +28,18 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-// Launch shapes.  Batched calls: one cluster per frame, 256-thread CTAs (4 resident per SM at 64 registers).
-// Single-frame calls: one 768-thread CTA per SM over the whole GPU.
+// Launch shapes.  Batched calls: one cluster per frame, 512-thread CTAs (2 resident per SM at 64 registers), normally 2 CTAs per
+// frame.  Measured on 1024 config-4 frames, pipelined 256-frame launches (ms per 1024 frames): 256-thread CTAs x cluster 4:
+// 48.06; 1024 x 1: 46.78; 1024 x 2: 47.27; 512 x 4: 47.43; 512 x 2: 46.08 -- the fewer DIFFERENT frames share an SM's L1 the
+// better (with 256-thread CTAs an SM serves four frames at once), and one 1024-thread CTA per frame loses more to its coarse
+// launch granularity than it wins.  Single-frame calls: one 768-thread CTA per SM over the whole GPU.
 #ifndef LM_CTAS
-#define LM_CTAS 4                  // resident CTAs per SM the batched shape is compiled for (register budget = 65536 / (256 * LM_CTAS))
+#define LM_CTAS 2                  // resident CTAs per SM the batched shape is compiled for (register budget = 65536 / (LM_BATCH_TPB * LM_CTAS))
 #endif
-constexpr int LM_TPB_CLUSTER = 256, LM_CTAS_CLUSTER = LM_CTAS;
+#ifndef LM_BATCH_TPB
+#define LM_BATCH_TPB 512           // threads per CTA of the batched shape
+#endif
+constexpr int LM_TPB_CLUSTER = LM_BATCH_TPB, LM_CTAS_CLUSTER = LM_CTAS;
 constexpr int LM_TPB_GRID = 768, LM_CTAS_GRID = 1;
 #ifndef LM_CARVEOUT
 #define LM_CARVEOUT 16
@@ -587,21 +593,21 @@ static int lm_max_active_clusters(int c) {
     return cached[c];
 }
 
-// cluster size for a batch of `count` frames: the time of the launch is ~ waves / (CTAs per frame), so take the size
-// that minimises it (a small batch gets big clusters to fill the GPU, a big batch small ones for fewer waves);
-// ties go to the smaller cluster (cheaper barrier, fewer redundant solves)
+// cluster size for a batch of `count` frames: the time of the launch is ~ waves / (CTAs per frame); among the sizes whose
+// estimate is within 15 % of the best one the SMALLEST wins (cheaper barrier, fewer redundant solves, and fewer warps than chunks
+// keeps the warps of a frame busy) -- a batch that fills the GPU gets 2 CTAs per frame, a small batch big clusters
 int fbpr_lm_auto_cluster(int count) {
-    // powers of two only: odd sizes are allowed when asked for (lm_cluster_size = 1..16) but measured no better
-    // (128 frames: 4 -> 5.78 ms, 8 -> 5.77, 9 -> 5.97, 10 -> 5.80, 16 -> 7.1)
-    const int sizes[5] = { 1, 2, 4, 8, 16 };
-    int best = 8; double bestScore = 1e30;
-    for (int k = 0; k < 5; k++) {
+    // powers of two only: odd sizes are allowed when asked for (lm_cluster_size = 1..16) but measured no better; one CTA per
+    // frame (16 warps for ~220 chunks) measured 1.46x slower than two and is only taken when asked for
+    const int sizes[4] = { 2, 4, 8, 16 };
+    double score[4]; double bestScore = 1e30;
+    for (int k = 0; k < 4; k++) {
         const int c = sizes[k], n = lm_max_active_clusters(c);
-        if (n <= 0) continue;
-        const double score = (double)((count + n - 1) / n) / (double)c;
-        if (score < bestScore * 0.999) { bestScore = score; best = c; }
+        score[k] = n > 0 ? (double)((count + n - 1) / n) / (double)c : 1e30;
+        if (score[k] < bestScore) bestScore = score[k];
     }
-    return best;
+    for (int k = 0; k < 4; k++) if (score[k] <= bestScore * 1.15) return sizes[k];
+    return 2;
 }
 
 int fbpr_launch_lm(const LmArgs& args, int count, int cluster_size, int grid_blocks, cudaStream_t st, long long* launches) {

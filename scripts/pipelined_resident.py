@@ -5,9 +5,10 @@ import numpy as np, torch, synth
 import feature_base_pointcloud_registration_b200 as fb
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+CL = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 frames = [synth.make_frame(4, i % 128) for i in range(F)]
 cfg = synth.CONFIGS[4]
-r = fb.Registration(frames[0]["params"], max_frames=F, max_map_corner=cfg["map_corner"] + 64, max_map_surf=cfg["map_surf"] + 64)
+r = fb.Registration(frames[0]["params"], max_frames=F, max_map_corner=cfg["map_corner"] + 64, max_map_surf=cfg["map_surf"] + 64, lm_cluster_size=CL)
 stream = torch.cuda.ExternalStream(r.stream(), device=torch.device("cuda", 0))
 for s, fr in enumerate(frames):
     r.set_raw_scan(s, fb.api.pack_raw(fr["scan"]), imu=fr["imu"], imu_available=fr["imu_available"]); r.set_local_map(s, fr["map_corner"], fr["map_surf"])
