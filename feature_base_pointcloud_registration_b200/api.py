@@ -420,8 +420,8 @@ class Registration:
 
     def selftest_smallmat(self, which, rows):
         """fbpr_selftest_smallmat: the device small-matrix routines on `rows` ([n, in_width] f32); which = name below."""
-        names = ["JACOBI3", "JACOBI6", "QR6", "LU6", "PLANE5X3", "NOT_DEGENERATE", "QR6_WARP"]
-        out_w = [12, 42, 6, 36, 3, 1, 6]
+        names = ["JACOBI3", "JACOBI6", "QR6", "LU6", "PLANE5X3", "NOT_DEGENERATE", "QR6_WARP", "SINCOS"]
+        out_w = [12, 42, 6, 36, 3, 1, 6, 2]
         k = names.index(which)
         a = _f32(rows).reshape(len(rows), -1)
         out = np.zeros((len(a), out_w[k]), np.float32)

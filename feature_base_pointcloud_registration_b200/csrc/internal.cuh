@@ -209,7 +209,7 @@ __device__ inline void sincosf_c(float x, float& s, float& c) {      // both at 
         const double z = xd * xd, v = z * xd;
         const double rs = __fma_rn(z, __fma_rn(z, __fma_rn(z, __fma_rn(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08), 2.75573137070700676789e-06),
                                                -1.98412698298579493134e-04), 8.33333333332248946124e-03);
-        s = (float)__fma_rn(v, __fma_rn(z, rs, -1.66666666666666324348e-01), xd);
+        s = fabsf(x) < 7.4505806e-9f ? x : (float)__fma_rn(v, __fma_rn(z, rs, -1.66666666666666324348e-01), xd);      // |x| < 2^-27: sin x = x (keeps -0, as fdlibm and glibc do)
         const double rc = z * __fma_rn(z, __fma_rn(z, __fma_rn(z, __fma_rn(z, __fma_rn(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09), -2.75573143513906633035e-07),
                                                                2.48015872894767294178e-05), -1.38888888888741095749e-03), 4.16666666666666019037e-02);
         const double ax = fabs(xd), zr = z * rc;

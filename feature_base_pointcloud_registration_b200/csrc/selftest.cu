@@ -53,6 +53,10 @@ __global__ void selftest_smallmat(int which, const float* __restrict__ in, int n
         for (int k = 0; k < 15; k++) A[k] = in[15 * i + k];
         dev_plane_solve(A, x);
         for (int k = 0; k < 3; k++) out[3 * i + k] = x[k];
+    } else if (which == FBPR_SELFTEST_SINCOS) {      // in: angle, out: sin, cos (sincosf_c: the polynomial kernels inside |x| <= pi/4, sincos(double) outside)
+        float sv, cv;
+        sincosf_c(in[i], sv, cv);
+        out[2 * i] = sv; out[2 * i + 1] = cv;
     } else if (which == FBPR_SELFTEST_NOT_DEGENERATE) {   // in: 6x6, out: 1.0 when the LDL^T certificate holds
         out[i] = dev_surely_not_degenerate(in + 36 * i) ? 1.f : 0.f;
     }
@@ -61,9 +65,9 @@ __global__ void selftest_smallmat(int which, const float* __restrict__ in, int n
 }  // namespace
 
 extern "C" int fbpr_selftest_smallmat(fbpr_handle* h, int which, const float* in, int n, float* out) {
-    static const int in_w[] = { 9, 36, 42, 36, 15, 36, 42 }, out_w[] = { 12, 42, 6, 36, 3, 1, 6 };
+    static const int in_w[] = { 9, 36, 42, 36, 15, 36, 42, 1 }, out_w[] = { 12, 42, 6, 36, 3, 1, 6, 2 };
     if (!h) return fbpr_fail_msg("null handle");
-    if (which < 0 || which > FBPR_SELFTEST_QR6_WARP || n < 0 || (n > 0 && (!in || !out))) return fbpr_fail_msg("bad selftest arguments");
+    if (which < 0 || which > FBPR_SELFTEST_SINCOS || n < 0 || (n > 0 && (!in || !out))) return fbpr_fail_msg("bad selftest arguments");
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)fbpr_stream(h);
     float *d_in = nullptr, *d_out = nullptr;

@@ -329,7 +329,8 @@ FBPR_API int fbpr_knn5_first_radius(fbpr_handle* h, int cells);
    cv::solve(DECOMP_QR) :1343, cv::Mat::inv :1370) and with Eigen's colPivHouseholderQr (:1169).  Row widths (floats) in / out:
    JACOBI3 9 / 12 (W, V rows), JACOBI6 36 / 42, QR6 42 (A then b) / 6, LU6 36 / 36, PLANE5X3 15 / 3, NOT_DEGENERATE 36 / 1. */
 enum { FBPR_SELFTEST_JACOBI3 = 0, FBPR_SELFTEST_JACOBI6, FBPR_SELFTEST_QR6, FBPR_SELFTEST_LU6, FBPR_SELFTEST_PLANE5X3, FBPR_SELFTEST_NOT_DEGENERATE,
-       FBPR_SELFTEST_QR6_WARP /* the warp-parallel form of QR6 that the LM kernel runs */ };
+       FBPR_SELFTEST_QR6_WARP /* the warp-parallel form of QR6 that the LM kernel runs */,
+       FBPR_SELFTEST_SINCOS   /* in: one angle, out: sin, cos under the f32 trig contract (float)sin((double)x) -- pcl::getTransformation's trig */ };
 FBPR_API int fbpr_selftest_smallmat(fbpr_handle* h, int which, const float* in, int n, float* out);
 
 #ifdef __cplusplus

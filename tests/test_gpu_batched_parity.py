@@ -253,6 +253,25 @@ def test_device_smallmat_against_committed_cv2_vectors(fb):
     r.close()
 
 
+def test_device_trig_contract_against_libm(fb):
+    """sincosf_c on the device (the trig of pcl::getTransformation, imageProjection.cpp:564-570, mapOptmization.h:309; polynomial
+    kernels inside |x| <= pi/4, sincos(double) outside) against (float)sin((double)x) / (float)cos((double)x) of this host's libm,
+    bit for bit: deskew-sized angles, the whole reduction-free range, both sides of its boundary, pose-sized angles."""
+    import math
+    r = fb.Registration(synth.params_for(1), max_frames=1, max_map_corner=1024, max_map_surf=1024)
+    rng = np.random.default_rng(7)
+    b = np.float32(0.78539816)
+    edge = np.array([np.nextafter(b, np.float32(0)), b, np.nextafter(b, np.float32(1)), -b, np.nextafter(-b, np.float32(-1)), 0.0, -0.0, 0.3, -0.3,
+                     np.nextafter(np.float32(0.3), np.float32(1)), 0.78125, 1e-30, -1e-20, 1e-6], np.float32)
+    x = np.concatenate([edge, rng.uniform(-0.05, 0.05, 40000), rng.uniform(-0.7854, 0.7854, 40000), rng.uniform(-3.2, 3.2, 40000),
+                        np.ldexp(rng.uniform(0.5, 1.0, 20000), rng.integers(-40, 0, 20000)) * rng.choice([-1.0, 1.0], 20000)]).astype(np.float32)
+    got = r.selftest_smallmat("SINCOS", x.reshape(-1, 1))
+    want = np.array([[np.float32(math.sin(float(v))), np.float32(math.cos(float(v)))] for v in x], np.float32)
+    bad = np.nonzero(np.any(got.view(np.uint32) != want.view(np.uint32), axis=1))[0]
+    assert len(bad) == 0, [(float(x[i]), got[i].tolist(), want[i].tolist()) for i in bad[:8]]
+    r.close()
+
+
 # ------------------------------------------------------------------ feature kernel: full-sort fallback and fuzz
 @pytest.mark.parametrize("n_scan,horizon", [(4, 4096), (16, 120), (2, 6000)])
 def test_feature_extraction_full_sort_fallback(fb, n_scan, horizon):
