@@ -334,12 +334,16 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             float ball0 = a.firstRadius;             // radius of the first search pass (metres)
             if (active) {
                 if (iter > 0) {
+                    // the point's record (anchor + cached indices) in ONE round trip: the index loads do not wait for the anchor's test
+                    const int4* c4 = reinterpret_cast<const int4*>(cache);
                     const float4 an = __ldcs(anchor);
+                    int4 cv[FBPR_KNN_CACHE / 4];
+                    #pragma unroll
+                    for (int k = 0; k < FBPR_KNN_CACHE / 4; k++) cv[k] = __ldcs(c4 + k);
                     if (an.w > 0.f) {
-                        const int4* c4 = reinterpret_cast<const int4*>(cache);
                         #pragma unroll
                         for (int half = 0; half < FBPR_KNN_CACHE / 8; half++) {     // 8 independent gathers in flight
-                            const int4 va = __ldcs(c4 + 2 * half), vb = __ldcs(c4 + 2 * half + 1);
+                            const int4 va = cv[2 * half], vb = cv[2 * half + 1];
                             const int ci[8] = { va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w };
                             float4 cm[8];
                             #pragma unroll
