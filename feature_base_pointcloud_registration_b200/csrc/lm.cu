@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(GRID ? LM_TPB_GRID : LM_TPB_CLUSTER, GRID ? LM
             const float4* mo = isCorner ? gc.pts : gs.pts;   // the map in original order (XYZI)
             ThreadKnn5 r;
             #pragma unroll
-            for (int k = 0; k < 5; k++) r.key[k] = ~0ull;
+            for (int i = 0; i < 5; i++) r.key[i] = ~0ull;
             // (1) candidate cache of this point's last full search: re-rank the cached map points (one thread); the
             //     result is the exact 5-NN when every uncached map point is provably farther (mapgrid.cuh)
             bool need = active;

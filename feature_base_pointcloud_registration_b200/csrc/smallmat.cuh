@@ -88,7 +88,6 @@ __device__ inline int dev_qr_solve6(float* A, float* b, float* x) {
     float vl[6], h[6];
     #pragma unroll
     for (int l = 0; l < n; l++) {
-        int vlSize = n - l;
         float vlNorm = 0.f;
         #pragma unroll
         for (int i = 0; i < n - l; i++) { vl[i] = A[(l + i) * n + l]; vlNorm += vl[i] * vl[i]; }

@@ -133,9 +133,6 @@ __global__ void __launch_bounds__(1024) rs_scan(const VoxSeg* segs, int pass, in
     const int ntiles = (d.n + TILE - 1) / TILE;
     const int total = 256 * ntiles;
     __shared__ unsigned wsum[32];
-    __shared__ unsigned carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
     const int per = (total + 1023) / 1024;            // consecutive entries per thread
     int lo = threadIdx.x * per, hi = min(lo + per, total);
     unsigned sum = 0;
