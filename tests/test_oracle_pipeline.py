@@ -215,3 +215,32 @@ def test_literal_sort_mode_changes_no_selection():
         assert np.abs(a[2] - b[2]).max() <= 1e-4
         moved += int(not np.array_equal(a[0]["surface"], b[0]["surface"]))
     assert moved > 0        # the mode really sorts differently
+
+
+def test_transform_update_against_scipy_slerp():
+    """transformUpdate (mapOptmization.h:1444-1479): tf::Quaternion::setRPY / slerp(0.05) / tf::Matrix3x3::getRPY on roll and pitch
+    separately, then the three clamps -- the oracle's restatement of the tf arithmetic against scipy's Rotation / Slerp (f64), to
+    the f32 rounding of the result; yaw and x, y untouched; no IMU or |imuPitchInit| >= 1.4: only the clamps."""
+    from scipy.spatial.transform import Rotation, Slerp
+    P = synth.params_for(1)
+    mo = oracle.MapOptimization(P)
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        pose = np.concatenate([rng.uniform(-1.3, 1.3, 2), rng.uniform(-3.1, 3.1, 1), rng.uniform(-40, 40, 3)]).astype(np.float32)
+        imu_r, imu_p = (float(np.float32(v)) for v in rng.uniform(-1.3, 1.3, 2))
+        mo.set_imu(1, imu_r, imu_p)
+        got = mo.transform_update(pose)
+        want = pose.astype(np.float64).copy()
+        for axis, k, tgt in (("x", 0, imu_r), ("y", 1, imu_p)):
+            key = Rotation.from_euler(axis, [[float(pose[k])], [tgt]])
+            want[k] = Slerp([0.0, 1.0], key)(0.05).as_euler("xyz")["xyz".index(axis)]
+        assert np.allclose(got[:2], want[:2], rtol=0, atol=3e-7), (pose, imu_r, imu_p, got, want)
+        assert np.array_equal(got[2:], pose[2:])
+    pose = np.array([0.3, -0.2, 1.0, 1, 2, 3], np.float32)
+    mo.set_imu(0, 0.9, 0.9)
+    assert np.array_equal(mo.transform_update(pose), pose)                  # no IMU: nothing to blend, nothing to clamp
+    mo.set_imu(1, 0.9, 1.45)
+    assert np.array_equal(mo.transform_update(pose), pose)                  # |imuPitchInit| >= 1.4: the blend is skipped (:1450)
+    P2 = dict(P); P2["rotation_tollerance"] = 0.1; P2["z_tollerance"] = 0.5
+    mo2 = oracle.MapOptimization(P2); mo2.set_imu(0, 0.0, 0.0)
+    assert np.array_equal(mo2.transform_update(pose), np.array([0.1, -0.1, 1.0, 1, 2, 0.5], np.float32))   # the three clamps (:1474-1476)
